@@ -1,0 +1,52 @@
+"""Shared helpers for the test-suite (oracle construction, golden loading)."""
+import json
+import os
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+GOLDEN_CASES = ["g1500_k2", "g3000_k3", "g2500_k1_5cm"]
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    g = {k: z[k] for k in z.files}
+    g["clicks"] = json.loads(str(g["clicks"]))
+    g["times"] = json.loads(str(g["times"]))
+    g["wseed"] = int(g["wseed"])
+    return g
+
+
+def layout():
+    with open(os.path.join(GOLDEN, "state_dict_layout.json")) as f:
+        return {k: tuple(v) for k, v in json.load(f).items()}
+
+
+def oracle_model(wseed, dtype=torch.float32):
+    from agile3d_b200.weights import default_args, synth_state_dict
+    from oracle.agile3d_ref import build_ref_model
+
+    m = build_ref_model(default_args()).eval()
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    m.load_state_dict(synth_state_dict(shapes, seed=wseed))
+    return m.to(dtype)
+
+
+def oracle_forward(model, coords, feats, raw, clicks, times, dtype=torch.float32):
+    """coords [N,4] int, feats [N,3], raw [N,3]; clicks/times lists of dicts -> (pcd, logits-per-layer-per-scene)."""
+    from oracle import me_ref as ME
+
+    x = ME.SparseTensor(coordinates=torch.as_tensor(coords), features=torch.as_tensor(feats).to(dtype))
+    with torch.no_grad():
+        pcd, aux, co, pos = model.forward_backbone(x, torch.as_tensor(raw).to(dtype))
+        out = model.forward_mask(pcd, aux, co, pos, clicks, times)
+    per_layer = [a["pred_masks"] for a in out["aux_outputs"]] + [out["pred_masks"]]
+    return pcd, aux, pos, per_layer
+
+
+def rel_err(a, b):
+    """max |a-b| / max |b|: the 'relative' in "within 1e-3 relative on fp32 mask logits"."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
