@@ -1,0 +1,71 @@
+"""ctypes binding of csrc/libagile3d_b200.so (C-ABI: include/agile3d_b200.h).
+
+There is deliberately no fallback: if the shared library is missing or a call fails, this raises.
+Build it with ``python -c "import __graft_entry__ as g; g.build()"`` (or ``make -C agile3d_b200/csrc``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libagile3d_b200.so")
+
+RELU = 1
+ALGO_AUTO, ALGO_SIMT, ALGO_TC = 0, 1, 2
+
+_lib = None
+
+_vp, _i32, _i64, _f32, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
+
+# name -> (restype, argtypes); every entry of include/agile3d_b200.h appears here
+SIGNATURES = {
+    "ag3d_abi_version": (_i32, []),
+    "ag3d_last_error": (C.c_char_p, []),
+    "ag3d_device_info": (_i32, [_vp, _vp, _vp]),
+    "ag3d_kernel_launches": (_i64, []),
+    "ag3d_hash_capacity": (_i64, [_i64]),
+    "ag3d_hash_build": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp]),
+    "ag3d_downsample_workspace_bytes": (_sz, [_i64]),
+    "ag3d_downsample": (_i32, [_vp, _i64, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ag3d_kernel_map": (_i32, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "ag3d_kernel_map_transposed": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp]),
+    "ag3d_spconv_fwd": (_i32, [_vp, _i32, _i32, _vp, _i32, _i64, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _i32, _i32,
+                               _i32, _vp]),
+    "ag3d_stem_conv_fwd": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
+    "ag3d_posenc_workspace_bytes": (_sz, [_i32]),
+    "ag3d_fourier_posenc": (_i32, [_vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "ag3d_c2s_workspace_bytes": (_sz, [_i32, _i32]),
+    "ag3d_c2s_attn_fwd": (_i32, [_vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ag3d_s2c_mask_fwd": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _i32, _i32, _i32,
+                                 _vp, _vp, _vp, _vp, _vp]),
+}
+
+
+class Ag3dError(RuntimeError):
+    pass
+
+
+def lib():
+    """The loaded library; raises (never falls back) when it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise Ag3dError(
+                f"{LIB_PATH} is missing: the CUDA library has not been built. "
+                "Run `python -c 'import __graft_entry__ as g; g.build()'` at the repo root. "
+                "agile3d_b200 has no CPU or PyTorch fallback.")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)          # AttributeError if the symbol is not exported
+            fn.restype, fn.argtypes = res, args
+        if handle.ag3d_abi_version() != 1:
+            raise Ag3dError("libagile3d_b200.so ABI version mismatch; rebuild")
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = lib().ag3d_last_error()
+        raise Ag3dError(f"{what} failed (code {rc}): {msg.decode() if msg else '?'}")

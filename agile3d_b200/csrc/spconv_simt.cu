@@ -1,0 +1,209 @@
+// K4 (exact-fp32 variant): output-stationary gather implicit GEMM on the CUDA cores, plus the 3->32 stem
+// evaluated directly against the hash table.  This is the bit-for-bit-fp32 arithmetic path (FFMA, fp32
+// accumulate) that the tcgen05 3xTF32 path (spconv_tc.cu) is validated against at full size.
+#include "common.cuh"
+
+namespace ag3d {
+
+// out tile BM x BN per CTA, 256 threads, thread tile 4 x TN, K-chunk 16 channels.
+constexpr int BM = 64;
+constexpr int BK = 16;
+constexpr int SIMT_THREADS = 256;
+
+template <int BN>
+__global__ void __launch_bounds__(SIMT_THREADS)
+spconv_simt_kernel(const float* __restrict__ in, int in_ld, int cin, const int* __restrict__ nbr, int K,
+                   long long n_out, const float* __restrict__ weight, int cout, const float* __restrict__ scale,
+                   const float* __restrict__ shift, const float* __restrict__ residual, int res_ld,
+                   float* __restrict__ out, int out_ld, int flags) {
+  constexpr int TN = BN / 16;
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN];
+  const int tid = threadIdx.x;
+  const int ty = tid >> 4, tx = tid & 15;
+  const long long row0 = (long long)blockIdx.x * BM;
+  const int col0 = blockIdx.y * BN;
+
+  float acc[4][TN];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  // gather role: thread -> (row a_r of the tile, 4-float chunk a_c of the 16-channel slab)
+  const int a_r = tid >> 2, a_c = tid & 3;
+  const long long my_row = row0 + a_r;
+  // weight role: thread -> (kk, 4-float chunk)
+  constexpr int B_VEC = BK * BN / 4;  // float4 per slab
+  const int b_kk = tid / (BN / 4), b_c = tid % (BN / 4);
+
+  for (int k = 0; k < K; ++k) {
+    int src = -1;
+    if (my_row < n_out) src = nbr ? __ldg(nbr + (long long)k * n_out + my_row) : (int)my_row;
+    if (!__syncthreads_or(src >= 0)) continue;  // no voxel of this tile has a neighbour at offset k
+    const float* wk = weight + (long long)k * cin * cout;
+    for (int c0 = 0; c0 < cin; c0 += BK) {
+      float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (src >= 0) av = __ldg(reinterpret_cast<const float4*>(in + (long long)src * in_ld + c0 + a_c * 4));
+      As[a_c * 4 + 0][a_r] = av.x;
+      As[a_c * 4 + 1][a_r] = av.y;
+      As[a_c * 4 + 2][a_r] = av.z;
+      As[a_c * 4 + 3][a_r] = av.w;
+      if (tid < B_VEC) {
+        const float4 bv =
+            __ldg(reinterpret_cast<const float4*>(wk + (long long)(c0 + b_kk) * cout + col0 + b_c * 4));
+        *reinterpret_cast<float4*>(&Bs[b_kk][b_c * 4]) = bv;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < BK; ++kk) {
+        const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+        float b[TN];
+#pragma unroll
+        for (int j = 0; j < TN; ++j) b[j] = Bs[kk][tx * TN + j];
+        const float ar[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(ar[i], b[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+  }
+
+  // fused epilogue: folded BatchNorm / bias, residual, ReLU, write into a channel slice
+  const bool relu = flags & AG3D_RELU;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long r = row0 + ty * 4 + i;
+    if (r >= n_out) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int c = col0 + tx * TN + j;
+      float v = acc[i][j];
+      if (scale) v *= __ldg(scale + c);
+      if (shift) v += __ldg(shift + c);
+      if (residual) v += __ldg(residual + r * res_ld + c);
+      if (relu) v = fmaxf(v, 0.f);
+      out[r * out_ld + c] = v;
+    }
+  }
+}
+
+// Stem: one warp per output voxel, lane = output channel.  The 125 offsets are probed 32 at a time.
+constexpr int STEM_CIN = 3;
+constexpr int STEM_COUT = 32;
+
+__global__ void __launch_bounds__(256)
+stem_conv_kernel(const int4* __restrict__ coords, const float* __restrict__ feats, long long n,
+                 const Slot* __restrict__ table, unsigned long long mask, int ksize,
+                 const float* __restrict__ weight, const float* __restrict__ scale,
+                 const float* __restrict__ shift, float* __restrict__ out, int out_ld, int flags) {
+  extern __shared__ float w_s[];  // [K][3][32]
+  const int K = ksize * ksize * ksize;
+  for (int i = threadIdx.x; i < K * STEM_CIN * STEM_COUT; i += blockDim.x) w_s[i] = __ldg(weight + i);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int half = ksize / 2;
+  long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long step = (long long)gridDim.x * (blockDim.x >> 5);
+  for (; row < n; row += step) {
+    const int4 c = __ldg(coords + row);
+    float acc = 0.f;
+    for (int kb = 0; kb < K; kb += 32) {
+      const int k = kb + lane;
+      int src = -1;
+      if (k < K) {
+        int r = k;
+        const int jx = r % ksize; r /= ksize;
+        const int jy = r % ksize; r /= ksize;
+        const int x = c.y + jx - half, y = c.z + jy - half, z = c.w + r - half;
+        if (coord_in_range(c.x, x, y, z)) src = table_find(table, mask, pack_key(c.x, x, y, z));
+      }
+      unsigned hits = __ballot_sync(0xffffffffu, src >= 0);
+      while (hits) {
+        const int b = __ffs(hits) - 1;
+        hits &= hits - 1;
+        const int s = __shfl_sync(0xffffffffu, src, b);
+        const float* f = feats + (long long)s * STEM_CIN;
+        const float* w = w_s + (kb + b) * STEM_CIN * STEM_COUT + lane;
+        acc = fmaf(__ldg(f + 0), w[0], acc);
+        acc = fmaf(__ldg(f + 1), w[STEM_COUT], acc);
+        acc = fmaf(__ldg(f + 2), w[2 * STEM_COUT], acc);
+      }
+    }
+    float v = acc;
+    if (scale) v *= __ldg(scale + lane);
+    if (shift) v += __ldg(shift + lane);
+    if (flags & AG3D_RELU) v = fmaxf(v, 0.f);
+    out[row * out_ld + lane] = v;
+  }
+}
+
+int spconv_tc_launch(const float* in, int in_ld, int cin, const int* nbr, int K, long long n_out,
+                     const float* weight, int cout, const float* scale, const float* shift, const float* residual,
+                     int res_ld, float* out, int out_ld, int flags, cudaStream_t st);
+bool spconv_tc_supported(int cin, int cout);
+
+}  // namespace ag3d
+
+using namespace ag3d;
+
+extern "C" {
+
+int ag3d_spconv_fwd(const float* in, int32_t in_ld, int32_t cin, const int32_t* nbr, int32_t K, int64_t n_out,
+                    const float* weight, int32_t cout, const float* scale, const float* shift,
+                    const float* residual, int32_t res_ld, float* out, int32_t out_ld, int32_t flags,
+                    int32_t algo, ag3d_stream_t stream) {
+  AG3D_CHECK_ARG(n_out > 0 && n_out < 2147483647LL, "row count out of range");
+  AG3D_CHECK_ARG(cin > 0 && cin % 32 == 0 && cout > 0 && cout % 32 == 0, "cin and cout must be multiples of 32");
+  AG3D_CHECK_ARG(K >= 1 && (nbr || K == 1), "K > 1 needs a neighbour table");
+  AG3D_CHECK_ARG(in && weight && out && aligned16(in) && aligned16(weight) && aligned16(out), "bad pointers");
+  AG3D_CHECK_ARG(in_ld % 4 == 0 && out_ld % 4 == 0 && in_ld >= cin && out_ld >= cout, "leading dims");
+  AG3D_CHECK_ARG(!residual || (res_ld >= cout && aligned16(residual) && res_ld % 4 == 0), "residual leading dim");
+  cudaStream_t st = as_stream(stream);
+  if (algo == AG3D_ALGO_AUTO) algo = spconv_tc_supported(cin, cout) ? AG3D_ALGO_TC : AG3D_ALGO_SIMT;
+  if (algo == AG3D_ALGO_TC) {
+    AG3D_CHECK_ARG(spconv_tc_supported(cin, cout), "shape not supported by the tcgen05 path");
+    return spconv_tc_launch(in, in_ld, cin, nbr, K, n_out, weight, cout, scale, shift, residual, res_ld, out,
+                            out_ld, flags, st);
+  }
+  AG3D_CHECK_ARG(algo == AG3D_ALGO_SIMT, "unknown algo");
+  const unsigned gx = (unsigned)((n_out + BM - 1) / BM);
+  if (cout % 64 == 0) {
+    spconv_simt_kernel<64><<<dim3(gx, cout / 64), SIMT_THREADS, 0, st>>>(
+        in, in_ld, cin, nbr, K, n_out, weight, cout, scale, shift, residual, res_ld, out, out_ld, flags);
+  } else {
+    spconv_simt_kernel<32><<<dim3(gx, cout / 32), SIMT_THREADS, 0, st>>>(
+        in, in_ld, cin, nbr, K, n_out, weight, cout, scale, shift, residual, res_ld, out, out_ld, flags);
+  }
+  AG3D_LAUNCH_CHECK("spconv_simt");
+  return AG3D_OK;
+}
+
+int ag3d_stem_conv_fwd(const int32_t* coords, const float* feats, int64_t n, const void* table, int64_t cap,
+                       int32_t ksize, const float* weight, const float* scale, const float* shift, float* out,
+                       int32_t out_ld, int32_t flags, ag3d_stream_t stream) {
+  AG3D_CHECK_ARG(n > 0 && n < 2147483647LL, "row count out of range");
+  AG3D_CHECK_ARG(ksize == 1 || ksize == 3 || ksize == 5, "stem kernel size must be 1, 3 or 5");
+  AG3D_CHECK_ARG(coords && aligned16(coords) && feats && weight && out, "bad pointers");
+  AG3D_CHECK_ARG(table && aligned16(table) && cap >= 2 && (cap & (cap - 1)) == 0, "bad hash table");
+  AG3D_CHECK_ARG(out_ld >= STEM_COUT, "out_ld");
+  const int K = ksize * ksize * ksize;
+  const size_t smem = (size_t)K * STEM_CIN * STEM_COUT * sizeof(float);
+  static bool attr_done = false;
+  if (!attr_done) {
+    AG3D_CUDA(cudaFuncSetAttribute(stem_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    attr_done = true;
+  }
+  long long blocks = (n + 7) / 8;
+  const long long cap_blocks = (long long)sm_count() * 8;
+  if (blocks > cap_blocks) blocks = cap_blocks;
+  stem_conv_kernel<<<(unsigned)blocks, 256, smem, as_stream(stream)>>>(
+      reinterpret_cast<const int4*>(coords), feats, n, static_cast<const Slot*>(table),
+      (unsigned long long)(cap - 1), ksize, weight, scale, shift, out, out_ld, flags);
+  AG3D_LAUNCH_CHECK("stem_conv");
+  return AG3D_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,284 @@
+"""Agile3d: the reference's model surface (models/agile3d.py:19-421) on the B200 library.
+
+    model = build_agile3d(args)                       # models/agile3d.py:399-421
+    pcd_features, aux, coordinates, pos_encodings_pcd = model.forward_backbone(x, raw_coordinates)   # :163-181
+    out = model.forward_mask(pcd_features, aux, coordinates, pos_encodings_pcd, click_idx, click_time_idx)  # :183-339
+    out['pred_masks'][b]  -> [Nv_b, 1 + K_b] fp32 logits, column index = object id
+
+The four values returned by ``forward_backbone`` are opaque handles, exactly as every reference caller treats
+them.  state_dict keys/shapes equal the reference's.
+
+Per click round the voxel features are streamed by exactly two kernels per decoder layer
+(ag3d_c2s_attn_fwd, ag3d_s2c_mask_fwd); the O(Nq) glue between them (projections of the <= few dozen click
+queries, click<->click self-attention, FFN) is tiny and stays in torch.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .backbone import PLANES, Res16UNet34C, SparseConv
+from .minkowski import SparseTensor
+
+
+class _AttnParams(nn.Module):
+    """Parameter layout of nn.MultiheadAttention (in_proj_weight [3d,d], in_proj_bias, out_proj.{weight,bias})."""
+
+    def __init__(self, d):
+        super().__init__()
+        self.in_proj_weight = nn.Parameter(torch.empty(3 * d, d))
+        self.in_proj_bias = nn.Parameter(torch.zeros(3 * d))
+        self.out_proj = nn.Linear(d, d)
+        nn.init.xavier_uniform_(self.in_proj_weight)
+        nn.init.xavier_uniform_(self.out_proj.weight)
+        nn.init.zeros_(self.out_proj.bias)
+
+
+class _CrossLayer(nn.Module):           # models/modules/attention_block.py:64-98
+    def __init__(self, d):
+        super().__init__()
+        self.multihead_attn = _AttnParams(d)
+        self.norm = nn.LayerNorm(d)
+
+
+class _SelfLayer(nn.Module):            # models/modules/attention_block.py:5-38
+    def __init__(self, d):
+        super().__init__()
+        self.self_attn = _AttnParams(d)
+        self.norm = nn.LayerNorm(d)
+
+
+class _FFNLayer(nn.Module):             # models/modules/attention_block.py:127-155
+    def __init__(self, d, dff):
+        super().__init__()
+        self.linear1 = nn.Linear(d, dff)
+        self.linear2 = nn.Linear(dff, d)
+        self.norm = nn.LayerNorm(d)
+        nn.init.xavier_uniform_(self.linear1.weight)
+        nn.init.xavier_uniform_(self.linear2.weight)
+
+
+class _FourierPos(nn.Module):           # models/position_embedding.py:44-72 (buffer is part of the checkpoint)
+    def __init__(self, d, gauss_scale):
+        super().__init__()
+        self.register_buffer("gauss_B", torch.empty((3, d // 2)).normal_() * gauss_scale)
+
+
+def _time_table(d_model, length):       # models/position_embedding.py:210-226
+    pe = torch.zeros(length, d_model)
+    pos = torch.arange(0, length).unsqueeze(1).float()
+    div = torch.exp(torch.arange(0, d_model, 2, dtype=torch.float) * -(math.log(10000.0) / d_model))
+    pe[:, 0::2] = torch.sin(pos * div)
+    pe[:, 1::2] = torch.cos(pos * div)
+    return pe
+
+
+class BackboneFeatures:
+    """Opaque handle for ``pcd_features`` / ``coordinates``: features of all scenes + per-scene row ranges."""
+
+    def __init__(self, F_, offsets, C=None):
+        self.F, self.offsets, self.C = F_, offsets, C
+
+    @property
+    def decomposed_features(self):
+        return [self.F[self.offsets[b]:self.offsets[b + 1]] for b in range(len(self.offsets) - 1)]
+
+    @property
+    def device(self):
+        return self.F.device
+
+
+class Agile3d(nn.Module):
+    def __init__(self, backbone, hidden_dim, num_heads, dim_feedforward, shared_decoder, num_decoders,
+                 num_bg_queries, dropout, pre_norm, positional_encoding_type, normalize_pos_enc, hlevels,
+                 voxel_size, gauss_scale, aux):
+        super().__init__()
+        if hidden_dim != 128 or num_heads != 8:
+            raise ValueError("the decoder kernels are specialised for hidden_dim=128, num_heads=8 (reference defaults)")
+        if positional_encoding_type != "fourier" or not normalize_pos_enc:
+            raise ValueError("only the reference default positional encoding (fourier, normalised) is built")
+        if pre_norm or dropout != 0.0:
+            raise ValueError("only post-norm, dropout=0 (reference defaults) are built")
+        if list(hlevels) != [4]:
+            raise ValueError("only hlevels=[4] (reference default: full-resolution voxels) is built")
+        self.hidden_dim, self.num_heads, self.num_decoders = hidden_dim, num_heads, num_decoders
+        self.num_bg_queries, self.shared_decoder, self.aux = num_bg_queries, shared_decoder, aux
+        self.hlevels, self.voxel_size = list(hlevels), voxel_size
+        d = hidden_dim
+        self.backbone = backbone
+        self.lin_squeeze_head = SparseConv(PLANES[7], d, 1, bias=True)
+        self.bg_query_feat = nn.Embedding(num_bg_queries, d)
+        self.bg_query_pos = nn.Embedding(num_bg_queries, d)
+        self.mask_embed_head = nn.Sequential(nn.Linear(d, d), nn.ReLU(), nn.Linear(d, d))
+        self.pos_enc = _FourierPos(d, gauss_scale)
+        n_shared = 1 if shared_decoder else num_decoders
+
+        def stack(make):
+            return nn.ModuleList([nn.ModuleList([make() for _ in self.hlevels]) for _ in range(n_shared)])
+
+        self.c2s_attention = stack(lambda: _CrossLayer(d))
+        self.s2c_attention = stack(lambda: _CrossLayer(d))
+        self.c2c_attention = stack(lambda: _SelfLayer(d))
+        self.ffn_attention = stack(lambda: _FFNLayer(d, dim_feedforward))
+        self.decoder_norm = nn.LayerNorm(d)
+        self.time_encode = _time_table(d, 200)       # plain attribute, not in the state_dict (agile3d.py:138)
+
+    # ------------------------------------------------------------------------------------------ backbone
+    @torch.no_grad()
+    def forward_backbone(self, x: SparseTensor, raw_coordinates=None):
+        if not isinstance(x, SparseTensor):
+            raise TypeError("forward_backbone expects an agile3d_b200.SparseTensor")
+        feats, fmaps, maps = self.backbone(x)
+        raw = raw_coordinates.to(device=x.F.device, dtype=torch.float32).contiguous()
+        if raw.shape != (x.F.shape[0], 3):
+            raise ValueError("raw_coordinates must be [N,3]")
+        # scene row ranges (scenes are contiguous and ordered: SURVEY.md A.2)
+        batch = x.C[:, 0]
+        n_scenes = int(batch[-1].item()) + 1
+        counts = torch.bincount(batch, minlength=n_scenes).tolist()
+        offsets = [0]
+        for c in counts:
+            offsets.append(offsets[-1] + c)
+        pos, rng = ops.fourier_posenc(raw, offsets, self.pos_enc.gauss_B)
+        pcd = torch.empty((feats.shape[0], self.hidden_dim), dtype=torch.float32, device=feats.device)
+        ops.spconv_fwd(feats, None, self.lin_squeeze_head.kernel, pcd, None,
+                       self.lin_squeeze_head.bias.detach().reshape(-1).contiguous(), relu=False,
+                       algo=self.backbone.algo)
+        pcd_features = BackboneFeatures(pcd, offsets, x.C)
+        coordinates = BackboneFeatures(raw, offsets, x.C)
+        coordinates.range = rng
+        # only the full-resolution level is ever read (hlevels=[4], agile3d.py:278); keep the reference's indexing
+        pos_encodings_pcd = [None, None, None, None, [[pos[offsets[b]:offsets[b + 1]] for b in range(n_scenes)]]]
+        return pcd_features, fmaps, coordinates, pos_encodings_pcd
+
+    # ------------------------------------------------------------------------------------------ decoder glue
+    def _click_pos(self, xyz, rng_b):
+        """fourier encoding of a few click coordinates (position_embedding.py:123-152), torch, [n,128]."""
+        lo, hi = rng_b[:3], rng_b[3:]
+        u = (xyz - lo) / (hi - lo)
+        t = (u * (2 * math.pi)) @ self.pos_enc.gauss_B
+        return torch.cat([t.sin(), t.cos()], dim=1)
+
+    @staticmethod
+    def _fold_c2s(p, tgt, qpos, H):
+        """qfold[(h,q),:] = Wk_h^T ((Wq_h (tgt+qpos) + bq_h) / sqrt(dh))."""
+        d = tgt.shape[1]
+        dh = d // H
+        Wq, Wk = p.in_proj_weight[:d], p.in_proj_weight[d:2 * d]
+        qp = F.linear(tgt + qpos, Wq, p.in_proj_bias[:d]).view(-1, H, dh) * (1.0 / math.sqrt(dh))
+        return torch.einsum("qhd,hdc->hqc", qp, Wk.view(H, dh, d)).reshape(-1, d).contiguous()
+
+    @staticmethod
+    def _finish_c2s(layer, tgt, ctx, H):
+        p = layer.multihead_attn
+        d = tgt.shape[1]
+        dh = d // H
+        Wv, bv = p.in_proj_weight[2 * d:], p.in_proj_bias[2 * d:]
+        heads = torch.einsum("hqc,hdc->qhd", ctx.view(H, -1, d), Wv.view(H, dh, d)) + bv.view(H, dh)
+        attn = F.linear(heads.reshape(-1, d), p.out_proj.weight, p.out_proj.bias)
+        return layer.norm(tgt + attn)
+
+    @staticmethod
+    def _self_attn(layer, tgt, qpos, H):
+        p = layer.self_attn
+        d = tgt.shape[1]
+        dh = d // H
+        qk = F.linear(tgt + qpos, p.in_proj_weight[:2 * d], p.in_proj_bias[:2 * d])
+        v = F.linear(tgt, p.in_proj_weight[2 * d:], p.in_proj_bias[2 * d:])
+        q, k = qk[:, :d].view(-1, H, dh).transpose(0, 1), qk[:, d:].view(-1, H, dh).transpose(0, 1)
+        a = torch.softmax((q * (1.0 / math.sqrt(dh))) @ k.transpose(1, 2), dim=-1)
+        o = (a @ v.view(-1, H, dh).transpose(0, 1)).transpose(0, 1).reshape(-1, d)
+        return layer.norm(tgt + F.linear(o, p.out_proj.weight, p.out_proj.bias))
+
+    @staticmethod
+    def _ffn(layer, tgt):
+        return layer.norm(tgt + layer.linear2(F.relu(layer.linear1(tgt))))
+
+    @staticmethod
+    def _fold_s2c(p, queries, qpos, H):
+        """A[(h,q),:] = Wq_h^T k_hq / sqrt(dh); c[(h,q)] = bq_h . k_hq / sqrt(dh); U[(h,q),:] = Wo[:,h] v_hq."""
+        d = queries.shape[1]
+        dh = d // H
+        Wq, bq = p.in_proj_weight[:d], p.in_proj_bias[:d]
+        kp = F.linear(queries + qpos, p.in_proj_weight[d:2 * d], p.in_proj_bias[d:2 * d]).view(-1, H, dh)
+        vp = F.linear(queries, p.in_proj_weight[2 * d:], p.in_proj_bias[2 * d:]).view(-1, H, dh)
+        sc = 1.0 / math.sqrt(dh)
+        A = (torch.einsum("qhd,hdc->hqc", kp, Wq.view(H, dh, d)) * sc).reshape(-1, d).contiguous()
+        c = (torch.einsum("qhd,hd->hq", kp, bq.view(H, dh)) * sc).reshape(-1).contiguous()
+        U = torch.einsum("chd,qhd->hqc", p.out_proj.weight.view(d, H, dh), vp).reshape(-1, d).contiguous()
+        return A, c, U
+
+    # ------------------------------------------------------------------------------------------ forward_mask
+    @torch.no_grad()
+    def forward_mask(self, pcd_features, aux, coordinates, pos_encodings_pcd, click_idx=None, click_time_idx=None):
+        if self.training:
+            raise NotImplementedError("train-mode forward_mask (autograd) is not built yet; call model.eval()")
+        H, d = self.num_heads, self.hidden_dim
+        dev = pcd_features.F.device
+        n_scenes = len(pcd_features.offsets) - 1
+        tt = self.time_encode.to(dev) if self.time_encode.device != dev else self.time_encode
+        self.time_encode = tt
+        per_scene = []
+        for b in range(n_scenes):
+            src0 = pcd_features.decomposed_features[b]
+            xyz = coordinates.decomposed_features[b]
+            pos = pos_encodings_pcd[self.hlevels[0]][0][b]
+            ck, ct = click_idx[b], click_time_idx[b]
+            K = len(ck) - 1
+            split = [len(ck[str(i)]) for i in range(1, K + 1)]
+            if min(split, default=1) < 1:
+                raise ValueError("every foreground object needs at least one click (agile3d.py:214)")
+            rows = [i for o in range(1, K + 1) for i in ck[str(o)]] + list(ck["0"])
+            times = [t for o in range(1, K + 1) for t in ct[str(o)]] + list(ct["0"])
+            n_fg, n_bgc = sum(split), len(ck["0"])
+            idx = torch.tensor(rows, dtype=torch.long, device=dev)
+            tix = torch.tensor(times, dtype=torch.long, device=dev)
+            click_feat = src0[idx]
+            click_pos = self._click_pos(xyz[idx], coordinates.range[b]) + tt[tix]
+            # query order: [fg clicks (object 1..K, click order) | 10 learned bg | bg clicks]   (agile3d.py:249-264)
+            fg_q, fg_pos = click_feat[:n_fg], click_pos[:n_fg]
+            bg_q = torch.cat([self.bg_query_feat.weight, click_feat[n_fg:]], 0)
+            bg_pos = torch.cat([self.bg_query_pos.weight, click_pos[n_fg:]], 0)
+            queries = torch.cat([fg_q, bg_q], 0)
+            qpos = torch.cat([fg_pos, bg_pos], 0)
+            nq = queries.shape[0]
+            q_obj = torch.tensor([o for o, n in enumerate(split, start=1) for _ in range(n)]
+                                 + [0] * (self.num_bg_queries + n_bgc), dtype=torch.int32, device=dev)
+            src, label, obj_count, outs = src0, None, None, []
+            for layer in range(self.num_decoders):
+                li = 0 if self.shared_decoder else layer
+                c2s, c2c = self.c2s_attention[li][0], self.c2c_attention[li][0]
+                ffn, s2c = self.ffn_attention[li][0], self.s2c_attention[li][0]
+                qfold = self._fold_c2s(c2s.multihead_attn, queries, qpos, H)
+                ctx = ops.c2s_attn_fwd(src, pos, qfold, nq, H, label, q_obj, obj_count)
+                q = self._finish_c2s(c2s, queries, ctx, H)
+                q = self._self_attn(c2c, q, qpos, H)
+                queries = self._ffn(ffn, q)
+                A, c, U = self._fold_s2c(s2c.multihead_attn, queries, qpos, H)
+                E = self.mask_embed_head(self.decoder_norm(queries)).contiguous()
+                src, logits, label, obj_count = ops.s2c_mask_fwd(
+                    src, pos, A, c, U, s2c.multihead_attn.out_proj.bias, s2c.norm.weight, s2c.norm.bias,
+                    s2c.norm.eps, E, q_obj, nq, H, K + 1,
+                    x_out=None if layer == 0 else src)       # never overwrite the caller's backbone features
+                outs.append(logits)
+            per_scene.append(outs)
+        per_layer = [list(p) for p in zip(*per_scene)]
+        out = {"pred_masks": per_layer[-1], "backbone_features": pcd_features}
+        if self.aux:
+            out["aux_outputs"] = [{"pred_masks": p} for p in per_layer[:-1]]
+        return out
+
+
+def build_agile3d(args):
+    """models/agile3d.py:399-421 (+ models/backbone.py:5-7)."""
+    backbone = Res16UNet34C(3, bn_momentum=args.bn_momentum, conv1_kernel_size=args.conv1_kernel_size)
+    return Agile3d(backbone=backbone, hidden_dim=args.hidden_dim, num_heads=args.num_heads,
+                   dim_feedforward=args.dim_feedforward, shared_decoder=args.shared_decoder,
+                   num_decoders=args.num_decoders, num_bg_queries=args.num_bg_queries, dropout=args.dropout,
+                   pre_norm=args.pre_norm, positional_encoding_type=args.positional_encoding_type,
+                   normalize_pos_enc=args.normalize_pos_enc, hlevels=args.hlevels, voxel_size=args.voxel_size,
+                   gauss_scale=args.gauss_scale, aux=args.aux)

@@ -1,0 +1,243 @@
+"""Thin torch-tensor wrappers over the C-ABI (include/agile3d_b200.h).  torch is plumbing here: it owns the
+device memory and the stream; every operation below is one call into libagile3d_b200.so."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ALGO_AUTO, ALGO_SIMT, ALGO_TC, RELU, check, lib  # noqa: F401
+
+SLOT_BYTES = 16
+
+
+class Profiler:
+    """Per-family CUDA-event timing + algorithmic bytes/flops, for bench.py's roofline line.  Events are recorded on
+    torch's current stream, which is the stream every kernel of this library is launched on."""
+
+    def __init__(self):
+        self.records = []       # (family, algorithmic_bytes, flops, start_event, end_event)
+
+    def summary(self):
+        torch.cuda.synchronize()
+        fam = {}
+        for name, nbytes, flops, e0, e1 in self.records:
+            f = fam.setdefault(name, {"launches": 0, "ms": 0.0, "bytes": 0, "flops": 0})
+            f["launches"] += 1
+            f["ms"] += e0.elapsed_time(e1)
+            f["bytes"] += int(nbytes)
+            f["flops"] += int(flops)
+        return fam
+
+
+_prof = None
+
+
+def set_profiler(p):
+    global _prof
+    _prof = p
+
+
+class _Timed:
+    def __init__(self, family, nbytes, flops=0):
+        self.args = (family, nbytes, flops)
+
+    def __enter__(self):
+        if _prof is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _prof is not None and exc[0] is None:
+            self.e1.record()
+            f, b, fl = self.args
+            _prof.records.append((f, b() if callable(b) else b, fl() if callable(fl) else fl, self.e0, self.e1))
+        return False
+
+
+def kernel_launches():
+    return int(lib().ag3d_kernel_launches())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.Ag3dError("agile3d_b200 ops need CUDA tensors (there is no CPU fallback)")
+
+
+def _rows2d(t, dtype=torch.float32):
+    """2-D tensor whose rows are contiguous (a channel slice of a wider buffer is fine) -> (ptr, ld)."""
+    if t.dim() != 2 or t.dtype != dtype or (t.shape[1] > 1 and t.stride(1) != 1):
+        raise _lib.Ag3dError(f"expected a row-contiguous 2-D {dtype} tensor, got {tuple(t.shape)} {t.dtype} {t.stride()}")
+    return _p(t), int(t.stride(0))
+
+
+def hash_build(coords):
+    """coords int32 [N,4] -> (table uint8[cap*16], cap).  Raises on duplicate / out-of-range coordinates."""
+    _need_cuda(coords)
+    n = coords.shape[0]
+    cap = lib().ag3d_hash_capacity(n)
+    table = torch.empty(cap * SLOT_BYTES, dtype=torch.uint8, device=coords.device)
+    status = torch.zeros(2, dtype=torch.int32, device=coords.device)
+    with _Timed("maps", 16 * n + 16 * cap):
+        check(lib().ag3d_hash_build(_p(coords), n, _p(table), cap, _p(status), _stream()), "ag3d_hash_build")
+    return table, cap, status
+
+
+def downsample(coords, new_stride):
+    """-> (coarse coords int32 [M,4], coarse table, cap, parent int32 [N]).  One host sync (reads M)."""
+    _need_cuda(coords)
+    n = coords.shape[0]
+    dev = coords.device
+    cap = lib().ag3d_hash_capacity(n)
+    table = torch.empty(cap * SLOT_BYTES, dtype=torch.uint8, device=dev)
+    parent = torch.empty(n, dtype=torch.int32, device=dev)
+    out = torch.empty((n, 4), dtype=torch.int32, device=dev)
+    out_n = torch.zeros(1, dtype=torch.int32, device=dev)
+    wsb = lib().ag3d_downsample_workspace_bytes(n)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    with _Timed("maps", 16 * n + 16 * cap + 4 * n):
+        check(lib().ag3d_downsample(_p(coords), n, new_stride, _p(table), cap, _p(parent), _p(out), _p(out_n),
+                                    _p(ws), wsb, _stream()), "ag3d_downsample")
+    m = int(out_n.item())
+    return out[:m], table, cap, parent
+
+
+def kernel_map(out_coords, in_table, cap, ksize, in_tensor_stride, dilation=1, count_pairs=False):
+    """-> nbr int32 [K, N_out] (and pair counts int32 [K] if asked)."""
+    _need_cuda(out_coords, in_table)
+    n_out = out_coords.shape[0]
+    K = ksize ** 3
+    nbr = torch.empty((K, n_out), dtype=torch.int32, device=out_coords.device)
+    pc = torch.zeros(K, dtype=torch.int32, device=out_coords.device) if count_pairs else None
+    with _Timed("maps", 16 * n_out + 16 * K * n_out + 4 * K * n_out):     # query read + probes + table write
+        check(lib().ag3d_kernel_map(_p(out_coords), n_out, _p(in_table), cap, ksize, in_tensor_stride, dilation,
+                                    _p(nbr), _p(pc), _stream()), "ag3d_kernel_map")
+    return (nbr, pc) if count_pairs else nbr
+
+
+def kernel_map_transposed(fine_coords, parent, fine_stride):
+    _need_cuda(fine_coords, parent)
+    n = fine_coords.shape[0]
+    nbr = torch.empty((8, n), dtype=torch.int32, device=fine_coords.device)
+    with _Timed("maps", 20 * n + 32 * n):
+        check(lib().ag3d_kernel_map_transposed(_p(fine_coords), _p(parent), n, fine_stride, _p(nbr), _stream()),
+              "ag3d_kernel_map_transposed")
+    return nbr
+
+
+def spconv_fwd(x, nbr, weight, out, scale=None, shift=None, residual=None, relu=False, algo=ALGO_AUTO):
+    """out[o] = act(scale * sum_k x[nbr[k][o]] @ weight[k] + shift (+ residual[o])).  x/out/residual may be channel
+    slices of wider buffers.  weight [K,cin,cout] (or [cin,cout] with nbr None)."""
+    _need_cuda(x, weight, out)
+    xp, x_ld = _rows2d(x)
+    op, o_ld = _rows2d(out)
+    rp, r_ld = (_rows2d(residual) if residual is not None else (C.c_void_p(0), 0))
+    w = weight if weight.dim() == 3 else weight.unsqueeze(0)
+    K, cin, cout = w.shape
+    if not w.is_contiguous() or w.dtype != torch.float32:
+        raise _lib.Ag3dError("weight must be contiguous fp32 [K,cin,cout]")
+    if x.shape[1] != cin or out.shape[1] != cout:
+        raise _lib.Ag3dError(f"channel mismatch: x {tuple(x.shape)}, w {tuple(w.shape)}, out {tuple(out.shape)}")
+    n_out = out.shape[0]
+    if nbr is not None and (tuple(nbr.shape) != (K, n_out) or not nbr.is_contiguous()):
+        raise _lib.Ag3dError(f"neighbour table must be contiguous int32 [{K},{n_out}], got {tuple(nbr.shape)}")
+    if nbr is None and x.shape[0] != n_out:
+        raise _lib.Ag3dError("1x1 conv needs as many input as output rows")
+    pairs = n_out
+    if _prof is not None and nbr is not None:
+        pairs = int((nbr >= 0).sum().item())
+    # 4*N_in*Cin + 4*N_out*Cout + 8*P + 4*K*Cin*Cout (+ 4*N_out*Cout residual); flops 2*P*Cin*Cout
+    nbytes = 4 * x.shape[0] * cin + 4 * n_out * cout + 8 * pairs + 4 * K * cin * cout \
+        + (4 * n_out * cout if residual is not None else 0)
+    with _Timed("spconv", nbytes, 2 * pairs * cin * cout):
+        check(lib().ag3d_spconv_fwd(xp, x_ld, cin, _p(nbr), K, n_out, _p(w), cout, _p(scale), _p(shift), rp, r_ld,
+                                    op, o_ld, RELU if relu else 0, algo, _stream()), "ag3d_spconv_fwd")
+    return out
+
+
+def stem_conv_fwd(coords, feats, table, cap, ksize, weight, out, scale=None, shift=None, relu=True):
+    _need_cuda(coords, feats, table, weight, out)
+    if feats.shape[1] != 3 or weight.shape[-2:] != (3, 32) or out.shape[1] != 32:
+        raise _lib.Ag3dError("stem conv is 3 -> 32 channels")
+    if not (feats.is_contiguous() and weight.is_contiguous()):
+        raise _lib.Ag3dError("stem inputs must be contiguous")
+    op, o_ld = _rows2d(out)
+    n, K = coords.shape[0], ksize ** 3
+    with _Timed("stem", 16 * n + 12 * n + 4 * n * 32 + 16 * K * n + 4 * K * 96):
+        check(lib().ag3d_stem_conv_fwd(_p(coords), _p(feats), n, _p(table), cap, ksize, _p(weight),
+                                       _p(scale), _p(shift), op, o_ld, RELU if relu else 0, _stream()),
+              "ag3d_stem_conv_fwd")
+    return out
+
+
+def fourier_posenc(xyz, scene_offsets, gauss_B):
+    """xyz f32 [N,3] (scenes contiguous), scene_offsets python list of B+1 ints -> (pos f32 [N,d], range f32 [B,6])."""
+    _need_cuda(xyz, gauss_B)
+    nb = len(scene_offsets) - 1
+    d = 2 * gauss_B.shape[1]
+    out = torch.empty((xyz.shape[0], d), dtype=torch.float32, device=xyz.device)
+    rng = torch.empty((nb, 6), dtype=torch.float32, device=xyz.device)
+    wsb = lib().ag3d_posenc_workspace_bytes(nb)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=xyz.device)
+    offs = (C.c_int32 * (nb + 1))(*scene_offsets)
+    with _Timed("posenc", 2 * 12 * xyz.shape[0] + 4 * d * xyz.shape[0]):
+        check(lib().ag3d_fourier_posenc(_p(xyz.contiguous()), C.cast(offs, C.c_void_p), nb, _p(gauss_B.contiguous()),
+                                        d, _p(out), _p(rng), _p(ws), wsb, _stream()), "ag3d_fourier_posenc")
+    return out, rng
+
+
+_c2s_ws = {}
+
+
+def c2s_attn_fwd(x, pos, qfold, nq, heads, label=None, q_obj=None, obj_count=None):
+    """-> ctx f32 [heads*nq, 128]."""
+    _need_cuda(x, pos, qfold)
+    for t in (x, pos, qfold):
+        if not t.is_contiguous() or t.dtype != torch.float32:
+            raise _lib.Ag3dError("c2s inputs must be contiguous fp32")
+    ctx = torch.empty((heads * nq, x.shape[1]), dtype=torch.float32, device=x.device)
+    wsb = lib().ag3d_c2s_workspace_bytes(nq, heads)
+    key = (x.device, torch.cuda.current_stream().cuda_stream)
+    ws = _c2s_ws.get(key)
+    if ws is None or ws.numel() < wsb:
+        ws = _c2s_ws[key] = torch.empty(wsb, dtype=torch.uint8, device=x.device)
+    nv = x.shape[0]
+    # x + pos reads, bool mask bytes (layers 2-3), the three [nq,128] query-side matrices
+    nbytes = 4 * nv * 128 * 2 + (nq * nv if label is not None else 0) + 4 * nq * 128 * 3
+    with _Timed("c2s", nbytes, 2 * 2 * nv * 128 * heads * nq):
+        check(lib().ag3d_c2s_attn_fwd(_p(x), _p(pos), nv, _p(qfold), nq, heads, _p(label), _p(q_obj),
+                                      _p(obj_count), _p(ctx), _p(ws), ws.numel(), _stream()), "ag3d_c2s_attn_fwd")
+    return ctx
+
+
+def s2c_mask_fwd(x, pos, A, c, U, bo, ln_w, ln_b, ln_eps, E, q_obj, nq, heads, n_obj, x_out=None):
+    """-> (x_out f32 [Nv,128], logits f32 [Nv,n_obj], label u8 [Nv], obj_count i32 [n_obj])."""
+    _need_cuda(x, pos, A, c, U, E, q_obj)
+    for t in (x, pos, A, c, U, bo, ln_w, ln_b, E):
+        if not t.is_contiguous() or t.dtype != torch.float32:
+            raise _lib.Ag3dError("s2c inputs must be contiguous fp32")
+    nv = x.shape[0]
+    if x_out is None:
+        x_out = torch.empty_like(x)
+    logits = torch.empty((nv, n_obj), dtype=torch.float32, device=x.device)
+    label = torch.empty(nv, dtype=torch.uint8, device=x.device)
+    obj_count = torch.zeros(n_obj, dtype=torch.int32, device=x.device)
+    # s2c (x, pos reads + x' write) + mask head (x' read, logits write, [nq,nv] bool mask write)
+    nbytes = 4 * nv * 128 * 3 + 4 * nv * 128 + 4 * nv * n_obj + nq * nv
+    with _Timed("s2c_mask", nbytes, 2 * nv * 128 * (2 * heads * nq + nq)):
+        check(lib().ag3d_s2c_mask_fwd(_p(x), _p(pos), nv, _p(A), _p(c), _p(U), _p(bo), _p(ln_w), _p(ln_b),
+                                      float(ln_eps), _p(E), _p(q_obj), nq, heads, n_obj, _p(x_out), _p(logits),
+                                      _p(label), _p(obj_count), _stream()), "ag3d_s2c_mask_fwd")
+    return x_out, logits, label, obj_count

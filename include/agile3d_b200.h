@@ -1,0 +1,145 @@
+/*
+ * agile3d_b200 — C-ABI of the Blackwell (sm_100a) hot path of AGILE3D.
+ *
+ * The reference (ywyue/AGILE3D) is pure Python: it has no FFI of its own.  What it binds for this path is
+ * the third-party MinkowskiEngine extension (coordinate manager, kernel maps, sparse convolution) plus ATen
+ * ops (nn.MultiheadAttention, LayerNorm, matmul).  Each entry point below names the reference call site /
+ * MinkowskiEngine operator it replaces.  INTEGRATION.md shows the ctypes stub a maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (torch's allocator), 16-byte aligned;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*) and allocates nothing;
+ *     scratch memory comes from a caller-supplied workspace whose size the *_workspace_bytes() query gives;
+ *   - return value: 0 = ok, negative = error (AG3D_E_*), message via ag3d_last_error() (thread-local);
+ *   - row-major fp32 features [N, C] with an explicit leading dimension (`*_ld`, in floats) so that a layer can
+ *     read or write a channel slice of a wider buffer (this is how `me.cat` costs nothing);
+ *   - voxel coordinates are int32 [N,4] = (batch, x, y, z), |x|,|y|,|z| < 32768, 0 <= batch < 65535;
+ *   - neighbour tables ("kernel maps") are int32 [K, N_out], offset-major: nbr[k*N_out + o] is the input row
+ *     that output row o sees through kernel offset k, or -1.  Offset order is MinkowskiEngine's (x fastest,
+ *     odd kernels centred, even kernels one-sided).
+ */
+#ifndef AGILE3D_B200_H_
+#define AGILE3D_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AG3D_ABI_VERSION 1
+
+#define AG3D_OK 0
+#define AG3D_E_INVALID (-1)   /* bad argument (shape, alignment, unsupported size) */
+#define AG3D_E_CUDA (-2)      /* a CUDA runtime call failed */
+#define AG3D_E_WORKSPACE (-3) /* workspace too small */
+
+/* spconv `flags` */
+#define AG3D_RELU 1
+/* spconv `algo` */
+#define AG3D_ALGO_AUTO 0
+#define AG3D_ALGO_SIMT 1 /* exact fp32 FFMA implicit GEMM */
+#define AG3D_ALGO_TC 2   /* tcgen05 3xTF32 implicit GEMM, accumulators in TMEM */
+
+typedef void* ag3d_stream_t; /* cudaStream_t */
+
+int ag3d_abi_version(void);
+const char* ag3d_last_error(void);
+/* sm count / compute capability of the current device */
+int ag3d_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
+/* number of CUDA kernels this library has launched in this process so far (bench.py's `gpu_launches`) */
+int64_t ag3d_kernel_launches(void);
+
+/* ---- coordinate hashing -------------------------------------------------------------------------------
+ * Replaces MinkowskiEngine CoordinateMapGPU::insert_and_map reached from ME.SparseTensor(coordinates=...)
+ * (reference engine.py:47-51, eval_multi_obj.py:94-98).  The table is open addressing with 16-byte slots
+ * {uint64 key, int32 first_row, int32 row}; capacity is a power of two >= 2*n.
+ * status[0] += number of duplicate rows, status[1] += number of out-of-range rows (caller zeroes it).      */
+int64_t ag3d_hash_capacity(int64_t n);
+int ag3d_hash_build(const int32_t* coords, int64_t n, void* table, int64_t cap, int32_t* status,
+                    ag3d_stream_t stream);
+
+/* ---- stride-2 coordinate map --------------------------------------------------------------------------
+ * Replaces CoordinateMap::stride reached from every conv(kernel 2, stride 2) (models/res16unet.py:51-59,
+ * 70-78,89-97,108-116) and MinkowskiAvgPooling(2,2) (models/agile3d.py:172-173).
+ * out_coords = unique(floor(c / new_stride) * new_stride), rows in order of first occurrence while scanning
+ * the fine rows (the canonical order).  Also builds the coarse level's hash table and
+ * parent[i] = coarse row of fine row i.  *out_n (device int32) receives the number of coarse rows;
+ * out_coords must have room for n rows.                                                                    */
+size_t ag3d_downsample_workspace_bytes(int64_t n);
+int ag3d_downsample(const int32_t* coords, int64_t n, int32_t new_stride, void* coarse_table, int64_t cap,
+                    int32_t* parent, int32_t* out_coords, int32_t* out_n, void* ws, size_t ws_bytes,
+                    ag3d_stream_t stream);
+
+/* ---- kernel maps --------------------------------------------------------------------------------------
+ * Replaces CoordinateMapGPU::kernel_map (first conv of each (level, kernel) pair; cached afterwards).
+ * Generic region: for every output coordinate o and offset k (ksize^3 offsets scaled by
+ * dilation*in_tensor_stride), nbr[k][o] = row of (o + off_k) in the input table or -1.
+ * pair_count (nullable, device int32[K], caller zeroes) receives the number of valid pairs per offset.      */
+int ag3d_kernel_map(const int32_t* out_coords, int64_t n_out, const void* in_table, int64_t cap, int32_t ksize,
+                    int32_t in_tensor_stride, int32_t dilation, int32_t* nbr, int32_t* pair_count,
+                    ag3d_stream_t stream);
+/* Transposed kernel-2/stride-2 map (MinkowskiConvolutionTranspose, models/modules/common.py:158-188):
+ * nbr[k][f] = parent[f] if k is the offset of fine voxel f inside its parent cell, else -1.                 */
+int ag3d_kernel_map_transposed(const int32_t* fine_coords, const int32_t* parent, int64_t n_fine,
+                               int32_t fine_stride, int32_t* nbr, ag3d_stream_t stream);
+
+/* ---- sparse convolution forward -----------------------------------------------------------------------
+ * Replaces MinkowskiConvolution / MinkowskiConvolutionTranspose forward (ConvolutionForwardKernelGPU) and
+ * the un-fused MinkowskiBatchNorm(eval) + MinkowskiReLU + residual add + me.cat around it
+ * (models/modules/resnet_block.py:48-64, models/res16unet.py:222-295).
+ *   out[o, :] = act( scale * sum_k in[nbr[k][o], :] @ W[k]  + shift  (+ residual[o, :]) )
+ * weight is MinkowskiEngine's [K, cin, cout]; nbr == NULL means K == 1 on the identity map (1x1 conv).
+ * scale/shift are the folded BatchNorm (or NULL/bias); residual is nullable.  cin, cout multiples of 32.   */
+int ag3d_spconv_fwd(const float* in, int32_t in_ld, int32_t cin, const int32_t* nbr, int32_t K, int64_t n_out,
+                    const float* weight, int32_t cout, const float* scale, const float* shift,
+                    const float* residual, int32_t res_ld, float* out, int32_t out_ld, int32_t flags,
+                    int32_t algo, ag3d_stream_t stream);
+/* Stem: conv0p1s1 (3 -> 32 channels, kernel 5, models/res16unet.py:39-47) evaluated directly against the
+ * hash table (no 125-column neighbour table is materialised) with folded bn0 + ReLU.                        */
+int ag3d_stem_conv_fwd(const int32_t* coords, const float* feats, int64_t n, const void* table, int64_t cap,
+                       int32_t ksize, const float* weight, const float* scale, const float* shift, float* out,
+                       int32_t out_ld, int32_t flags, ag3d_stream_t stream);
+
+/* ---- fourier positional encoding ----------------------------------------------------------------------
+ * Replaces Agile3d.get_pos_encs -> PositionEmbeddingCoordsSine.get_fourier_embeddings
+ * (models/agile3d.py:141-161, models/position_embedding.py:13-41,123-152) for the full-resolution level:
+ * per scene b (rows scene_offsets[b]..scene_offsets[b+1]): u = (xyz - min) / (max - min);
+ * out = [sin(2*pi*u @ B), cos(2*pi*u @ B)]  with B = gauss_B [3, d/2].  range_out (nullable) receives
+ * [n_scenes, 6] = (min xyz, max xyz) for the click-query encodings.                                         */
+size_t ag3d_posenc_workspace_bytes(int32_t n_scenes);
+int ag3d_fourier_posenc(const float* xyz, const int32_t* scene_offsets_host, int32_t n_scenes,
+                        const float* gauss_B, int32_t d_pos, float* out, float* range_out, void* ws,
+                        size_t ws_bytes, ag3d_stream_t stream);
+
+/* ---- click -> scene cross-attention (c2s) -------------------------------------------------------------
+ * Replaces nn.MultiheadAttention inside CrossAttentionLayer.forward_post as called at
+ * models/agile3d.py:283-290 (models/modules/attention_block.py:86-98), with the key/value projections
+ * folded into the queries: qfold[(h,q), :] = Wk_h^T q_h / sqrt(d_h), rows h-major.
+ *   ctx[(h,q), :] = sum_v softmax_v( qfold[(h,q)] . (x_v + pos_v)  [masked] ) * x_v
+ * Mask (models/agile3d.py:365-380): query q of object q_obj[q] is blocked at voxel v iff label[v] != q_obj[q],
+ * unless obj_count[q_obj[q]] == 0 (no voxel carries that label -> the row is un-masked).  label == NULL
+ * means no mask (first decoder layer).                                                                      */
+size_t ag3d_c2s_workspace_bytes(int32_t nq, int32_t heads);
+int ag3d_c2s_attn_fwd(const float* x, const float* pos, int64_t nv, const float* qfold, int32_t nq,
+                      int32_t heads, const uint8_t* label, const int32_t* q_obj, const int32_t* obj_count,
+                      float* ctx, void* ws, size_t ws_bytes, ag3d_stream_t stream);
+
+/* ---- scene -> click cross-attention + LayerNorm + mask head (s2c) --------------------------------------
+ * Replaces CrossAttentionLayer.forward_post as called at models/agile3d.py:305-312 plus
+ * Agile3d.mask_module (models/agile3d.py:342-384), one pass over the voxels:
+ *   S[v,(h,q)] = (x_v + pos_v) . A[(h,q)] + c[(h,q)];  a = softmax over q inside each head
+ *   y_v = LayerNorm(x_v + sum_{h,q} a[v,(h,q)] U[(h,q)] + bo)              -> x_out
+ *   logits[v, o] = max_{q : q_obj[q] == o} y_v . E[q]  (o = 0 background)    -> logits [nv, n_obj]
+ *   label[v] = argmax_o logits[v, o] (first maximum);  obj_count[o] += #voxels labelled o (caller zeroes).
+ * x_out may alias x.  nq <= 32 in this version.                                                             */
+int ag3d_s2c_mask_fwd(const float* x, const float* pos, int64_t nv, const float* A, const float* c,
+                      const float* U, const float* bo, const float* ln_w, const float* ln_b, float ln_eps,
+                      const float* E, const int32_t* q_obj, int32_t nq, int32_t heads, int32_t n_obj,
+                      float* x_out, float* logits, uint8_t* label, int32_t* obj_count, ag3d_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AGILE3D_B200_H_ */

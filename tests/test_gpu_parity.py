@@ -1,0 +1,330 @@
+"""GPU parity tests (-m gpu): every C-ABI entry point against the CPU oracle on the same seeded inputs, the golden
+vectors of the unmodified reference end to end, and size-independent properties at BASELINE.json's full size.
+
+Tolerances: integer/index outputs bit-exact; fp32 features and mask logits within 1e-3 relative
+(max|a-b| / max|b|, BASELINE.json north_star) — op-level checks use 1e-4 or tighter where the arithmetic is fp32.
+"""
+import numpy as np
+import pytest
+import torch
+
+import emulate
+from helpers import GOLDEN_CASES, load_golden, oracle_forward, oracle_model, rel_err
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _cuda_ok():
+    return torch.cuda.is_available()
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    if not _cuda_ok():
+        pytest.skip("no CUDA device")
+    from agile3d_b200._lib import lib
+    lib()     # raises if the library is not built: GPU tests must never pass on a fallback
+
+
+def _random_cloud(n, extent, seed, batch=1, negative=False):
+    rng = np.random.default_rng(seed)
+    rows = []
+    for b in range(batch):
+        c = rng.integers(-extent if negative else 0, extent, size=(n, 3))
+        # surface-like: squash one axis
+        c[:, 2] = c[:, 2] // 8
+        c = np.unique(c, axis=0)
+        rng.shuffle(c)
+        rows.append(np.concatenate([np.full((c.shape[0], 1), b), c], 1))
+    return np.concatenate(rows, 0).astype(np.int32)
+
+
+# ------------------------------------------------------------------------------------------------ coordinates
+@pytest.mark.parametrize("n,extent,batch,neg", [(500, 20, 1, False), (20000, 64, 2, True), (3000, 40, 3, False)])
+def test_maps_bit_exact(n, extent, batch, neg):
+    from agile3d_b200.backbone import CoordinateMaps
+    coords = _random_cloud(n, extent, seed=n, batch=batch, negative=neg)
+    maps = CoordinateMaps(torch.from_numpy(coords).to(DEV), count_pairs=True)
+    # oracle
+    cur = torch.from_numpy(coords)
+    levels, parents = [cur], []
+    for lvl in range(4):
+        c, _, _, par = emulate.downsample(levels[-1], 2 << lvl)
+        levels.append(c)
+        parents.append(par)
+    for lvl in range(5):
+        assert torch.equal(maps.coords[lvl].cpu(), levels[lvl]), f"coarse coords level {lvl}"
+        ref = emulate.kernel_map(levels[lvl], levels[lvl], 0, 3, 1 << lvl)
+        assert torch.equal(maps.k3[lvl].cpu(), ref), f"3x3x3 map level {lvl}"
+        assert maps.pair_counts[("k3", lvl)] == int((ref >= 0).sum())
+    for lvl in range(4):
+        assert torch.equal(maps.parents[lvl].cpu(), parents[lvl]), f"parents level {lvl}"
+        ref = emulate.kernel_map(levels[lvl + 1], levels[lvl], 0, 2, 1 << lvl)
+        assert torch.equal(maps.down[lvl].cpu(), ref), f"stride-2 map level {lvl}"
+        ref_t = emulate.kernel_map_transposed(levels[lvl], parents[lvl], 1 << lvl)
+        assert torch.equal(maps.up[lvl].cpu(), ref_t), f"transposed map level {lvl}"
+
+
+def test_kernel_map_5x5x5_and_dilation():
+    from agile3d_b200 import ops
+    coords = torch.from_numpy(_random_cloud(4000, 30, seed=11))
+    table, cap, _ = ops.hash_build(coords.to(DEV))
+    got = ops.kernel_map(coords.to(DEV), table, cap, 5, 1)
+    assert torch.equal(got.cpu(), emulate.kernel_map(coords, coords, 0, 5, 1))
+    got = ops.kernel_map(coords.to(DEV), table, cap, 3, 1, dilation=2)
+    assert torch.equal(got.cpu(), emulate.kernel_map(coords, coords, 0, 3, 1, 2))
+
+
+def test_duplicate_and_out_of_range_coordinates_rejected():
+    from agile3d_b200.backbone import CoordinateMaps
+    c = torch.tensor([[0, 1, 2, 3], [0, 1, 2, 3], [0, 4, 4, 4]], dtype=torch.int32, device=DEV)
+    with pytest.raises(ValueError):
+        CoordinateMaps(c)
+    c = torch.tensor([[0, 1, 2, 3], [0, 40000, 2, 3]], dtype=torch.int32, device=DEV)
+    with pytest.raises(ValueError):
+        CoordinateMaps(c)
+
+
+def test_single_voxel_scene():
+    from agile3d_b200.backbone import CoordinateMaps
+    m = CoordinateMaps(torch.tensor([[0, 5, 5, 5]], dtype=torch.int32, device=DEV))
+    assert m.sizes == [1, 1, 1, 1, 1]
+    assert m.k3[0].cpu()[:, 0].tolist() == [-1] * 13 + [0] + [-1] * 13
+
+
+# ------------------------------------------------------------------------------------------------ sparse conv
+@pytest.mark.parametrize("cin,cout,ks", [(32, 32, 3), (64, 96, 3), (96, 128, 3), (128, 256, 3), (384, 256, 3),
+                                         (32, 32, 2), (256, 128, 2)])
+def test_spconv_simt_vs_oracle(cin, cout, ks):
+    from agile3d_b200 import ops
+    coords = torch.from_numpy(_random_cloud(3000, 28, seed=cin + cout, batch=2))
+    n = coords.shape[0]
+    g = torch.Generator().manual_seed(cin * 7 + cout)
+    x = torch.randn((n, cin), generator=g)
+    w = torch.randn((ks ** 3, cin, cout), generator=g) / np.sqrt(cin * 8)
+    scale, shift = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g)
+    if ks == 3:
+        nbr = emulate.kernel_map(coords, coords, 0, 3, 1)
+        out_n = n
+    else:
+        coarse, _, _, _ = emulate.downsample(coords, 2)
+        nbr = emulate.kernel_map(coarse, coords, 0, 2, 1)
+        out_n = coarse.shape[0]
+    res = torch.randn((out_n, cout), generator=g)
+    ref = emulate.spconv_fwd(x, nbr, w, torch.empty(out_n, cout), scale, shift, res, relu=True)
+    # input is a channel slice of a wider buffer, output a slice of another: exercises the leading dimensions
+    xin = torch.zeros((n, cin + 32), device=DEV)
+    xin[:, 32:] = x.to(DEV)
+    outb = torch.full((out_n, cout + 64), -7.0, device=DEV)
+    ops.spconv_fwd(xin[:, 32:], nbr.to(DEV), w.to(DEV), outb[:, 64:], scale.to(DEV), shift.to(DEV), res.to(DEV),
+                   relu=True, algo=ops.ALGO_SIMT)
+    assert rel_err(outb[:, 64:].cpu().numpy(), ref.numpy()) < 1e-5
+    assert bool((outb[:, :64] == -7.0).all()), "wrote outside the channel slice"
+
+
+def test_spconv_1x1_and_transposed():
+    from agile3d_b200 import ops
+    coords = torch.from_numpy(_random_cloud(2500, 26, seed=5))
+    coarse, _, _, par = emulate.downsample(coords, 2)
+    g = torch.Generator().manual_seed(3)
+    xc = torch.randn((coarse.shape[0], 64), generator=g)
+    w = torch.randn((8, 64, 96), generator=g) * 0.1
+    nbr_t = emulate.kernel_map_transposed(coords, par, 1)
+    ref = emulate.spconv_fwd(xc, nbr_t, w, torch.empty(coords.shape[0], 96))
+    got = torch.empty((coords.shape[0], 96), device=DEV)
+    ops.spconv_fwd(xc.to(DEV), nbr_t.to(DEV), w.to(DEV), got, algo=ops.ALGO_SIMT)
+    assert rel_err(got.cpu().numpy(), ref.numpy()) < 1e-5
+    w1 = torch.randn((96, 128), generator=g) * 0.1
+    b1 = torch.randn(128, generator=g)
+    ref1 = ref @ w1 + b1
+    got1 = torch.empty((coords.shape[0], 128), device=DEV)
+    ops.spconv_fwd(got, None, w1.to(DEV), got1, None, b1.to(DEV), algo=ops.ALGO_SIMT)
+    assert rel_err(got1.cpu().numpy(), ref1.numpy()) < 1e-5
+
+
+def test_stem_conv_vs_oracle():
+    from agile3d_b200 import ops
+    coords = torch.from_numpy(_random_cloud(5000, 30, seed=9, batch=2, negative=True))
+    g = torch.Generator().manual_seed(1)
+    f = torch.rand((coords.shape[0], 3), generator=g)
+    w = torch.randn((125, 3, 32), generator=g) * 0.1
+    sc, sh = torch.rand(32, generator=g) + 0.5, torch.randn(32, generator=g) * 0.1
+    ref = emulate.stem_conv_fwd(coords, f, coords, 0, 5, w, torch.empty(coords.shape[0], 32), sc, sh, relu=True)
+    table, cap, _ = ops.hash_build(coords.to(DEV))
+    buf = torch.zeros((coords.shape[0], 128), device=DEV)
+    ops.stem_conv_fwd(coords.to(DEV), f.to(DEV), table, cap, 5, w.to(DEV), buf[:, 96:], sc.to(DEV), sh.to(DEV))
+    assert rel_err(buf[:, 96:].cpu().numpy(), ref.numpy()) < 1e-5
+    assert float(buf[:, :96].abs().max()) == 0.0
+
+
+# ------------------------------------------------------------------------------------------------ pos-enc
+def test_fourier_posenc_vs_oracle():
+    from agile3d_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    xyz = torch.rand((7000, 3), generator=g) * torch.tensor([8.0, 6.0, 3.0])
+    B = torch.randn((3, 64), generator=g)
+    offs = [0, 2500, 7000]
+    ref, ref_rng = emulate.fourier_posenc(xyz, offs, B)
+    got, rng = ops.fourier_posenc(xyz.to(DEV), offs, B.to(DEV))
+    assert torch.equal(rng.cpu(), ref_rng)
+    assert float((got.cpu() - ref).abs().max()) < 2e-5
+
+
+# ------------------------------------------------------------------------------------------------ decoder kernels
+def _decoder_inputs(nv, nq, n_obj, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn((nv, 128), generator=g)
+    pos = torch.randn((nv, 128), generator=g) * 0.7
+    qf = torch.randn((8 * nq, 128), generator=g) * 0.08
+    n_fg = nq - 10
+    q_obj = torch.tensor(sorted((i % (n_obj - 1)) + 1 for i in range(n_fg)) + [0] * 10, dtype=torch.int32) \
+        if n_obj > 1 else torch.zeros(nq, dtype=torch.int32)
+    return g, x, pos, qf, q_obj
+
+
+@pytest.mark.parametrize("nv,nq,n_obj", [(1000, 11, 2), (5003, 15, 3), (20000, 20, 6), (4100, 27, 9), (3000, 45, 11)])
+def test_c2s_vs_oracle(nv, nq, n_obj):
+    from agile3d_b200 import ops
+    g, x, pos, qf, q_obj = _decoder_inputs(nv, nq, n_obj, seed=nv + nq)
+    ref = emulate.c2s_attn_fwd(x.double(), pos.double(), qf.double(), nq, 8)
+    got = ops.c2s_attn_fwd(x.to(DEV), pos.to(DEV), qf.to(DEV), nq, 8)
+    assert rel_err(got.cpu().numpy(), ref.numpy()) < 1e-4
+    # masked: the last object's label never occurs -> its rows must be un-masked (agile3d.py:369,375)
+    label = torch.randint(0, max(n_obj - 1, 1), (nv,), generator=g).to(torch.uint8)
+    cnt = torch.bincount(label.long(), minlength=n_obj).to(torch.int32)
+    ref = emulate.c2s_attn_fwd(x.double(), pos.double(), qf.double(), nq, 8, label, q_obj, cnt)
+    got = ops.c2s_attn_fwd(x.to(DEV), pos.to(DEV), qf.to(DEV), nq, 8, label.to(DEV), q_obj.to(DEV), cnt.to(DEV))
+    assert rel_err(got.cpu().numpy(), ref.numpy()) < 1e-4
+
+
+@pytest.mark.parametrize("nv,nq,n_obj", [(1000, 11, 2), (5003, 15, 3), (20000, 20, 6), (4100, 25, 9), (777, 32, 12)])
+def test_s2c_mask_vs_oracle(nv, nq, n_obj):
+    from agile3d_b200 import ops
+    g, x, pos, _, q_obj = _decoder_inputs(nv, nq, n_obj, seed=nv * 3 + nq)
+    A = torch.randn((8 * nq, 128), generator=g) * 0.05
+    c = torch.randn(8 * nq, generator=g) * 0.1
+    U = torch.randn((8 * nq, 128), generator=g) * 0.3
+    bo, lw, lb = torch.randn(128, generator=g) * 0.1, torch.rand(128, generator=g) + 0.5, torch.randn(128, generator=g) * 0.1
+    E = torch.randn((nq, 128), generator=g) * 0.2
+    d = lambda t: t.double()
+    ry, rl, rlab, rcnt = emulate.s2c_mask_fwd(d(x), d(pos), d(A), d(c), d(U), d(bo), d(lw), d(lb), 1e-5, d(E), q_obj,
+                                              nq, 8, n_obj)
+    t = lambda v: v.to(DEV)
+    y, lg, lab, cnt = ops.s2c_mask_fwd(t(x), t(pos), t(A), t(c), t(U), t(bo), t(lw), t(lb), 1e-5, t(E), t(q_obj), nq,
+                                       8, n_obj)
+    assert rel_err(y.cpu().numpy(), ry.numpy()) < 1e-4
+    assert rel_err(lg.cpu().numpy(), rl.numpy()) < 1e-4
+    # labels: exact wherever the top-2 margin of the fp64 logits exceeds the fp32 noise
+    top2 = torch.topk(rl, min(2, n_obj), dim=1)[0]
+    safe = (top2[:, 0] - top2[:, -1]) > 1e-3 if n_obj > 1 else torch.ones(nv, dtype=torch.bool)
+    assert torch.equal(lab.cpu()[safe], rlab[safe])
+    assert int(cnt.sum()) == nv and torch.equal(cnt.cpu(), torch.bincount(lab.cpu().long(), minlength=n_obj).int())
+    # in-place variant (x_out aliases x) gives the same answer
+    xd = t(x).clone()
+    y2, lg2, _, _ = ops.s2c_mask_fwd(xd, t(pos), t(A), t(c), t(U), t(bo), t(lw), t(lb), 1e-5, t(E), t(q_obj), nq, 8,
+                                     n_obj, x_out=xd)
+    assert torch.equal(y2, y) and torch.equal(lg2, lg)
+
+
+# ------------------------------------------------------------------------------------------------ end to end
+def _gpu_model(wseed, algo=None):
+    import agile3d_b200
+    from agile3d_b200.weights import default_args, synth_state_dict
+    m = agile3d_b200.build_model(default_args()).eval()
+    m.load_state_dict(synth_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, seed=wseed))
+    m = m.to(DEV)
+    if algo is not None:
+        m.backbone.algo = algo
+    return m
+
+
+def _run_gpu(m, coords, feats, raw, clicks, times):
+    import agile3d_b200
+    x = agile3d_b200.SparseTensor(coordinates=torch.as_tensor(coords), features=torch.as_tensor(feats), device=DEV)
+    h = m.forward_backbone(x, torch.as_tensor(raw).to(DEV))
+    out = m.forward_mask(*h, clicks, times)
+    layers = [a["pred_masks"] for a in out["aux_outputs"]] + [out["pred_masks"]]
+    return h, layers
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_end_to_end_vs_reference_golden(name):
+    """The CUDA path against the outputs of the UNMODIFIED reference model files (tests/golden)."""
+    g = load_golden(name)
+    m = _gpu_model(g["wseed"])
+    h, layers = _run_gpu(m, g["coords"], g["feats"], g["raw_coords"], [g["clicks"]], [g["times"]])
+    assert [a.shape[0] for a in h[1]] == g["level_sizes"].tolist()
+    assert rel_err(h[0].F.cpu().numpy()[::4], g["pcd_features"]) < 1e-3
+    assert float((h[3][4][0][0].cpu()[::16] - torch.from_numpy(g["pos_enc"])).abs().max()) < 2e-5
+    for l in range(3):
+        e = rel_err(layers[l][0].cpu().numpy(), g["logits"][l])
+        assert e < 1e-3, f"layer {l}: rel err {e}"
+
+
+def test_end_to_end_vs_fp64_oracle_batched():
+    """Batch of two scenes against the fp64 oracle (the truth for the 1e-3 criterion)."""
+    from agile3d_b200.scenes import make_clicks, make_scene
+    sa = make_scene(6000, 0.02, seed=21, n_box=8)
+    sb = make_scene(9000, 0.05, seed=22, n_box=10)
+    ca, ta, _ = make_clicks(sa, 3, 2, 1, seed=1)
+    cb, tb, _ = make_clicks(sb, 5, 2, 0, seed=2)
+    coords = np.concatenate([np.concatenate([np.zeros((sa["coords"].shape[0], 1), np.int32), sa["coords"]], 1),
+                             np.concatenate([np.ones((sb["coords"].shape[0], 1), np.int32), sb["coords"]], 1)], 0)
+    feats = np.concatenate([sa["feats"], sb["feats"]], 0)
+    raw = np.concatenate([sa["raw_coords"], sb["raw_coords"]], 0)
+    ref_m = oracle_model(7, torch.float64)
+    _, _, _, ref_layers = oracle_forward(ref_m, coords, feats, raw, [ca, cb], [ta, tb], dtype=torch.float64)
+    m = _gpu_model(7)
+    _, layers = _run_gpu(m, coords, feats, raw, [ca, cb], [ta, tb])
+    for l in range(3):
+        for b in range(2):
+            e = rel_err(layers[l][b].cpu().numpy(), ref_layers[l][b].numpy())
+            assert e < 1e-3, f"layer {l} scene {b}: rel err {e}"
+
+
+def test_forward_mask_is_repeatable_and_handles_unmutated():
+    g = load_golden("g3000_k3")
+    m = _gpu_model(g["wseed"])
+    h, layers = _run_gpu(m, g["coords"], g["feats"], g["raw_coords"], [g["clicks"]], [g["times"]])
+    before = h[0].F.clone()
+    out2 = m.forward_mask(*h, [g["clicks"]], [g["times"]])
+    assert torch.equal(h[0].F, before)
+    assert torch.equal(out2["pred_masks"][0], layers[2][0])
+
+
+# ------------------------------------------------------------------------------------------------ full size
+def test_full_size_properties_150k():
+    """BASELINE.json headline shape (150k voxels, 10 clicks -> 20 queries): properties that need no CPU oracle."""
+    from agile3d_b200.backbone import CoordinateMaps
+    from agile3d_b200.scenes import make_clicks, make_scene
+    sc = make_scene(150000, 0.02, seed=1000 * 2 + 0)
+    n = sc["coords"].shape[0]
+    assert abs(n - 150000) <= 3000
+    coords = torch.from_numpy(np.concatenate([np.zeros((n, 1), np.int32), sc["coords"]], 1)).to(DEV)
+    maps = CoordinateMaps(coords, count_pairs=True)
+    nbr = maps.k3[0]
+    # centre offset is the identity; the 3x3x3 map is symmetric: nbr[k][o] = i  <=>  nbr[26-k][i] = o
+    assert torch.equal(nbr[13], torch.arange(n, dtype=torch.int32, device=DEV))
+    for k in (0, 5, 12):
+        o = torch.nonzero(nbr[k] >= 0).squeeze(1)
+        i = nbr[k][o].long()
+        assert torch.equal(nbr[26 - k][i], o.to(torch.int32))
+    # every fine voxel has exactly one parent entry in the transposed map; parents partition the level
+    assert int((maps.up[0] >= 0).sum()) == n
+    assert int((maps.down[0] >= 0).sum()) == n
+    assert maps.sizes[0] > maps.sizes[1] > maps.sizes[2] > maps.sizes[3] > maps.sizes[4] > 0
+    # determinism of the canonical row order
+    maps2 = CoordinateMaps(coords)
+    assert all(torch.equal(a, b) for a, b in zip(maps.coords, maps2.coords))
+    assert torch.equal(maps.k3[1], maps2.k3[1])
+    # whole model: finite, repeatable, logits columns = 1 + K
+    clicks, times, _ = make_clicks(sc, 5, 2, 0, seed=0)
+    m = _gpu_model(5)
+    h, layers = _run_gpu(m, coords.cpu().numpy(), sc["feats"], sc["raw_coords"], [clicks], [times])
+    assert layers[2][0].shape == (n, 6) and bool(torch.isfinite(layers[2][0]).all())
+    _, layers2 = _run_gpu(m, coords.cpu().numpy(), sc["feats"], sc["raw_coords"], [clicks], [times])
+    assert torch.equal(layers2[2][0], layers[2][0])
+    # clicked voxels of object j carry the object's own click feature: the scene is consistent row-wise
+    assert h[0].F.shape == (n, 128)
