@@ -155,13 +155,22 @@ class Res16UNet34C(nn.Module):
         self.algo = ops.ALGO_AUTO
         self._fold_cache = None
 
-    # -- folded BatchNorm constants, recomputed only when a parameter/buffer changed
+    # -- per-checkpoint constants (folded BatchNorm scale/shift, bf16 hi/lo weight images for the tensor-core
+    #    path), recomputed only when a parameter/buffer changed
     def _folded(self):
-        key = tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+        key = (self.algo,) + tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
         if self._fold_cache is None or self._fold_cache[0] != key:
             table = {name: mod.folded() for name, mod in self.named_modules() if isinstance(mod, SparseBatchNorm)}
+            if self.algo != ops.ALGO_SIMT:
+                for name, mod in self.named_modules():
+                    if isinstance(mod, SparseConv) and mod.cin % 32 == 0:
+                        table["tc:" + name] = ops.prepare_tc_weight(mod.kernel)
             self._fold_cache = (key, table)
         return self._fold_cache[1]
+
+    def _conv(self, name, conv, x, nbr, out, scale, shift, fold, residual=None, relu=False):
+        return ops.spconv_fwd(x, nbr, conv.kernel, out, scale, shift, residual=residual, relu=relu, algo=self.algo,
+                              weight_tc=fold.get("tc:" + name))
 
     def _block(self, prefix, blk, x, nbr, fold, out=None):
         n = x.shape[0]
@@ -169,17 +178,17 @@ class Res16UNet34C(nn.Module):
         planes = blk.conv1.cout
         s1, b1 = fold[prefix + ".norm1"]
         t = torch.empty((n, planes), dtype=torch.float32, device=dev)
-        ops.spconv_fwd(x, nbr, blk.conv1.kernel, t, s1, b1, relu=True, algo=self.algo)
+        self._conv(prefix + ".conv1", blk.conv1, x, nbr, t, s1, b1, fold, relu=True)
         if blk.downsample is not None:
             sd, bd = fold[prefix + ".downsample.1"]
             res = torch.empty((n, planes), dtype=torch.float32, device=dev)
-            ops.spconv_fwd(x, None, blk.downsample[0].kernel, res, sd, bd, relu=False, algo=self.algo)
+            self._conv(prefix + ".downsample.0", blk.downsample[0], x, None, res, sd, bd, fold)
         else:
             res = x
         s2, b2 = fold[prefix + ".norm2"]
         if out is None:
             out = torch.empty((n, planes), dtype=torch.float32, device=dev)
-        ops.spconv_fwd(t, nbr, blk.conv2.kernel, out, s2, b2, residual=res, relu=True, algo=self.algo)
+        self._conv(prefix + ".conv2", blk.conv2, t, nbr, out, s2, b2, fold, residual=res, relu=True)
         return out
 
     def _stage_fwd(self, name, x, nbr, fold, final_out=None):
@@ -212,7 +221,7 @@ class Res16UNet34C(nn.Module):
             conv = getattr(self, f"conv{tag}s2")
             s, b = fold[f"bn{i + 1}"]
             d = torch.empty((N[i + 1], conv.cout), **f32)
-            ops.spconv_fwd(y, maps.down[i], conv.kernel, d, s, b, relu=True, algo=self.algo)
+            self._conv(f"conv{tag}s2", conv, y, maps.down[i], d, s, b, fold, relu=True)
             dst = cat[i + 1][:, up_c[i + 1]:] if i < 3 else None       # block output doubles as the skip
             y = self._stage_fwd(f"block{i + 1}", d, maps.k3[i + 1], fold, final_out=dst)
         fmaps = [y]
@@ -220,7 +229,7 @@ class Res16UNet34C(nn.Module):
             lvl = 3 - j
             conv = getattr(self, f"convtr{tag}s2")
             s, b = fold[f"bntr{4 + j}"]
-            ops.spconv_fwd(y, maps.up[lvl], conv.kernel, cat[lvl][:, :up_c[lvl]], s, b, relu=True, algo=self.algo)
+            self._conv(f"convtr{tag}s2", conv, y, maps.up[lvl], cat[lvl][:, :up_c[lvl]], s, b, fold, relu=True)
             y = self._stage_fwd(f"block{5 + j}", cat[lvl], maps.k3[lvl], fold)
             fmaps.append(y)
         return y, fmaps, maps

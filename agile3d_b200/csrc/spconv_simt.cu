@@ -141,7 +141,7 @@ stem_conv_kernel(const int4* __restrict__ coords, const float* __restrict__ feat
 }
 
 int spconv_tc_launch(const float* in, int in_ld, int cin, const int* nbr, int K, long long n_out,
-                     const float* weight, int cout, const float* scale, const float* shift, const float* residual,
+                     const void* wprep, int cout, const float* scale, const float* shift, const float* residual,
                      int res_ld, float* out, int out_ld, int flags, cudaStream_t st);
 bool spconv_tc_supported(int cin, int cout);
 
@@ -152,23 +152,26 @@ using namespace ag3d;
 extern "C" {
 
 int ag3d_spconv_fwd(const float* in, int32_t in_ld, int32_t cin, const int32_t* nbr, int32_t K, int64_t n_out,
-                    const float* weight, int32_t cout, const float* scale, const float* shift,
+                    const float* weight, const void* weight_tc, int32_t cout, const float* scale, const float* shift,
                     const float* residual, int32_t res_ld, float* out, int32_t out_ld, int32_t flags,
                     int32_t algo, ag3d_stream_t stream) {
   AG3D_CHECK_ARG(n_out > 0 && n_out < 2147483647LL, "row count out of range");
   AG3D_CHECK_ARG(cin > 0 && cin % 32 == 0 && cout > 0 && cout % 32 == 0, "cin and cout must be multiples of 32");
   AG3D_CHECK_ARG(K >= 1 && (nbr || K == 1), "K > 1 needs a neighbour table");
-  AG3D_CHECK_ARG(in && weight && out && aligned16(in) && aligned16(weight) && aligned16(out), "bad pointers");
+  AG3D_CHECK_ARG(in && out && aligned16(in) && aligned16(out), "bad pointers");
+  AG3D_CHECK_ARG(weight || weight_tc, "need weight (fp32) or weight_tc (prepared)");
   AG3D_CHECK_ARG(in_ld % 4 == 0 && out_ld % 4 == 0 && in_ld >= cin && out_ld >= cout, "leading dims");
   AG3D_CHECK_ARG(!residual || (res_ld >= cout && aligned16(residual) && res_ld % 4 == 0), "residual leading dim");
   cudaStream_t st = as_stream(stream);
-  if (algo == AG3D_ALGO_AUTO) algo = spconv_tc_supported(cin, cout) ? AG3D_ALGO_TC : AG3D_ALGO_SIMT;
+  if (algo == AG3D_ALGO_AUTO)
+    algo = (weight_tc && K <= 32 && spconv_tc_supported(cin, cout)) ? AG3D_ALGO_TC : AG3D_ALGO_SIMT;
   if (algo == AG3D_ALGO_TC) {
     AG3D_CHECK_ARG(spconv_tc_supported(cin, cout), "shape not supported by the tcgen05 path");
-    return spconv_tc_launch(in, in_ld, cin, nbr, K, n_out, weight, cout, scale, shift, residual, res_ld, out,
+    return spconv_tc_launch(in, in_ld, cin, nbr, K, n_out, weight_tc, cout, scale, shift, residual, res_ld, out,
                             out_ld, flags, st);
   }
   AG3D_CHECK_ARG(algo == AG3D_ALGO_SIMT, "unknown algo");
+  AG3D_CHECK_ARG(weight && aligned16(weight), "the fp32 path needs the fp32 weight");
   const unsigned gx = (unsigned)((n_out + BM - 1) / BM);
   if (cout % 64 == 0) {
     spconv_simt_kernel<64><<<dim3(gx, cout / 64), SIMT_THREADS, 0, st>>>(

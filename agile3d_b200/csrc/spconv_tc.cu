@@ -1,10 +1,468 @@
-// placeholder until the tcgen05 kernel lands
+// K4 (tensor-core variant): output-stationary sparse convolution as an implicit GEMM on the 5th-gen tensor cores.
+//
+//   out[o, :] = act( scale * sum_k in[nbr[k][o], :] @ W[k] + shift (+ residual[o, :]) )
+//
+// Structure (one CTA, 1 per SM, 320 threads):
+//   * the CTA owns T consecutive 128-row output tiles; their fp32 accumulators [128 x Cout] live in TMEM
+//     (T * pow2(Cout) <= 512 columns) for the whole kernel;
+//   * the weight operand is *stationary*: for every (kernel offset k, 32-channel slab c) the pre-split weight
+//     slab is brought into shared memory ONCE by the TMA engine (cp.async.bulk, one elected thread) and reused by
+//     all T tiles, which divides the weight traffic from L2 by T;
+//   * 8 producer warps gather the 32-channel slab of the neighbour rows (coalesced 128-bit loads through the
+//     offset-major neighbour table), split every fp32 value into two bf16 pieces (hi = rn(x), lo = rn(x - hi)) and
+//     store both pieces into a ring of shared-memory stages in the UMMA canonical K-major layout;
+//   * one elected thread issues tcgen05.mma (kind::f16, bf16 inputs, fp32 accumulate): per 16-channel step the three
+//     products hi*hi + hi*lo + lo*hi ("bf16x3", relative error <= ~1e-5) accumulate into TMEM;
+//   * tcgen05.commit hands shared-memory stages back to the producers and finally signals the epilogue;
+//   * the 8 producer warps then become the epilogue: tcgen05.ld the accumulators, apply folded BatchNorm /
+//     bias, residual, ReLU and write the channel slice of the output buffer.
+// (tile, k) pairs in which no row of the tile has a neighbour are skipped by all roles.
+#include <cuda_bf16.h>
+
+#include <algorithm>
+
 #include "common.cuh"
+
 namespace ag3d {
-bool spconv_tc_supported(int, int) { return false; }
-int spconv_tc_launch(const float*, int, int, const int*, int, long long, const float*, int, const float*, const float*,
-                     const float*, int, float*, int, int, cudaStream_t) {
-  set_error("tcgen05 path not built");
-  return AG3D_E_INVALID;
+
+constexpr int TC_BM = 128;                       // rows per accumulator tile (UMMA M)
+constexpr int TC_BK = 32;                        // input channels per pipeline stage
+constexpr int TC_PROD_WARPS = 8;
+constexpr int TC_PROD_THREADS = TC_PROD_WARPS * 32;
+constexpr int TC_THREADS = TC_PROD_THREADS + 64; // + MMA warp + weight-loader warp
+constexpr int TC_MAX_T = 4;
+constexpr int A_LBO = 2048 + 32;                 // bytes between K-adjacent 8x16B core matrices of an A piece (padded)
+constexpr int A_PIECE = 4 * A_LBO;               // one bf16 piece of a [128 x 32] slab = 4 K-chunks
+constexpr int A_STAGE = 2 * A_PIECE;             // hi piece + lo piece
+constexpr int TC_BAR_BYTES = 512;
+constexpr unsigned SPIN_LIMIT = 1u << 24;
+
+// ---------------------------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  unsigned spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) break;
+    if (++spins > SPIN_LIMIT) __trap();   // a protocol bug must fail loudly, never hang the GPU
+  }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// UMMA shared-memory matrix descriptor, K-major, no swizzle: 8-row x 16-byte core matrices (128 contiguous
+// bytes); LBO = byte distance between core matrices adjacent in K, SBO = between core matrices adjacent in M/N.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
+  return d;                 // base_offset 0, lbo_mode 0, layout_type 0 = SWIZZLE_NONE
+}
+
+// instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = n
+__host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);   // .x (low 16 bits) = lo
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+// x = hi + lo + O(2^-18 |x|):  hi = rn_bf16(x), lo = rn_bf16(x - hi)
+__device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t& lo) {
+  hi = pack_bf16x2(x, y);
+  const float xh = __uint_as_float(hi << 16), yh = __uint_as_float(hi & 0xFFFF0000u);
+  lo = pack_bf16x2(x - xh, y - yh);
+}
+
+// ---------------------------------------------------------------------------------------------- weight prep
+// W [K][cin][cout] fp32  ->  Wp [K][cin/32][piece 2][kc 4][cout][8] bf16 : the exact shared-memory image of every
+// (k, slab) weight stage (UMMA K-major canonical layout with SBO = 128, LBO = cout*16), so one 1-D bulk copy
+// loads a stage.
+__global__ void weight_prep_kernel(const float* __restrict__ w, int K, int cin, int cout, uint4* __restrict__ wp) {
+  const long long total = (long long)K * (cin / TC_BK) * 4 * cout;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(t % cout);
+    long long r = t / cout;
+    const int kc = (int)(r % 4); r /= 4;
+    const int slab = (int)(r % (cin / TC_BK));
+    const int k = (int)(r / (cin / TC_BK));
+    const float* src = w + ((long long)k * cin + slab * TC_BK + kc * 8) * cout + n;
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) split2(__ldg(src + (2 * e) * (long long)cout), __ldg(src + (2 * e + 1) * (long long)cout), hi[e], lo[e]);
+    const long long stage = ((long long)k * (cin / TC_BK) + slab) * (2 * 4 * (long long)cout);
+    wp[stage + (0 * 4 + kc) * (long long)cout + n] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    wp[stage + (1 * 4 + kc) * (long long)cout + n] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- main kernel
+struct TcParams {
+  const float* in; int in_ld; int cin;
+  const int* nbr; int K; long long n_out;
+  const uint4* wp; int cout;
+  const float* scale; const float* shift; const float* residual; int res_ld;
+  float* out; int out_ld; int flags;
+  int T;            // tiles per CTA
+  int NA;           // A ring stages
+  int cpad;         // TMEM columns per tile (pow2 >= cout)
+  int tmem_cols;    // allocation (pow2, 32..512)
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  // barrier block
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  // bars[0..7] a_full, [8..15] a_empty, [16..17] b_full, [18..19] b_empty, [20] acc_full
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 256);
+  uint32_t* kmask_s = reinterpret_cast<uint32_t*>(smem + 272);   // [TC_MAX_T]
+  const uint32_t b_stage_bytes = (uint32_t)p.cout * 128u;
+  unsigned char* b_smem = smem + TC_BAR_BYTES;
+  unsigned char* a_smem = b_smem + 2 * b_stage_bytes;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long tiles_total = (p.n_out + TC_BM - 1) / TC_BM;
+  const long long tile0 = (long long)blockIdx.x * p.T;
+  const int T_here = (int)min((long long)p.T, tiles_total - tile0);
+  const long long row0 = tile0 * TC_BM;
+  const int n_slab = p.cin / TC_BK;
+
+  const uint32_t bar_base = smem_u32(bars);
+  auto a_full = [&](int s) { return bar_base + 8u * s; };
+  auto a_empty = [&](int s) { return bar_base + 8u * (8 + s); };
+  auto b_full = [&](int s) { return bar_base + 8u * (16 + s); };
+  auto b_empty = [&](int s) { return bar_base + 8u * (18 + s); };
+  const uint32_t acc_full = bar_base + 8u * 20;
+
+  if (tid == 0) {
+    for (int s = 0; s < p.NA; ++s) { mbar_init(a_full(s), TC_PROD_WARPS); mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+    mbar_init(acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid < TC_MAX_T) kmask_s[tid] = 0;
+  if (warp == TC_PROD_WARPS) {   // MMA warp owns the TMEM allocation
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  // ---- which kernel offsets does each tile need?  (skip (tile, k) pairs without any neighbour)
+  if (tid < TC_PROD_THREADS) {
+    for (int j = 0; j < T_here; ++j) {
+      const long long row = row0 + (long long)j * TC_BM + (tid & 127);
+      for (int k = tid >> 7; k < p.K; k += 2) {
+        int idx = -1;
+        if (row < p.n_out) idx = p.nbr ? __ldg(p.nbr + (long long)k * p.n_out + row) : (int)row;
+        const bool any = __any_sync(0xffffffffu, idx >= 0);
+        if (lane == 0 && any) atomicOr(&kmask_s[j], 1u << k);
+      }
+    }
+  }
+  __syncthreads();
+  uint32_t kmask[TC_MAX_T];
+  uint32_t kunion = 0;
+#pragma unroll
+  for (int j = 0; j < TC_MAX_T; ++j) {
+    kmask[j] = (j < T_here) ? kmask_s[j] : 0u;
+    kunion |= kmask[j];
+  }
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < TC_PROD_WARPS) {
+    // =========================================================================== A producers
+    const int cc = tid & 7;          // 16-byte chunk (4 fp32 channels) inside the 32-channel slab
+    const int rbase = tid >> 3;      // rows rbase + 32*i
+    // byte offset of this thread's 8-byte half core-matrix row inside a piece, for row r: kc = cc>>1
+    uint32_t st_off[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = rbase + 32 * i;
+      st_off[i] = (uint32_t)((cc >> 1) * A_LBO + (r >> 3) * 128 + (r & 7) * 16 + (cc & 1) * 8);
+    }
+    float4 cur[4];
+    bool pending = false;
+    int n_done = 0;                  // stages finished so far (ring position)
+    auto finish = [&]() {
+      const int s = n_done % p.NA;
+      const uint32_t use = (uint32_t)(n_done / p.NA);
+      mbar_wait(a_empty(s), (use & 1u) ^ 1u);
+      unsigned char* st = a_smem + (size_t)s * A_STAGE;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint32_t h0, l0, h1, l1;
+        split2(cur[i].x, cur[i].y, h0, l0);
+        split2(cur[i].z, cur[i].w, h1, l1);
+        *reinterpret_cast<uint2*>(st + st_off[i]) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(st + A_PIECE + st_off[i]) = make_uint2(l0, l1);
+      }
+      fence_proxy_async();           // generic-proxy stores -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_full(s));
+      ++n_done;
+    };
+    for (int k = 0; k < p.K; ++k) {
+      if (!((kunion >> k) & 1u)) continue;
+      for (int c = 0; c < n_slab; ++c) {
+        for (int j = 0; j < T_here; ++j) {
+          if (!((kmask[j] >> k) & 1u)) continue;
+          float4 nxt[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const long long row = row0 + (long long)j * TC_BM + rbase + 32 * i;
+            int idx = -1;
+            if (row < p.n_out) idx = p.nbr ? __ldg(p.nbr + (long long)k * p.n_out + row) : (int)row;
+            nxt[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (idx >= 0)
+              nxt[i] = __ldg(reinterpret_cast<const float4*>(p.in + (long long)idx * p.in_ld + c * TC_BK + cc * 4));
+          }
+          if (pending) finish();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
+          pending = true;
+        }
+      }
+    }
+    if (pending) finish();
+
+    // =========================================================================== epilogue
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const int q = warp & 3, half = warp >> 2;
+    const int ncol = p.cout >> 1;    // columns per warp half (multiple of 16)
+    const bool relu = p.flags & AG3D_RELU;
+    for (int j = 0; j < T_here; ++j) {
+      const long long row = row0 + (long long)j * TC_BM + q * 32 + lane;
+      const bool live = kmask[j] != 0u;
+      for (int c0 = half * ncol; c0 < (half + 1) * ncol; c0 += 16) {
+        float v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * p.cpad + c0), v);
+        if (row < p.n_out) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            float x = live ? v[e] : 0.f;
+            if (p.scale) x *= __ldg(p.scale + c0 + e);
+            if (p.shift) x += __ldg(p.shift + c0 + e);
+            v[e] = x;
+          }
+          if (p.residual) {
+#pragma unroll
+            for (int e4 = 0; e4 < 4; ++e4) {
+              const float4 r4 = __ldg(reinterpret_cast<const float4*>(p.residual + row * p.res_ld + c0 + e4 * 4));
+              v[e4 * 4 + 0] += r4.x; v[e4 * 4 + 1] += r4.y; v[e4 * 4 + 2] += r4.z; v[e4 * 4 + 3] += r4.w;
+            }
+          }
+          if (relu) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.f);
+          }
+#pragma unroll
+          for (int e4 = 0; e4 < 4; ++e4)
+            *reinterpret_cast<float4*>(p.out + row * p.out_ld + c0 + e4 * 4) =
+                make_float4(v[e4 * 4], v[e4 * 4 + 1], v[e4 * 4 + 2], v[e4 * 4 + 3]);
+        }
+      }
+    }
+  } else if (warp == TC_PROD_WARPS) {
+    // =========================================================================== MMA issuer (one thread)
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(p.cout);
+      const uint32_t b_lbo = (uint32_t)p.cout * 16u;
+      uint32_t started = 0;            // bit j: accumulator j has been written
+      int n_a = 0, n_b = 0;
+      for (int k = 0; k < p.K; ++k) {
+        if (!((kunion >> k) & 1u)) continue;
+        for (int c = 0; c < n_slab; ++c) {
+          const int sb = n_b & 1;
+          mbar_wait(b_full(sb), (uint32_t)(n_b >> 1) & 1u);
+          tc_fence_after();
+          const uint32_t b_hi = smem_u32(b_smem + (size_t)sb * b_stage_bytes);
+          const uint32_t b_lo = b_hi + 4u * b_lbo;
+          for (int j = 0; j < T_here; ++j) {
+            if (!((kmask[j] >> k) & 1u)) continue;
+            const int s = n_a % p.NA;
+            mbar_wait(a_full(s), (uint32_t)(n_a / p.NA) & 1u);
+            tc_fence_after();
+            const uint32_t a_hi = smem_u32(a_smem + (size_t)s * A_STAGE);
+            const uint32_t a_lo = a_hi + A_PIECE;
+            const uint32_t d = tmem_base + (uint32_t)(j * p.cpad);
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {           // two 16-channel MMA steps per 32-channel slab
+              const uint64_t da_hi = umma_desc(a_hi + ks * 2 * A_LBO, A_LBO, 128);
+              const uint64_t da_lo = umma_desc(a_lo + ks * 2 * A_LBO, A_LBO, 128);
+              const uint64_t db_hi = umma_desc(b_hi + ks * 2 * b_lbo, b_lbo, 128);
+              const uint64_t db_lo = umma_desc(b_lo + ks * 2 * b_lbo, b_lbo, 128);
+              umma_bf16(d, da_hi, db_hi, idesc, (started >> j) & 1u);
+              started |= 1u << j;
+              umma_bf16(d, da_hi, db_lo, idesc, 1u);
+              umma_bf16(d, da_lo, db_hi, idesc, 1u);
+            }
+            umma_commit(a_empty(s));   // stage s may be overwritten once these MMAs have read it
+            ++n_a;
+          }
+          umma_commit(b_empty(sb));
+          ++n_b;
+        }
+      }
+      umma_commit(acc_full);
+    }
+  } else {
+    // =========================================================================== weight loader (TMA engine)
+    if (lane == 0) {
+      int n_b = 0;
+      for (int k = 0; k < p.K; ++k) {
+        if (!((kunion >> k) & 1u)) continue;
+        for (int c = 0; c < n_slab; ++c) {
+          const int sb = n_b & 1;
+          mbar_wait(b_empty(sb), ((uint32_t)(n_b >> 1) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(b_full(sb), b_stage_bytes);
+          const unsigned char* src = reinterpret_cast<const unsigned char*>(p.wp) +
+                                     ((size_t)k * n_slab + c) * (size_t)b_stage_bytes;
+          bulk_g2s(smem_u32(b_smem + (size_t)sb * b_stage_bytes), src, b_stage_bytes, b_full(sb));
+          ++n_b;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == TC_PROD_WARPS) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+static int pow2_at_least(int v, int lo) {
+  int r = lo;
+  while (r < v) r <<= 1;
+  return r;
+}
+
+bool spconv_tc_supported(int cin, int cout) {
+  return cin % TC_BK == 0 && cout % 32 == 0 && cout >= 32 && cout <= 256 && cin >= 32;
+}
+
+int spconv_tc_launch(const float* in, int in_ld, int cin, const int* nbr, int K, long long n_out,
+                     const void* wprep, int cout, const float* scale, const float* shift, const float* residual,
+                     int res_ld, float* out, int out_ld, int flags, cudaStream_t st) {
+  AG3D_CHECK_ARG(K <= 32, "the tensor-core path handles at most 32 kernel offsets");
+  AG3D_CHECK_ARG(wprep && aligned16(wprep), "prepared weights missing (ag3d_spconv_tc_prepare_weight)");
+  TcParams p;
+  p.in = in; p.in_ld = in_ld; p.cin = cin; p.nbr = nbr; p.K = K; p.n_out = n_out;
+  p.wp = static_cast<const uint4*>(wprep); p.cout = cout;
+  p.scale = scale; p.shift = shift; p.residual = residual; p.res_ld = res_ld;
+  p.out = out; p.out_ld = out_ld; p.flags = flags;
+  p.cpad = pow2_at_least(cout, 32);
+  const int t_max = std::min(TC_MAX_T, 512 / p.cpad);
+  const long long tiles = (n_out + TC_BM - 1) / TC_BM;
+  const int sms = sm_count();
+  // tiles per CTA: minimise waves * (T gathers + one weight stage), weight stage cost relative to a gather = cout/128
+  int best_t = 1;
+  double best_cost = 1e30;
+  for (int t = 1; t <= t_max; ++t) {
+    const long long ctas = (tiles + t - 1) / t;
+    const long long waves = (ctas + sms - 1) / sms;
+    const double cost = (double)waves * ((double)t + (double)cout / 128.0);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best_t = t; }
+  }
+  p.T = best_t;
+  p.tmem_cols = pow2_at_least(p.T * p.cpad, 32);
+  const size_t fixed = TC_BAR_BYTES + 2 * (size_t)cout * 128;
+  int na = (int)((200 * 1024 - fixed) / A_STAGE);
+  if (na > 8) na = 8;
+  AG3D_CHECK_ARG(na >= 2, "internal: shared memory budget");
+  p.NA = na;
+  const size_t smem = fixed + (size_t)na * A_STAGE;
+  static bool attr = false;
+  if (!attr) {
+    AG3D_CUDA(cudaFuncSetAttribute(spconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr = true;
+  }
+  const unsigned grid = (unsigned)((tiles + p.T - 1) / p.T);
+  spconv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(p);
+  AG3D_LAUNCH_CHECK("spconv_tc");
+  return AG3D_OK;
+}
+
 }  // namespace ag3d
+
+using namespace ag3d;
+
+extern "C" {
+
+size_t ag3d_spconv_tc_weight_bytes(int32_t K, int32_t cin, int32_t cout) {
+  return (size_t)K * (size_t)(cin / TC_BK) * (size_t)cout * 128;
+}
+
+int ag3d_spconv_tc_prepare_weight(const float* weight, int32_t K, int32_t cin, int32_t cout, void* wprep,
+                                  ag3d_stream_t stream) {
+  AG3D_CHECK_ARG(K >= 1 && spconv_tc_supported(cin, cout), "shape not supported by the tensor-core path");
+  AG3D_CHECK_ARG(weight && wprep && aligned16(wprep), "bad pointers");
+  const long long total = (long long)K * (cin / TC_BK) * 4 * cout;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 4096) blocks = 4096;
+  weight_prep_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(weight, K, cin, cout, static_cast<uint4*>(wprep));
+  AG3D_LAUNCH_CHECK("weight_prep");
+  return AG3D_OK;
+}
+
+}  // extern "C"

@@ -145,9 +145,13 @@ class Agile3d(nn.Module):
             offsets.append(offsets[-1] + c)
         pos, rng = ops.fourier_posenc(raw, offsets, self.pos_enc.gauss_B)
         pcd = torch.empty((feats.shape[0], self.hidden_dim), dtype=torch.float32, device=feats.device)
-        ops.spconv_fwd(feats, None, self.lin_squeeze_head.kernel, pcd, None,
-                       self.lin_squeeze_head.bias.detach().reshape(-1).contiguous(), relu=False,
-                       algo=self.backbone.algo)
+        head = self.lin_squeeze_head
+        hkey = (self.backbone.algo, head.kernel.data_ptr(), head.kernel._version)
+        if getattr(self, "_head_tc", (None, None))[0] != hkey:
+            wtc = ops.prepare_tc_weight(head.kernel) if self.backbone.algo != ops.ALGO_SIMT else None
+            self._head_tc = (hkey, wtc)
+        ops.spconv_fwd(feats, None, head.kernel, pcd, None, head.bias.detach().reshape(-1).contiguous(), relu=False,
+                       algo=self.backbone.algo, weight_tc=self._head_tc[1])
         pcd_features = BackboneFeatures(pcd, offsets, x.C)
         coordinates = BackboneFeatures(raw, offsets, x.C)
         coordinates.range = rng

@@ -137,7 +137,19 @@ def kernel_map_transposed(fine_coords, parent, fine_stride):
     return nbr
 
 
-def spconv_fwd(x, nbr, weight, out, scale=None, shift=None, residual=None, relu=False, algo=ALGO_AUTO):
+def prepare_tc_weight(weight):
+    """fp32 [K,cin,cout] (or [cin,cout]) -> opaque uint8 tensor holding the bf16 hi/lo stage images of the tcgen05 path."""
+    _need_cuda(weight)
+    w = weight.detach()
+    w = (w if w.dim() == 3 else w.unsqueeze(0)).contiguous().float()
+    K, cin, cout = w.shape
+    nbytes = lib().ag3d_spconv_tc_weight_bytes(K, cin, cout)
+    buf = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+    check(lib().ag3d_spconv_tc_prepare_weight(_p(w), K, cin, cout, _p(buf), _stream()), "ag3d_spconv_tc_prepare_weight")
+    return buf
+
+
+def spconv_fwd(x, nbr, weight, out, scale=None, shift=None, residual=None, relu=False, algo=ALGO_AUTO, weight_tc=None):
     """out[o] = act(scale * sum_k x[nbr[k][o]] @ weight[k] + shift (+ residual[o])).  x/out/residual may be channel
     slices of wider buffers.  weight [K,cin,cout] (or [cin,cout] with nbr None)."""
     _need_cuda(x, weight, out)
@@ -162,8 +174,8 @@ def spconv_fwd(x, nbr, weight, out, scale=None, shift=None, residual=None, relu=
     nbytes = 4 * x.shape[0] * cin + 4 * n_out * cout + 8 * pairs + 4 * K * cin * cout \
         + (4 * n_out * cout if residual is not None else 0)
     with _Timed("spconv", nbytes, 2 * pairs * cin * cout):
-        check(lib().ag3d_spconv_fwd(xp, x_ld, cin, _p(nbr), K, n_out, _p(w), cout, _p(scale), _p(shift), rp, r_ld,
-                                    op, o_ld, RELU if relu else 0, algo, _stream()), "ag3d_spconv_fwd")
+        check(lib().ag3d_spconv_fwd(xp, x_ld, cin, _p(nbr), K, n_out, _p(w), _p(weight_tc), cout, _p(scale), _p(shift),
+                                    rp, r_ld, op, o_ld, RELU if relu else 0, algo, _stream()), "ag3d_spconv_fwd")
     return out
 
 

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define AG3D_ABI_VERSION 1
+#define AG3D_ABI_VERSION 2
 
 #define AG3D_OK 0
 #define AG3D_E_INVALID (-1)   /* bad argument (shape, alignment, unsupported size) */
@@ -40,7 +40,7 @@ extern "C" {
 /* spconv `algo` */
 #define AG3D_ALGO_AUTO 0
 #define AG3D_ALGO_SIMT 1 /* exact fp32 FFMA implicit GEMM */
-#define AG3D_ALGO_TC 2   /* tcgen05 3xTF32 implicit GEMM, accumulators in TMEM */
+#define AG3D_ALGO_TC 2   /* tcgen05 bf16x3 (hi*hi + hi*lo + lo*hi, fp32 accumulate in TMEM) implicit GEMM */
 
 typedef void* ag3d_stream_t; /* cudaStream_t */
 
@@ -91,9 +91,14 @@ int ag3d_kernel_map_transposed(const int32_t* fine_coords, const int32_t* parent
  * (models/modules/resnet_block.py:48-64, models/res16unet.py:222-295).
  *   out[o, :] = act( scale * sum_k in[nbr[k][o], :] @ W[k]  + shift  (+ residual[o, :]) )
  * weight is MinkowskiEngine's [K, cin, cout]; nbr == NULL means K == 1 on the identity map (1x1 conv).
- * scale/shift are the folded BatchNorm (or NULL/bias); residual is nullable.  cin, cout multiples of 32.   */
+ * scale/shift are the folded BatchNorm (or NULL/bias); residual is nullable.  cin, cout multiples of 32.
+ * weight_tc (nullable) is the same weight pre-split into bf16 hi/lo stage images by
+ * ag3d_spconv_tc_prepare_weight; AG3D_ALGO_AUTO takes the tensor-core path when it is given.                */
+size_t ag3d_spconv_tc_weight_bytes(int32_t K, int32_t cin, int32_t cout);
+int ag3d_spconv_tc_prepare_weight(const float* weight, int32_t K, int32_t cin, int32_t cout, void* weight_tc,
+                                  ag3d_stream_t stream);
 int ag3d_spconv_fwd(const float* in, int32_t in_ld, int32_t cin, const int32_t* nbr, int32_t K, int64_t n_out,
-                    const float* weight, int32_t cout, const float* scale, const float* shift,
+                    const float* weight, const void* weight_tc, int32_t cout, const float* scale, const float* shift,
                     const float* residual, int32_t res_ld, float* out, int32_t out_ld, int32_t flags,
                     int32_t algo, ag3d_stream_t stream);
 /* Stem: conv0p1s1 (3 -> 32 channels, kernel 5, models/res16unet.py:39-47) evaluated directly against the

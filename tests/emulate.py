@@ -62,7 +62,11 @@ def kernel_map_transposed(fine_coords, parent, fine_stride):
     return torch.from_numpy(nbr)
 
 
-def spconv_fwd(x, nbr, weight, out, scale=None, shift=None, residual=None, relu=False, algo=0):
+def prepare_tc_weight(weight):
+    return None
+
+
+def spconv_fwd(x, nbr, weight, out, scale=None, shift=None, residual=None, relu=False, algo=0, weight_tc=None):
     w = weight.detach()
     w = w if w.dim() == 3 else w.unsqueeze(0)
     acc = torch.zeros((out.shape[0], w.shape[2]), dtype=torch.float32)
@@ -127,7 +131,7 @@ def s2c_mask_fwd(x, pos, A, c, U, bo, ln_w, ln_b, ln_eps, E, q_obj, nq, heads, n
     return y, logits, label, obj_count
 
 
-ALL = ["hash_build", "downsample", "kernel_map", "kernel_map_transposed", "spconv_fwd", "stem_conv_fwd",
+ALL = ["prepare_tc_weight", "hash_build", "downsample", "kernel_map", "kernel_map_transposed", "spconv_fwd", "stem_conv_fwd",
        "fourier_posenc", "c2s_attn_fwd", "s2c_mask_fwd"]
 
 
