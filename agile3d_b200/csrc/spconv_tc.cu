@@ -158,6 +158,7 @@ struct TcParams {
   float* out; int out_ld; int flags;
   int T;            // tiles per CTA
   int NA;           // A ring stages
+  int NB;           // weight stages
   int cpad;         // TMEM columns per tile (pow2 >= cout)
   int tmem_cols;    // allocation (pow2, 32..512)
 };
@@ -166,12 +167,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams
   extern __shared__ __align__(128) unsigned char smem[];
   // barrier block
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
-  // bars[0..7] a_full, [8..15] a_empty, [16..17] b_full, [18..19] b_empty, [20] acc_full
+  // bars[0..7] a_full, [8..15] a_empty, [16..19] b_full, [20..23] b_empty, [24] acc_full
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 256);
   uint32_t* kmask_s = reinterpret_cast<uint32_t*>(smem + 272);   // [TC_MAX_T]
   const uint32_t b_stage_bytes = (uint32_t)p.cout * 128u;
   unsigned char* b_smem = smem + TC_BAR_BYTES;
-  unsigned char* a_smem = b_smem + 2 * b_stage_bytes;
+  unsigned char* a_smem = b_smem + (size_t)p.NB * b_stage_bytes;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long tiles_total = (p.n_out + TC_BM - 1) / TC_BM;
@@ -184,12 +185,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams
   auto a_full = [&](int s) { return bar_base + 8u * s; };
   auto a_empty = [&](int s) { return bar_base + 8u * (8 + s); };
   auto b_full = [&](int s) { return bar_base + 8u * (16 + s); };
-  auto b_empty = [&](int s) { return bar_base + 8u * (18 + s); };
-  const uint32_t acc_full = bar_base + 8u * 20;
+  auto b_empty = [&](int s) { return bar_base + 8u * (20 + s); };
+  const uint32_t acc_full = bar_base + 8u * 24;
 
   if (tid == 0) {
     for (int s = 0; s < p.NA; ++s) { mbar_init(a_full(s), TC_PROD_WARPS); mbar_init(a_empty(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+    for (int s = 0; s < p.NB; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
     mbar_init(acc_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -237,10 +238,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams
       const int r = rbase + 32 * i;
       st_off[i] = (uint32_t)((cc >> 1) * A_LBO + (r >> 3) * 128 + (r & 7) * 16 + (cc & 1) * 8);
     }
-    float4 cur[4];
-    bool pending = false;
     int n_done = 0;                  // stages finished so far (ring position)
-    auto finish = [&]() {
+    auto finish = [&](const float4 (&buf)[4]) {
       const int s = n_done % p.NA;
       const uint32_t use = (uint32_t)(n_done / p.NA);
       mbar_wait(a_empty(s), (use & 1u) ^ 1u);
@@ -248,8 +247,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         uint32_t h0, l0, h1, l1;
-        split2(cur[i].x, cur[i].y, h0, l0);
-        split2(cur[i].z, cur[i].w, h1, l1);
+        split2(buf[i].x, buf[i].y, h0, l0);
+        split2(buf[i].z, buf[i].w, h1, l1);
         *reinterpret_cast<uint2*>(st + st_off[i]) = make_uint2(h0, h1);
         *reinterpret_cast<uint2*>(st + A_PIECE + st_off[i]) = make_uint2(l0, l1);
       }
@@ -258,29 +257,55 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams
       if (lane == 0) mbar_arrive(a_full(s));
       ++n_done;
     };
-    for (int k = 0; k < p.K; ++k) {
-      if (!((kunion >> k) & 1u)) continue;
-      for (int c = 0; c < n_slab; ++c) {
-        for (int j = 0; j < T_here; ++j) {
-          if (!((kmask[j] >> k) & 1u)) continue;
-          float4 nxt[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const long long row = row0 + (long long)j * TC_BM + rbase + 32 * i;
-            int idx = -1;
-            if (row < p.n_out) idx = p.nbr ? __ldg(p.nbr + (long long)k * p.n_out + row) : (int)row;
-            nxt[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (idx >= 0)
-              nxt[i] = __ldg(reinterpret_cast<const float4*>(p.in + (long long)idx * p.in_ld + c * TC_BK + cc * 4));
-          }
-          if (pending) finish();
-#pragma unroll
-          for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
-          pending = true;
+    // stage iterator in (k, slab, tile) order, skipping (tile, k) pairs without neighbours
+    int it_k = 0, it_c = 0, it_j = -1;
+    auto advance = [&]() {
+      while (true) {
+        if (++it_j >= T_here) {
+          it_j = 0;
+          if (++it_c >= n_slab) { it_c = 0; ++it_k; }
         }
+        if (it_k >= p.K) return;
+        if ((kmask_s[it_j] >> it_k) & 1u) return;
+        if (!((kunion >> it_k) & 1u)) { it_c = n_slab - 1; it_j = T_here - 1; }   // whole offset unused: jump
       }
+    };
+    int idx_ld[4];                   // neighbour rows of the next stage to load (prefetched one stage ahead)
+    auto load_idx = [&]() {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const long long row = row0 + (long long)it_j * TC_BM + rbase + 32 * i;
+        idx_ld[i] = -1;
+        if (row < p.n_out) idx_ld[i] = p.nbr ? __ldg(p.nbr + (long long)it_k * p.n_out + row) : (int)row;
+      }
+    };
+    auto issue = [&](float4 (&buf)[4]) -> bool {
+      if (it_k >= p.K) return false;
+      const float* src = p.in + it_c * TC_BK + cc * 4;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        buf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (idx_ld[i] >= 0) buf[i] = __ldg(reinterpret_cast<const float4*>(src + (long long)idx_ld[i] * p.in_ld));
+      }
+      advance();
+      if (it_k < p.K) load_idx();
+      return true;
+    };
+    advance();
+    if (it_k < p.K) load_idx();
+    // three stages of gathers in flight per thread (12 x 16 B): the gather is latency-bound otherwise
+    float4 b0[4], b1[4], b2[4];
+    bool v0 = issue(b0), v1 = issue(b1), v2 = issue(b2);
+    while (v0) {
+      finish(b0);
+      v0 = issue(b0);
+      if (!v1) break;
+      finish(b1);
+      v1 = issue(b1);
+      if (!v2) break;
+      finish(b2);
+      v2 = issue(b2);
     }
-    if (pending) finish();
 
     // =========================================================================== epilogue
     mbar_wait(acc_full, 0);
@@ -330,8 +355,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams
       for (int k = 0; k < p.K; ++k) {
         if (!((kunion >> k) & 1u)) continue;
         for (int c = 0; c < n_slab; ++c) {
-          const int sb = n_b & 1;
-          mbar_wait(b_full(sb), (uint32_t)(n_b >> 1) & 1u);
+          const int sb = n_b % p.NB;
+          mbar_wait(b_full(sb), (uint32_t)(n_b / p.NB) & 1u);
           tc_fence_after();
           const uint32_t b_hi = smem_u32(b_smem + (size_t)sb * b_stage_bytes);
           const uint32_t b_lo = b_hi + 4u * b_lbo;
@@ -370,8 +395,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams
       for (int k = 0; k < p.K; ++k) {
         if (!((kunion >> k) & 1u)) continue;
         for (int c = 0; c < n_slab; ++c) {
-          const int sb = n_b & 1;
-          mbar_wait(b_empty(sb), ((uint32_t)(n_b >> 1) & 1u) ^ 1u);
+          const int sb = n_b % p.NB;
+          mbar_wait(b_empty(sb), ((uint32_t)(n_b / p.NB) & 1u) ^ 1u);
           mbar_arrive_expect_tx(b_full(sb), b_stage_bytes);
           const unsigned char* src = reinterpret_cast<const unsigned char*>(p.wp) +
                                      ((size_t)k * n_slab + c) * (size_t)b_stage_bytes;
@@ -426,7 +451,8 @@ int spconv_tc_launch(const float* in, int in_ld, int cin, const int* nbr, int K,
   }
   p.T = best_t;
   p.tmem_cols = pow2_at_least(p.T * p.cpad, 32);
-  const size_t fixed = TC_BAR_BYTES + 2 * (size_t)cout * 128;
+  p.NB = (cout <= 128) ? 4 : 2;
+  const size_t fixed = TC_BAR_BYTES + (size_t)p.NB * (size_t)cout * 128;
   int na = (int)((200 * 1024 - fixed) / A_STAGE);
   if (na > 8) na = 8;
   AG3D_CHECK_ARG(na >= 2, "internal: shared memory budget");

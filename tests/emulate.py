@@ -69,7 +69,7 @@ def prepare_tc_weight(weight):
 def spconv_fwd(x, nbr, weight, out, scale=None, shift=None, residual=None, relu=False, algo=0, weight_tc=None):
     w = weight.detach()
     w = w if w.dim() == 3 else w.unsqueeze(0)
-    acc = torch.zeros((out.shape[0], w.shape[2]), dtype=torch.float32)
+    acc = torch.zeros((out.shape[0], w.shape[2]), dtype=x.dtype)
     for k in range(w.shape[0]):
         if nbr is None:
             acc += x @ w[k]
