@@ -2,19 +2,19 @@
 //
 //   out[o, :] = act( scale * sum_k in[nbr[k][o], :] @ W[k] + shift (+ residual[o, :]) )
 //
-// Structure (one CTA, 1 per SM, 320 threads):
+// Structure (one CTA, 1 per SM, 576 threads):
 //   * the CTA owns T consecutive 128-row output tiles; their fp32 accumulators [128 x Cout] live in TMEM
 //     (T * pow2(Cout) <= 512 columns) for the whole kernel;
 //   * the weight operand is *stationary*: for every (kernel offset k, 32-channel slab c) the pre-split weight
 //     slab is brought into shared memory ONCE by the TMA engine (cp.async.bulk, one elected thread) and reused by
 //     all T tiles, which divides the weight traffic from L2 by T;
-//   * 8 producer warps gather the 32-channel slab of the neighbour rows (coalesced 128-bit loads through the
+//   * 16 producer warps gather the 32-channel slab of the neighbour rows (coalesced 128-bit loads through the
 //     offset-major neighbour table), split every fp32 value into two bf16 pieces (hi = rn(x), lo = rn(x - hi)) and
 //     store both pieces into a ring of shared-memory stages in the UMMA canonical K-major layout;
 //   * one elected thread issues tcgen05.mma (kind::f16, bf16 inputs, fp32 accumulate): per 16-channel step the three
 //     products hi*hi + hi*lo + lo*hi ("bf16x3", relative error <= ~1e-5) accumulate into TMEM;
 //   * tcgen05.commit hands shared-memory stages back to the producers and finally signals the epilogue;
-//   * the 8 producer warps then become the epilogue: tcgen05.ld the accumulators, apply folded BatchNorm /
+//   * the 16 producer warps then become the epilogue: tcgen05.ld the accumulators, apply folded BatchNorm /
 //     bias, residual, ReLU and write the channel slice of the output buffer.
 // (tile, k) pairs in which no row of the tile has a neighbour are skipped by all roles.
 #include <cuda_bf16.h>
@@ -27,7 +27,7 @@ namespace ag3d {
 
 constexpr int TC_BM = 128;                       // rows per accumulator tile (UMMA M)
 constexpr int TC_BK = 32;                        // input channels per pipeline stage
-constexpr int TC_PROD_WARPS = 8;
+constexpr int TC_PROD_WARPS = 16;
 constexpr int TC_PROD_THREADS = TC_PROD_WARPS * 32;
 constexpr int TC_THREADS = TC_PROD_THREADS + 64; // + MMA warp + weight-loader warp
 constexpr int TC_MAX_T = 4;
@@ -159,15 +159,15 @@ struct TcParams {
   int T;            // tiles per CTA
   int NA;           // A ring stages
   int NB;           // weight stages
+  int na_log2, nb_log2;
   int cpad;         // TMEM columns per tile (pow2 >= cout)
   int tmem_cols;    // allocation (pow2, 32..512)
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
-  // barrier block
+  // barrier block: bars[0..7] a_full, [8..15] a_empty, [16..19] b_full, [20..23] b_empty, [24] acc_full
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
-  // bars[0..7] a_full, [8..15] a_empty, [16..19] b_full, [20..23] b_empty, [24] acc_full
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 256);
   uint32_t* kmask_s = reinterpret_cast<uint32_t*>(smem + 272);   // [TC_MAX_T]
   const uint32_t b_stage_bytes = (uint32_t)p.cout * 128u;
@@ -180,6 +180,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams
   const int T_here = (int)min((long long)p.T, tiles_total - tile0);
   const long long row0 = tile0 * TC_BM;
   const int n_slab = p.cin / TC_BK;
+  const int na_mask = p.NA - 1, na_shift = p.na_log2;       // ring sizes are powers of two
+  const int nb_mask = p.NB - 1, nb_shift = p.nb_log2;
 
   const uint32_t bar_base = smem_u32(bars);
   auto a_full = [&](int s) { return bar_base + 8u * s; };
@@ -206,46 +208,49 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams
   tc_fence_after();
 
   // ---- which kernel offsets does each tile need?  (skip (tile, k) pairs without any neighbour)
+  // thread -> one row of one tile (512 producer threads = 4 tiles x 128 rows); all K loads are issued before the votes
   if (tid < TC_PROD_THREADS) {
-    for (int j = 0; j < T_here; ++j) {
-      const long long row = row0 + (long long)j * TC_BM + (tid & 127);
-      for (int k = tid >> 7; k < p.K; k += 2) {
-        int idx = -1;
-        if (row < p.n_out) idx = p.nbr ? __ldg(p.nbr + (long long)k * p.n_out + row) : (int)row;
-        const bool any = __any_sync(0xffffffffu, idx >= 0);
-        if (lane == 0 && any) atomicOr(&kmask_s[j], 1u << k);
+    const int j = tid >> 7;
+    const long long row = row0 + tid;                            // tile j, row tid & 127
+    uint32_t mine = 0;
+    if (j < T_here && row < p.n_out) {
+      if (p.nbr) {
+        const int* col = p.nbr + row;
+#pragma unroll 9
+        for (int k = 0; k < p.K; ++k) mine |= (__ldg(col + (long long)k * p.n_out) >= 0 ? 1u : 0u) << k;
+      } else {
+        mine = 1u;
       }
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine |= __shfl_xor_sync(0xffffffffu, mine, o);
+    if (lane == 0 && mine) atomicOr(&kmask_s[j], mine);
   }
   __syncthreads();
-  uint32_t kmask[TC_MAX_T];
   uint32_t kunion = 0;
 #pragma unroll
-  for (int j = 0; j < TC_MAX_T; ++j) {
-    kmask[j] = (j < T_here) ? kmask_s[j] : 0u;
-    kunion |= kmask[j];
-  }
+  for (int j = 0; j < TC_MAX_T; ++j) kunion |= (j < T_here) ? kmask_s[j] : 0u;
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < TC_PROD_WARPS) {
     // =========================================================================== A producers
     const int cc = tid & 7;          // 16-byte chunk (4 fp32 channels) inside the 32-channel slab
-    const int rbase = tid >> 3;      // rows rbase + 32*i
-    // byte offset of this thread's 8-byte half core-matrix row inside a piece, for row r: kc = cc>>1
-    uint32_t st_off[4];
+    const int rbase = tid >> 3;      // rows rbase + 64*i, i = 0, 1
+    uint32_t st_off[2];              // byte offset of this thread's 8-byte half core-matrix row inside a piece
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int r = rbase + 32 * i;
+    for (int i = 0; i < 2; ++i) {
+      const int r = rbase + 64 * i;
       st_off[i] = (uint32_t)((cc >> 1) * A_LBO + (r >> 3) * 128 + (r & 7) * 16 + (cc & 1) * 8);
     }
+    const long long rows_left = p.n_out - row0 - rbase;     // row (j, i) is real iff j*128 + 64*i < rows_left
+    const float* in_cc = p.in + cc * 4;
     int n_done = 0;                  // stages finished so far (ring position)
-    auto finish = [&](const float4 (&buf)[4]) {
-      const int s = n_done % p.NA;
-      const uint32_t use = (uint32_t)(n_done / p.NA);
-      mbar_wait(a_empty(s), (use & 1u) ^ 1u);
+    auto finish = [&](const float4 (&buf)[2]) {
+      const int s = n_done & na_mask;
+      mbar_wait(a_empty(s), (((uint32_t)n_done >> na_shift) & 1u) ^ 1u);
       unsigned char* st = a_smem + (size_t)s * A_STAGE;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < 2; ++i) {
         uint32_t h0, l0, h1, l1;
         split2(buf[i].x, buf[i].y, h0, l0);
         split2(buf[i].z, buf[i].w, h1, l1);
@@ -259,33 +264,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams
     };
     // stage iterator in (k, slab, tile) order, skipping (tile, k) pairs without neighbours
     int it_k = 0, it_c = 0, it_j = -1;
+    const int* nbr_k = p.nbr ? p.nbr + row0 + rbase : nullptr;   // + it_k * n_out
     auto advance = [&]() {
       while (true) {
         if (++it_j >= T_here) {
           it_j = 0;
-          if (++it_c >= n_slab) { it_c = 0; ++it_k; }
+          if (++it_c >= n_slab) { it_c = 0; ++it_k; if (nbr_k) nbr_k += p.n_out; }
         }
         if (it_k >= p.K) return;
         if ((kmask_s[it_j] >> it_k) & 1u) return;
         if (!((kunion >> it_k) & 1u)) { it_c = n_slab - 1; it_j = T_here - 1; }   // whole offset unused: jump
       }
     };
-    int idx_ld[4];                   // neighbour rows of the next stage to load (prefetched one stage ahead)
+    int idx_ld[2];                   // neighbour rows of the next stage to load (prefetched one stage ahead)
     auto load_idx = [&]() {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const long long row = row0 + (long long)it_j * TC_BM + rbase + 32 * i;
+      for (int i = 0; i < 2; ++i) {
+        const int off = it_j * TC_BM + 64 * i;
         idx_ld[i] = -1;
-        if (row < p.n_out) idx_ld[i] = p.nbr ? __ldg(p.nbr + (long long)it_k * p.n_out + row) : (int)row;
+        if (off < rows_left) idx_ld[i] = nbr_k ? __ldg(nbr_k + off) : (int)(row0 + rbase + off);
       }
     };
-    auto issue = [&](float4 (&buf)[4]) -> bool {
+    auto issue = [&](float4 (&buf)[2]) -> bool {
       if (it_k >= p.K) return false;
-      const float* src = p.in + it_c * TC_BK + cc * 4;
+      const float* src = in_cc + it_c * TC_BK;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < 2; ++i) {
         buf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (idx_ld[i] >= 0) buf[i] = __ldg(reinterpret_cast<const float4*>(src + (long long)idx_ld[i] * p.in_ld));
+        if (idx_ld[i] >= 0) buf[i] = __ldg(reinterpret_cast<const float4*>(src + (size_t)idx_ld[i] * (size_t)p.in_ld));
       }
       advance();
       if (it_k < p.K) load_idx();
@@ -293,9 +299,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams
     };
     advance();
     if (it_k < p.K) load_idx();
-    // three stages of gathers in flight per thread (12 x 16 B): the gather is latency-bound otherwise
-    float4 b0[4], b1[4], b2[4];
-    bool v0 = issue(b0), v1 = issue(b1), v2 = issue(b2);
+    // four stages of gathers in flight per thread: the gather is latency-bound otherwise
+    float4 b0[2], b1[2], b2[2], b3[2];
+    bool v0 = issue(b0), v1 = issue(b1), v2 = issue(b2), v3 = issue(b3);
     while (v0) {
       finish(b0);
       v0 = issue(b0);
@@ -305,33 +311,55 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams
       if (!v2) break;
       finish(b2);
       v2 = issue(b2);
+      if (!v3) break;
+      finish(b3);
+      v3 = issue(b3);
     }
 
     // =========================================================================== epilogue
+    // 16 warps: TMEM lane quarter q = warp & 3; warp group g = warp >> 2 takes column half (g & 1) of the tiles
+    // with (tile & 1) == (g >> 1)
     mbar_wait(acc_full, 0);
     tc_fence_after();
-    const int q = warp & 3, half = warp >> 2;
-    const int ncol = p.cout >> 1;    // columns per warp half (multiple of 16)
+    const int q = warp & 3, g = warp >> 2;
+    const int half = g & 1;
+    const int ncol = p.cout >> 1;    // columns per half (multiple of 16)
     const bool relu = p.flags & AG3D_RELU;
-    for (int j = 0; j < T_here; ++j) {
+    for (int j = g >> 1; j < T_here; j += 2) {
       const long long row = row0 + (long long)j * TC_BM + q * 32 + lane;
-      const bool live = kmask[j] != 0u;
+      const bool live = kmask_s[j] != 0u;
       for (int c0 = half * ncol; c0 < (half + 1) * ncol; c0 += 16) {
         float v[16];
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * p.cpad + c0), v);
         if (row < p.n_out) {
+          float4 r4[4];
+          if (p.residual) {
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            float x = live ? v[e] : 0.f;
-            if (p.scale) x *= __ldg(p.scale + c0 + e);
-            if (p.shift) x += __ldg(p.shift + c0 + e);
-            v[e] = x;
+            for (int e4 = 0; e4 < 4; ++e4)
+              r4[e4] = __ldg(reinterpret_cast<const float4*>(p.residual + row * p.res_ld + c0 + e4 * 4));
+          }
+          if (!live) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = 0.f;
+          }
+          if (p.scale) {
+#pragma unroll
+            for (int e4 = 0; e4 < 4; ++e4) {
+              const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + e4 * 4));
+              v[e4 * 4 + 0] *= s4.x; v[e4 * 4 + 1] *= s4.y; v[e4 * 4 + 2] *= s4.z; v[e4 * 4 + 3] *= s4.w;
+            }
+          }
+          if (p.shift) {
+#pragma unroll
+            for (int e4 = 0; e4 < 4; ++e4) {
+              const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + e4 * 4));
+              v[e4 * 4 + 0] += s4.x; v[e4 * 4 + 1] += s4.y; v[e4 * 4 + 2] += s4.z; v[e4 * 4 + 3] += s4.w;
+            }
           }
           if (p.residual) {
 #pragma unroll
             for (int e4 = 0; e4 < 4; ++e4) {
-              const float4 r4 = __ldg(reinterpret_cast<const float4*>(p.residual + row * p.res_ld + c0 + e4 * 4));
-              v[e4 * 4 + 0] += r4.x; v[e4 * 4 + 1] += r4.y; v[e4 * 4 + 2] += r4.z; v[e4 * 4 + 3] += r4.w;
+              v[e4 * 4 + 0] += r4[e4].x; v[e4 * 4 + 1] += r4[e4].y; v[e4 * 4 + 2] += r4[e4].z; v[e4 * 4 + 3] += r4[e4].w;
             }
           }
           if (relu) {
@@ -355,15 +383,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams
       for (int k = 0; k < p.K; ++k) {
         if (!((kunion >> k) & 1u)) continue;
         for (int c = 0; c < n_slab; ++c) {
-          const int sb = n_b % p.NB;
-          mbar_wait(b_full(sb), (uint32_t)(n_b / p.NB) & 1u);
+          const int sb = n_b & nb_mask;
+          mbar_wait(b_full(sb), ((uint32_t)n_b >> nb_shift) & 1u);
           tc_fence_after();
           const uint32_t b_hi = smem_u32(b_smem + (size_t)sb * b_stage_bytes);
           const uint32_t b_lo = b_hi + 4u * b_lbo;
           for (int j = 0; j < T_here; ++j) {
-            if (!((kmask[j] >> k) & 1u)) continue;
-            const int s = n_a % p.NA;
-            mbar_wait(a_full(s), (uint32_t)(n_a / p.NA) & 1u);
+            if (!((kmask_s[j] >> k) & 1u)) continue;
+            const int s = n_a & na_mask;
+            mbar_wait(a_full(s), ((uint32_t)n_a >> na_shift) & 1u);
             tc_fence_after();
             const uint32_t a_hi = smem_u32(a_smem + (size_t)s * A_STAGE);
             const uint32_t a_lo = a_hi + A_PIECE;
@@ -395,8 +423,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams
       for (int k = 0; k < p.K; ++k) {
         if (!((kunion >> k) & 1u)) continue;
         for (int c = 0; c < n_slab; ++c) {
-          const int sb = n_b % p.NB;
-          mbar_wait(b_empty(sb), ((uint32_t)(n_b / p.NB) & 1u) ^ 1u);
+          const int sb = n_b & nb_mask;
+          mbar_wait(b_empty(sb), (((uint32_t)n_b >> nb_shift) & 1u) ^ 1u);
           mbar_arrive_expect_tx(b_full(sb), b_stage_bytes);
           const unsigned char* src = reinterpret_cast<const unsigned char*>(p.wp) +
                                      ((size_t)k * n_slab + c) * (size_t)b_stage_bytes;
@@ -454,9 +482,10 @@ int spconv_tc_launch(const float* in, int in_ld, int cin, const int* nbr, int K,
   p.NB = (cout <= 128) ? 4 : 2;
   const size_t fixed = TC_BAR_BYTES + (size_t)p.NB * (size_t)cout * 128;
   int na = (int)((200 * 1024 - fixed) / A_STAGE);
-  if (na > 8) na = 8;
-  AG3D_CHECK_ARG(na >= 2, "internal: shared memory budget");
+  na = na >= 8 ? 8 : (na >= 4 ? 4 : 2);
   p.NA = na;
+  p.na_log2 = na == 8 ? 3 : (na == 4 ? 2 : 1);
+  p.nb_log2 = p.NB == 4 ? 2 : 1;
   const size_t smem = fixed + (size_t)na * A_STAGE;
   static bool attr = false;
   if (!attr) {
