@@ -32,8 +32,9 @@ SIGNATURES = {
     "ag3d_kernel_map_transposed": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp]),
     "ag3d_spconv_tc_weight_bytes": (_sz, [_i32, _i32, _i32]),
     "ag3d_spconv_tc_prepare_weight": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp]),
+    "ag3d_spconv_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32]),
     "ag3d_spconv_fwd": (_i32, [_vp, _i32, _i32, _vp, _i32, _i64, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _i32, _i32,
-                               _i32, _vp]),
+                               _i32, _vp, _sz, _vp]),
     "ag3d_stem_conv_fwd": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
     "ag3d_posenc_workspace_bytes": (_sz, [_i32]),
     "ag3d_fourier_posenc": (_i32, [_vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _sz, _vp]),
@@ -61,7 +62,7 @@ def lib():
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(handle, name)          # AttributeError if the symbol is not exported
             fn.restype, fn.argtypes = res, args
-        if handle.ag3d_abi_version() != 2:
+        if handle.ag3d_abi_version() != 3:
             raise Ag3dError("libagile3d_b200.so ABI version mismatch; rebuild")
         _lib = handle
     return _lib

@@ -142,8 +142,9 @@ stem_conv_kernel(const int4* __restrict__ coords, const float* __restrict__ feat
 
 int spconv_tc_launch(const float* in, int in_ld, int cin, const int* nbr, int K, long long n_out,
                      const void* wprep, int cout, const float* scale, const float* shift, const float* residual,
-                     int res_ld, float* out, int out_ld, int flags, cudaStream_t st);
+                     int res_ld, float* out, int out_ld, int flags, void* ws, size_t ws_bytes, cudaStream_t st);
 bool spconv_tc_supported(int cin, int cout);
+size_t spconv_tc_workspace_bytes(long long n_out, int K, int cout);
 
 }  // namespace ag3d
 
@@ -154,7 +155,7 @@ extern "C" {
 int ag3d_spconv_fwd(const float* in, int32_t in_ld, int32_t cin, const int32_t* nbr, int32_t K, int64_t n_out,
                     const float* weight, const void* weight_tc, int32_t cout, const float* scale, const float* shift,
                     const float* residual, int32_t res_ld, float* out, int32_t out_ld, int32_t flags,
-                    int32_t algo, ag3d_stream_t stream) {
+                    int32_t algo, void* ws, size_t ws_bytes, ag3d_stream_t stream) {
   AG3D_CHECK_ARG(n_out > 0 && n_out < 2147483647LL, "row count out of range");
   AG3D_CHECK_ARG(cin > 0 && cin % 32 == 0 && cout > 0 && cout % 32 == 0, "cin and cout must be multiples of 32");
   AG3D_CHECK_ARG(K >= 1 && (nbr || K == 1), "K > 1 needs a neighbour table");
@@ -168,7 +169,7 @@ int ag3d_spconv_fwd(const float* in, int32_t in_ld, int32_t cin, const int32_t* 
   if (algo == AG3D_ALGO_TC) {
     AG3D_CHECK_ARG(spconv_tc_supported(cin, cout), "shape not supported by the tcgen05 path");
     return spconv_tc_launch(in, in_ld, cin, nbr, K, n_out, weight_tc, cout, scale, shift, residual, res_ld, out,
-                            out_ld, flags, st);
+                            out_ld, flags, ws, ws_bytes, st);
   }
   AG3D_CHECK_ARG(algo == AG3D_ALGO_SIMT, "unknown algo");
   AG3D_CHECK_ARG(weight && aligned16(weight), "the fp32 path needs the fp32 weight");
@@ -182,6 +183,12 @@ int ag3d_spconv_fwd(const float* in, int32_t in_ld, int32_t cin, const int32_t* 
   }
   AG3D_LAUNCH_CHECK("spconv_simt");
   return AG3D_OK;
+}
+
+size_t ag3d_spconv_workspace_bytes(int64_t n_out, int32_t K, int32_t cin, int32_t cout) {
+  (void)cin;
+  if (n_out <= 0 || K < 1 || K > 32 || cout % 32 != 0 || cout < 32 || cout > 256) return 0;
+  return spconv_tc_workspace_bytes(n_out, K, cout);
 }
 
 int ag3d_stem_conv_fwd(const int32_t* coords, const float* feats, int64_t n, const void* table, int64_t cap,

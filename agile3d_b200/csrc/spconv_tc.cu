@@ -160,6 +160,8 @@ struct TcParams {
   int NA;           // A ring stages
   int NB;           // weight stages
   int na_log2, nb_log2;
+  int k_per;        // kernel offsets per CTA row (split-K over gridDim.y); k range = [by*k_per, min(K, (by+1)*k_per))
+  float* partial;   // split-K: raw accumulators [gridDim.y][n_out][cout]; NULL = fused epilogue
   int cpad;         // TMEM columns per tile (pow2 >= cout)
   int tmem_cols;    // allocation (pow2, 32..512)
 };
@@ -180,6 +182,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams
   const int T_here = (int)min((long long)p.T, tiles_total - tile0);
   const long long row0 = tile0 * TC_BM;
   const int n_slab = p.cin / TC_BK;
+  const int k_lo = blockIdx.y * p.k_per;
+  const int k_hi = min(p.K, k_lo + p.k_per);
   const int na_mask = p.NA - 1, na_shift = p.na_log2;       // ring sizes are powers of two
   const int nb_mask = p.NB - 1, nb_shift = p.nb_log2;
 
@@ -217,9 +221,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams
       if (p.nbr) {
         const int* col = p.nbr + row;
 #pragma unroll 9
-        for (int k = 0; k < p.K; ++k) mine |= (__ldg(col + (long long)k * p.n_out) >= 0 ? 1u : 0u) << k;
+        for (int k = k_lo; k < k_hi; ++k) mine |= (__ldg(col + (long long)k * p.n_out) >= 0 ? 1u : 0u) << k;
       } else {
-        mine = 1u;
+        mine = 1u;                                              // identity map: K == 1, never split
       }
     }
 #pragma unroll
@@ -263,15 +267,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams
       ++n_done;
     };
     // stage iterator in (k, slab, tile) order, skipping (tile, k) pairs without neighbours
-    int it_k = 0, it_c = 0, it_j = -1;
-    const int* nbr_k = p.nbr ? p.nbr + row0 + rbase : nullptr;   // + it_k * n_out
+    int it_k = k_lo, it_c = 0, it_j = -1;
+    const int* nbr_k = p.nbr ? p.nbr + (long long)k_lo * p.n_out + row0 + rbase : nullptr;   // row of offset it_k
     auto advance = [&]() {
       while (true) {
         if (++it_j >= T_here) {
           it_j = 0;
           if (++it_c >= n_slab) { it_c = 0; ++it_k; if (nbr_k) nbr_k += p.n_out; }
         }
-        if (it_k >= p.K) return;
+        if (it_k >= k_hi) return;
         if ((kmask_s[it_j] >> it_k) & 1u) return;
         if (!((kunion >> it_k) & 1u)) { it_c = n_slab - 1; it_j = T_here - 1; }   // whole offset unused: jump
       }
@@ -286,7 +290,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams
       }
     };
     auto issue = [&](float4 (&buf)[2]) -> bool {
-      if (it_k >= p.K) return false;
+      if (it_k >= k_hi) return false;
       const float* src = in_cc + it_c * TC_BK;
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
@@ -294,11 +298,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams
         if (idx_ld[i] >= 0) buf[i] = __ldg(reinterpret_cast<const float4*>(src + (size_t)idx_ld[i] * (size_t)p.in_ld));
       }
       advance();
-      if (it_k < p.K) load_idx();
+      if (it_k < k_hi) load_idx();
       return true;
     };
     advance();
-    if (it_k < p.K) load_idx();
+    if (it_k < k_hi) load_idx();
     // four stages of gathers in flight per thread: the gather is latency-bound otherwise
     float4 b0[2], b1[2], b2[2], b3[2];
     bool v0 = issue(b0), v1 = issue(b1), v2 = issue(b2), v3 = issue(b3);
@@ -331,7 +335,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams
       for (int c0 = half * ncol; c0 < (half + 1) * ncol; c0 += 16) {
         float v[16];
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * p.cpad + c0), v);
-        if (row < p.n_out) {
+        if (row < p.n_out && p.partial) {       // split-K: raw partial sums, reduced + finished by splitk_reduce_kernel
+          float* dst = p.partial + ((size_t)blockIdx.y * (size_t)p.n_out + (size_t)row) * p.cout + c0;
+#pragma unroll
+          for (int e4 = 0; e4 < 4; ++e4)
+            *reinterpret_cast<float4*>(dst + e4 * 4) =
+                live ? make_float4(v[e4 * 4], v[e4 * 4 + 1], v[e4 * 4 + 2], v[e4 * 4 + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        } else if (row < p.n_out) {
           float4 r4[4];
           if (p.residual) {
 #pragma unroll
@@ -380,7 +390,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams
       const uint32_t b_lbo = (uint32_t)p.cout * 16u;
       uint32_t started = 0;            // bit j: accumulator j has been written
       int n_a = 0, n_b = 0;
-      for (int k = 0; k < p.K; ++k) {
+      for (int k = k_lo; k < k_hi; ++k) {
         if (!((kunion >> k) & 1u)) continue;
         for (int c = 0; c < n_slab; ++c) {
           const int sb = n_b & nb_mask;
@@ -420,7 +430,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams
     // =========================================================================== weight loader (TMA engine)
     if (lane == 0) {
       int n_b = 0;
-      for (int k = 0; k < p.K; ++k) {
+      for (int k = k_lo; k < k_hi; ++k) {
         if (!((kunion >> k) & 1u)) continue;
         for (int c = 0; c < n_slab; ++c) {
           const int sb = n_b & nb_mask;
@@ -443,6 +453,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams
   }
 }
 
+// out = act(scale * sum_y partial[y] + shift (+ residual)), y in fixed order (deterministic)
+__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int ksplit, long long n_out, int cout,
+                                     const float* __restrict__ scale, const float* __restrict__ shift,
+                                     const float* __restrict__ residual, int res_ld, float* __restrict__ out,
+                                     int out_ld, int flags) {
+  const int c4n = cout >> 2;
+  const long long total = n_out * c4n;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const long long row = t / c4n;
+    const int c = (int)(t % c4n) * 4;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int y = 0; y < ksplit; ++y) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(partial + ((size_t)y * n_out + row) * cout + c));
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    if (scale) { const float4 s = __ldg(reinterpret_cast<const float4*>(scale + c)); a.x *= s.x; a.y *= s.y; a.z *= s.z; a.w *= s.w; }
+    if (shift) { const float4 s = __ldg(reinterpret_cast<const float4*>(shift + c)); a.x += s.x; a.y += s.y; a.z += s.z; a.w += s.w; }
+    if (residual) { const float4 s = __ldg(reinterpret_cast<const float4*>(residual + row * res_ld + c)); a.x += s.x; a.y += s.y; a.z += s.z; a.w += s.w; }
+    if (flags & AG3D_RELU) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
+    *reinterpret_cast<float4*>(out + row * out_ld + c) = a;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- host side
 static int pow2_at_least(int v, int lo) {
   int r = lo;
@@ -450,25 +484,16 @@ static int pow2_at_least(int v, int lo) {
   return r;
 }
 
-bool spconv_tc_supported(int cin, int cout) {
-  return cin % TC_BK == 0 && cout % 32 == 0 && cout >= 32 && cout <= 256 && cin >= 32;
-}
+struct TcPlan { int cpad, T, ksplit, k_per; };
 
-int spconv_tc_launch(const float* in, int in_ld, int cin, const int* nbr, int K, long long n_out,
-                     const void* wprep, int cout, const float* scale, const float* shift, const float* residual,
-                     int res_ld, float* out, int out_ld, int flags, cudaStream_t st) {
-  AG3D_CHECK_ARG(K <= 32, "the tensor-core path handles at most 32 kernel offsets");
-  AG3D_CHECK_ARG(wprep && aligned16(wprep), "prepared weights missing (ag3d_spconv_tc_prepare_weight)");
-  TcParams p;
-  p.in = in; p.in_ld = in_ld; p.cin = cin; p.nbr = nbr; p.K = K; p.n_out = n_out;
-  p.wp = static_cast<const uint4*>(wprep); p.cout = cout;
-  p.scale = scale; p.shift = shift; p.residual = residual; p.res_ld = res_ld;
-  p.out = out; p.out_ld = out_ld; p.flags = flags;
-  p.cpad = pow2_at_least(cout, 32);
-  const int t_max = std::min(TC_MAX_T, 512 / p.cpad);
+// tiles per CTA: minimise waves * (T gathers + one weight stage); weight stage cost relative to a gather = cout/128.
+// Small levels (few tiles) are weight-streaming bound on a handful of SMs: split the kernel offsets over gridDim.y.
+static TcPlan tc_plan(long long n_out, int K, int cout) {
+  TcPlan pl;
+  pl.cpad = pow2_at_least(cout, 32);
+  const int t_max = std::min(TC_MAX_T, 512 / pl.cpad);
   const long long tiles = (n_out + TC_BM - 1) / TC_BM;
   const int sms = sm_count();
-  // tiles per CTA: minimise waves * (T gathers + one weight stage), weight stage cost relative to a gather = cout/128
   int best_t = 1;
   double best_cost = 1e30;
   for (int t = 1; t <= t_max; ++t) {
@@ -477,7 +502,45 @@ int spconv_tc_launch(const float* in, int in_ld, int cin, const int* nbr, int K,
     const double cost = (double)waves * ((double)t + (double)cout / 128.0);
     if (cost < best_cost - 1e-9) { best_cost = cost; best_t = t; }
   }
-  p.T = best_t;
+  pl.T = best_t;
+  const long long ctas = (tiles + pl.T - 1) / pl.T;
+  int ksplit = 1;
+  if (K > 1 && ctas * 2 <= sms) ksplit = (int)std::min<long long>(K, sms / ctas);
+  pl.k_per = (K + ksplit - 1) / ksplit;
+  pl.ksplit = (K + pl.k_per - 1) / pl.k_per;
+  return pl;
+}
+
+size_t spconv_tc_workspace_bytes(long long n_out, int K, int cout) {
+  const TcPlan pl = tc_plan(n_out, K, cout);
+  return pl.ksplit > 1 ? (size_t)pl.ksplit * (size_t)n_out * cout * sizeof(float) : 0;
+}
+
+bool spconv_tc_supported(int cin, int cout) {
+  return cin % TC_BK == 0 && cout % 32 == 0 && cout >= 32 && cout <= 256 && cin >= 32;
+}
+
+int spconv_tc_launch(const float* in, int in_ld, int cin, const int* nbr, int K, long long n_out,
+                     const void* wprep, int cout, const float* scale, const float* shift, const float* residual,
+                     int res_ld, float* out, int out_ld, int flags, void* ws, size_t ws_bytes, cudaStream_t st) {
+  AG3D_CHECK_ARG(K <= 32, "the tensor-core path handles at most 32 kernel offsets");
+  AG3D_CHECK_ARG(wprep && aligned16(wprep), "prepared weights missing (ag3d_spconv_tc_prepare_weight)");
+  TcParams p;
+  p.in = in; p.in_ld = in_ld; p.cin = cin; p.nbr = nbr; p.K = K; p.n_out = n_out;
+  p.wp = static_cast<const uint4*>(wprep); p.cout = cout;
+  p.scale = scale; p.shift = shift; p.residual = residual; p.res_ld = res_ld;
+  p.out = out; p.out_ld = out_ld; p.flags = flags;
+  const TcPlan plan = tc_plan(n_out, K, cout);
+  p.cpad = plan.cpad;
+  p.T = plan.T;
+  p.k_per = plan.k_per;
+  const long long tiles = (n_out + TC_BM - 1) / TC_BM;
+  p.partial = nullptr;
+  if (plan.ksplit > 1) {
+    AG3D_CHECK_ARG(ws && aligned16(ws) && ws_bytes >= (size_t)plan.ksplit * (size_t)n_out * cout * sizeof(float),
+                   "split-K workspace too small (ag3d_spconv_workspace_bytes)");
+    p.partial = static_cast<float*>(ws);
+  }
   p.tmem_cols = pow2_at_least(p.T * p.cpad, 32);
   p.NB = (cout <= 128) ? 4 : 2;
   const size_t fixed = TC_BAR_BYTES + (size_t)p.NB * (size_t)cout * 128;
@@ -492,9 +555,17 @@ int spconv_tc_launch(const float* in, int in_ld, int cin, const int* nbr, int K,
     AG3D_CUDA(cudaFuncSetAttribute(spconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr = true;
   }
-  const unsigned grid = (unsigned)((tiles + p.T - 1) / p.T);
+  const dim3 grid((unsigned)((tiles + p.T - 1) / p.T), (unsigned)plan.ksplit);
   spconv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(p);
   AG3D_LAUNCH_CHECK("spconv_tc");
+  if (plan.ksplit > 1) {
+    const long long total = n_out * (cout / 4);
+    long long blocks = (total + 255) / 256;
+    if (blocks > (long long)sm_count() * 8) blocks = (long long)sm_count() * 8;
+    splitk_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(p.partial, plan.ksplit, n_out, cout, scale, shift, residual,
+                                                          res_ld, out, out_ld, flags);
+    AG3D_LAUNCH_CHECK("splitk_reduce");
+  }
   return AG3D_OK;
 }
 

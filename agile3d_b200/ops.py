@@ -58,6 +58,18 @@ class _Timed:
         return False
 
 
+_ws_cache = {}
+
+
+def _workspace(tag, device, nbytes):
+    """Grow-only scratch buffer per (purpose, device, stream); stream-ordered reuse is safe on one stream."""
+    key = (tag, device, torch.cuda.current_stream().cuda_stream)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = _ws_cache[key] = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=device)
+    return buf
+
+
 def kernel_launches():
     return int(lib().ag3d_kernel_launches())
 
@@ -173,9 +185,15 @@ def spconv_fwd(x, nbr, weight, out, scale=None, shift=None, residual=None, relu=
     # 4*N_in*Cin + 4*N_out*Cout + 8*P + 4*K*Cin*Cout (+ 4*N_out*Cout residual); flops 2*P*Cin*Cout
     nbytes = 4 * x.shape[0] * cin + 4 * n_out * cout + 8 * pairs + 4 * K * cin * cout \
         + (4 * n_out * cout if residual is not None else 0)
+    ws, wsb = None, 0
+    if weight_tc is not None and algo != ALGO_SIMT:
+        wsb = lib().ag3d_spconv_workspace_bytes(n_out, K, cin, cout)
+        if wsb:
+            ws = _workspace("spconv", x.device, wsb)
     with _Timed("spconv", nbytes, 2 * pairs * cin * cout):
         check(lib().ag3d_spconv_fwd(xp, x_ld, cin, _p(nbr), K, n_out, _p(w), _p(weight_tc), cout, _p(scale), _p(shift),
-                                    rp, r_ld, op, o_ld, RELU if relu else 0, algo, _stream()), "ag3d_spconv_fwd")
+                                    rp, r_ld, op, o_ld, RELU if relu else 0, algo, _p(ws), wsb, _stream()),
+              "ag3d_spconv_fwd")
     return out
 
 

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define AG3D_ABI_VERSION 2
+#define AG3D_ABI_VERSION 3
 
 #define AG3D_OK 0
 #define AG3D_E_INVALID (-1)   /* bad argument (shape, alignment, unsupported size) */
@@ -97,10 +97,12 @@ int ag3d_kernel_map_transposed(const int32_t* fine_coords, const int32_t* parent
 size_t ag3d_spconv_tc_weight_bytes(int32_t K, int32_t cin, int32_t cout);
 int ag3d_spconv_tc_prepare_weight(const float* weight, int32_t K, int32_t cin, int32_t cout, void* weight_tc,
                                   ag3d_stream_t stream);
+/* workspace (split-K partial sums of the tensor-core path on levels with few rows); 0 when none is needed */
+size_t ag3d_spconv_workspace_bytes(int64_t n_out, int32_t K, int32_t cin, int32_t cout);
 int ag3d_spconv_fwd(const float* in, int32_t in_ld, int32_t cin, const int32_t* nbr, int32_t K, int64_t n_out,
                     const float* weight, const void* weight_tc, int32_t cout, const float* scale, const float* shift,
                     const float* residual, int32_t res_ld, float* out, int32_t out_ld, int32_t flags,
-                    int32_t algo, ag3d_stream_t stream);
+                    int32_t algo, void* ws, size_t ws_bytes, ag3d_stream_t stream);
 /* Stem: conv0p1s1 (3 -> 32 channels, kernel 5, models/res16unet.py:39-47) evaluated directly against the
  * hash table (no 125-column neighbour table is materialised) with folded bn0 + ReLU.                        */
 int ag3d_stem_conv_fwd(const int32_t* coords, const float* feats, int64_t n, const void* table, int64_t cap,

@@ -31,6 +31,7 @@ def _rand_map(n_out, n_in, K, density, g):
     (1000, 1000, 27, 64, 64, 0.45), (5000, 5000, 27, 128, 256, 0.45), (3000, 11000, 8, 32, 32, 0.5),
     (9000, 2500, 8, 256, 128, 0.125), (2000, 2000, 27, 96, 96, 0.002), (3000, 3000, 27, 384, 256, 0.4),
     (4000, 4000, 27, 192, 128, 0.4), (40000, 40000, 27, 96, 96, 0.46),
+    (400, 400, 27, 256, 256, 0.4), (2300, 2300, 27, 384, 256, 0.4), (1800, 400, 8, 256, 256, 0.125), (130, 130, 27, 128, 128, 0.5),
 ])
 def test_spconv_tc_vs_fp32(n_out, n_in, K, cin, cout, density):
     from agile3d_b200 import ops

@@ -84,6 +84,10 @@ def main():
     oks.append(case("K=8 wide", 9000, 2500, 8, 256, 128, density=0.125, relu=True, seed=4))
     oks.append(case("K=27 very sparse (offset skipping)", 2000, 2000, 27, 96, 96, density=0.002, seed=5))
     oks.append(case("384->256", 3000, 3000, 27, 384, 256, density=0.4, residual=True, relu=True, seed=6))
+    oks.append(case("split-K: 400 rows 256->256", 400, 400, 27, 256, 256, density=0.4, residual=True, relu=True, seed=11))
+    oks.append(case("split-K: 2300 rows 384->256", 2300, 2300, 27, 384, 256, density=0.4, residual=True, relu=True,
+                    slices=True, seed=12))
+    oks.append(case("split-K: K=8 up 400->1800 rows", 1800, 400, 8, 256, 256, density=0.125, relu=True, seed=13))
     oks.append(case("full size 96->96", 150000, 150000, 27, 96, 96, density=0.46, residual=True, relu=True, seed=7))
     print("ALL OK" if all(oks) else "SOME BAD")
     # timing of the big case, both paths
