@@ -2,19 +2,19 @@
 //
 //   out[o, :] = act( scale * sum_k in[nbr[k][o], :] @ W[k] + shift (+ residual[o, :]) )
 //
-// Structure (one CTA, 1 per SM, 576 threads):
+// Structure (one CTA, 1 per SM, 320 threads):
 //   * the CTA owns T consecutive 128-row output tiles; their fp32 accumulators [128 x Cout] live in TMEM
 //     (T * pow2(Cout) <= 512 columns) for the whole kernel;
 //   * the weight operand is *stationary*: for every (kernel offset k, 32-channel slab c) the pre-split weight
 //     slab is brought into shared memory ONCE by the TMA engine (cp.async.bulk, one elected thread) and reused by
 //     all T tiles, which divides the weight traffic from L2 by T;
-//   * 16 producer warps gather the 32-channel slab of the neighbour rows (coalesced 128-bit loads through the
+//   * 8 producer warps gather the 32-channel slab of the neighbour rows (coalesced 128-bit loads through the
 //     offset-major neighbour table), split every fp32 value into two bf16 pieces (hi = rn(x), lo = rn(x - hi)) and
 //     store both pieces into a ring of shared-memory stages in the UMMA canonical K-major layout;
 //   * one elected thread issues tcgen05.mma (kind::f16, bf16 inputs, fp32 accumulate): per 16-channel step the three
 //     products hi*hi + hi*lo + lo*hi ("bf16x3", relative error <= ~1e-5) accumulate into TMEM;
 //   * tcgen05.commit hands shared-memory stages back to the producers and finally signals the epilogue;
-//   * the 16 producer warps then become the epilogue: tcgen05.ld the accumulators, apply folded BatchNorm /
+//   * the 8 producer warps then become the epilogue: tcgen05.ld the accumulators, apply folded BatchNorm /
 //     bias, residual, ReLU and write the channel slice of the output buffer.
 // (tile, k) pairs in which no row of the tile has a neighbour are skipped by all roles.
 #include <cuda_bf16.h>
@@ -27,7 +27,7 @@ namespace ag3d {
 
 constexpr int TC_BM = 128;                       // rows per accumulator tile (UMMA M)
 constexpr int TC_BK = 32;                        // input channels per pipeline stage
-constexpr int TC_PROD_WARPS = 16;
+constexpr int TC_PROD_WARPS = 8;
 constexpr int TC_PROD_THREADS = TC_PROD_WARPS * 32;
 constexpr int TC_THREADS = TC_PROD_THREADS + 64; // + MMA warp + weight-loader warp
 constexpr int TC_MAX_T = 4;
@@ -35,6 +35,8 @@ constexpr int A_LBO = 2048 + 32;                 // bytes between K-adjacent 8x1
 constexpr int A_PIECE = 4 * A_LBO;               // one bf16 piece of a [128 x 32] slab = 4 K-chunks
 constexpr int A_STAGE = 2 * A_PIECE;             // hi piece + lo piece
 constexpr int TC_BAR_BYTES = 512;
+constexpr int TC_MAX_STAGES = 32 * 12 * TC_MAX_T;   // K <= 32 offsets, cin <= 384 (12 slabs), T tiles
+constexpr int TC_LIST_BYTES = TC_MAX_STAGES * 4;
 constexpr unsigned SPIN_LIMIT = 1u << 24;
 
 // ---------------------------------------------------------------------------------------------- PTX helpers
@@ -49,20 +51,24 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok = 0;
+__device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   unsigned spins = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (ok) break;
+  while (!mbar_try(bar, parity))
     if (++spins > SPIN_LIMIT) __trap();   // a protocol bug must fail loudly, never hang the GPU
-  }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (!mbar_try(bar, parity)) mbar_wait_slow(bar, parity);
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -172,8 +178,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 256);
   uint32_t* kmask_s = reinterpret_cast<uint32_t*>(smem + 272);   // [TC_MAX_T]
+  int* n_stage_s = reinterpret_cast<int*>(smem + 288);
+  uint32_t* stage_list = reinterpret_cast<uint32_t*>(smem + TC_BAR_BYTES);   // [TC_MAX_STAGES] (k << 16 | slab << 8 | tile)
   const uint32_t b_stage_bytes = (uint32_t)p.cout * 128u;
-  unsigned char* b_smem = smem + TC_BAR_BYTES;
+  unsigned char* b_smem = smem + TC_BAR_BYTES + TC_LIST_BYTES;
   unsigned char* a_smem = b_smem + (size_t)p.NB * b_stage_bytes;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -211,100 +219,119 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams
   __syncthreads();
   tc_fence_after();
 
-  // ---- which kernel offsets does each tile need?  (skip (tile, k) pairs without any neighbour)
-  // thread -> one row of one tile (512 producer threads = 4 tiles x 128 rows); all K loads are issued before the votes
+  // ---- which kernel offsets does each tile need?  (tile, k) pairs without any neighbour are skipped by all roles.
+  // 256 producer threads: thread -> row (tid & 127) of tiles (tid >> 7) and (tid >> 7) + 2; all loads issued first.
   if (tid < TC_PROD_THREADS) {
-    const int j = tid >> 7;
-    const long long row = row0 + tid;                            // tile j, row tid & 127
-    uint32_t mine = 0;
-    if (j < T_here && row < p.n_out) {
-      if (p.nbr) {
-        const int* col = p.nbr + row;
-#pragma unroll 9
-        for (int k = k_lo; k < k_hi; ++k) mine |= (__ldg(col + (long long)k * p.n_out) >= 0 ? 1u : 0u) << k;
-      } else {
-        mine = 1u;                                              // identity map: K == 1, never split
-      }
-    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mine |= __shfl_xor_sync(0xffffffffu, mine, o);
-    if (lane == 0 && mine) atomicOr(&kmask_s[j], mine);
+    for (int jj = 0; jj < 2; ++jj) {
+      const int j = (tid >> 7) + 2 * jj;
+      const long long row = row0 + (long long)j * TC_BM + (tid & 127);
+      uint32_t mine = 0;
+      if (j < T_here && row < p.n_out) {
+        if (p.nbr) {
+          const int* col = p.nbr + row;
+#pragma unroll 9
+          for (int k = k_lo; k < k_hi; ++k) mine |= (__ldg(col + (long long)k * p.n_out) >= 0 ? 1u : 0u) << k;
+        } else {
+          mine = 1u;                                              // identity map: K == 1, never split
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mine |= __shfl_xor_sync(0xffffffffu, mine, o);
+      if (lane == 0 && mine && j < TC_MAX_T) atomicOr(&kmask_s[j], mine);
+    }
   }
   __syncthreads();
-  uint32_t kunion = 0;
+  // ---- stage list in (k, slab, tile) order: lane k of warp 0 emits the stages of offset k
+  if (warp == 0) {
+    const int k = k_lo + lane;
+    uint32_t tiles_k = 0;                                       // bit j: tile j needs offset k
+    if (k < k_hi)
+      for (int j = 0; j < T_here; ++j) tiles_k |= ((kmask_s[j] >> k) & 1u) << j;
+    const int cnt = n_slab * __popc(tiles_k);
+    int incl = cnt;
 #pragma unroll
-  for (int j = 0; j < TC_MAX_T; ++j) kunion |= (j < T_here) ? kmask_s[j] : 0u;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    int pos = incl - cnt;
+    for (int c = 0; c < n_slab; ++c)
+      for (int j = 0; j < T_here; ++j)
+        if ((tiles_k >> j) & 1u) stage_list[pos++] = ((uint32_t)k << 16) | ((uint32_t)c << 8) | (uint32_t)j;
+    if (lane == 31) *n_stage_s = incl;
+  }
+  __syncthreads();
+  const int n_stage = *n_stage_s;
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < TC_PROD_WARPS) {
     // =========================================================================== A producers
-    const int cc = tid & 7;          // 16-byte chunk (4 fp32 channels) inside the 32-channel slab
-    const int rbase = tid >> 3;      // rows rbase + 64*i, i = 0, 1
-    uint32_t st_off[2];              // byte offset of this thread's 8-byte half core-matrix row inside a piece
+    // thread -> 8 channels (one 16-byte bf16 K-chunk kc) of rows rbase and rbase + 64
+    const int kc = tid & 3;
+    const int rbase = tid >> 2;
+    uint32_t st_off[2];
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const int r = rbase + 64 * i;
-      st_off[i] = (uint32_t)((cc >> 1) * A_LBO + (r >> 3) * 128 + (r & 7) * 16 + (cc & 1) * 8);
+      st_off[i] = (uint32_t)(kc * A_LBO + (r >> 3) * 128 + (r & 7) * 16);
     }
     const long long rows_left = p.n_out - row0 - rbase;     // row (j, i) is real iff j*128 + 64*i < rows_left
-    const float* in_cc = p.in + cc * 4;
+    const float* in_kc = p.in + kc * 8;
+    const int* nbr_r = p.nbr ? p.nbr + row0 + rbase : nullptr;
+
+    int idx_ld[2];                   // neighbour rows of stage n_issued (prefetched one stage ahead)
+    uint32_t c_ld = 0;
+    int n_issued = 0;
+    auto load_idx = [&]() {          // decode stage n_issued and fetch its neighbour rows
+      const uint32_t e = stage_list[n_issued];
+      const int k = (int)(e >> 16), j = (int)(e & 0xFFu);
+      c_ld = (e >> 8) & 0xFFu;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int off = j * TC_BM + 64 * i;
+        idx_ld[i] = -1;
+        if (off < rows_left) idx_ld[i] = nbr_r ? __ldg(nbr_r + (long long)k * p.n_out + off) : (int)(row0 + rbase + off);
+      }
+    };
+    auto issue = [&](float4 (&buf)[4]) -> bool {
+      if (n_issued >= n_stage) return false;
+      const float* src = in_kc + c_ld * TC_BK;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        buf[2 * i] = buf[2 * i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (idx_ld[i] >= 0) {
+          const float4* r = reinterpret_cast<const float4*>(src + (size_t)idx_ld[i] * (size_t)p.in_ld);
+          buf[2 * i] = __ldg(r);
+          buf[2 * i + 1] = __ldg(r + 1);
+        }
+      }
+      if (++n_issued < n_stage) load_idx();
+      return true;
+    };
     int n_done = 0;                  // stages finished so far (ring position)
-    auto finish = [&](const float4 (&buf)[2]) {
+    auto finish = [&](const float4 (&buf)[4]) {
       const int s = n_done & na_mask;
       mbar_wait(a_empty(s), (((uint32_t)n_done >> na_shift) & 1u) ^ 1u);
       unsigned char* st = a_smem + (size_t)s * A_STAGE;
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
-        uint32_t h0, l0, h1, l1;
-        split2(buf[i].x, buf[i].y, h0, l0);
-        split2(buf[i].z, buf[i].w, h1, l1);
-        *reinterpret_cast<uint2*>(st + st_off[i]) = make_uint2(h0, h1);
-        *reinterpret_cast<uint2*>(st + A_PIECE + st_off[i]) = make_uint2(l0, l1);
+        uint32_t h[4], l[4];
+        split2(buf[2 * i].x, buf[2 * i].y, h[0], l[0]);
+        split2(buf[2 * i].z, buf[2 * i].w, h[1], l[1]);
+        split2(buf[2 * i + 1].x, buf[2 * i + 1].y, h[2], l[2]);
+        split2(buf[2 * i + 1].z, buf[2 * i + 1].w, h[3], l[3]);
+        *reinterpret_cast<uint4*>(st + st_off[i]) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(st + A_PIECE + st_off[i]) = make_uint4(l[0], l[1], l[2], l[3]);
       }
       fence_proxy_async();           // generic-proxy stores -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(a_full(s));
       ++n_done;
     };
-    // stage iterator in (k, slab, tile) order, skipping (tile, k) pairs without neighbours
-    int it_k = k_lo, it_c = 0, it_j = -1;
-    const int* nbr_k = p.nbr ? p.nbr + (long long)k_lo * p.n_out + row0 + rbase : nullptr;   // row of offset it_k
-    auto advance = [&]() {
-      while (true) {
-        if (++it_j >= T_here) {
-          it_j = 0;
-          if (++it_c >= n_slab) { it_c = 0; ++it_k; if (nbr_k) nbr_k += p.n_out; }
-        }
-        if (it_k >= k_hi) return;
-        if ((kmask_s[it_j] >> it_k) & 1u) return;
-        if (!((kunion >> it_k) & 1u)) { it_c = n_slab - 1; it_j = T_here - 1; }   // whole offset unused: jump
-      }
-    };
-    int idx_ld[2];                   // neighbour rows of the next stage to load (prefetched one stage ahead)
-    auto load_idx = [&]() {
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int off = it_j * TC_BM + 64 * i;
-        idx_ld[i] = -1;
-        if (off < rows_left) idx_ld[i] = nbr_k ? __ldg(nbr_k + off) : (int)(row0 + rbase + off);
-      }
-    };
-    auto issue = [&](float4 (&buf)[2]) -> bool {
-      if (it_k >= k_hi) return false;
-      const float* src = in_cc + it_c * TC_BK;
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        buf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (idx_ld[i] >= 0) buf[i] = __ldg(reinterpret_cast<const float4*>(src + (size_t)idx_ld[i] * (size_t)p.in_ld));
-      }
-      advance();
-      if (it_k < k_hi) load_idx();
-      return true;
-    };
-    advance();
-    if (it_k < k_hi) load_idx();
-    // four stages of gathers in flight per thread: the gather is latency-bound otherwise
-    float4 b0[2], b1[2], b2[2], b3[2];
+    if (n_stage > 0) load_idx();
+    // four stages of gathers in flight per thread (16 x 16 B): the gather is latency-bound otherwise
+    float4 b0[4], b1[4], b2[4], b3[4];
     bool v0 = issue(b0), v1 = issue(b1), v2 = issue(b2), v3 = issue(b3);
     while (v0) {
       finish(b0);
@@ -321,15 +348,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams
     }
 
     // =========================================================================== epilogue
-    // 16 warps: TMEM lane quarter q = warp & 3; warp group g = warp >> 2 takes column half (g & 1) of the tiles
-    // with (tile & 1) == (g >> 1)
+    // 8 warps: TMEM lane quarter q = warp & 3, column half = warp >> 2
     mbar_wait(acc_full, 0);
     tc_fence_after();
-    const int q = warp & 3, g = warp >> 2;
-    const int half = g & 1;
+    const int q = warp & 3, half = warp >> 2;
     const int ncol = p.cout >> 1;    // columns per half (multiple of 16)
     const bool relu = p.flags & AG3D_RELU;
-    for (int j = g >> 1; j < T_here; j += 2) {
+    for (int j = 0; j < T_here; ++j) {
       const long long row = row0 + (long long)j * TC_BM + q * 32 + lane;
       const bool live = kmask_s[j] != 0u;
       for (int c0 = half * ncol; c0 < (half + 1) * ncol; c0 += 16) {
@@ -389,40 +414,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams
       const uint32_t idesc = umma_idesc_bf16(p.cout);
       const uint32_t b_lbo = (uint32_t)p.cout * 16u;
       uint32_t started = 0;            // bit j: accumulator j has been written
-      int n_a = 0, n_b = 0;
-      for (int k = k_lo; k < k_hi; ++k) {
-        if (!((kunion >> k) & 1u)) continue;
-        for (int c = 0; c < n_slab; ++c) {
+      int n_b = -1;                    // weight stage in use
+      uint32_t prev_kc = 0xFFFFFFFFu;
+      uint32_t b_hi = 0, b_lo = 0;
+      for (int n = 0; n < n_stage; ++n) {
+        const uint32_t e = stage_list[n];
+        const int j = (int)(e & 0xFFu);
+        if ((e >> 8) != prev_kc) {     // first tile of a new (k, slab): release the previous weight stage, take the next
+          if (n_b >= 0) umma_commit(b_empty(n_b & nb_mask));
+          ++n_b;
+          prev_kc = e >> 8;
           const int sb = n_b & nb_mask;
           mbar_wait(b_full(sb), ((uint32_t)n_b >> nb_shift) & 1u);
-          tc_fence_after();
-          const uint32_t b_hi = smem_u32(b_smem + (size_t)sb * b_stage_bytes);
-          const uint32_t b_lo = b_hi + 4u * b_lbo;
-          for (int j = 0; j < T_here; ++j) {
-            if (!((kmask_s[j] >> k) & 1u)) continue;
-            const int s = n_a & na_mask;
-            mbar_wait(a_full(s), ((uint32_t)n_a >> na_shift) & 1u);
-            tc_fence_after();
-            const uint32_t a_hi = smem_u32(a_smem + (size_t)s * A_STAGE);
-            const uint32_t a_lo = a_hi + A_PIECE;
-            const uint32_t d = tmem_base + (uint32_t)(j * p.cpad);
-#pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {           // two 16-channel MMA steps per 32-channel slab
-              const uint64_t da_hi = umma_desc(a_hi + ks * 2 * A_LBO, A_LBO, 128);
-              const uint64_t da_lo = umma_desc(a_lo + ks * 2 * A_LBO, A_LBO, 128);
-              const uint64_t db_hi = umma_desc(b_hi + ks * 2 * b_lbo, b_lbo, 128);
-              const uint64_t db_lo = umma_desc(b_lo + ks * 2 * b_lbo, b_lbo, 128);
-              umma_bf16(d, da_hi, db_hi, idesc, (started >> j) & 1u);
-              started |= 1u << j;
-              umma_bf16(d, da_hi, db_lo, idesc, 1u);
-              umma_bf16(d, da_lo, db_hi, idesc, 1u);
-            }
-            umma_commit(a_empty(s));   // stage s may be overwritten once these MMAs have read it
-            ++n_a;
-          }
-          umma_commit(b_empty(sb));
-          ++n_b;
+          b_hi = smem_u32(b_smem + (size_t)sb * b_stage_bytes);
+          b_lo = b_hi + 4u * b_lbo;
         }
+        const int s = n & na_mask;
+        mbar_wait(a_full(s), ((uint32_t)n >> na_shift) & 1u);
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(a_smem + (size_t)s * A_STAGE);
+        const uint32_t a_lo = a_hi + A_PIECE;
+        const uint32_t d = tmem_base + (uint32_t)(j * p.cpad);
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {           // two 16-channel MMA steps per 32-channel slab
+          const uint64_t da_hi = umma_desc(a_hi + ks * 2 * A_LBO, A_LBO, 128);
+          const uint64_t da_lo = umma_desc(a_lo + ks * 2 * A_LBO, A_LBO, 128);
+          const uint64_t db_hi = umma_desc(b_hi + ks * 2 * b_lbo, b_lbo, 128);
+          const uint64_t db_lo = umma_desc(b_lo + ks * 2 * b_lbo, b_lbo, 128);
+          umma_bf16(d, da_hi, db_hi, idesc, (started >> j) & 1u);
+          started |= 1u << j;
+          umma_bf16(d, da_hi, db_lo, idesc, 1u);
+          umma_bf16(d, da_lo, db_hi, idesc, 1u);
+        }
+        umma_commit(a_empty(s));       // stage s may be overwritten once these MMAs have read it
       }
       umma_commit(acc_full);
     }
@@ -430,17 +454,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams
     // =========================================================================== weight loader (TMA engine)
     if (lane == 0) {
       int n_b = 0;
-      for (int k = k_lo; k < k_hi; ++k) {
-        if (!((kunion >> k) & 1u)) continue;
-        for (int c = 0; c < n_slab; ++c) {
-          const int sb = n_b & nb_mask;
-          mbar_wait(b_empty(sb), (((uint32_t)n_b >> nb_shift) & 1u) ^ 1u);
-          mbar_arrive_expect_tx(b_full(sb), b_stage_bytes);
-          const unsigned char* src = reinterpret_cast<const unsigned char*>(p.wp) +
-                                     ((size_t)k * n_slab + c) * (size_t)b_stage_bytes;
-          bulk_g2s(smem_u32(b_smem + (size_t)sb * b_stage_bytes), src, b_stage_bytes, b_full(sb));
-          ++n_b;
-        }
+      uint32_t prev_kc = 0xFFFFFFFFu;
+      for (int n = 0; n < n_stage; ++n) {
+        const uint32_t e = stage_list[n];
+        if ((e >> 8) == prev_kc) continue;
+        prev_kc = e >> 8;
+        const int k = (int)(e >> 16), c = (int)((e >> 8) & 0xFFu);
+        const int sb = n_b & nb_mask;
+        mbar_wait(b_empty(sb), (((uint32_t)n_b >> nb_shift) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(b_full(sb), b_stage_bytes);
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(p.wp) +
+                                   ((size_t)k * n_slab + c) * (size_t)b_stage_bytes;
+        bulk_g2s(smem_u32(b_smem + (size_t)sb * b_stage_bytes), src, b_stage_bytes, b_full(sb));
+        ++n_b;
       }
     }
   }
@@ -517,7 +543,7 @@ size_t spconv_tc_workspace_bytes(long long n_out, int K, int cout) {
 }
 
 bool spconv_tc_supported(int cin, int cout) {
-  return cin % TC_BK == 0 && cout % 32 == 0 && cout >= 32 && cout <= 256 && cin >= 32;
+  return cin % TC_BK == 0 && cin >= 32 && cin <= 384 && cout % 32 == 0 && cout >= 32 && cout <= 256;
 }
 
 int spconv_tc_launch(const float* in, int in_ld, int cin, const int* nbr, int K, long long n_out,
@@ -543,7 +569,7 @@ int spconv_tc_launch(const float* in, int in_ld, int cin, const int* nbr, int K,
   }
   p.tmem_cols = pow2_at_least(p.T * p.cpad, 32);
   p.NB = (cout <= 128) ? 4 : 2;
-  const size_t fixed = TC_BAR_BYTES + (size_t)p.NB * (size_t)cout * 128;
+  const size_t fixed = TC_BAR_BYTES + TC_LIST_BYTES + (size_t)p.NB * (size_t)cout * 128;
   int na = (int)((200 * 1024 - fixed) / A_STAGE);
   na = na >= 8 ? 8 : (na >= 4 ? 4 : 2);
   p.NA = na;
