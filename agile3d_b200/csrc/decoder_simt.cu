@@ -479,6 +479,12 @@ constexpr size_t c2s_smem_bytes() {
 
 static inline int c2s_groups(int nq) { return (nq + 19) / 20; }
 
+size_t s2c_tc_workspace_bytes(int nq);
+int s2c_tc_launch(const float* x, const float* pos, long long nv, const float* A, const float* c, const float* U,
+                  const float* bo, const float* ln_w, const float* ln_b, float ln_eps, const float* E,
+                  const int* q_obj, int nq, int heads, int n_obj, float* x_out, float* logits, unsigned char* label,
+                  int* obj_count, void* ws, size_t ws_bytes, cudaStream_t st);
+
 }  // namespace ag3d
 
 using namespace ag3d;
@@ -539,10 +545,13 @@ int ag3d_c2s_attn_fwd(const float* x, const float* pos, int64_t nv, const float*
   return AG3D_OK;
 }
 
+size_t ag3d_s2c_workspace_bytes(int32_t nq) { return (nq >= 1 && nq <= 32) ? s2c_tc_workspace_bytes(nq) : 0; }
+
 int ag3d_s2c_mask_fwd(const float* x, const float* pos, int64_t nv, const float* A, const float* c,
                       const float* U, const float* bo, const float* ln_w, const float* ln_b, float ln_eps,
                       const float* E, const int32_t* q_obj, int32_t nq, int32_t heads, int32_t n_obj,
-                      float* x_out, float* logits, uint8_t* label, int32_t* obj_count, ag3d_stream_t stream) {
+                      float* x_out, float* logits, uint8_t* label, int32_t* obj_count, int32_t algo, void* ws,
+                      size_t ws_bytes, ag3d_stream_t stream) {
   AG3D_CHECK_ARG(nv > 0 && nq > 0, "empty problem");
   AG3D_CHECK_ARG(heads == 8, "heads must be 8 (hidden 128 = 8 x 16)");
   AG3D_CHECK_ARG(nq <= 32, "this version handles at most 32 click queries per scene in s2c");
@@ -552,6 +561,11 @@ int ag3d_s2c_mask_fwd(const float* x, const float* pos, int64_t nv, const float*
   AG3D_CHECK_ARG(aligned16(x) && aligned16(pos) && aligned16(A) && aligned16(U) && aligned16(E) && aligned16(x_out),
                  "pointers must be 16-byte aligned");
   cudaStream_t st = as_stream(stream);
+  if (algo == AG3D_ALGO_AUTO) algo = ws ? AG3D_ALGO_TC : AG3D_ALGO_SIMT;
+  if (algo == AG3D_ALGO_TC)
+    return s2c_tc_launch(x, pos, nv, A, c, U, bo, ln_w, ln_b, ln_eps, E, q_obj, nq, heads, n_obj, x_out, logits,
+                         label, obj_count, ws, ws_bytes, st);
+  AG3D_CHECK_ARG(algo == AG3D_ALGO_SIMT, "unknown algo");
   const unsigned grid = (unsigned)((nv + TV - 1) / TV);
   const int J2 = (heads * nq + 15) / 16;
 #define LAUNCH_S2C(JJ)                                                                                      \

@@ -1,0 +1,439 @@
+// K10 (tensor-core variant): scene -> click cross-attention + residual + LayerNorm + mask head, one pass over the
+// voxels, three chained tcgen05 GEMMs per 128-voxel tile with fp32 accumulators in TMEM:
+//   S = (x+pos) . A^T            [128 x HQP]   (bf16x3)      -> per-head softmax in registers -> P (bf16 hi/lo, smem)
+//   O = P . U                    [128 x 128]   (bf16x3)      -> + bo + x -> LayerNorm -> y (global) and Y (bf16 hi/lo, smem)
+//   Z = Y . E^T                  [128 x 32]    (bf16x3)      -> per-object max -> logits, label, histogram
+// The three small right-hand operands (A, U^T, E; <= 176 KB as bf16 hi/lo images, L2 resident) are streamed per
+// tile through a ring of shared-memory stages by the TMA engine (cp.async.bulk); the voxel tile itself is read
+// from HBM exactly once.  Column layout of S/P: head-major with every head padded to NQ16 (16 or 32) columns so
+// that a 16-column TMEM load never straddles heads; padded columns carry a bias of -inf (probability 0).
+// Roles: 8 compute warps (tile load + split, softmax, LayerNorm, mask head), 1 MMA-issuer thread, 1 loader thread.
+#include <float.h>
+#include <math.h>
+
+#include <algorithm>
+
+#include "tc_common.cuh"
+
+namespace ag3d {
+
+constexpr int DT_D = 128;
+constexpr int DT_COMPUTE_THREADS = 256;
+constexpr int DT_THREADS = DT_COMPUTE_THREADS + 64;
+constexpr int DT_NQP = 32;               // mask-head columns (queries padded to 32)
+constexpr int DT_MISC_BYTES = 8192;      // barriers + small per-CTA arrays
+constexpr uint32_t TM_S = 0, TM_O = 256, TM_Z = 384;   // TMEM column offsets
+
+// ---------------------------------------------------------------------------------------------- operand prep
+// Builds the bf16 hi/lo shared-memory images of the right-hand operands (consumption order G1 | G2 | G3) and the
+// padded score bias.  A, U: [heads*nq, 128] fp32 (row = h*nq + q); E: [nq, 128]; c: [heads*nq].
+template <int NQ16>
+__global__ void s2c_prep_kernel(const float* __restrict__ A, const float* __restrict__ cvec,
+                                const float* __restrict__ U, const float* __restrict__ E, int nq, int heads,
+                                uint4* __restrict__ img, float* __restrict__ cpad) {
+  constexpr int HQP = 8 * NQ16;
+  constexpr int SLABS_P = HQP / 32;
+  constexpr int N1 = 4 * 4 * HQP, N2 = SLABS_P * 4 * 128, N3 = 4 * 4 * DT_NQP;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < HQP) {
+    const int h = t / NQ16, qq = t % NQ16;
+    cpad[t] = (qq < nq && h < heads) ? cvec[h * nq + qq] : -INFINITY;
+  }
+  if (t >= N1 + N2 + N3) return;
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v[e] = 0.f;
+  size_t hi_idx, lo_idx;
+  if (t < N1) {                                   // G1: B[n = padded column][k = channel]
+    const int n = t % HQP, kc = (t / HQP) % 4, s = t / (HQP * 4);
+    const int h = n / NQ16, qq = n % NQ16;
+    if (qq < nq) {
+      const float* src = A + (size_t)(h * nq + qq) * DT_D + s * 32 + kc * 8;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = __ldg(src + e);
+    }
+    const size_t base = (size_t)s * (HQP * 8);
+    hi_idx = base + (size_t)(0 * 4 + kc) * HQP + n;
+    lo_idx = base + (size_t)(1 * 4 + kc) * HQP + n;
+  } else if (t < N1 + N2) {                       // G2: B[n = channel][k = padded column]
+    const int u = t - N1;
+    const int n = u % 128, kc = (u / 128) % 4, s = u / 512;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int col = s * 32 + kc * 8 + e;
+      const int h = col / NQ16, qq = col % NQ16;
+      if (qq < nq) v[e] = __ldg(U + (size_t)(h * nq + qq) * DT_D + n);
+    }
+    const size_t base = (size_t)4 * HQP * 8 + (size_t)s * 1024;
+    hi_idx = base + (size_t)(0 * 4 + kc) * 128 + n;
+    lo_idx = base + (size_t)(1 * 4 + kc) * 128 + n;
+  } else {                                        // G3: B[n = query][k = channel]
+    const int u = t - N1 - N2;
+    const int n = u % DT_NQP, kc = (u / DT_NQP) % 4, s = u / (DT_NQP * 4);
+    if (n < nq) {
+      const float* src = E + (size_t)n * DT_D + s * 32 + kc * 8;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = __ldg(src + e);
+    }
+    const size_t base = (size_t)4 * HQP * 8 + (size_t)SLABS_P * 1024 + (size_t)s * 256;
+    hi_idx = base + (size_t)(0 * 4 + kc) * DT_NQP + n;
+    lo_idx = base + (size_t)(1 * 4 + kc) * DT_NQP + n;
+  }
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) split2(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
+  img[hi_idx] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  img[lo_idx] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+template <int NQ16>
+constexpr size_t s2c_img_bytes() {
+  constexpr int HQP = 8 * NQ16;
+  return (size_t)(4 * HQP * 8 + (HQP / 32) * 1024 + 4 * 256) * 16;
+}
+
+// ---------------------------------------------------------------------------------------------- main kernel
+struct S2cParams {
+  const float* x; const float* pos; long long nv;
+  const uint4* img; const float* cpad;
+  const float* bo; const float* ln_w; const float* ln_b; float ln_eps;
+  const int* q_obj; int nq; int n_obj;
+  float* x_out; float* logits; unsigned char* label; int* obj_count;
+};
+
+template <int NQ16>
+struct S2cCfg {
+  static constexpr int HQP = 8 * NQ16;
+  static constexpr int SLABS_P = HQP / 32;
+  static constexpr int R_SLABS = SLABS_P > 4 ? SLABS_P : 4;
+  static constexpr int B_STAGE = HQP * 128 > 16384 ? HQP * 128 : 16384;
+  static constexpr int NBR = (HQP <= 128) ? 3 : 2;
+  static constexpr size_t SMEM = DT_MISC_BYTES + (size_t)R_SLABS * A_STAGE + (size_t)NBR * B_STAGE;
+};
+
+template <int NQ16>
+__global__ void __launch_bounds__(DT_THREADS, 1) s2c_tc_kernel(const S2cParams p) {
+  using Cfg = S2cCfg<NQ16>;
+  constexpr int HQP = Cfg::HQP, SLABS_P = Cfg::SLABS_P, NBR = Cfg::NBR;
+  constexpr uint32_t B_STAGE = Cfg::B_STAGE;
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);            // [0..5] phase barriers, [8..] ring
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 192);
+  int* hist_s = reinterpret_cast<int*>(smem + 256);              // [32]
+  int* qobj_s = reinterpret_cast<int*>(smem + 384);              // [32]
+  float* vec_s = reinterpret_cast<float*>(smem + 512);           // bo[128] | ln_w[128] | ln_b[128]
+  float* cpad_s = reinterpret_cast<float*>(smem + 2048);         // [HQP <= 256]
+  float* lnred_s = reinterpret_cast<float*>(smem + 3072);        // [2][128][2]  (sum / sq-dev partials per column half)
+  unsigned char* R = smem + DT_MISC_BYTES;                       // XP -> P -> Y operand tiles (bf16 hi/lo slabs)
+  unsigned char* ring = R + (size_t)Cfg::R_SLABS * A_STAGE;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t bar_base = smem_u32(bars);
+  const uint32_t xp_full = bar_base, s_full = bar_base + 8, p_full = bar_base + 16, o_full = bar_base + 24,
+                 y_full = bar_base + 32, z_full = bar_base + 40;
+  auto b_full = [&](int s) { return bar_base + 8u * (8 + s); };
+  auto b_empty = [&](int s) { return bar_base + 8u * (12 + s); };
+
+  if (tid == 0) {
+    mbar_init(xp_full, 8); mbar_init(p_full, 8); mbar_init(y_full, 8);
+    mbar_init(s_full, 1); mbar_init(o_full, 1); mbar_init(z_full, 1);
+    for (int s = 0; s < NBR; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid < 32) { hist_s[tid] = 0; qobj_s[tid] = (tid < p.nq) ? p.q_obj[tid] : -1; }
+  for (int i = tid; i < 128; i += DT_THREADS) {
+    vec_s[i] = p.bo[i]; vec_s[128 + i] = p.ln_w[i]; vec_s[256 + i] = p.ln_b[i];
+  }
+  for (int i = tid; i < HQP; i += DT_THREADS) cpad_s[i] = p.cpad[i];
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const long long n_tiles = (p.nv + TC_BM - 1) / TC_BM;
+
+  if (warp < 8) {
+    // ======================================================================================= compute warps
+    const int q4 = warp & 3, g = warp >> 2;
+    const int r = q4 * 32 + lane;                       // tile row owned in the TMEM phases
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q4 * 32) << 16);
+    const int ld_kc = tid & 3, ld_rb = tid >> 2;        // tile-load mapping: 8 channels x rows ld_rb, ld_rb + 64
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const uint32_t ph = (uint32_t)it & 1u;
+      const long long row0 = tile * TC_BM;
+      // ---- P0: x + pos -> bf16 hi/lo, four 32-channel slabs (UMMA K-major A operand)
+#pragma unroll
+      for (int sp = 0; sp < 2; ++sp) {
+        float4 xv[2][2][2], pv[2][2][2];
+#pragma unroll
+        for (int s2 = 0; s2 < 2; ++s2)
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const long long row = row0 + ld_rb + 64 * i;
+            const size_t off = (size_t)row * DT_D + (sp * 2 + s2) * 32 + ld_kc * 8;
+#pragma unroll
+            for (int hlf = 0; hlf < 2; ++hlf) {
+              xv[s2][i][hlf] = pv[s2][i][hlf] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (row < p.nv) {
+                xv[s2][i][hlf] = *reinterpret_cast<const float4*>(p.x + off + hlf * 4);
+                pv[s2][i][hlf] = __ldg(reinterpret_cast<const float4*>(p.pos + off + hlf * 4));
+              }
+            }
+          }
+#pragma unroll
+        for (int s2 = 0; s2 < 2; ++s2)
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const float4 a = xv[s2][i][0], b = xv[s2][i][1], c = pv[s2][i][0], d = pv[s2][i][1];
+            uint32_t h[4], l[4];
+            split2(a.x + c.x, a.y + c.y, h[0], l[0]);
+            split2(a.z + c.z, a.w + c.w, h[1], l[1]);
+            split2(b.x + d.x, b.y + d.y, h[2], l[2]);
+            split2(b.z + d.z, b.w + d.w, h[3], l[3]);
+            unsigned char* dst = R + (size_t)(sp * 2 + s2) * A_STAGE + a_piece_off(ld_rb + 64 * i, ld_kc);
+            *reinterpret_cast<uint4*>(dst) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(dst + A_PIECE) = make_uint4(l[0], l[1], l[2], l[3]);
+          }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(xp_full);
+
+      // ---- P1: per-head softmax over the queries; this thread: row r, heads 4g .. 4g+3
+      mbar_wait(s_full, ph);
+      tc_fence_after();
+#pragma unroll
+      for (int hh = 0; hh < 4; ++hh) {
+        const int col0 = (4 * g + hh) * NQ16;
+        float sc[NQ16];
+#pragma unroll
+        for (int ch = 0; ch < NQ16 / 16; ++ch) tmem_ld16(t_lane + TM_S + col0 + ch * 16, sc + ch * 16);
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < NQ16; ++i) { sc[i] += cpad_s[col0 + i]; mx = fmaxf(mx, sc[i]); }
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < NQ16; ++i) { sc[i] = __expf(sc[i] - mx); sum += sc[i]; }
+        const float inv = 1.f / sum;
+#pragma unroll
+        for (int c8 = 0; c8 < NQ16 / 8; ++c8) {
+          uint32_t h[4], l[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) split2(sc[c8 * 8 + 2 * e] * inv, sc[c8 * 8 + 2 * e + 1] * inv, h[e], l[e]);
+          const int col = col0 + c8 * 8;
+          unsigned char* dst = R + (size_t)(col >> 5) * A_STAGE + a_piece_off(r, (col >> 3) & 3);
+          *reinterpret_cast<uint4*>(dst) = make_uint4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<uint4*>(dst + A_PIECE) = make_uint4(l[0], l[1], l[2], l[3]);
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+
+      // ---- P2: o + bo + x -> LayerNorm -> y; this thread: row r, channels 64g .. 64g+63
+      mbar_wait(o_full, ph);
+      tc_fence_after();
+      const long long row = row0 + r;
+      const bool valid = row < p.nv;
+      float v[64];
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) tmem_ld16(t_lane + TM_O + 64 * g + ch * 16, v + ch * 16);
+      float sum = 0.f;
+#pragma unroll
+      for (int c4 = 0; c4 < 16; ++c4) {
+        float4 xr = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) xr = *reinterpret_cast<const float4*>(p.x + (size_t)row * DT_D + 64 * g + c4 * 4);
+        const float4 b4 = *reinterpret_cast<const float4*>(vec_s + 64 * g + c4 * 4);
+        v[c4 * 4 + 0] = xr.x + (v[c4 * 4 + 0] + b4.x);
+        v[c4 * 4 + 1] = xr.y + (v[c4 * 4 + 1] + b4.y);
+        v[c4 * 4 + 2] = xr.z + (v[c4 * 4 + 2] + b4.z);
+        v[c4 * 4 + 3] = xr.w + (v[c4 * 4 + 3] + b4.w);
+        sum += (v[c4 * 4 + 0] + v[c4 * 4 + 1]) + (v[c4 * 4 + 2] + v[c4 * 4 + 3]);
+      }
+      lnred_s[(0 * 128 + r) * 2 + g] = sum;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float mean = (lnred_s[(0 * 128 + r) * 2 + 0] + lnred_s[(0 * 128 + r) * 2 + 1]) * (1.f / DT_D);
+      float sq = 0.f;
+#pragma unroll
+      for (int c = 0; c < 64; ++c) { const float d = v[c] - mean; sq = fmaf(d, d, sq); }
+      lnred_s[(1 * 128 + r) * 2 + g] = sq;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float var = (lnred_s[(1 * 128 + r) * 2 + 0] + lnred_s[(1 * 128 + r) * 2 + 1]) * (1.f / DT_D);
+      const float rstd = 1.f / sqrtf(var + p.ln_eps);
+#pragma unroll
+      for (int c8 = 0; c8 < 8; ++c8) {
+        float y[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int c = 64 * g + c8 * 8 + e;
+          y[e] = (v[c8 * 8 + e] - mean) * rstd * vec_s[128 + c] + vec_s[256 + c];
+        }
+        if (valid) {
+          float* o = p.x_out + (size_t)row * DT_D + 64 * g + c8 * 8;
+          *reinterpret_cast<float4*>(o) = make_float4(y[0], y[1], y[2], y[3]);
+          *reinterpret_cast<float4*>(o + 4) = make_float4(y[4], y[5], y[6], y[7]);
+        }
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) split2(y[2 * e], y[2 * e + 1], h[e], l[e]);
+        const int c = 64 * g + c8 * 8;
+        unsigned char* dst = R + (size_t)(c >> 5) * A_STAGE + a_piece_off(r, (c >> 3) & 3);
+        *reinterpret_cast<uint4*>(dst) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(dst + A_PIECE) = make_uint4(l[0], l[1], l[2], l[3]);
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(y_full);
+
+      // ---- P3: mask head (column half 0 only: 32 query columns)
+      mbar_wait(z_full, ph);
+      tc_fence_after();
+      if (g == 0) {
+        float z[DT_NQP];
+        tmem_ld16(t_lane + TM_Z, z);
+        tmem_ld16(t_lane + TM_Z + 16, z + 16);
+        if (valid) {
+          float best = -INFINITY;
+          int arg = 0;
+          for (int ob = 0; ob < p.n_obj; ++ob) {
+            float m = -INFINITY;
+#pragma unroll
+            for (int q = 0; q < DT_NQP; ++q) m = (qobj_s[q] == ob) ? fmaxf(m, z[q]) : m;
+            p.logits[(size_t)row * p.n_obj + ob] = m;
+            if (m > best || ob == 0) { best = m; arg = ob; }
+          }
+          p.label[row] = (unsigned char)arg;
+          atomicAdd(&hist_s[arg], 1);
+        }
+      }
+      tc_fence_before();
+    }
+  } else if (warp == 8) {
+    // ======================================================================================= MMA issuer
+    if (lane == 0) {
+      const uint32_t id_s = umma_idesc_bf16(HQP), id_o = umma_idesc_bf16(128), id_z = umma_idesc_bf16(DT_NQP);
+      const uint32_t r_base = smem_u32(R);
+      int nb = 0, it = 0;
+      // one GEMM = `slabs` x (2 k-steps x 3 products); B operand of slab s at ring stage (b_off + s*b_slab)
+      auto gemm = [&](int slabs, uint32_t d, uint32_t idesc, uint32_t b_lbo, bool stage_per_slab, uint32_t b_slab) {
+        uint32_t b_hi = 0;
+        for (int s = 0; s < slabs; ++s) {
+          if (stage_per_slab || s == 0) {
+            const int sb = nb % NBR;
+            mbar_wait(b_full(sb), (uint32_t)(nb / NBR) & 1u);
+            tc_fence_after();
+            b_hi = smem_u32(ring + (size_t)sb * B_STAGE);
+          }
+          const uint32_t bh = b_hi + (stage_per_slab ? 0u : (uint32_t)s * b_slab);
+          const uint32_t bl = bh + 4u * b_lbo;
+          const uint32_t a_hi = r_base + (uint32_t)s * A_STAGE, a_lo = a_hi + A_PIECE;
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            const uint64_t da_hi = umma_desc(a_hi + ks * 2 * A_LBO, A_LBO, 128);
+            const uint64_t da_lo = umma_desc(a_lo + ks * 2 * A_LBO, A_LBO, 128);
+            const uint64_t db_hi = umma_desc(bh + ks * 2 * b_lbo, b_lbo, 128);
+            const uint64_t db_lo = umma_desc(bl + ks * 2 * b_lbo, b_lbo, 128);
+            umma_bf16(d, da_hi, db_hi, idesc, (s | ks) ? 1u : 0u);
+            umma_bf16(d, da_hi, db_lo, idesc, 1u);
+            umma_bf16(d, da_lo, db_hi, idesc, 1u);
+          }
+          if (stage_per_slab || s == slabs - 1) { umma_commit(b_empty(nb % NBR)); ++nb; }
+        }
+      };
+      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const uint32_t ph = (uint32_t)it & 1u;
+        mbar_wait(xp_full, ph);
+        tc_fence_after();
+        gemm(4, tmem_base + TM_S, id_s, (uint32_t)HQP * 16u, true, 0);
+        umma_commit(s_full);
+        mbar_wait(p_full, ph);
+        tc_fence_after();
+        gemm(SLABS_P, tmem_base + TM_O, id_o, 128u * 16u, true, 0);
+        umma_commit(o_full);
+        mbar_wait(y_full, ph);
+        tc_fence_after();
+        gemm(4, tmem_base + TM_Z, id_z, (uint32_t)DT_NQP * 16u, false, 4096u);
+        umma_commit(z_full);
+      }
+    }
+  } else {
+    // ======================================================================================= operand loader
+    if (lane == 0) {
+      const unsigned char* img = reinterpret_cast<const unsigned char*>(p.img);
+      int nb = 0;
+      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        size_t off = 0;
+        for (int st = 0; st < 4 + SLABS_P + 1; ++st) {
+          const uint32_t bytes = st < 4 ? (uint32_t)HQP * 128u : 16384u;
+          const int sb = nb % NBR;
+          mbar_wait(b_empty(sb), ((uint32_t)(nb / NBR) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(b_full(sb), bytes);
+          bulk_g2s(smem_u32(ring + (size_t)sb * B_STAGE), img + off, bytes, b_full(sb));
+          off += bytes;
+          ++nb;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (tid < p.n_obj && hist_s[tid]) atomicAdd(p.obj_count + tid, hist_s[tid]);
+  if (warp == 8) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+template <int NQ16>
+static int s2c_tc_launch_t(const float* x, const float* pos, long long nv, const float* A, const float* c,
+                           const float* U, const float* bo, const float* ln_w, const float* ln_b, float ln_eps,
+                           const float* E, const int* q_obj, int nq, int heads, int n_obj, float* x_out,
+                           float* logits, unsigned char* label, int* obj_count, void* ws, cudaStream_t st) {
+  using Cfg = S2cCfg<NQ16>;
+  constexpr int HQP = Cfg::HQP;
+  uint4* img = static_cast<uint4*>(ws);
+  float* cpad = reinterpret_cast<float*>(static_cast<unsigned char*>(ws) + s2c_img_bytes<NQ16>());
+  constexpr int total = 4 * 4 * HQP + Cfg::SLABS_P * 4 * 128 + 4 * 4 * DT_NQP;
+  s2c_prep_kernel<NQ16><<<(total + 255) / 256, 256, 0, st>>>(A, c, U, E, nq, heads, img, cpad);
+  AG3D_LAUNCH_CHECK("s2c_prep");
+  static bool attr = false;
+  if (!attr) {
+    AG3D_CUDA(cudaFuncSetAttribute(s2c_tc_kernel<NQ16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    attr = true;
+  }
+  S2cParams p;
+  p.x = x; p.pos = pos; p.nv = nv; p.img = img; p.cpad = cpad; p.bo = bo; p.ln_w = ln_w; p.ln_b = ln_b;
+  p.ln_eps = ln_eps; p.q_obj = q_obj; p.nq = nq; p.n_obj = n_obj; p.x_out = x_out; p.logits = logits;
+  p.label = label; p.obj_count = obj_count;
+  long long tiles = (nv + TC_BM - 1) / TC_BM;
+  const int grid = (int)std::min<long long>(tiles, sm_count());
+  s2c_tc_kernel<NQ16><<<grid, DT_THREADS, Cfg::SMEM, st>>>(p);
+  AG3D_LAUNCH_CHECK("s2c_tc");
+  return AG3D_OK;
+}
+
+size_t s2c_tc_workspace_bytes(int nq) {
+  return (nq <= 16 ? s2c_img_bytes<16>() + 128 * 4 : s2c_img_bytes<32>() + 256 * 4) + 256;
+}
+
+int s2c_tc_launch(const float* x, const float* pos, long long nv, const float* A, const float* c, const float* U,
+                  const float* bo, const float* ln_w, const float* ln_b, float ln_eps, const float* E,
+                  const int* q_obj, int nq, int heads, int n_obj, float* x_out, float* logits, unsigned char* label,
+                  int* obj_count, void* ws, size_t ws_bytes, cudaStream_t st) {
+  AG3D_CHECK_ARG(heads == 8 && nq <= 32, "tensor-core s2c handles 8 heads and at most 32 queries");
+  AG3D_CHECK_ARG(ws && aligned16(ws) && ws_bytes >= s2c_tc_workspace_bytes(nq), "s2c workspace too small");
+  if (nq <= 16)
+    return s2c_tc_launch_t<16>(x, pos, nv, A, c, U, bo, ln_w, ln_b, ln_eps, E, q_obj, nq, heads, n_obj, x_out, logits,
+                               label, obj_count, ws, st);
+  return s2c_tc_launch_t<32>(x, pos, nv, A, c, U, bo, ln_w, ln_b, ln_eps, E, q_obj, nq, heads, n_obj, x_out, logits,
+                             label, obj_count, ws, st);
+}
+
+}  // namespace ag3d

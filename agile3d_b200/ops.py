@@ -252,7 +252,7 @@ def c2s_attn_fwd(x, pos, qfold, nq, heads, label=None, q_obj=None, obj_count=Non
     return ctx
 
 
-def s2c_mask_fwd(x, pos, A, c, U, bo, ln_w, ln_b, ln_eps, E, q_obj, nq, heads, n_obj, x_out=None):
+def s2c_mask_fwd(x, pos, A, c, U, bo, ln_w, ln_b, ln_eps, E, q_obj, nq, heads, n_obj, x_out=None, algo=ALGO_AUTO):
     """-> (x_out f32 [Nv,128], logits f32 [Nv,n_obj], label u8 [Nv], obj_count i32 [n_obj])."""
     _need_cuda(x, pos, A, c, U, E, q_obj)
     for t in (x, pos, A, c, U, bo, ln_w, ln_b, E):
@@ -266,8 +266,12 @@ def s2c_mask_fwd(x, pos, A, c, U, bo, ln_w, ln_b, ln_eps, E, q_obj, nq, heads, n
     obj_count = torch.zeros(n_obj, dtype=torch.int32, device=x.device)
     # s2c (x, pos reads + x' write) + mask head (x' read, logits write, [nq,nv] bool mask write)
     nbytes = 4 * nv * 128 * 3 + 4 * nv * 128 + 4 * nv * n_obj + nq * nv
+    ws, wsb = None, 0
+    if algo != ALGO_SIMT:
+        wsb = lib().ag3d_s2c_workspace_bytes(nq)
+        ws = _workspace("s2c", x.device, wsb) if wsb else None
     with _Timed("s2c_mask", nbytes, 2 * nv * 128 * (2 * heads * nq + nq)):
         check(lib().ag3d_s2c_mask_fwd(_p(x), _p(pos), nv, _p(A), _p(c), _p(U), _p(bo), _p(ln_w), _p(ln_b),
                                       float(ln_eps), _p(E), _p(q_obj), nq, heads, n_obj, _p(x_out), _p(logits),
-                                      _p(label), _p(obj_count), _stream()), "ag3d_s2c_mask_fwd")
+                                      _p(label), _p(obj_count), algo, _p(ws), wsb, _stream()), "ag3d_s2c_mask_fwd")
     return x_out, logits, label, obj_count

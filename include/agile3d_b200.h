@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define AG3D_ABI_VERSION 3
+#define AG3D_ABI_VERSION 4
 
 #define AG3D_OK 0
 #define AG3D_E_INVALID (-1)   /* bad argument (shape, alignment, unsupported size) */
@@ -140,11 +140,14 @@ int ag3d_c2s_attn_fwd(const float* x, const float* pos, int64_t nv, const float*
  *   y_v = LayerNorm(x_v + sum_{h,q} a[v,(h,q)] U[(h,q)] + bo)              -> x_out
  *   logits[v, o] = max_{q : q_obj[q] == o} y_v . E[q]  (o = 0 background)    -> logits [nv, n_obj]
  *   label[v] = argmax_o logits[v, o] (first maximum);  obj_count[o] += #voxels labelled o (caller zeroes).
- * x_out may alias x.  nq <= 32 in this version.                                                             */
+ * x_out may alias x.  nq <= 32 in this version.  algo: AG3D_ALGO_SIMT = fp32 FFMA kernel; AG3D_ALGO_TC = three
+ * chained tcgen05 GEMMs (bf16x3, fp32 accumulate in TMEM), needs the workspace; AUTO = TC when ws is given.      */
+size_t ag3d_s2c_workspace_bytes(int32_t nq);
 int ag3d_s2c_mask_fwd(const float* x, const float* pos, int64_t nv, const float* A, const float* c,
                       const float* U, const float* bo, const float* ln_w, const float* ln_b, float ln_eps,
                       const float* E, const int32_t* q_obj, int32_t nq, int32_t heads, int32_t n_obj,
-                      float* x_out, float* logits, uint8_t* label, int32_t* obj_count, ag3d_stream_t stream);
+                      float* x_out, float* logits, uint8_t* label, int32_t* obj_count, int32_t algo, void* ws,
+                      size_t ws_bytes, ag3d_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -114,7 +114,7 @@ def c2s_attn_fwd(x, pos, qfold, nq, heads, label=None, q_obj=None, obj_count=Non
     return torch.softmax(s, dim=1) @ x
 
 
-def s2c_mask_fwd(x, pos, A, c, U, bo, ln_w, ln_b, ln_eps, E, q_obj, nq, heads, n_obj, x_out=None):
+def s2c_mask_fwd(x, pos, A, c, U, bo, ln_w, ln_b, ln_eps, E, q_obj, nq, heads, n_obj, x_out=None, algo=0):
     s = (x + pos) @ A.T + c                                   # [Nv, H*nq]
     a = torch.softmax(s.view(-1, heads, nq), dim=2).reshape(-1, heads * nq)
     y = torch.nn.functional.layer_norm(x + (a @ U + bo), (x.shape[1],), ln_w, ln_b, ln_eps)

@@ -21,7 +21,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     for n in names:
         assert hasattr(handle, n), f"{n} declared in the header but not exported"
     handle.ag3d_abi_version.restype = ctypes.c_int32
-    assert handle.ag3d_abi_version() == 3
+    assert handle.ag3d_abi_version() == 4
 
 
 def test_ctypes_signature_table_covers_the_header():
@@ -37,5 +37,5 @@ def test_argument_validation_without_gpu():
     rc = L.ag3d_spconv_fwd(None, 32, 33, None, 1, 10, None, None, 32, None, None, None, 0, None, 32, 0, 1, None, 0, None)
     assert rc == -1 and b"multiples of 32" in L.ag3d_last_error()
     rc = L.ag3d_s2c_mask_fwd(None, None, 10, None, None, None, None, None, None, 1e-5, None, None, 40, 8, 3, None,
-                             None, None, None, None)
+                             None, None, None, 0, None, 0, None)
     assert rc == -1 and b"32 click queries" in L.ag3d_last_error()

@@ -199,8 +199,10 @@ def test_c2s_vs_oracle(nv, nq, n_obj):
     assert rel_err(got.cpu().numpy(), ref.numpy()) < 1e-4
 
 
-@pytest.mark.parametrize("nv,nq,n_obj", [(1000, 11, 2), (5003, 15, 3), (20000, 20, 6), (4100, 25, 9), (777, 32, 12)])
-def test_s2c_mask_vs_oracle(nv, nq, n_obj):
+@pytest.mark.parametrize("algo", [1, 2], ids=["simt", "tc"])
+@pytest.mark.parametrize("nv,nq,n_obj", [(1000, 11, 2), (5003, 15, 3), (20000, 20, 6), (4100, 25, 9), (777, 32, 12),
+                                         (128, 16, 4), (129, 17, 5)])
+def test_s2c_mask_vs_oracle(nv, nq, n_obj, algo):
     from agile3d_b200 import ops
     g, x, pos, _, q_obj = _decoder_inputs(nv, nq, n_obj, seed=nv * 3 + nq)
     A = torch.randn((8 * nq, 128), generator=g) * 0.05
@@ -213,7 +215,7 @@ def test_s2c_mask_vs_oracle(nv, nq, n_obj):
                                               nq, 8, n_obj)
     t = lambda v: v.to(DEV)
     y, lg, lab, cnt = ops.s2c_mask_fwd(t(x), t(pos), t(A), t(c), t(U), t(bo), t(lw), t(lb), 1e-5, t(E), t(q_obj), nq,
-                                       8, n_obj)
+                                       8, n_obj, algo=algo)
     assert rel_err(y.cpu().numpy(), ry.numpy()) < 1e-4
     assert rel_err(lg.cpu().numpy(), rl.numpy()) < 1e-4
     # labels: exact wherever the top-2 margin of the fp64 logits exceeds the fp32 noise
@@ -224,7 +226,7 @@ def test_s2c_mask_vs_oracle(nv, nq, n_obj):
     # in-place variant (x_out aliases x) gives the same answer
     xd = t(x).clone()
     y2, lg2, _, _ = ops.s2c_mask_fwd(xd, t(pos), t(A), t(c), t(U), t(bo), t(lw), t(lb), 1e-5, t(E), t(q_obj), nq, 8,
-                                     n_obj, x_out=xd)
+                                     n_obj, x_out=xd, algo=algo)
     assert torch.equal(y2, y) and torch.equal(lg2, lg)
 
 
