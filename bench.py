@@ -323,7 +323,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=2, help="scenes per step per GPU")
+    ap.add_argument("--batch", type=int, default=8, help="scenes per step per GPU (BASELINE configs[2] batches 8 scenes)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
