@@ -39,7 +39,7 @@ SIGNATURES = {
     "ag3d_posenc_workspace_bytes": (_sz, [_i32]),
     "ag3d_fourier_posenc": (_i32, [_vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _sz, _vp]),
     "ag3d_c2s_workspace_bytes": (_sz, [_i32, _i32]),
-    "ag3d_c2s_attn_fwd": (_i32, [_vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ag3d_c2s_attn_fwd": (_i32, [_vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _sz, _vp]),
     "ag3d_s2c_workspace_bytes": (_sz, [_i32]),
     "ag3d_s2c_mask_fwd": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _i32, _i32, _i32,
                                  _vp, _vp, _vp, _vp, _i32, _vp, _sz, _vp]),
@@ -63,7 +63,7 @@ def lib():
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(handle, name)          # AttributeError if the symbol is not exported
             fn.restype, fn.argtypes = res, args
-        if handle.ag3d_abi_version() != 4:
+        if handle.ag3d_abi_version() != 5:
             raise Ag3dError("libagile3d_b200.so ABI version mismatch; rebuild")
         _lib = handle
     return _lib

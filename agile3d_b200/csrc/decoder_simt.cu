@@ -479,6 +479,10 @@ constexpr size_t c2s_smem_bytes() {
 
 static inline int c2s_groups(int nq) { return (nq + 19) / 20; }
 
+size_t c2s_tc_workspace_bytes(int nq, int heads);
+int c2s_tc_launch(const float* x, const float* pos, long long nv, const float* qfold, int nq, int heads,
+                  const unsigned char* label, const int* q_obj, const int* obj_count, void* ws, size_t ws_bytes,
+                  cudaStream_t st, float** part_m, float** part_l, float** part_acc, int* n_cta_out, int* nqg_out);
 size_t s2c_tc_workspace_bytes(int nq);
 int s2c_tc_launch(const float* x, const float* pos, long long nv, const float* A, const float* c, const float* U,
                   const float* bo, const float* ln_w, const float* ln_b, float ln_eps, const float* E,
@@ -494,12 +498,14 @@ extern "C" {
 size_t ag3d_c2s_workspace_bytes(int32_t nq, int32_t heads) {
   const int groups = c2s_groups(nq);
   const size_t rows = (size_t)groups * (size_t)(sm_count() > 0 ? sm_count() : 148) * 160;
-  return rows * (D + 2) * sizeof(float) + 256;
+  const size_t simt = rows * (D + 2) * sizeof(float) + 256;
+  const size_t tc = c2s_tc_workspace_bytes(nq, heads);
+  return simt > tc ? simt : tc;
 }
 
 int ag3d_c2s_attn_fwd(const float* x, const float* pos, int64_t nv, const float* qfold, int32_t nq,
                       int32_t heads, const uint8_t* label, const int32_t* q_obj, const int32_t* obj_count,
-                      float* ctx, void* ws, size_t ws_bytes, ag3d_stream_t stream) {
+                      float* ctx, int32_t algo, void* ws, size_t ws_bytes, ag3d_stream_t stream) {
   AG3D_CHECK_ARG(nv > 0 && nq > 0, "empty problem");
   AG3D_CHECK_ARG(heads == 8, "heads must be 8 (hidden 128 = 8 x 16)");
   AG3D_CHECK_ARG(x && pos && qfold && ctx && aligned16(x) && aligned16(pos) && aligned16(qfold) && aligned16(ctx),
@@ -510,6 +516,18 @@ int ag3d_c2s_attn_fwd(const float* x, const float* pos, int64_t nv, const float*
     return AG3D_E_WORKSPACE;
   }
   cudaStream_t st = as_stream(stream);
+  if (algo == AG3D_ALGO_AUTO) algo = AG3D_ALGO_TC;
+  if (algo == AG3D_ALGO_TC) {
+    float *pm, *pl, *pa;
+    int n_cta_tc, nqg_tc;
+    if (int rc = c2s_tc_launch(x, pos, nv, qfold, nq, heads, label, q_obj, obj_count, ws, ws_bytes, st, &pm, &pl, &pa,
+                               &n_cta_tc, &nqg_tc))
+      return rc;
+    c2s_merge_kernel<<<heads * nq, D, 0, st>>>(pm, pl, pa, n_cta_tc, 128, nq, nqg_tc, ctx);
+    AG3D_LAUNCH_CHECK("c2s_merge");
+    return AG3D_OK;
+  }
+  AG3D_CHECK_ARG(algo == AG3D_ALGO_SIMT, "unknown algo");
   const int groups = c2s_groups(nq);
   const int nqg = (nq + groups - 1) / groups;
   int J = (heads * nqg + 31) / 32;                     // template instances: 3, 4, 5

@@ -107,6 +107,22 @@ __device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t&
 }
 
 
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// instruction descriptor with explicit operand majors (bit 15: A is MN-major, bit 16: B is MN-major)
+__host__ __device__ __forceinline__ uint32_t umma_idesc_bf16_major(int n, int a_mn, int b_mn) {
+  return umma_idesc_bf16(n) | ((uint32_t)(a_mn & 1) << 15) | ((uint32_t)(b_mn & 1) << 16);
+}
+
 // byte offset of row r, 8-channel chunk kc inside a [128 x 32] bf16 piece (UMMA K-major, no swizzle, SBO = 128)
 __device__ __forceinline__ uint32_t a_piece_off(int r, int kc) {
   return (uint32_t)(kc * A_LBO + (r >> 3) * 128 + (r & 7) * 16);

@@ -231,7 +231,7 @@ def fourier_posenc(xyz, scene_offsets, gauss_B):
 _c2s_ws = {}
 
 
-def c2s_attn_fwd(x, pos, qfold, nq, heads, label=None, q_obj=None, obj_count=None):
+def c2s_attn_fwd(x, pos, qfold, nq, heads, label=None, q_obj=None, obj_count=None, algo=ALGO_AUTO):
     """-> ctx f32 [heads*nq, 128]."""
     _need_cuda(x, pos, qfold)
     for t in (x, pos, qfold):
@@ -248,7 +248,7 @@ def c2s_attn_fwd(x, pos, qfold, nq, heads, label=None, q_obj=None, obj_count=Non
     nbytes = 4 * nv * 128 * 2 + (nq * nv if label is not None else 0) + 4 * nq * 128 * 3
     with _Timed("c2s", nbytes, 2 * 2 * nv * 128 * heads * nq):
         check(lib().ag3d_c2s_attn_fwd(_p(x), _p(pos), nv, _p(qfold), nq, heads, _p(label), _p(q_obj),
-                                      _p(obj_count), _p(ctx), _p(ws), ws.numel(), _stream()), "ag3d_c2s_attn_fwd")
+                                      _p(obj_count), _p(ctx), algo, _p(ws), ws.numel(), _stream()), "ag3d_c2s_attn_fwd")
     return ctx
 
 

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define AG3D_ABI_VERSION 4
+#define AG3D_ABI_VERSION 5
 
 #define AG3D_OK 0
 #define AG3D_E_INVALID (-1)   /* bad argument (shape, alignment, unsupported size) */
@@ -127,11 +127,12 @@ int ag3d_fourier_posenc(const float* xyz, const int32_t* scene_offsets_host, int
  *   ctx[(h,q), :] = sum_v softmax_v( qfold[(h,q)] . (x_v + pos_v)  [masked] ) * x_v
  * Mask (models/agile3d.py:365-380): query q of object q_obj[q] is blocked at voxel v iff label[v] != q_obj[q],
  * unless obj_count[q_obj[q]] == 0 (no voxel carries that label -> the row is un-masked).  label == NULL
- * means no mask (first decoder layer).                                                                      */
+ * means no mask (first decoder layer).  algo: AG3D_ALGO_SIMT = fp32 FFMA kernel, AG3D_ALGO_TC (= AUTO) = tcgen05
+ * flash-decoding kernel (bf16x3, online softmax, context accumulators resident in TMEM).                      */
 size_t ag3d_c2s_workspace_bytes(int32_t nq, int32_t heads);
 int ag3d_c2s_attn_fwd(const float* x, const float* pos, int64_t nv, const float* qfold, int32_t nq,
                       int32_t heads, const uint8_t* label, const int32_t* q_obj, const int32_t* obj_count,
-                      float* ctx, void* ws, size_t ws_bytes, ag3d_stream_t stream);
+                      float* ctx, int32_t algo, void* ws, size_t ws_bytes, ag3d_stream_t stream);
 
 /* ---- scene -> click cross-attention + LayerNorm + mask head (s2c) --------------------------------------
  * Replaces CrossAttentionLayer.forward_post as called at models/agile3d.py:305-312 plus

@@ -104,7 +104,7 @@ def fourier_posenc(xyz, scene_offsets, gauss_B):
     return torch.cat(outs, 0), torch.stack(rng, 0)
 
 
-def c2s_attn_fwd(x, pos, qfold, nq, heads, label=None, q_obj=None, obj_count=None):
+def c2s_attn_fwd(x, pos, qfold, nq, heads, label=None, q_obj=None, obj_count=None, algo=0):
     s = qfold @ (x + pos).T                                   # [H*nq, Nv]
     if label is not None:
         for r in range(heads * nq):

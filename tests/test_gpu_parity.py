@@ -184,18 +184,21 @@ def _decoder_inputs(nv, nq, n_obj, seed):
     return g, x, pos, qf, q_obj
 
 
-@pytest.mark.parametrize("nv,nq,n_obj", [(1000, 11, 2), (5003, 15, 3), (20000, 20, 6), (4100, 27, 9), (3000, 45, 11)])
-def test_c2s_vs_oracle(nv, nq, n_obj):
+@pytest.mark.parametrize("algo", [1, 2], ids=["simt", "tc"])
+@pytest.mark.parametrize("nv,nq,n_obj", [(1000, 11, 2), (5003, 15, 3), (20000, 20, 6), (4100, 27, 9), (3000, 45, 11),
+                                         (64, 16, 3), (65, 12, 2)])
+def test_c2s_vs_oracle(nv, nq, n_obj, algo):
     from agile3d_b200 import ops
     g, x, pos, qf, q_obj = _decoder_inputs(nv, nq, n_obj, seed=nv + nq)
     ref = emulate.c2s_attn_fwd(x.double(), pos.double(), qf.double(), nq, 8)
-    got = ops.c2s_attn_fwd(x.to(DEV), pos.to(DEV), qf.to(DEV), nq, 8)
+    got = ops.c2s_attn_fwd(x.to(DEV), pos.to(DEV), qf.to(DEV), nq, 8, algo=algo)
     assert rel_err(got.cpu().numpy(), ref.numpy()) < 1e-4
     # masked: the last object's label never occurs -> its rows must be un-masked (agile3d.py:369,375)
     label = torch.randint(0, max(n_obj - 1, 1), (nv,), generator=g).to(torch.uint8)
     cnt = torch.bincount(label.long(), minlength=n_obj).to(torch.int32)
     ref = emulate.c2s_attn_fwd(x.double(), pos.double(), qf.double(), nq, 8, label, q_obj, cnt)
-    got = ops.c2s_attn_fwd(x.to(DEV), pos.to(DEV), qf.to(DEV), nq, 8, label.to(DEV), q_obj.to(DEV), cnt.to(DEV))
+    got = ops.c2s_attn_fwd(x.to(DEV), pos.to(DEV), qf.to(DEV), nq, 8, label.to(DEV), q_obj.to(DEV), cnt.to(DEV),
+                           algo=algo)
     assert rel_err(got.cpu().numpy(), ref.numpy()) < 1e-4
 
 
