@@ -101,9 +101,29 @@ class SparseTensor:
         if coordinates.shape[0] != features.shape[0]:
             raise ValueError("coordinates and features disagree on N")
         dev = torch.device(device) if device is not None else features.device
+        self._offsets = None
+        if coordinates.device.type == "cpu" and coordinates.shape[0] > 0:
+            self._offsets = self._offsets_from(coordinates[:, 0])      # free on the host, saves a device sync later
         self.C = coordinates.to(device=dev, dtype=torch.int32).contiguous()
         self.F = features.to(device=dev, dtype=torch.float32).contiguous()
         self.maps = None                      # filled by backbone.CoordinateMaps
+
+    @staticmethod
+    def _offsets_from(batch_col):
+        b = batch_col.to(torch.int64)
+        if b.numel() > 1 and bool((b[1:] < b[:-1]).any()):
+            raise ValueError("rows of a scene must be contiguous and scenes in batch order (batched_coordinates)")
+        counts = torch.bincount(b, minlength=int(b[-1]) + 1).tolist()
+        offs = [0]
+        for c in counts:
+            offs.append(offs[-1] + c)
+        return offs
+
+    def scene_offsets(self):
+        """Row ranges of the scenes: offsets[b] .. offsets[b+1] (scenes are contiguous)."""
+        if self._offsets is None:
+            self._offsets = self._offsets_from(self.C[:, 0].cpu())
+        return self._offsets
 
     @property
     def coordinates(self):

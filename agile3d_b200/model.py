@@ -137,12 +137,8 @@ class Agile3d(nn.Module):
         if raw.shape != (x.F.shape[0], 3):
             raise ValueError("raw_coordinates must be [N,3]")
         # scene row ranges (scenes are contiguous and ordered: SURVEY.md A.2)
-        batch = x.C[:, 0]
-        n_scenes = int(batch[-1].item()) + 1
-        counts = torch.bincount(batch, minlength=n_scenes).tolist()
-        offsets = [0]
-        for c in counts:
-            offsets.append(offsets[-1] + c)
+        offsets = x.scene_offsets()
+        n_scenes = len(offsets) - 1
         pos, rng = ops.fourier_posenc(raw, offsets, self.pos_enc.gauss_B)
         pcd = torch.empty((feats.shape[0], self.hidden_dim), dtype=torch.float32, device=feats.device)
         head = self.lin_squeeze_head
@@ -160,42 +156,44 @@ class Agile3d(nn.Module):
         return pcd_features, fmaps, coordinates, pos_encodings_pcd
 
     # ------------------------------------------------------------------------------------------ decoder glue
-    def _click_pos(self, xyz, rng_b):
-        """fourier encoding of a few click coordinates (position_embedding.py:123-152), torch, [n,128]."""
-        lo, hi = rng_b[:3], rng_b[3:]
+    # The O(Nq) query-side algebra is batched over all scenes of a batch that have the same number of queries
+    # (leading dimension B), so its launch count does not grow with the batch size.
+    def _click_pos(self, xyz, lo, hi):
+        """fourier encoding of click coordinates (position_embedding.py:123-152): xyz, lo, hi [n,3] -> [n,128]."""
         u = (xyz - lo) / (hi - lo)
         t = (u * (2 * math.pi)) @ self.pos_enc.gauss_B
         return torch.cat([t.sin(), t.cos()], dim=1)
 
     @staticmethod
     def _fold_c2s(p, tgt, qpos, H):
-        """qfold[(h,q),:] = Wk_h^T ((Wq_h (tgt+qpos) + bq_h) / sqrt(dh))."""
-        d = tgt.shape[1]
+        """qfold[b,(h,q),:] = Wk_h^T ((Wq_h (tgt+qpos) + bq_h) / sqrt(dh));  tgt, qpos [B,Q,d] -> [B,H*Q,d]."""
+        B, Q, d = tgt.shape
         dh = d // H
         Wq, Wk = p.in_proj_weight[:d], p.in_proj_weight[d:2 * d]
-        qp = F.linear(tgt + qpos, Wq, p.in_proj_bias[:d]).view(-1, H, dh) * (1.0 / math.sqrt(dh))
-        return torch.einsum("qhd,hdc->hqc", qp, Wk.view(H, dh, d)).reshape(-1, d).contiguous()
+        qp = F.linear(tgt + qpos, Wq, p.in_proj_bias[:d]).view(B, Q, H, dh) * (1.0 / math.sqrt(dh))
+        return torch.einsum("bqhd,hdc->bhqc", qp, Wk.view(H, dh, d)).reshape(B, H * Q, d).contiguous()
 
     @staticmethod
     def _finish_c2s(layer, tgt, ctx, H):
         p = layer.multihead_attn
-        d = tgt.shape[1]
+        B, Q, d = tgt.shape
         dh = d // H
         Wv, bv = p.in_proj_weight[2 * d:], p.in_proj_bias[2 * d:]
-        heads = torch.einsum("hqc,hdc->qhd", ctx.view(H, -1, d), Wv.view(H, dh, d)) + bv.view(H, dh)
-        attn = F.linear(heads.reshape(-1, d), p.out_proj.weight, p.out_proj.bias)
+        heads = torch.einsum("bhqc,hdc->bqhd", ctx.view(B, H, Q, d), Wv.view(H, dh, d)) + bv.view(H, dh)
+        attn = F.linear(heads.reshape(B, Q, d), p.out_proj.weight, p.out_proj.bias)
         return layer.norm(tgt + attn)
 
     @staticmethod
     def _self_attn(layer, tgt, qpos, H):
         p = layer.self_attn
-        d = tgt.shape[1]
+        B, Q, d = tgt.shape
         dh = d // H
         qk = F.linear(tgt + qpos, p.in_proj_weight[:2 * d], p.in_proj_bias[:2 * d])
-        v = F.linear(tgt, p.in_proj_weight[2 * d:], p.in_proj_bias[2 * d:])
-        q, k = qk[:, :d].view(-1, H, dh).transpose(0, 1), qk[:, d:].view(-1, H, dh).transpose(0, 1)
-        a = torch.softmax((q * (1.0 / math.sqrt(dh))) @ k.transpose(1, 2), dim=-1)
-        o = (a @ v.view(-1, H, dh).transpose(0, 1)).transpose(0, 1).reshape(-1, d)
+        v = F.linear(tgt, p.in_proj_weight[2 * d:], p.in_proj_bias[2 * d:]).view(B, Q, H, dh).transpose(1, 2)
+        q = qk[..., :d].reshape(B, Q, H, dh).transpose(1, 2)
+        k = qk[..., d:].reshape(B, Q, H, dh).transpose(1, 2)
+        a = torch.softmax((q * (1.0 / math.sqrt(dh))) @ k.transpose(2, 3), dim=-1)
+        o = (a @ v).transpose(1, 2).reshape(B, Q, d)
         return layer.norm(tgt + F.linear(o, p.out_proj.weight, p.out_proj.bias))
 
     @staticmethod
@@ -204,16 +202,16 @@ class Agile3d(nn.Module):
 
     @staticmethod
     def _fold_s2c(p, queries, qpos, H):
-        """A[(h,q),:] = Wq_h^T k_hq / sqrt(dh); c[(h,q)] = bq_h . k_hq / sqrt(dh); U[(h,q),:] = Wo[:,h] v_hq."""
-        d = queries.shape[1]
+        """A[b,(h,q),:] = Wq_h^T k_hq / sqrt(dh); c[b,(h,q)] = bq_h . k_hq / sqrt(dh); U[b,(h,q),:] = Wo[:,h] v_hq."""
+        B, Q, d = queries.shape
         dh = d // H
         Wq, bq = p.in_proj_weight[:d], p.in_proj_bias[:d]
-        kp = F.linear(queries + qpos, p.in_proj_weight[d:2 * d], p.in_proj_bias[d:2 * d]).view(-1, H, dh)
-        vp = F.linear(queries, p.in_proj_weight[2 * d:], p.in_proj_bias[2 * d:]).view(-1, H, dh)
+        kp = F.linear(queries + qpos, p.in_proj_weight[d:2 * d], p.in_proj_bias[d:2 * d]).view(B, Q, H, dh)
+        vp = F.linear(queries, p.in_proj_weight[2 * d:], p.in_proj_bias[2 * d:]).view(B, Q, H, dh)
         sc = 1.0 / math.sqrt(dh)
-        A = (torch.einsum("qhd,hdc->hqc", kp, Wq.view(H, dh, d)) * sc).reshape(-1, d).contiguous()
-        c = (torch.einsum("qhd,hd->hq", kp, bq.view(H, dh)) * sc).reshape(-1).contiguous()
-        U = torch.einsum("chd,qhd->hqc", p.out_proj.weight.view(d, H, dh), vp).reshape(-1, d).contiguous()
+        A = (torch.einsum("bqhd,hdc->bhqc", kp, Wq.view(H, dh, d)) * sc).reshape(B, H * Q, d).contiguous()
+        c = (torch.einsum("bqhd,hd->bhq", kp, bq.view(H, dh)) * sc).reshape(B, H * Q).contiguous()
+        U = torch.einsum("chd,bqhd->bhqc", p.out_proj.weight.view(d, H, dh), vp).reshape(B, H * Q, d).contiguous()
         return A, c, U
 
     # ------------------------------------------------------------------------------------------ forward_mask
@@ -223,14 +221,14 @@ class Agile3d(nn.Module):
             raise NotImplementedError("train-mode forward_mask (autograd) is not built yet; call model.eval()")
         H, d = self.num_heads, self.hidden_dim
         dev = pcd_features.F.device
-        n_scenes = len(pcd_features.offsets) - 1
+        offsets = pcd_features.offsets
+        n_scenes = len(offsets) - 1
         tt = self.time_encode.to(dev) if self.time_encode.device != dev else self.time_encode
         self.time_encode = tt
-        per_scene = []
+        # ---- host side: flatten the click dictionaries (query order per scene: [fg clicks by object id then click
+        #      order | 10 learned bg | bg clicks], agile3d.py:249-264) and group scenes by their query count
+        meta, groups = [], {}
         for b in range(n_scenes):
-            src0 = pcd_features.decomposed_features[b]
-            xyz = coordinates.decomposed_features[b]
-            pos = pos_encodings_pcd[self.hlevels[0]][0][b]
             ck, ct = click_idx[b], click_time_idx[b]
             K = len(ck) - 1
             split = [len(ck[str(i)]) for i in range(1, K + 1)]
@@ -239,42 +237,54 @@ class Agile3d(nn.Module):
             rows = [i for o in range(1, K + 1) for i in ck[str(o)]] + list(ck["0"])
             times = [t for o in range(1, K + 1) for t in ct[str(o)]] + list(ct["0"])
             n_fg, n_bgc = sum(split), len(ck["0"])
-            idx = torch.tensor(rows, dtype=torch.long, device=dev)
-            tix = torch.tensor(times, dtype=torch.long, device=dev)
-            click_feat = src0[idx]
-            click_pos = self._click_pos(xyz[idx], coordinates.range[b]) + tt[tix]
-            # query order: [fg clicks (object 1..K, click order) | 10 learned bg | bg clicks]   (agile3d.py:249-264)
-            fg_q, fg_pos = click_feat[:n_fg], click_pos[:n_fg]
-            bg_q = torch.cat([self.bg_query_feat.weight, click_feat[n_fg:]], 0)
-            bg_pos = torch.cat([self.bg_query_pos.weight, click_pos[n_fg:]], 0)
-            queries = torch.cat([fg_q, bg_q], 0)
-            qpos = torch.cat([fg_pos, bg_pos], 0)
-            nq = queries.shape[0]
-            q_obj = torch.tensor([o for o, n in enumerate(split, start=1) for _ in range(n)]
-                                 + [0] * (self.num_bg_queries + n_bgc), dtype=torch.int32, device=dev)
-            src, label, obj_count, outs = src0, None, None, []
+            q_obj = [o for o, n in enumerate(split, start=1) for _ in range(n)] + [0] * (self.num_bg_queries + n_bgc)
+            meta.append((K, n_fg, n_bgc, rows, times, q_obj))
+            groups.setdefault((n_fg, n_bgc), []).append(b)
+        results = [None] * n_scenes
+        pos_list = pos_encodings_pcd[self.hlevels[0]][0]
+        for (n_fg, n_bgc), members in groups.items():
+            B, nq = len(members), n_fg + self.num_bg_queries + n_bgc
+            n_click = n_fg + n_bgc
+            grow = torch.tensor([offsets[b] + r for b in members for r in meta[b][3]], dtype=torch.long, device=dev)
+            tix = torch.tensor([t for b in members for t in meta[b][4]], dtype=torch.long, device=dev)
+            q_obj = torch.tensor([meta[b][5] for b in members], dtype=torch.int32, device=dev)          # [B, nq]
+            rng = coordinates.range[torch.tensor(members, device=dev)].repeat_interleave(n_click, dim=0)  # [B*n_click, 6]
+            click_feat = pcd_features.F[grow].view(B, n_click, d)
+            click_pos = (self._click_pos(coordinates.F[grow], rng[:, :3], rng[:, 3:]) + tt[tix]).view(B, n_click, d)
+            bgq = self.bg_query_feat.weight.unsqueeze(0).expand(B, -1, -1)
+            bgp = self.bg_query_pos.weight.unsqueeze(0).expand(B, -1, -1)
+            queries = torch.cat([click_feat[:, :n_fg], bgq, click_feat[:, n_fg:]], 1)                  # [B, nq, d]
+            qpos = torch.cat([click_pos[:, :n_fg], bgp, click_pos[:, n_fg:]], 1)
+            srcs = [pcd_features.F[offsets[b]:offsets[b + 1]] for b in members]
+            labels, counts = [None] * B, [None] * B
+            outs = [[] for _ in members]
+            ctx = torch.empty((B, H * nq, d), dtype=torch.float32, device=dev)
             for layer in range(self.num_decoders):
                 li = 0 if self.shared_decoder else layer
                 c2s, c2c = self.c2s_attention[li][0], self.c2c_attention[li][0]
                 ffn, s2c = self.ffn_attention[li][0], self.s2c_attention[li][0]
                 qfold = self._fold_c2s(c2s.multihead_attn, queries, qpos, H)
-                ctx = ops.c2s_attn_fwd(src, pos, qfold, nq, H, label, q_obj, obj_count)
+                for i, b in enumerate(members):
+                    ops.c2s_attn_fwd(srcs[i], pos_list[b], qfold[i], nq, H, labels[i], q_obj[i], counts[i], out=ctx[i])
                 q = self._finish_c2s(c2s, queries, ctx, H)
                 q = self._self_attn(c2c, q, qpos, H)
                 queries = self._ffn(ffn, q)
                 A, c, U = self._fold_s2c(s2c.multihead_attn, queries, qpos, H)
                 E = self.mask_embed_head(self.decoder_norm(queries)).contiguous()
-                src, logits, label, obj_count = ops.s2c_mask_fwd(
-                    src, pos, A, c, U, s2c.multihead_attn.out_proj.bias, s2c.norm.weight, s2c.norm.bias,
-                    s2c.norm.eps, E, q_obj, nq, H, K + 1,
-                    x_out=None if layer == 0 else src)       # never overwrite the caller's backbone features
-                outs.append(logits)
-            per_scene.append(outs)
-        per_layer = [list(p) for p in zip(*per_scene)]
+                for i, b in enumerate(members):
+                    srcs[i], logits, labels[i], counts[i] = ops.s2c_mask_fwd(
+                        srcs[i], pos_list[b], A[i], c[i], U[i], s2c.multihead_attn.out_proj.bias, s2c.norm.weight,
+                        s2c.norm.bias, s2c.norm.eps, E[i], q_obj[i], nq, H, meta[b][0] + 1,
+                        x_out=None if layer == 0 else srcs[i])      # never overwrite the caller's backbone features
+                    outs[i].append(logits)
+            for i, b in enumerate(members):
+                results[b] = outs[i]
+        per_layer = [list(p) for p in zip(*results)]
         out = {"pred_masks": per_layer[-1], "backbone_features": pcd_features}
         if self.aux:
             out["aux_outputs"] = [{"pred_masks": p} for p in per_layer[:-1]]
         return out
+
 
 
 def build_agile3d(args):

@@ -231,13 +231,15 @@ def fourier_posenc(xyz, scene_offsets, gauss_B):
 _c2s_ws = {}
 
 
-def c2s_attn_fwd(x, pos, qfold, nq, heads, label=None, q_obj=None, obj_count=None, algo=ALGO_AUTO):
+def c2s_attn_fwd(x, pos, qfold, nq, heads, label=None, q_obj=None, obj_count=None, algo=ALGO_AUTO, out=None):
     """-> ctx f32 [heads*nq, 128]."""
     _need_cuda(x, pos, qfold)
     for t in (x, pos, qfold):
         if not t.is_contiguous() or t.dtype != torch.float32:
             raise _lib.Ag3dError("c2s inputs must be contiguous fp32")
-    ctx = torch.empty((heads * nq, x.shape[1]), dtype=torch.float32, device=x.device)
+    ctx = out if out is not None else torch.empty((heads * nq, x.shape[1]), dtype=torch.float32, device=x.device)
+    if tuple(ctx.shape) != (heads * nq, x.shape[1]) or not ctx.is_contiguous():
+        raise _lib.Ag3dError("c2s output must be contiguous [heads*nq, 128]")
     wsb = lib().ag3d_c2s_workspace_bytes(nq, heads)
     key = (x.device, torch.cuda.current_stream().cuda_stream)
     ws = _c2s_ws.get(key)

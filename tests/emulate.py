@@ -104,14 +104,18 @@ def fourier_posenc(xyz, scene_offsets, gauss_B):
     return torch.cat(outs, 0), torch.stack(rng, 0)
 
 
-def c2s_attn_fwd(x, pos, qfold, nq, heads, label=None, q_obj=None, obj_count=None, algo=0):
+def c2s_attn_fwd(x, pos, qfold, nq, heads, label=None, q_obj=None, obj_count=None, algo=0, out=None):
     s = qfold @ (x + pos).T                                   # [H*nq, Nv]
     if label is not None:
         for r in range(heads * nq):
             o = int(q_obj[r % nq])
             if int(obj_count[o]) > 0:
                 s[r, label != o] = float("-inf")
-    return torch.softmax(s, dim=1) @ x
+    r = torch.softmax(s, dim=1) @ x
+    if out is not None:
+        out.copy_(r)
+        return out
+    return r
 
 
 def s2c_mask_fwd(x, pos, A, c, U, bo, ln_w, ln_b, ln_eps, E, q_obj, nq, heads, n_obj, x_out=None, algo=0):
