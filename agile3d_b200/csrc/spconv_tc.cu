@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams
   const uint32_t acc_full = bar_base + 8u * 24;
 
   if (tid == 0) {
-    for (int s = 0; s < p.NA; ++s) { mbar_init(a_full(s), TC_PROD_WARPS); mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < p.NA; ++s) { mbar_init(a_full(s), TC_PROD_WARPS / 2); mbar_init(a_empty(s), 1); }
     for (int s = 0; s < p.NB; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
     mbar_init(acc_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -167,38 +167,45 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams
 
   if (warp < TC_PROD_WARPS) {
     // =========================================================================== A producers
-    // thread -> 8 channels (one 16-byte bf16 K-chunk kc) of rows rbase and rbase + 64
-    const int kc = tid & 3;
-    const int rbase = tid >> 2;
-    uint32_t st_off[2];
+    // Two producer groups of 4 warps work on alternating stages (group = warp >> 2 takes stages group, group+2, ...)
+    // so that two stages are always being converted/stored concurrently: the per-stage chain (barrier wait -> split
+    // -> st.shared -> proxy fence -> arrive) is latency bound when every warp has to touch every stage.
+    // thread -> 8 channels (one 16-byte bf16 K-chunk kc) of rows rbase + 32*i, i = 0..3
+    constexpr int PG = 2;                                   // producer groups
+    constexpr int PR = 4;                                   // rows per thread per stage
+    const int grp = warp >> 2;
+    const int tg = tid & 127;
+    const int kc = tg & 3;
+    const int rbase = tg >> 2;                              // 0..31
+    uint32_t st_off[PR];
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int r = rbase + 64 * i;
+    for (int i = 0; i < PR; ++i) {
+      const int r = rbase + 32 * i;
       st_off[i] = (uint32_t)(kc * A_LBO + (r >> 3) * 128 + (r & 7) * 16);
     }
-    const long long rows_left = p.n_out - row0 - rbase;     // row (j, i) is real iff j*128 + 64*i < rows_left
+    const long long rows_left = p.n_out - row0 - rbase;     // row (j, i) is real iff j*128 + 32*i < rows_left
     const float* in_kc = p.in + kc * 8;
     const int* nbr_r = p.nbr ? p.nbr + row0 + rbase : nullptr;
 
-    int idx_ld[2];                   // neighbour rows of stage n_issued (prefetched one stage ahead)
+    int idx_ld[PR];                  // neighbour rows of stage n_issued (prefetched one own-stage ahead)
     uint32_t c_ld = 0;
-    int n_issued = 0;
+    int n_issued = grp;
     auto load_idx = [&]() {          // decode stage n_issued and fetch its neighbour rows
       const uint32_t e = stage_list[n_issued];
       const int k = (int)(e >> 16), j = (int)(e & 0xFFu);
       c_ld = (e >> 8) & 0xFFu;
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int off = j * TC_BM + 64 * i;
+      for (int i = 0; i < PR; ++i) {
+        const int off = j * TC_BM + 32 * i;
         idx_ld[i] = -1;
         if (off < rows_left) idx_ld[i] = nbr_r ? __ldg(nbr_r + (long long)k * p.n_out + off) : (int)(row0 + rbase + off);
       }
     };
-    auto issue = [&](float4 (&buf)[4]) -> bool {
+    auto issue = [&](float4 (&buf)[2 * PR]) -> bool {
       if (n_issued >= n_stage) return false;
       const float* src = in_kc + c_ld * TC_BK;
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
+      for (int i = 0; i < PR; ++i) {
         buf[2 * i] = buf[2 * i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (idx_ld[i] >= 0) {
           const float4* r = reinterpret_cast<const float4*>(src + (size_t)idx_ld[i] * (size_t)p.in_ld);
@@ -206,16 +213,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams
           buf[2 * i + 1] = __ldg(r + 1);
         }
       }
-      if (++n_issued < n_stage) load_idx();
+      n_issued += PG;
+      if (n_issued < n_stage) load_idx();
       return true;
     };
-    int n_done = 0;                  // stages finished so far (ring position)
-    auto finish = [&](const float4 (&buf)[4]) {
+    int n_done = grp;                // next stage this group finishes (ring position)
+    auto finish = [&](const float4 (&buf)[2 * PR]) {
       const int s = n_done & na_mask;
       mbar_wait(a_empty(s), (((uint32_t)n_done >> na_shift) & 1u) ^ 1u);
       unsigned char* st = a_smem + (size_t)s * A_STAGE;
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
+      for (int i = 0; i < PR; ++i) {
         uint32_t h[4], l[4];
         split2(buf[2 * i].x, buf[2 * i].y, h[0], l[0]);
         split2(buf[2 * i].z, buf[2 * i].w, h[1], l[1]);
@@ -227,12 +235,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams
       fence_proxy_async();           // generic-proxy stores -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(a_full(s));
-      ++n_done;
+      n_done += PG;
     };
-    if (n_stage > 0) load_idx();
-    // four stages of gathers in flight per thread (16 x 16 B): the gather is latency-bound otherwise
-    float4 b0[4], b1[4], b2[4], b3[4];
-    bool v0 = issue(b0), v1 = issue(b1), v2 = issue(b2), v3 = issue(b3);
+    if (n_issued < n_stage) load_idx();
+    // three own stages of gathers in flight per thread (24 x 16 B): the gather is latency-bound otherwise
+    float4 b0[2 * PR], b1[2 * PR], b2[2 * PR];
+    bool v0 = issue(b0), v1 = issue(b1), v2 = issue(b2);
     while (v0) {
       finish(b0);
       v0 = issue(b0);
@@ -242,10 +250,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams
       if (!v2) break;
       finish(b2);
       v2 = issue(b2);
-      if (!v3) break;
-      finish(b3);
-      v3 = issue(b3);
     }
+
 
     // =========================================================================== epilogue
     // 8 warps: TMEM lane quarter q = warp & 3, column half = warp >> 2
