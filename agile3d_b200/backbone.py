@@ -169,8 +169,11 @@ class Res16UNet34C(nn.Module):
         return self._fold_cache[1]
 
     def _conv(self, name, conv, x, nbr, out, scale, shift, fold, residual=None, relu=False):
+        # tensor-core mode keeps every backbone activation as bf16 hi/lo pair rows ("split", same bytes as fp32):
+        # producers split once in their epilogue, consumers gather with cp.async and no conversion work
+        sp = self.algo != ops.ALGO_SIMT
         return ops.spconv_fwd(x, nbr, conv.kernel, out, scale, shift, residual=residual, relu=relu, algo=self.algo,
-                              weight_tc=fold.get("tc:" + name))
+                              weight_tc=fold.get("tc:" + name), in_split=sp, out_split=sp, res_split=sp)
 
     def _block(self, prefix, blk, x, nbr, fold, out=None):
         n = x.shape[0]
@@ -215,7 +218,8 @@ class Res16UNet34C(nn.Module):
         # stem: conv0p1s1 + bn0 + relu -> skip slice of the level-0 concat buffer
         s0, b0 = fold["bn0"]
         ops.stem_conv_fwd(maps.coords[0], st.F, maps.tables[0], maps.caps[0], self.conv1_kernel_size,
-                          self.conv0p1s1.kernel, cat[0][:, up_c[0]:], s0, b0, relu=True)
+                          self.conv0p1s1.kernel, cat[0][:, up_c[0]:], s0, b0, relu=True,
+                          out_split=self.algo != ops.ALGO_SIMT)
         y = cat[0][:, up_c[0]:]
         for i, tag in enumerate(_ENC):                                  # encoder
             conv = getattr(self, f"conv{tag}s2")

@@ -1,6 +1,8 @@
 // K4 (exact-fp32 variant): output-stationary gather implicit GEMM on the CUDA cores, plus the 3->32 stem
 // evaluated directly against the hash table.  This is the bit-for-bit-fp32 arithmetic path (FFMA, fp32
 // accumulate) that the tcgen05 3xTF32 path (spconv_tc.cu) is validated against at full size.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace ag3d {
@@ -136,7 +138,15 @@ stem_conv_kernel(const int4* __restrict__ coords, const float* __restrict__ feat
     if (scale) v *= __ldg(scale + lane);
     if (shift) v += __ldg(shift + lane);
     if (flags & AG3D_RELU) v = fmaxf(v, 0.f);
-    out[row * out_ld + lane] = v;
+    if (flags & AG3D_OUT_SPLIT) {      // bf16 hi/lo pair rows: chunk of 8 channels = 16 B hi | 16 B lo
+      const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+      const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(out + row * out_ld) + (lane >> 3) * 16 + (lane & 7);
+      dst[0] = hi;
+      dst[8] = lo;
+    } else {
+      out[row * out_ld + lane] = v;
+    }
   }
 }
 
@@ -173,6 +183,7 @@ int ag3d_spconv_fwd(const float* in, int32_t in_ld, int32_t cin, const int32_t* 
   }
   AG3D_CHECK_ARG(algo == AG3D_ALGO_SIMT, "unknown algo");
   AG3D_CHECK_ARG(weight && aligned16(weight), "the fp32 path needs the fp32 weight");
+  AG3D_CHECK_ARG(!(flags & (AG3D_IN_SPLIT | AG3D_OUT_SPLIT | AG3D_RES_SPLIT)), "the fp32 path takes fp32 feature rows only");
   const unsigned gx = (unsigned)((n_out + BM - 1) / BM);
   if (cout % 64 == 0) {
     spconv_simt_kernel<64><<<dim3(gx, cout / 64), SIMT_THREADS, 0, st>>>(

@@ -18,6 +18,7 @@
 //     bias, residual, ReLU and write the channel slice of the output buffer.
 // (tile, k) pairs in which no row of the tile has a neighbour are skipped by all roles.
 #include <algorithm>
+#include <cstdlib>
 
 #include "tc_common.cuh"
 
@@ -55,6 +56,43 @@ __global__ void weight_prep_kernel(const float* __restrict__ w, int K, int cin, 
   }
 }
 
+// ---------------------------------------------------------------------------------------------- split format
+// "split" feature rows: every 8-channel chunk is stored as 16 B of bf16 hi followed by 16 B of bf16 lo
+// (x = hi + lo + O(2^-17 |x|)); a row of C channels occupies exactly the 4*C bytes of the fp32 row, so leading
+// dimensions, channel slices and concat buffers are unchanged.
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 16 channels stored split (4 x 16 B: hi0 lo0 hi1 lo1) -> 16 floats, in place in r4[4]
+__device__ __forceinline__ void unsplit16(float4 (&r4)[4]) {
+  float v[16];
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const uint32_t* h = reinterpret_cast<const uint32_t*>(&r4[2 * c]);
+    const uint32_t* l = reinterpret_cast<const uint32_t*>(&r4[2 * c + 1]);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      v[c * 8 + 2 * e] = __uint_as_float(h[e] << 16) + __uint_as_float(l[e] << 16);
+      v[c * 8 + 2 * e + 1] = __uint_as_float(h[e] & 0xFFFF0000u) + __uint_as_float(l[e] & 0xFFFF0000u);
+    }
+  }
+#pragma unroll
+  for (int e4 = 0; e4 < 4; ++e4) r4[e4] = make_float4(v[e4 * 4], v[e4 * 4 + 1], v[e4 * 4 + 2], v[e4 * 4 + 3]);
+}
+__device__ __forceinline__ void store_split16(float4* dst, const float* v) {
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) split2(v[c * 8 + 2 * e], v[c * 8 + 2 * e + 1], h[e], l[e]);
+    reinterpret_cast<uint4*>(dst)[2 * c] = make_uint4(h[0], h[1], h[2], h[3]);
+    reinterpret_cast<uint4*>(dst)[2 * c + 1] = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- main kernel
 struct TcParams {
   const float* in; int in_ld; int cin;
@@ -62,12 +100,14 @@ struct TcParams {
   const uint4* wp; int cout;
   const float* scale; const float* shift; const float* residual; int res_ld;
   float* out; int out_ld; int flags;
+  int in_split, out_split, res_split;   // feature format: 0 = fp32, 1 = bf16 hi/lo pairs (AG3D_*_SPLIT)
   int T;            // tiles per CTA
   int NA;           // A ring stages
   int NB;           // weight stages
   int na_log2, nb_log2;
   int k_per;        // kernel offsets per CTA row (split-K over gridDim.y); k range = [by*k_per, min(K, (by+1)*k_per))
   float* partial;   // split-K: raw accumulators [gridDim.y][n_out][cout]; NULL = fused epilogue
+  int debug;        // profiling experiments only (AG3D_TC_DEBUG): 1 = skip MMAs, 2 = skip gather loads, 4 = one product
   int cpad;         // TMEM columns per tile (pow2 >= cout)
   int tmem_cols;    // allocation (pow2, 32..512)
 };
@@ -103,7 +143,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams
   const uint32_t acc_full = bar_base + 8u * 24;
 
   if (tid == 0) {
-    for (int s = 0; s < p.NA; ++s) { mbar_init(a_full(s), TC_PROD_WARPS / 2); mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < p.NA; ++s) { mbar_init(a_full(s), p.in_split ? 128 : TC_PROD_WARPS / 2); mbar_init(a_empty(s), 1); }
     for (int s = 0; s < p.NB; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
     mbar_init(acc_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -187,71 +227,110 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams
     const float* in_kc = p.in + kc * 8;
     const int* nbr_r = p.nbr ? p.nbr + row0 + rbase : nullptr;
 
-    int idx_ld[PR];                  // neighbour rows of stage n_issued (prefetched one own-stage ahead)
-    uint32_t c_ld = 0;
-    int n_issued = grp;
-    auto load_idx = [&]() {          // decode stage n_issued and fetch its neighbour rows
-      const uint32_t e = stage_list[n_issued];
-      const int k = (int)(e >> 16), j = (int)(e & 0xFFu);
-      c_ld = (e >> 8) & 0xFFu;
+    if (p.in_split) {
+      // ---- input already stored as bf16 hi/lo pairs: the gather is a pure byte copy, done by cp.async straight
+      //      into the operand stage (no registers, no ALU); completion is tracked by the stage's mbarrier, so up to
+      //      NA stages of gathers are in flight per group.
+      const unsigned char* in_b = reinterpret_cast<const unsigned char*>(p.in) + kc * 32;
+      const size_t row_bytes = (size_t)p.in_ld * 4;
+      int idx_cur[PR], idx_nxt[PR];
+      uint32_t c_cur = 0, c_nxt = 0;
+      auto fetch_idx = [&](int n, int (&idx)[PR], uint32_t& cslab) {
+        const uint32_t e = stage_list[n];
+        const int k = (int)(e >> 16), j = (int)(e & 0xFFu);
+        cslab = (e >> 8) & 0xFFu;
 #pragma unroll
-      for (int i = 0; i < PR; ++i) {
-        const int off = j * TC_BM + 32 * i;
-        idx_ld[i] = -1;
-        if (off < rows_left) idx_ld[i] = nbr_r ? __ldg(nbr_r + (long long)k * p.n_out + off) : (int)(row0 + rbase + off);
-      }
-    };
-    auto issue = [&](float4 (&buf)[2 * PR]) -> bool {
-      if (n_issued >= n_stage) return false;
-      const float* src = in_kc + c_ld * TC_BK;
-#pragma unroll
-      for (int i = 0; i < PR; ++i) {
-        buf[2 * i] = buf[2 * i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (idx_ld[i] >= 0) {
-          const float4* r = reinterpret_cast<const float4*>(src + (size_t)idx_ld[i] * (size_t)p.in_ld);
-          buf[2 * i] = __ldg(r);
-          buf[2 * i + 1] = __ldg(r + 1);
+        for (int i = 0; i < PR; ++i) {
+          const int off = j * TC_BM + 32 * i;
+          idx[i] = -1;
+          if (off < rows_left) idx[i] = nbr_r ? __ldg(nbr_r + (long long)k * p.n_out + off) : (int)(row0 + rbase + off);
         }
-      }
-      n_issued += PG;
-      if (n_issued < n_stage) load_idx();
-      return true;
-    };
-    int n_done = grp;                // next stage this group finishes (ring position)
-    auto finish = [&](const float4 (&buf)[2 * PR]) {
-      const int s = n_done & na_mask;
-      mbar_wait(a_empty(s), (((uint32_t)n_done >> na_shift) & 1u) ^ 1u);
-      unsigned char* st = a_smem + (size_t)s * A_STAGE;
+      };
+      if (grp < n_stage) fetch_idx(grp, idx_cur, c_cur);
+      for (int n = grp; n < n_stage; n += PG) {
+        if (n + PG < n_stage) fetch_idx(n + PG, idx_nxt, c_nxt);
+        const int s = n & na_mask;
+        mbar_wait(a_empty(s), (((uint32_t)n >> na_shift) & 1u) ^ 1u);
+        const uint32_t st = smem_u32(a_smem + (size_t)s * A_STAGE);
+        const unsigned char* src = in_b + (size_t)c_cur * 128;
 #pragma unroll
-      for (int i = 0; i < PR; ++i) {
-        uint32_t h[4], l[4];
-        split2(buf[2 * i].x, buf[2 * i].y, h[0], l[0]);
-        split2(buf[2 * i].z, buf[2 * i].w, h[1], l[1]);
-        split2(buf[2 * i + 1].x, buf[2 * i + 1].y, h[2], l[2]);
-        split2(buf[2 * i + 1].z, buf[2 * i + 1].w, h[3], l[3]);
-        *reinterpret_cast<uint4*>(st + st_off[i]) = make_uint4(h[0], h[1], h[2], h[3]);
-        *reinterpret_cast<uint4*>(st + A_PIECE + st_off[i]) = make_uint4(l[0], l[1], l[2], l[3]);
+        for (int i = 0; i < PR; ++i) {
+          const bool ok = idx_cur[i] >= 0;
+          const unsigned char* g = ok ? src + (size_t)idx_cur[i] * row_bytes : src;
+          cp_async16_zfill(st + st_off[i], g, ok ? 16u : 0u);
+          cp_async16_zfill(st + A_PIECE + st_off[i], g + 16, ok ? 16u : 0u);
+        }
+        cp_async_mbar_arrive_noinc(a_full(s));
+#pragma unroll
+        for (int i = 0; i < PR; ++i) idx_cur[i] = idx_nxt[i];
+        c_cur = c_nxt;
       }
-      fence_proxy_async();           // generic-proxy stores -> visible to the tensor core (async proxy)
-      __syncwarp();
-      if (lane == 0) mbar_arrive(a_full(s));
-      n_done += PG;
-    };
-    if (n_issued < n_stage) load_idx();
-    // three own stages of gathers in flight per thread (24 x 16 B): the gather is latency-bound otherwise
-    float4 b0[2 * PR], b1[2 * PR], b2[2 * PR];
-    bool v0 = issue(b0), v1 = issue(b1), v2 = issue(b2);
-    while (v0) {
-      finish(b0);
-      v0 = issue(b0);
-      if (!v1) break;
-      finish(b1);
-      v1 = issue(b1);
-      if (!v2) break;
-      finish(b2);
-      v2 = issue(b2);
+    } else {
+      int idx_ld[PR];                  // neighbour rows of stage n_issued (prefetched one own-stage ahead)
+      uint32_t c_ld = 0;
+      int n_issued = grp;
+      auto load_idx = [&]() {          // decode stage n_issued and fetch its neighbour rows
+        const uint32_t e = stage_list[n_issued];
+        const int k = (int)(e >> 16), j = (int)(e & 0xFFu);
+        c_ld = (e >> 8) & 0xFFu;
+  #pragma unroll
+        for (int i = 0; i < PR; ++i) {
+          const int off = j * TC_BM + 32 * i;
+          idx_ld[i] = -1;
+          if (off < rows_left) idx_ld[i] = nbr_r ? __ldg(nbr_r + (long long)k * p.n_out + off) : (int)(row0 + rbase + off);
+        }
+      };
+      auto issue = [&](float4 (&buf)[2 * PR]) -> bool {
+        if (n_issued >= n_stage) return false;
+        const float* src = in_kc + c_ld * TC_BK;
+  #pragma unroll
+        for (int i = 0; i < PR; ++i) {
+          buf[2 * i] = buf[2 * i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (idx_ld[i] >= 0 && !(p.debug & 2)) {
+            const float4* r = reinterpret_cast<const float4*>(src + (size_t)idx_ld[i] * (size_t)p.in_ld);
+            buf[2 * i] = __ldg(r);
+            buf[2 * i + 1] = __ldg(r + 1);
+          }
+        }
+        n_issued += PG;
+        if (n_issued < n_stage) load_idx();
+        return true;
+      };
+      int n_done = grp;                // next stage this group finishes (ring position)
+      auto finish = [&](const float4 (&buf)[2 * PR]) {
+        const int s = n_done & na_mask;
+        if (!(p.debug & 16)) mbar_wait(a_empty(s), (((uint32_t)n_done >> na_shift) & 1u) ^ 1u);
+        unsigned char* st = a_smem + (size_t)s * A_STAGE;
+  #pragma unroll
+        for (int i = 0; i < PR; ++i) {
+          uint32_t h[4], l[4];
+          split2(buf[2 * i].x, buf[2 * i].y, h[0], l[0]);
+          split2(buf[2 * i].z, buf[2 * i].w, h[1], l[1]);
+          split2(buf[2 * i + 1].x, buf[2 * i + 1].y, h[2], l[2]);
+          split2(buf[2 * i + 1].z, buf[2 * i + 1].w, h[3], l[3]);
+          *reinterpret_cast<uint4*>(st + st_off[i]) = make_uint4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<uint4*>(st + A_PIECE + st_off[i]) = make_uint4(l[0], l[1], l[2], l[3]);
+        }
+        if (!(p.debug & 8)) fence_proxy_async();   // generic-proxy stores -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_full(s));
+        n_done += PG;
+      };
+      if (n_issued < n_stage) load_idx();
+      // three own stages of gathers in flight per thread (24 x 16 B): the gather is latency-bound otherwise
+      float4 b0[2 * PR], b1[2 * PR], b2[2 * PR];
+      bool v0 = issue(b0), v1 = issue(b1), v2 = issue(b2);
+      while (v0) {
+        finish(b0);
+        v0 = issue(b0);
+        if (!v1) break;
+        finish(b1);
+        v1 = issue(b1);
+        if (!v2) break;
+        finish(b2);
+        v2 = issue(b2);
+      }
     }
-
 
     // =========================================================================== epilogue
     // 8 warps: TMEM lane quarter q = warp & 3, column half = warp >> 2
@@ -278,6 +357,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams
 #pragma unroll
             for (int e4 = 0; e4 < 4; ++e4)
               r4[e4] = __ldg(reinterpret_cast<const float4*>(p.residual + row * p.res_ld + c0 + e4 * 4));
+            if (p.res_split) unsplit16(r4);
           }
           if (!live) {
 #pragma unroll
@@ -307,10 +387,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams
 #pragma unroll
             for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.f);
           }
+          float4* dst = reinterpret_cast<float4*>(p.out + row * p.out_ld + c0);
+          if (p.out_split) {
+            store_split16(dst, v);
+          } else {
 #pragma unroll
-          for (int e4 = 0; e4 < 4; ++e4)
-            *reinterpret_cast<float4*>(p.out + row * p.out_ld + c0 + e4 * 4) =
-                make_float4(v[e4 * 4], v[e4 * 4 + 1], v[e4 * 4 + 2], v[e4 * 4 + 3]);
+            for (int e4 = 0; e4 < 4; ++e4)
+              dst[e4] = make_float4(v[e4 * 4], v[e4 * 4 + 1], v[e4 * 4 + 2], v[e4 * 4 + 3]);
+          }
         }
       }
     }
@@ -337,6 +421,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams
         }
         const int s = n & na_mask;
         mbar_wait(a_full(s), ((uint32_t)n >> na_shift) & 1u);
+        if (p.in_split) fence_proxy_async();   // cp.async (generic proxy) writes -> tensor core (async proxy) reads
         tc_fence_after();
         const uint32_t a_hi = smem_u32(a_smem + (size_t)s * A_STAGE);
         const uint32_t a_lo = a_hi + A_PIECE;
@@ -347,10 +432,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams
           const uint64_t da_lo = umma_desc(a_lo + ks * 2 * A_LBO, A_LBO, 128);
           const uint64_t db_hi = umma_desc(b_hi + ks * 2 * b_lbo, b_lbo, 128);
           const uint64_t db_lo = umma_desc(b_lo + ks * 2 * b_lbo, b_lbo, 128);
-          umma_bf16(d, da_hi, db_hi, idesc, (started >> j) & 1u);
-          started |= 1u << j;
-          umma_bf16(d, da_hi, db_lo, idesc, 1u);
-          umma_bf16(d, da_lo, db_hi, idesc, 1u);
+          if (!(p.debug & 1)) {
+            umma_bf16(d, da_hi, db_hi, idesc, (started >> j) & 1u);
+            started |= 1u << j;
+            if (!(p.debug & 4)) {
+              umma_bf16(d, da_hi, db_lo, idesc, 1u);
+              umma_bf16(d, da_lo, db_hi, idesc, 1u);
+            }
+          }
         }
         umma_commit(a_empty(s));       // stage s may be overwritten once these MMAs have read it
       }
@@ -385,27 +474,54 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams
   }
 }
 
-// out = act(scale * sum_y partial[y] + shift (+ residual)), y in fixed order (deterministic)
+// out = act(scale * sum_y partial[y] + shift (+ residual)), y in fixed order (deterministic); 16 channels per thread
 __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int ksplit, long long n_out, int cout,
                                      const float* __restrict__ scale, const float* __restrict__ shift,
                                      const float* __restrict__ residual, int res_ld, float* __restrict__ out,
                                      int out_ld, int flags) {
-  const int c4n = cout >> 2;
-  const long long total = n_out * c4n;
+  const int c16n = cout >> 4;
+  const long long total = n_out * c16n;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
        t += (long long)gridDim.x * blockDim.x) {
-    const long long row = t / c4n;
-    const int c = (int)(t % c4n) * 4;
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    const long long row = t / c16n;
+    const int c = (int)(t % c16n) * 16;
+    float v[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] = 0.f;
     for (int y = 0; y < ksplit; ++y) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(partial + ((size_t)y * n_out + row) * cout + c));
-      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+      const float4* src = reinterpret_cast<const float4*>(partial + ((size_t)y * n_out + row) * cout + c);
+#pragma unroll
+      for (int e4 = 0; e4 < 4; ++e4) {
+        const float4 a = __ldg(src + e4);
+        v[e4 * 4] += a.x; v[e4 * 4 + 1] += a.y; v[e4 * 4 + 2] += a.z; v[e4 * 4 + 3] += a.w;
+      }
     }
-    if (scale) { const float4 s = __ldg(reinterpret_cast<const float4*>(scale + c)); a.x *= s.x; a.y *= s.y; a.z *= s.z; a.w *= s.w; }
-    if (shift) { const float4 s = __ldg(reinterpret_cast<const float4*>(shift + c)); a.x += s.x; a.y += s.y; a.z += s.z; a.w += s.w; }
-    if (residual) { const float4 s = __ldg(reinterpret_cast<const float4*>(residual + row * res_ld + c)); a.x += s.x; a.y += s.y; a.z += s.z; a.w += s.w; }
-    if (flags & AG3D_RELU) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
-    *reinterpret_cast<float4*>(out + row * out_ld + c) = a;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      if (scale) v[e] *= __ldg(scale + c + e);
+      if (shift) v[e] += __ldg(shift + c + e);
+    }
+    if (residual) {
+      float4 r4[4];
+#pragma unroll
+      for (int e4 = 0; e4 < 4; ++e4) r4[e4] = __ldg(reinterpret_cast<const float4*>(residual + row * res_ld + c) + e4);
+      if (flags & AG3D_RES_SPLIT) unsplit16(r4);
+#pragma unroll
+      for (int e4 = 0; e4 < 4; ++e4) {
+        v[e4 * 4] += r4[e4].x; v[e4 * 4 + 1] += r4[e4].y; v[e4 * 4 + 2] += r4[e4].z; v[e4 * 4 + 3] += r4[e4].w;
+      }
+    }
+    if (flags & AG3D_RELU) {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.f);
+    }
+    float4* dst = reinterpret_cast<float4*>(out + row * out_ld + c);
+    if (flags & AG3D_OUT_SPLIT) {
+      store_split16(dst, v);
+    } else {
+#pragma unroll
+      for (int e4 = 0; e4 < 4; ++e4) dst[e4] = make_float4(v[e4 * 4], v[e4 * 4 + 1], v[e4 * 4 + 2], v[e4 * 4 + 3]);
+    }
   }
 }
 
@@ -462,12 +578,20 @@ int spconv_tc_launch(const float* in, int in_ld, int cin, const int* nbr, int K,
   p.wp = static_cast<const uint4*>(wprep); p.cout = cout;
   p.scale = scale; p.shift = shift; p.residual = residual; p.res_ld = res_ld;
   p.out = out; p.out_ld = out_ld; p.flags = flags;
+  p.in_split = (flags & AG3D_IN_SPLIT) ? 1 : 0;
+  p.out_split = (flags & AG3D_OUT_SPLIT) ? 1 : 0;
+  p.res_split = (flags & AG3D_RES_SPLIT) ? 1 : 0;
   const TcPlan plan = tc_plan(n_out, K, cout);
   p.cpad = plan.cpad;
   p.T = plan.T;
   p.k_per = plan.k_per;
   const long long tiles = (n_out + TC_BM - 1) / TC_BM;
   p.partial = nullptr;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("AG3D_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
+    p.debug = dbg;
+  }
   if (plan.ksplit > 1) {
     AG3D_CHECK_ARG(ws && aligned16(ws) && ws_bytes >= (size_t)plan.ksplit * (size_t)n_out * cout * sizeof(float),
                    "split-K workspace too small (ag3d_spconv_workspace_bytes)");
@@ -491,7 +615,7 @@ int spconv_tc_launch(const float* in, int in_ld, int cin, const int* nbr, int K,
   spconv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(p);
   AG3D_LAUNCH_CHECK("spconv_tc");
   if (plan.ksplit > 1) {
-    const long long total = n_out * (cout / 4);
+    const long long total = n_out * (cout / 16);
     long long blocks = (total + 255) / 256;
     if (blocks > (long long)sm_count() * 8) blocks = (long long)sm_count() * 8;
     splitk_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(p.partial, plan.ksplit, n_out, cout, scale, shift, residual,

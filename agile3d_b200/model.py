@@ -147,7 +147,8 @@ class Agile3d(nn.Module):
             wtc = ops.prepare_tc_weight(head.kernel) if self.backbone.algo != ops.ALGO_SIMT else None
             self._head_tc = (hkey, wtc)
         ops.spconv_fwd(feats, None, head.kernel, pcd, None, head.bias.detach().reshape(-1).contiguous(), relu=False,
-                       algo=self.backbone.algo, weight_tc=self._head_tc[1])
+                       algo=self.backbone.algo, weight_tc=self._head_tc[1],
+                       in_split=self.backbone.algo != ops.ALGO_SIMT)
         pcd_features = BackboneFeatures(pcd, offsets, x.C)
         coordinates = BackboneFeatures(raw, offsets, x.C)
         coordinates.range = rng

@@ -161,7 +161,27 @@ def prepare_tc_weight(weight):
     return buf
 
 
-def spconv_fwd(x, nbr, weight, out, scale=None, shift=None, residual=None, relu=False, algo=ALGO_AUTO, weight_tc=None):
+IN_SPLIT, OUT_SPLIT, RES_SPLIT = 2, 4, 8
+
+
+def pack_split(x):
+    """fp32 [N,C] -> "split" rows (bf16 hi | bf16 lo per 8-channel chunk) viewed as fp32 [N,C] (same bytes)."""
+    n, c = x.shape
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.float()).to(torch.bfloat16)
+    both = torch.stack([hi.view(n, c // 8, 8), lo.view(n, c // 8, 8)], dim=2)        # [N, C/8, 2, 8] bf16
+    return both.contiguous().view(torch.int16).view(n, c * 2).view(torch.float32).view(n, c)
+
+
+def unpack_split(xs):
+    """inverse of pack_split (up to the 2^-17 relative truncation): split rows [N,C] -> fp32 [N,C]."""
+    n, c = xs.shape
+    both = xs.contiguous().view(torch.int16).view(n, c // 8, 2, 8).view(torch.bfloat16).float()
+    return (both[:, :, 0] + both[:, :, 1]).reshape(n, c)
+
+
+def spconv_fwd(x, nbr, weight, out, scale=None, shift=None, residual=None, relu=False, algo=ALGO_AUTO, weight_tc=None,
+               in_split=False, out_split=False, res_split=False):
     """out[o] = act(scale * sum_k x[nbr[k][o]] @ weight[k] + shift (+ residual[o])).  x/out/residual may be channel
     slices of wider buffers.  weight [K,cin,cout] (or [cin,cout] with nbr None)."""
     _need_cuda(x, weight, out)
@@ -185,6 +205,8 @@ def spconv_fwd(x, nbr, weight, out, scale=None, shift=None, residual=None, relu=
     # 4*N_in*Cin + 4*N_out*Cout + 8*P + 4*K*Cin*Cout (+ 4*N_out*Cout residual); flops 2*P*Cin*Cout
     nbytes = 4 * x.shape[0] * cin + 4 * n_out * cout + 8 * pairs + 4 * K * cin * cout \
         + (4 * n_out * cout if residual is not None else 0)
+    flags = (RELU if relu else 0) | (IN_SPLIT if in_split else 0) | (OUT_SPLIT if out_split else 0) \
+        | (RES_SPLIT if (res_split and residual is not None) else 0)
     ws, wsb = None, 0
     if weight_tc is not None and algo != ALGO_SIMT:
         wsb = lib().ag3d_spconv_workspace_bytes(n_out, K, cin, cout)
@@ -192,12 +214,12 @@ def spconv_fwd(x, nbr, weight, out, scale=None, shift=None, residual=None, relu=
             ws = _workspace("spconv", x.device, wsb)
     with _Timed("spconv", nbytes, 2 * pairs * cin * cout):
         check(lib().ag3d_spconv_fwd(xp, x_ld, cin, _p(nbr), K, n_out, _p(w), _p(weight_tc), cout, _p(scale), _p(shift),
-                                    rp, r_ld, op, o_ld, RELU if relu else 0, algo, _p(ws), wsb, _stream()),
+                                    rp, r_ld, op, o_ld, flags, algo, _p(ws), wsb, _stream()),
               "ag3d_spconv_fwd")
     return out
 
 
-def stem_conv_fwd(coords, feats, table, cap, ksize, weight, out, scale=None, shift=None, relu=True):
+def stem_conv_fwd(coords, feats, table, cap, ksize, weight, out, scale=None, shift=None, relu=True, out_split=False):
     _need_cuda(coords, feats, table, weight, out)
     if feats.shape[1] != 3 or weight.shape[-2:] != (3, 32) or out.shape[1] != 32:
         raise _lib.Ag3dError("stem conv is 3 -> 32 channels")
@@ -207,7 +229,8 @@ def stem_conv_fwd(coords, feats, table, cap, ksize, weight, out, scale=None, shi
     n, K = coords.shape[0], ksize ** 3
     with _Timed("stem", 16 * n + 12 * n + 4 * n * 32 + 16 * K * n + 4 * K * 96):
         check(lib().ag3d_stem_conv_fwd(_p(coords), _p(feats), n, _p(table), cap, ksize, _p(weight),
-                                       _p(scale), _p(shift), op, o_ld, RELU if relu else 0, _stream()),
+                                       _p(scale), _p(shift), op, o_ld,
+                                       (RELU if relu else 0) | (OUT_SPLIT if out_split else 0), _stream()),
               "ag3d_stem_conv_fwd")
     return out
 

@@ -35,8 +35,15 @@ extern "C" {
 #define AG3D_E_CUDA (-2)      /* a CUDA runtime call failed */
 #define AG3D_E_WORKSPACE (-3) /* workspace too small */
 
-/* spconv `flags` */
+/* spconv / stem `flags` */
 #define AG3D_RELU 1
+/* feature format of the input / output / residual rows: default fp32; *_SPLIT = every 8-channel chunk stored as
+ * 16 B of bf16 hi + 16 B of bf16 lo (x = hi + lo, relative error <= 2^-17), same bytes and leading dimension as
+ * fp32.  The tensor-core path gathers split rows with cp.async and no conversion work; the fp32 FFMA path takes
+ * fp32 rows only.                                                                                              */
+#define AG3D_IN_SPLIT 2
+#define AG3D_OUT_SPLIT 4
+#define AG3D_RES_SPLIT 8
 /* spconv `algo` */
 #define AG3D_ALGO_AUTO 0
 #define AG3D_ALGO_SIMT 1 /* exact fp32 FFMA implicit GEMM */

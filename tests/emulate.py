@@ -66,7 +66,7 @@ def prepare_tc_weight(weight):
     return None
 
 
-def spconv_fwd(x, nbr, weight, out, scale=None, shift=None, residual=None, relu=False, algo=0, weight_tc=None):
+def spconv_fwd(x, nbr, weight, out, scale=None, shift=None, residual=None, relu=False, algo=0, weight_tc=None, **fmt):
     w = weight.detach()
     w = w if w.dim() == 3 else w.unsqueeze(0)
     acc = torch.zeros((out.shape[0], w.shape[2]), dtype=x.dtype)
@@ -88,7 +88,7 @@ def spconv_fwd(x, nbr, weight, out, scale=None, shift=None, residual=None, relu=
     return out
 
 
-def stem_conv_fwd(coords, feats, table, cap, ksize, weight, out, scale=None, shift=None, relu=True):
+def stem_conv_fwd(coords, feats, table, cap, ksize, weight, out, scale=None, shift=None, relu=True, out_split=False):
     nbr = kernel_map(coords, table, cap, ksize, 1)
     return spconv_fwd(feats, nbr, weight, out, scale, shift, None, relu)
 

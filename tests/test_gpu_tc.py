@@ -83,3 +83,51 @@ def test_end_to_end_tc_backbone_vs_reference_golden(name):
     for l in range(3):
         e = rel_err(layers[l].cpu().numpy(), g["logits"][l])
         assert e < 1e-3, f"layer {l}: {e}"
+
+
+@pytest.mark.parametrize("n_out,n_in,K,cin,cout,density", [
+    (300, 300, 1, 96, 96, 1.0), (1000, 1000, 27, 64, 64, 0.45), (5000, 5000, 27, 128, 256, 0.45),
+    (9000, 2500, 8, 256, 128, 0.125), (400, 400, 27, 256, 256, 0.4), (40000, 40000, 27, 96, 96, 0.46),
+])
+def test_spconv_tc_split_rows_vs_fp32(n_out, n_in, K, cin, cout, density):
+    """Same layer with every feature tensor stored as bf16 hi/lo pair rows (the backbone's tensor-core format)."""
+    from agile3d_b200 import ops
+    g = torch.Generator().manual_seed(n_out + K + cin)
+    x = torch.randn((n_in, cin), generator=g).to(DEV)
+    w = (torch.randn((K, cin, cout), generator=g) / np.sqrt(cin * max(1.0, K * density))).to(DEV)
+    nbr = None if density >= 1.0 else _rand_map(n_out, n_in, K, density, g).to(DEV)
+    sc, sh = (torch.rand(cout, generator=g) + 0.5).to(DEV), (torch.randn(cout, generator=g) * 0.1).to(DEV)
+    res = torch.randn((n_out, cout), generator=g).to(DEV)
+    ref = torch.empty((n_out, cout), device=DEV)
+    ops.spconv_fwd(x, nbr, w, ref, sc, sh, res, relu=True, algo=ops.ALGO_SIMT)
+    # pack/unpack round trip is exact to 2^-17
+    assert rel_err(ops.unpack_split(ops.pack_split(x)).cpu().numpy(), x.cpu().numpy()) < 1e-5
+    xin = torch.zeros((n_in, cin + 32), device=DEV)
+    xin[:, 32:] = ops.pack_split(x)
+    buf = torch.full((n_out, cout + 64), -7.0, device=DEV)
+    ops.spconv_fwd(xin[:, 32:], nbr, w, buf[:, 64:], sc, sh, ops.pack_split(res), relu=True, algo=ops.ALGO_TC,
+                   weight_tc=ops.prepare_tc_weight(w), in_split=True, out_split=True, res_split=True)
+    got = ops.unpack_split(buf[:, 64:].contiguous())
+    assert rel_err(got.cpu().numpy(), ref.cpu().numpy()) < 2e-4
+    assert bool((buf[:, :64] == -7.0).all())
+    # split input, fp32 output (the head convolution)
+    out32 = torch.empty((n_out, cout), device=DEV)
+    ops.spconv_fwd(xin[:, 32:], nbr, w, out32, sc, sh, res, relu=True, algo=ops.ALGO_TC,
+                   weight_tc=ops.prepare_tc_weight(w), in_split=True)
+    assert rel_err(out32.cpu().numpy(), ref.cpu().numpy()) < 2e-4
+
+
+def test_stem_split_output():
+    from agile3d_b200 import ops
+    rng = np.random.default_rng(3)
+    c = np.unique(rng.integers(0, 30, size=(4000, 3)), axis=0)
+    coords = torch.from_numpy(np.concatenate([np.zeros((c.shape[0], 1)), c], 1).astype(np.int32)).to(DEV)
+    g = torch.Generator().manual_seed(1)
+    f = torch.rand((coords.shape[0], 3), generator=g).to(DEV)
+    w = (torch.randn((125, 3, 32), generator=g) * 0.1).to(DEV)
+    table, cap, _ = ops.hash_build(coords)
+    a = torch.empty((coords.shape[0], 32), device=DEV)
+    b = torch.empty((coords.shape[0], 32), device=DEV)
+    ops.stem_conv_fwd(coords, f, table, cap, 5, w, a)
+    ops.stem_conv_fwd(coords, f, table, cap, 5, w, b, out_split=True)
+    assert rel_err(ops.unpack_split(b).cpu().numpy(), a.cpu().numpy()) < 1e-5
