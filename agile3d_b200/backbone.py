@@ -153,6 +153,7 @@ class Res16UNet34C(nn.Module):
             setattr(self, f"block{5 + j}", _stage(P[4 + j] + skips[j], P[4 + j], L[4 + j], m))
             c = P[4 + j]
         self.algo = ops.ALGO_AUTO
+        self.split_rows = False     # keep activations as bf16 hi/lo pair rows between tensor-core layers (measured slower)
         self._fold_cache = None
 
     # -- per-checkpoint constants (folded BatchNorm scale/shift, bf16 hi/lo weight images for the tensor-core
@@ -171,7 +172,7 @@ class Res16UNet34C(nn.Module):
     def _conv(self, name, conv, x, nbr, out, scale, shift, fold, residual=None, relu=False):
         # tensor-core mode keeps every backbone activation as bf16 hi/lo pair rows ("split", same bytes as fp32):
         # producers split once in their epilogue, consumers gather with cp.async and no conversion work
-        sp = self.algo != ops.ALGO_SIMT
+        sp = self.split_rows and self.algo != ops.ALGO_SIMT
         return ops.spconv_fwd(x, nbr, conv.kernel, out, scale, shift, residual=residual, relu=relu, algo=self.algo,
                               weight_tc=fold.get("tc:" + name), in_split=sp, out_split=sp, res_split=sp)
 
@@ -219,7 +220,7 @@ class Res16UNet34C(nn.Module):
         s0, b0 = fold["bn0"]
         ops.stem_conv_fwd(maps.coords[0], st.F, maps.tables[0], maps.caps[0], self.conv1_kernel_size,
                           self.conv0p1s1.kernel, cat[0][:, up_c[0]:], s0, b0, relu=True,
-                          out_split=self.algo != ops.ALGO_SIMT)
+                          out_split=self.split_rows and self.algo != ops.ALGO_SIMT)
         y = cat[0][:, up_c[0]:]
         for i, tag in enumerate(_ENC):                                  # encoder
             conv = getattr(self, f"conv{tag}s2")

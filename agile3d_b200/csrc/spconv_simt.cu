@@ -138,12 +138,12 @@ stem_conv_kernel(const int4* __restrict__ coords, const float* __restrict__ feat
     if (scale) v *= __ldg(scale + lane);
     if (shift) v += __ldg(shift + lane);
     if (flags & AG3D_RELU) v = fmaxf(v, 0.f);
-    if (flags & AG3D_OUT_SPLIT) {      // bf16 hi/lo pair rows: chunk of 8 channels = 16 B hi | 16 B lo
+    if (flags & AG3D_OUT_SPLIT) {      // bf16 hi/lo pair rows: 32-channel slab = 64 B hi | 64 B lo
       const __nv_bfloat16 hi = __float2bfloat16_rn(v);
       const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(out + row * out_ld) + (lane >> 3) * 16 + (lane & 7);
+      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(out + row * out_ld) + lane;
       dst[0] = hi;
-      dst[8] = lo;
+      dst[32] = lo;
     } else {
       out[row * out_ld + lane] = v;
     }

@@ -57,40 +57,39 @@ __global__ void weight_prep_kernel(const float* __restrict__ w, int K, int cin, 
 }
 
 // ---------------------------------------------------------------------------------------------- split format
-// "split" feature rows: every 8-channel chunk is stored as 16 B of bf16 hi followed by 16 B of bf16 lo
-// (x = hi + lo + O(2^-17 |x|)); a row of C channels occupies exactly the 4*C bytes of the fp32 row, so leading
-// dimensions, channel slices and concat buffers are unchanged.
+// "split" feature rows: every 32-channel slab (128 B) is stored as 64 B of bf16 hi (32 channels) followed by 64 B of
+// bf16 lo (x = hi + lo + O(2^-17 |x|)).  A row of C channels occupies exactly the 4*C bytes of the fp32 row, so
+// leading dimensions, 32-channel-aligned slices and concat buffers are unchanged, and a gathered slab is 128
+// contiguous bytes whose 16-byte pieces are exactly the UMMA core-matrix rows (4 hi pieces, then 4 lo pieces).
 __device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
-// 16 channels stored split (4 x 16 B: hi0 lo0 hi1 lo1) -> 16 floats, in place in r4[4]
-__device__ __forceinline__ void unsplit16(float4 (&r4)[4]) {
-  float v[16];
+// byte offset of the hi half of channels c0 .. c0+15 (c0 % 16 == 0) inside a split row; the lo half is 64 B further
+__device__ __forceinline__ size_t split_off16(int c0) { return (size_t)(c0 >> 5) * 128 + (size_t)((c0 >> 4) & 1) * 32; }
+
+__device__ __forceinline__ void load_split16(const float* row, int c0, float* v) {
+  const uint4* h = reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(row) + split_off16(c0));
+  const uint4 hh[2] = {__ldg(h), __ldg(h + 1)}, ll[2] = {__ldg(h + 4), __ldg(h + 5)};
+  const uint32_t* hp = reinterpret_cast<const uint32_t*>(hh);
+  const uint32_t* lp = reinterpret_cast<const uint32_t*>(ll);
 #pragma unroll
-  for (int c = 0; c < 2; ++c) {
-    const uint32_t* h = reinterpret_cast<const uint32_t*>(&r4[2 * c]);
-    const uint32_t* l = reinterpret_cast<const uint32_t*>(&r4[2 * c + 1]);
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      v[c * 8 + 2 * e] = __uint_as_float(h[e] << 16) + __uint_as_float(l[e] << 16);
-      v[c * 8 + 2 * e + 1] = __uint_as_float(h[e] & 0xFFFF0000u) + __uint_as_float(l[e] & 0xFFFF0000u);
-    }
+  for (int e = 0; e < 8; ++e) {
+    v[2 * e] = __uint_as_float(hp[e] << 16) + __uint_as_float(lp[e] << 16);
+    v[2 * e + 1] = __uint_as_float(hp[e] & 0xFFFF0000u) + __uint_as_float(lp[e] & 0xFFFF0000u);
   }
-#pragma unroll
-  for (int e4 = 0; e4 < 4; ++e4) r4[e4] = make_float4(v[e4 * 4], v[e4 * 4 + 1], v[e4 * 4 + 2], v[e4 * 4 + 3]);
 }
-__device__ __forceinline__ void store_split16(float4* dst, const float* v) {
+__device__ __forceinline__ void store_split16(float* row, int c0, const float* v) {
+  uint32_t h[8], l[8];
 #pragma unroll
-  for (int c = 0; c < 2; ++c) {
-    uint32_t h[4], l[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) split2(v[c * 8 + 2 * e], v[c * 8 + 2 * e + 1], h[e], l[e]);
-    reinterpret_cast<uint4*>(dst)[2 * c] = make_uint4(h[0], h[1], h[2], h[3]);
-    reinterpret_cast<uint4*>(dst)[2 * c + 1] = make_uint4(l[0], l[1], l[2], l[3]);
-  }
+  for (int e = 0; e < 8; ++e) split2(v[2 * e], v[2 * e + 1], h[e], l[e]);
+  uint4* d = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(row) + split_off16(c0));
+  d[0] = make_uint4(h[0], h[1], h[2], h[3]);
+  d[1] = make_uint4(h[4], h[5], h[6], h[7]);
+  d[4] = make_uint4(l[0], l[1], l[2], l[3]);
+  d[5] = make_uint4(l[4], l[5], l[6], l[7]);
 }
 
 // ---------------------------------------------------------------------------------------------- main kernel
@@ -121,7 +120,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams
   int* n_stage_s = reinterpret_cast<int*>(smem + 288);
   uint32_t* stage_list = reinterpret_cast<uint32_t*>(smem + TC_BAR_BYTES);   // [TC_MAX_STAGES] (k << 16 | slab << 8 | tile)
   const uint32_t b_stage_bytes = (uint32_t)p.cout * 128u;
-  unsigned char* b_smem = smem + TC_BAR_BYTES + TC_LIST_BYTES;
+  int* nbr_s = reinterpret_cast<int*>(smem + TC_BAR_BYTES + TC_LIST_BYTES);   // [k_per][T*128] this CTA's slice of the map
+  const int TR = p.T * TC_BM;
+  unsigned char* b_smem = smem + TC_BAR_BYTES + TC_LIST_BYTES + (size_t)p.k_per * TR * 4;
   unsigned char* a_smem = b_smem + (size_t)p.NB * b_stage_bytes;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -167,13 +168,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams
       const int j = (tid >> 7) + 2 * jj;
       const long long row = row0 + (long long)j * TC_BM + (tid & 127);
       uint32_t mine = 0;
-      if (j < T_here && row < p.n_out) {
-        if (p.nbr) {
-          const int* col = p.nbr + row;
+      if (j < p.T) {
+        int* dst = nbr_s + j * TC_BM + (tid & 127);                 // column of this row in the staged slice
+        if (j < T_here && row < p.n_out) {
+          if (p.nbr) {
+            const int* col = p.nbr + row;
 #pragma unroll 9
-          for (int k = k_lo; k < k_hi; ++k) mine |= (__ldg(col + (long long)k * p.n_out) >= 0 ? 1u : 0u) << k;
+            for (int k = k_lo; k < k_hi; ++k) {
+              const int v = __ldg(col + (long long)k * p.n_out);
+              dst[(k - k_lo) * TR] = v;
+              mine |= (v >= 0 ? 1u : 0u) << k;
+            }
+          } else {
+            dst[0] = (int)row;                                      // identity map: K == 1, never split
+            mine = 1u;
+          }
         } else {
-          mine = 1u;                                              // identity map: K == 1, never split
+          for (int k = k_lo; k < k_hi; ++k) dst[(k - k_lo) * TR] = -1;
         }
       }
 #pragma unroll
@@ -223,32 +234,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams
       const int r = rbase + 32 * i;
       st_off[i] = (uint32_t)(kc * A_LBO + (r >> 3) * 128 + (r & 7) * 16);
     }
-    const long long rows_left = p.n_out - row0 - rbase;     // row (j, i) is real iff j*128 + 32*i < rows_left
     const float* in_kc = p.in + kc * 8;
-    const int* nbr_r = p.nbr ? p.nbr + row0 + rbase : nullptr;
 
     if (p.in_split) {
       // ---- input already stored as bf16 hi/lo pairs: the gather is a pure byte copy, done by cp.async straight
       //      into the operand stage (no registers, no ALU); completion is tracked by the stage's mbarrier, so up to
       //      NA stages of gathers are in flight per group.
-      const unsigned char* in_b = reinterpret_cast<const unsigned char*>(p.in) + kc * 32;
+      const unsigned char* in_b = reinterpret_cast<const unsigned char*>(p.in) + kc * 16;   // hi piece kc; lo at +64
       const size_t row_bytes = (size_t)p.in_ld * 4;
-      int idx_cur[PR], idx_nxt[PR];
-      uint32_t c_cur = 0, c_nxt = 0;
-      auto fetch_idx = [&](int n, int (&idx)[PR], uint32_t& cslab) {
+      for (int n = grp; n < n_stage; n += PG) {
         const uint32_t e = stage_list[n];
         const int k = (int)(e >> 16), j = (int)(e & 0xFFu);
-        cslab = (e >> 8) & 0xFFu;
+        const uint32_t c_cur = (e >> 8) & 0xFFu;
+        const int* col = nbr_s + (k - k_lo) * TR + j * TC_BM + rbase;
+        int idx_cur[PR];
 #pragma unroll
-        for (int i = 0; i < PR; ++i) {
-          const int off = j * TC_BM + 32 * i;
-          idx[i] = -1;
-          if (off < rows_left) idx[i] = nbr_r ? __ldg(nbr_r + (long long)k * p.n_out + off) : (int)(row0 + rbase + off);
-        }
-      };
-      if (grp < n_stage) fetch_idx(grp, idx_cur, c_cur);
-      for (int n = grp; n < n_stage; n += PG) {
-        if (n + PG < n_stage) fetch_idx(n + PG, idx_nxt, c_nxt);
+        for (int i = 0; i < PR; ++i) idx_cur[i] = col[32 * i];
         const int s = n & na_mask;
         mbar_wait(a_empty(s), (((uint32_t)n >> na_shift) & 1u) ^ 1u);
         const uint32_t st = smem_u32(a_smem + (size_t)s * A_STAGE);
@@ -258,12 +259,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams
           const bool ok = idx_cur[i] >= 0;
           const unsigned char* g = ok ? src + (size_t)idx_cur[i] * row_bytes : src;
           cp_async16_zfill(st + st_off[i], g, ok ? 16u : 0u);
-          cp_async16_zfill(st + A_PIECE + st_off[i], g + 16, ok ? 16u : 0u);
+          cp_async16_zfill(st + A_PIECE + st_off[i], g + 64, ok ? 16u : 0u);
         }
         cp_async_mbar_arrive_noinc(a_full(s));
-#pragma unroll
-        for (int i = 0; i < PR; ++i) idx_cur[i] = idx_nxt[i];
-        c_cur = c_nxt;
       }
     } else {
       int idx_ld[PR];                  // neighbour rows of stage n_issued (prefetched one own-stage ahead)
@@ -273,12 +271,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams
         const uint32_t e = stage_list[n_issued];
         const int k = (int)(e >> 16), j = (int)(e & 0xFFu);
         c_ld = (e >> 8) & 0xFFu;
-  #pragma unroll
-        for (int i = 0; i < PR; ++i) {
-          const int off = j * TC_BM + 32 * i;
-          idx_ld[i] = -1;
-          if (off < rows_left) idx_ld[i] = nbr_r ? __ldg(nbr_r + (long long)k * p.n_out + off) : (int)(row0 + rbase + off);
-        }
+        const int* col = nbr_s + (k - k_lo) * TR + j * TC_BM + rbase;
+#pragma unroll
+        for (int i = 0; i < PR; ++i) idx_ld[i] = col[32 * i];
       };
       auto issue = [&](float4 (&buf)[2 * PR]) -> bool {
         if (n_issued >= n_stage) return false;
@@ -339,7 +334,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams
     const int q = warp & 3, half = warp >> 2;
     const int ncol = p.cout >> 1;    // columns per half (multiple of 16)
     const bool relu = p.flags & AG3D_RELU;
-    for (int j = 0; j < T_here; ++j) {
+    for (int j = 0; j < ((p.debug & 64) ? 0 : T_here); ++j) {
       const long long row = row0 + (long long)j * TC_BM + q * 32 + lane;
       const bool live = kmask_s[j] != 0u;
       for (int c0 = half * ncol; c0 < (half + 1) * ncol; c0 += 16) {
@@ -354,10 +349,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams
         } else if (row < p.n_out) {
           float4 r4[4];
           if (p.residual) {
+            if (p.res_split) {
+              load_split16(p.residual + row * p.res_ld, c0, reinterpret_cast<float*>(r4));
+            } else {
 #pragma unroll
-            for (int e4 = 0; e4 < 4; ++e4)
-              r4[e4] = __ldg(reinterpret_cast<const float4*>(p.residual + row * p.res_ld + c0 + e4 * 4));
-            if (p.res_split) unsplit16(r4);
+              for (int e4 = 0; e4 < 4; ++e4)
+                r4[e4] = __ldg(reinterpret_cast<const float4*>(p.residual + row * p.res_ld + c0 + e4 * 4));
+            }
           }
           if (!live) {
 #pragma unroll
@@ -389,7 +387,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams
           }
           float4* dst = reinterpret_cast<float4*>(p.out + row * p.out_ld + c0);
           if (p.out_split) {
-            store_split16(dst, v);
+            store_split16(p.out + row * p.out_ld, c0, v);
           } else {
 #pragma unroll
             for (int e4 = 0; e4 < 4; ++e4)
@@ -457,10 +455,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams
         const int k = (int)(e >> 16), c = (int)((e >> 8) & 0xFFu);
         const int sb = n_b & nb_mask;
         mbar_wait(b_empty(sb), (((uint32_t)n_b >> nb_shift) & 1u) ^ 1u);
-        mbar_arrive_expect_tx(b_full(sb), b_stage_bytes);
-        const unsigned char* src = reinterpret_cast<const unsigned char*>(p.wp) +
-                                   ((size_t)k * n_slab + c) * (size_t)b_stage_bytes;
-        bulk_g2s(smem_u32(b_smem + (size_t)sb * b_stage_bytes), src, b_stage_bytes, b_full(sb));
+        if (p.debug & 32) {
+          mbar_arrive(b_full(sb));
+        } else {
+          mbar_arrive_expect_tx(b_full(sb), b_stage_bytes);
+          const unsigned char* src = reinterpret_cast<const unsigned char*>(p.wp) +
+                                     ((size_t)k * n_slab + c) * (size_t)b_stage_bytes;
+          bulk_g2s(smem_u32(b_smem + (size_t)sb * b_stage_bytes), src, b_stage_bytes, b_full(sb));
+        }
         ++n_b;
       }
     }
@@ -503,9 +505,12 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int kspl
     }
     if (residual) {
       float4 r4[4];
+      if (flags & AG3D_RES_SPLIT) {
+        load_split16(residual + row * res_ld, c, reinterpret_cast<float*>(r4));
+      } else {
 #pragma unroll
-      for (int e4 = 0; e4 < 4; ++e4) r4[e4] = __ldg(reinterpret_cast<const float4*>(residual + row * res_ld + c) + e4);
-      if (flags & AG3D_RES_SPLIT) unsplit16(r4);
+        for (int e4 = 0; e4 < 4; ++e4) r4[e4] = __ldg(reinterpret_cast<const float4*>(residual + row * res_ld + c) + e4);
+      }
 #pragma unroll
       for (int e4 = 0; e4 < 4; ++e4) {
         v[e4 * 4] += r4[e4].x; v[e4 * 4 + 1] += r4[e4].y; v[e4 * 4 + 2] += r4[e4].z; v[e4 * 4 + 3] += r4[e4].w;
@@ -517,7 +522,7 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int kspl
     }
     float4* dst = reinterpret_cast<float4*>(out + row * out_ld + c);
     if (flags & AG3D_OUT_SPLIT) {
-      store_split16(dst, v);
+      store_split16(out + row * out_ld, c, v);
     } else {
 #pragma unroll
       for (int e4 = 0; e4 < 4; ++e4) dst[e4] = make_float4(v[e4 * 4], v[e4 * 4 + 1], v[e4 * 4 + 2], v[e4 * 4 + 3]);
@@ -599,7 +604,7 @@ int spconv_tc_launch(const float* in, int in_ld, int cin, const int* nbr, int K,
   }
   p.tmem_cols = pow2_at_least(p.T * p.cpad, 32);
   p.NB = (cout <= 128) ? 4 : 2;
-  const size_t fixed = TC_BAR_BYTES + TC_LIST_BYTES + (size_t)p.NB * (size_t)cout * 128;
+  const size_t fixed = TC_BAR_BYTES + TC_LIST_BYTES + (size_t)p.k_per * p.T * TC_BM * 4 + (size_t)p.NB * (size_t)cout * 128;
   int na = (int)((200 * 1024 - fixed) / A_STAGE);
   na = na >= 8 ? 8 : (na >= 4 ? 4 : 2);
   p.NA = na;

@@ -148,7 +148,7 @@ class Agile3d(nn.Module):
             self._head_tc = (hkey, wtc)
         ops.spconv_fwd(feats, None, head.kernel, pcd, None, head.bias.detach().reshape(-1).contiguous(), relu=False,
                        algo=self.backbone.algo, weight_tc=self._head_tc[1],
-                       in_split=self.backbone.algo != ops.ALGO_SIMT)
+                       in_split=self.backbone.split_rows and self.backbone.algo != ops.ALGO_SIMT)
         pcd_features = BackboneFeatures(pcd, offsets, x.C)
         coordinates = BackboneFeatures(raw, offsets, x.C)
         coordinates.range = rng

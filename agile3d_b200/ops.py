@@ -165,18 +165,18 @@ IN_SPLIT, OUT_SPLIT, RES_SPLIT = 2, 4, 8
 
 
 def pack_split(x):
-    """fp32 [N,C] -> "split" rows (bf16 hi | bf16 lo per 8-channel chunk) viewed as fp32 [N,C] (same bytes)."""
+    """fp32 [N,C] -> "split" rows (64 B bf16 hi | 64 B bf16 lo per 32-channel slab) viewed as fp32 [N,C] (same bytes)."""
     n, c = x.shape
     hi = x.to(torch.bfloat16)
     lo = (x - hi.float()).to(torch.bfloat16)
-    both = torch.stack([hi.view(n, c // 8, 8), lo.view(n, c // 8, 8)], dim=2)        # [N, C/8, 2, 8] bf16
+    both = torch.stack([hi.view(n, c // 32, 32), lo.view(n, c // 32, 32)], dim=2)    # [N, C/32, 2, 32] bf16
     return both.contiguous().view(torch.int16).view(n, c * 2).view(torch.float32).view(n, c)
 
 
 def unpack_split(xs):
     """inverse of pack_split (up to the 2^-17 relative truncation): split rows [N,C] -> fp32 [N,C]."""
     n, c = xs.shape
-    both = xs.contiguous().view(torch.int16).view(n, c // 8, 2, 8).view(torch.bfloat16).float()
+    both = xs.contiguous().view(torch.int16).view(n, c // 32, 2, 32).view(torch.bfloat16).float()
     return (both[:, :, 0] + both[:, :, 1]).reshape(n, c)
 
 

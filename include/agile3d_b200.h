@@ -37,8 +37,8 @@ extern "C" {
 
 /* spconv / stem `flags` */
 #define AG3D_RELU 1
-/* feature format of the input / output / residual rows: default fp32; *_SPLIT = every 8-channel chunk stored as
- * 16 B of bf16 hi + 16 B of bf16 lo (x = hi + lo, relative error <= 2^-17), same bytes and leading dimension as
+/* feature format of the input / output / residual rows: default fp32; *_SPLIT = every 32-channel slab stored as
+ * 64 B of bf16 hi + 64 B of bf16 lo (x = hi + lo, relative error <= 2^-17), same bytes and leading dimension as
  * fp32.  The tensor-core path gathers split rows with cp.async and no conversion work; the fp32 FFMA path takes
  * fp32 rows only.                                                                                              */
 #define AG3D_IN_SPLIT 2
