@@ -153,7 +153,7 @@ class Res16UNet34C(nn.Module):
             setattr(self, f"block{5 + j}", _stage(P[4 + j] + skips[j], P[4 + j], L[4 + j], m))
             c = P[4 + j]
         self.algo = ops.ALGO_AUTO
-        self.split_rows = False     # keep activations as bf16 hi/lo pair rows between tensor-core layers (measured slower)
+        self.split_rows = True      # keep activations as bf16 hi/lo pair rows between tensor-core layers
         self._fold_cache = None
 
     # -- per-checkpoint constants (folded BatchNorm scale/shift, bf16 hi/lo weight images for the tensor-core

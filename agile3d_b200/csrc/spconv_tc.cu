@@ -111,7 +111,9 @@ struct TcParams {
   int tmem_cols;    // allocation (pow2, 32..512)
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams p) {
+// SPLIT = input rows are bf16 hi/lo pairs: cp.async gather, few registers, two CTAs per SM
+template <bool SPLIT>
+__global__ void __launch_bounds__(TC_THREADS, SPLIT ? 2 : 1) spconv_tc_kernel(const TcParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   // barrier block: bars[0..7] a_full, [8..15] a_empty, [16..19] b_full, [20..23] b_empty, [24] acc_full
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
@@ -122,7 +124,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams
   const uint32_t b_stage_bytes = (uint32_t)p.cout * 128u;
   int* nbr_s = reinterpret_cast<int*>(smem + TC_BAR_BYTES + TC_LIST_BYTES);   // [k_per][T*128] this CTA's slice of the map
   const int TR = p.T * TC_BM;
-  unsigned char* b_smem = smem + TC_BAR_BYTES + TC_LIST_BYTES + (size_t)p.k_per * TR * 4;
+  unsigned char* b_smem = smem + TC_BAR_BYTES + TC_LIST_BYTES + (SPLIT ? (size_t)0 : (size_t)p.k_per * TR * 4);
   unsigned char* a_smem = b_smem + (size_t)p.NB * b_stage_bytes;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -144,7 +146,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams
   const uint32_t acc_full = bar_base + 8u * 24;
 
   if (tid == 0) {
-    for (int s = 0; s < p.NA; ++s) { mbar_init(a_full(s), p.in_split ? 128 : TC_PROD_WARPS / 2); mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < p.NA; ++s) { mbar_init(a_full(s), SPLIT ? 128 : TC_PROD_WARPS / 2); mbar_init(a_empty(s), 1); }
     for (int s = 0; s < p.NB; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
     mbar_init(acc_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -176,14 +178,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams
 #pragma unroll 9
             for (int k = k_lo; k < k_hi; ++k) {
               const int v = __ldg(col + (long long)k * p.n_out);
-              dst[(k - k_lo) * TR] = v;
+              if constexpr (!SPLIT) dst[(k - k_lo) * TR] = v;
               mine |= (v >= 0 ? 1u : 0u) << k;
             }
           } else {
-            dst[0] = (int)row;                                      // identity map: K == 1, never split
+            if constexpr (!SPLIT) dst[0] = (int)row;                // identity map: K == 1, never split
             mine = 1u;
           }
-        } else {
+        } else if constexpr (!SPLIT) {
           for (int k = k_lo; k < k_hi; ++k) dst[(k - k_lo) * TR] = -1;
         }
       }
@@ -236,20 +238,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams
     }
     const float* in_kc = p.in + kc * 8;
 
-    if (p.in_split) {
+    if constexpr (SPLIT) {
       // ---- input already stored as bf16 hi/lo pairs: the gather is a pure byte copy, done by cp.async straight
       //      into the operand stage (no registers, no ALU); completion is tracked by the stage's mbarrier, so up to
       //      NA stages of gathers are in flight per group.
       const unsigned char* in_b = reinterpret_cast<const unsigned char*>(p.in) + kc * 16;   // hi piece kc; lo at +64
       const size_t row_bytes = (size_t)p.in_ld * 4;
-      for (int n = grp; n < n_stage; n += PG) {
+      const long long rows_left = p.n_out - row0 - rbase;   // row (j, i) is real iff j*128 + 32*i < rows_left
+      const int* nbr_r = p.nbr ? p.nbr + row0 + rbase : nullptr;
+      int idx_cur[PR], idx_nxt[PR];
+      uint32_t c_cur = 0, c_nxt = 0;
+      auto fetch_idx = [&](int n, int (&idx)[PR], uint32_t& cslab) {
         const uint32_t e = stage_list[n];
         const int k = (int)(e >> 16), j = (int)(e & 0xFFu);
-        const uint32_t c_cur = (e >> 8) & 0xFFu;
-        const int* col = nbr_s + (k - k_lo) * TR + j * TC_BM + rbase;
-        int idx_cur[PR];
+        cslab = (e >> 8) & 0xFFu;
 #pragma unroll
-        for (int i = 0; i < PR; ++i) idx_cur[i] = col[32 * i];
+        for (int i = 0; i < PR; ++i) {
+          const int off = j * TC_BM + 32 * i;
+          idx[i] = -1;
+          if (off < rows_left) idx[i] = nbr_r ? __ldg(nbr_r + (long long)k * p.n_out + off) : (int)(row0 + rbase + off);
+        }
+      };
+      if (grp < n_stage) fetch_idx(grp, idx_cur, c_cur);
+      for (int n = grp; n < n_stage; n += PG) {
+        if (n + PG < n_stage) fetch_idx(n + PG, idx_nxt, c_nxt);
         const int s = n & na_mask;
         mbar_wait(a_empty(s), (((uint32_t)n >> na_shift) & 1u) ^ 1u);
         const uint32_t st = smem_u32(a_smem + (size_t)s * A_STAGE);
@@ -262,6 +274,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams
           cp_async16_zfill(st + A_PIECE + st_off[i], g + 64, ok ? 16u : 0u);
         }
         cp_async_mbar_arrive_noinc(a_full(s));
+#pragma unroll
+        for (int i = 0; i < PR; ++i) idx_cur[i] = idx_nxt[i];
+        c_cur = c_nxt;
       }
     } else {
       int idx_ld[PR];                  // neighbour rows of stage n_issued (prefetched one own-stage ahead)
@@ -419,7 +434,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spconv_tc_kernel(const TcParams
         }
         const int s = n & na_mask;
         mbar_wait(a_full(s), ((uint32_t)n >> na_shift) & 1u);
-        if (p.in_split) fence_proxy_async();   // cp.async (generic proxy) writes -> tensor core (async proxy) reads
+        if constexpr (SPLIT) fence_proxy_async();   // cp.async (generic proxy) writes -> tensor core (async proxy) reads
         tc_fence_after();
         const uint32_t a_hi = smem_u32(a_smem + (size_t)s * A_STAGE);
         const uint32_t a_lo = a_hi + A_PIECE;
@@ -541,10 +556,11 @@ struct TcPlan { int cpad, T, ksplit, k_per; };
 
 // tiles per CTA: minimise waves * (T gathers + one weight stage); weight stage cost relative to a gather = cout/128.
 // Small levels (few tiles) are weight-streaming bound on a handful of SMs: split the kernel offsets over gridDim.y.
-static TcPlan tc_plan(long long n_out, int K, int cout) {
+static TcPlan tc_plan(long long n_out, int K, int cout, bool split = false) {
   TcPlan pl;
   pl.cpad = pow2_at_least(cout, 32);
-  const int t_max = std::min(TC_MAX_T, 512 / pl.cpad);
+  // split mode runs two CTAs per SM: each may hold 256 TMEM columns
+  const int t_max = std::max(1, std::min(split ? 2 : TC_MAX_T, (split ? 256 : 512) / pl.cpad));
   const long long tiles = (n_out + TC_BM - 1) / TC_BM;
   const int sms = sm_count();
   int best_t = 1;
@@ -565,7 +581,9 @@ static TcPlan tc_plan(long long n_out, int K, int cout) {
 }
 
 size_t spconv_tc_workspace_bytes(long long n_out, int K, int cout) {
-  const TcPlan pl = tc_plan(n_out, K, cout);
+  const TcPlan pl = tc_plan(n_out, K, cout, false);
+  const TcPlan ps = tc_plan(n_out, K, cout, true);
+  if (ps.ksplit > pl.ksplit) return (size_t)ps.ksplit * (size_t)n_out * cout * sizeof(float);
   return pl.ksplit > 1 ? (size_t)pl.ksplit * (size_t)n_out * cout * sizeof(float) : 0;
 }
 
@@ -586,7 +604,8 @@ int spconv_tc_launch(const float* in, int in_ld, int cin, const int* nbr, int K,
   p.in_split = (flags & AG3D_IN_SPLIT) ? 1 : 0;
   p.out_split = (flags & AG3D_OUT_SPLIT) ? 1 : 0;
   p.res_split = (flags & AG3D_RES_SPLIT) ? 1 : 0;
-  const TcPlan plan = tc_plan(n_out, K, cout);
+  const bool split = p.in_split != 0;
+  const TcPlan plan = tc_plan(n_out, K, cout, split);
   p.cpad = plan.cpad;
   p.T = plan.T;
   p.k_per = plan.k_per;
@@ -603,9 +622,11 @@ int spconv_tc_launch(const float* in, int in_ld, int cin, const int* nbr, int K,
     p.partial = static_cast<float*>(ws);
   }
   p.tmem_cols = pow2_at_least(p.T * p.cpad, 32);
-  p.NB = (cout <= 128) ? 4 : 2;
-  const size_t fixed = TC_BAR_BYTES + TC_LIST_BYTES + (size_t)p.k_per * p.T * TC_BM * 4 + (size_t)p.NB * (size_t)cout * 128;
-  int na = (int)((200 * 1024 - fixed) / A_STAGE);
+  p.NB = (cout <= 128 && !split) ? 4 : 2;
+  const size_t fixed = TC_BAR_BYTES + TC_LIST_BYTES + (split ? 0 : (size_t)p.k_per * p.T * TC_BM * 4) +
+                       (size_t)p.NB * (size_t)cout * 128;
+  const size_t budget = split ? 110 * 1024 : 200 * 1024;     // split: two CTAs per SM
+  int na = (int)((budget - fixed) / A_STAGE);
   na = na >= 8 ? 8 : (na >= 4 ? 4 : 2);
   p.NA = na;
   p.na_log2 = na == 8 ? 3 : (na == 4 ? 2 : 1);
@@ -613,11 +634,13 @@ int spconv_tc_launch(const float* in, int in_ld, int cin, const int* nbr, int K,
   const size_t smem = fixed + (size_t)na * A_STAGE;
   static bool attr = false;
   if (!attr) {
-    AG3D_CUDA(cudaFuncSetAttribute(spconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    AG3D_CUDA(cudaFuncSetAttribute(spconv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    AG3D_CUDA(cudaFuncSetAttribute(spconv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
     attr = true;
   }
   const dim3 grid((unsigned)((tiles + p.T - 1) / p.T), (unsigned)plan.ksplit);
-  spconv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(p);
+  if (split) spconv_tc_kernel<true><<<grid, TC_THREADS, smem, st>>>(p);
+  else spconv_tc_kernel<false><<<grid, TC_THREADS, smem, st>>>(p);
   AG3D_LAUNCH_CHECK("spconv_tc");
   if (plan.ksplit > 1) {
     const long long total = n_out * (cout / 16);
