@@ -184,10 +184,10 @@ def run_ours(args, rank, world, local_rank):
     from agile3d_b200.weights import default_args, synth_state_dict
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    import torch.distributed as dist
+    from agile3d_b200 import dist as agd
     dist_on = world > 1
-    if dist_on:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+    agd.init_from_env(backend="nccl", device=dev)       # no-op for a single process
     model = agile3d_b200.build_model(default_args()).eval()
     model.load_state_dict(synth_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, seed=5))
     model = model.to(dev)
@@ -223,7 +223,7 @@ def run_ours(args, rank, world, local_rank):
     def barrier():
         torch.cuda.synchronize()
         if dist_on:
-            dist.barrier()
+            agd.barrier()
             torch.cuda.synchronize()
 
     def timed(fn, steps):
@@ -234,10 +234,7 @@ def run_ours(args, rank, world, local_rank):
             fn(i)
         e1.record()
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if dist_on:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+        return agd.max_over_ranks(e0.elapsed_time(e1), device=dev)     # slowest rank = the job's time
 
     for i in range(max(args.warmup, 3)):
         step_resident(i)
@@ -263,8 +260,7 @@ def run_ours(args, rank, world, local_rank):
         ops.set_profiler(None)
         fam = prof.summary()
 
-    if dist_on:
-        dist.barrier()
+    agd.barrier()
     if rank != 0:
         if dist_on:
             dist.destroy_process_group()
