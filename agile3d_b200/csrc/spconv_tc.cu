@@ -567,14 +567,15 @@ static TcPlan tc_plan(long long n_out, int K, int cout, bool split = false) {
   double best_cost = 1e30;
   for (int t = 1; t <= t_max; ++t) {
     const long long ctas = (tiles + t - 1) / t;
-    const long long waves = (ctas + sms - 1) / sms;
+    const long long waves = (ctas + sms * (split ? 2 : 1) - 1) / (sms * (split ? 2 : 1));
     const double cost = (double)waves * ((double)t + (double)cout / 128.0);
     if (cost < best_cost - 1e-9) { best_cost = cost; best_t = t; }
   }
   pl.T = best_t;
   const long long ctas = (tiles + pl.T - 1) / pl.T;
+  const long long slots = (long long)sms * (split ? 2 : 1);     // co-resident CTAs
   int ksplit = 1;
-  if (K > 1 && ctas * 2 <= sms) ksplit = (int)std::min<long long>(K, sms / ctas);
+  if (K > 1 && ctas * 2 <= slots) ksplit = (int)std::min<long long>(K, slots / ctas);
   pl.k_per = (K + ksplit - 1) / ksplit;
   pl.ksplit = (K + pl.k_per - 1) / pl.k_per;
   return pl;

@@ -174,7 +174,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": "scenes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -309,12 +309,29 @@ def run_ours(args, rank, world, local_rank):
                          "sample": f"{n_s}-voxel crop of a {n_full}-voxel scene, 1 run, scaled by voxel count; "
                                    "oracle/ fp32 torch restatement (MinkowskiEngine itself is not installable here)"},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist_on:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """Exactly one JSON line on the real stdout (libraries such as NCCL may print banners to fd 1)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)           # keep the real stdout for the JSON line ...
+    os.dup2(2, 1)                      # ... and send everything else written to fd 1 to stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
