@@ -39,10 +39,35 @@ SIGNATURES = {
     "ag3d_posenc_workspace_bytes": (_sz, [_i32]),
     "ag3d_fourier_posenc": (_i32, [_vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _sz, _vp]),
     "ag3d_c2s_workspace_bytes": (_sz, [_i32, _i32]),
-    "ag3d_c2s_attn_fwd": (_i32, [_vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _sz, _vp]),
+    "ag3d_c2s_attn_fwd": (_i32, [_vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _sz, _vp]),
     "ag3d_s2c_workspace_bytes": (_sz, [_i32]),
     "ag3d_s2c_mask_fwd": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _i32, _i32, _i32,
                                  _vp, _vp, _vp, _vp, _i32, _vp, _sz, _vp]),
+    # ---- training step
+    "ag3d_colreduce_workspace_bytes": (_sz, [_i32]),
+    "ag3d_bn_stats": (_i32, [_vp, _i32, _i32, _i64, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ag3d_bn_apply": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i64, _i32, _vp, _i32, _vp]),
+    "ag3d_bn_bwd": (_i32, [_vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _i32, _i64, _i32, _vp, _i32, _vp, _i32,
+                           _vp, _vp, _vp, _sz, _vp]),
+    "ag3d_col_sum": (_i32, [_vp, _i32, _i32, _i64, _vp, _vp, _sz, _vp]),
+    "ag3d_spconv_bwd_data": (_i32, [_vp, _i32, _i32, _vp, _i32, _i64, _vp, _vp, _i32, _vp, _i32, _vp, _i32, _i32, _vp,
+                                    _sz, _vp]),
+    "ag3d_spconv_bwd_weight_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32]),
+    "ag3d_spconv_bwd_weight": (_i32, [_vp, _i32, _i32, _vp, _i32, _i64, _vp, _i32, _i32, _vp, _i32, _vp, _sz, _vp]),
+    "ag3d_stem_bwd_weight_workspace_bytes": (_sz, [_i32]),
+    "ag3d_stem_bwd_weight": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, _vp, _i32, _vp, _i32, _vp, _sz, _vp]),
+    "ag3d_decoder_bwd_rows": (_i32, [_i32, _i32]),
+    "ag3d_c2s_attn_bwd": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "ag3d_s2c_bwd_workspace_bytes": (_sz, [_i32]),
+    "ag3d_s2c_mask_bwd": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _i32, _i32,
+                                 _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ag3d_loss_workspace_bytes": (_sz, []),
+    "ag3d_loss_fwd": (_i32, [_vp, _i32, _i64, _vp, _vp, _f32, _vp, _vp, _sz, _vp]),
+    "ag3d_loss_bwd": (_i32, [_vp, _i32, _i64, _vp, _vp, _f32, _vp, _vp, _vp]),
+    "ag3d_click_loss_weights": (_i32, [_vp, _i64, _vp, _i32, _f32, _f32, _f32, _vp, _vp]),
+    "ag3d_grad_norm_workspace_bytes": (_sz, []),
+    "ag3d_grad_norm": (_i32, [_vp, _i64, _vp, _vp, _sz, _vp]),
+    "ag3d_adamw_step": (_i32, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _vp, _f32, _vp]),
 }
 
 
@@ -63,7 +88,7 @@ def lib():
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(handle, name)          # AttributeError if the symbol is not exported
             fn.restype, fn.argtypes = res, args
-        if handle.ag3d_abi_version() != 5:
+        if handle.ag3d_abi_version() != 6:
             raise Ag3dError("libagile3d_b200.so ABI version mismatch; rebuild")
         _lib = handle
     return _lib

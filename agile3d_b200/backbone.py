@@ -203,10 +203,11 @@ class Res16UNet34C(nn.Module):
 
     @torch.no_grad()
     def forward(self, st):
-        """st: agile3d_b200.SparseTensor -> (features [N0, 96], [5 feature maps], CoordinateMaps)."""
+        """st: agile3d_b200.SparseTensor -> (features [N0, 96], [5 feature maps], CoordinateMaps).  Eval mode only;
+        train mode goes through train_forward / train_backward (batch-statistics BatchNorm, saved activations)."""
         if self.training:
-            raise NotImplementedError("train-mode (batch-statistics BatchNorm + backward) is not built yet; "
-                                      "call model.eval() — see DESIGN.md 'out of scope this round'")
+            raise RuntimeError("Res16UNet34C.forward is the eval-mode graph; Agile3d.forward_backbone dispatches "
+                               "to train_forward in train mode")
         if st.maps is None:
             st.maps = CoordinateMaps(st.C)
         maps, fold, dev = st.maps, self._folded(), st.F.device
@@ -238,3 +239,179 @@ class Res16UNet34C(nn.Module):
             y = self._stage_fwd(f"block{5 + j}", cat[lvl], maps.k3[lvl], fold)
             fmaps.append(y)
         return y, fmaps, maps
+
+
+    # ====================================================================================== train mode
+    # Reference semantics: MinkowskiBatchNorm with batch statistics over all voxels of the batch (biased variance
+    # for normalisation, unbiased for the running update), autograd through every layer (engine.py:53,146).
+    # Here: every conv writes its raw output z, ag3d_bn_stats/ag3d_bn_apply produce y (+residual, ReLU); the
+    # backward walks the recorded layers in reverse: ag3d_bn_bwd -> ag3d_spconv_bwd_weight -> ag3d_spconv_bwd_data
+    # (the forward kernel over the transposed map, skip-branch gradients added in its epilogue).
+    def _train_weights(self):
+        """name -> (W [K,cin,cout], W tc image, W_t [K,cout,cin] for the data gradient, W_t tc image)."""
+        key = (self.algo,) + tuple((p.data_ptr(), p._version) for p in self.parameters())
+        cache = getattr(self, "_train_cache", None)
+        if cache is not None and cache[0] == key:
+            return cache[1]
+        table = {}
+        tc = self.algo != ops.ALGO_SIMT
+        for name, mod in self.named_modules():
+            if not isinstance(mod, SparseConv) or mod.cin % 32 != 0:
+                continue
+            w = mod.kernel.detach()
+            w3 = (w if w.dim() == 3 else w.unsqueeze(0)).contiguous()
+            wt = (w3.flip(0) if w3.shape[0] == 27 else w3).transpose(1, 2).contiguous()
+            table[name] = (w3, ops.prepare_tc_weight(w3) if tc else None, wt, self._prep_t(wt) if tc else None)
+        self._train_cache = (key, table)
+        return table
+
+    @staticmethod
+    def _chunks(c):
+        """output-channel chunks the tensor-core kernel accepts (<= 256, multiples of 32)."""
+        return [(0, c)] if c <= 256 else [(o, min(o + 192, c)) for o in range(0, c, 192)]
+
+    def _prep_t(self, wt):
+        return [ops.prepare_tc_weight(wt[:, :, a:b].contiguous()) for a, b in self._chunks(wt.shape[2])]
+
+    def _dgrad(self, name, dz, nbr_t, n_in, W, residual=None):
+        """din [n_in, cin] = sum_k dz[nbr_t[k]] @ W_t[k] (+ residual)."""
+        _, _, wt, wt_tc = W[name]
+        cin = wt.shape[2]
+        din = torch.empty((n_in, cin), dtype=torch.float32, device=dz.device)
+        for i, (a, b) in enumerate(self._chunks(cin)):
+            whole = (a, b) == (0, cin)
+            ops.spconv_fwd(dz, nbr_t, wt if whole else wt[:, :, a:b].contiguous(), din[:, a:b],
+                           residual=None if residual is None else residual[:, a:b], algo=self.algo,
+                           weight_tc=wt_tc[i] if wt_tc is not None else None)
+        return din
+
+    def _conv_bn_fwd(self, name, bn_name, x, nbr, nbr_t, n_out, out, W, residual=None, relu=True):
+        w3, wtc = W[name][0], W[name][1]
+        bn = self.get_submodule(bn_name).bn
+        z = torch.empty((n_out, w3.shape[2]), dtype=torch.float32, device=x.device)
+        ops.spconv_fwd(x, nbr, w3, z, algo=self.algo, weight_tc=wtc)
+        mean, invstd = ops.bn_stats(z, bn.eps, bn.momentum, bn.running_mean, bn.running_var)
+        bn.num_batches_tracked += 1
+        ops.bn_apply(z, mean, invstd, bn.weight.detach(), bn.bias.detach(), out, residual=residual, relu=relu)
+        return dict(name=name, bn=bn_name, x=x, nbr=nbr, nbr_t=nbr_t, z=z, y=out, mean=mean, invstd=invstd, relu=relu)
+
+    def _conv_bn_bwd(self, rec, dy, W, grads, g_out=None, want_dx=True, dx_residual=None):
+        """dy: gradient of the layer's output y (overwritten with dz).  -> din (or None)."""
+        bn = self.get_submodule(rec["bn"]).bn
+        dgamma, dbeta = ops.bn_bwd(rec["z"], rec["y"] if rec["relu"] else None, dy, rec["mean"], rec["invstd"],
+                                   bn.weight.detach(), dy, relu=rec["relu"], g_out=g_out)
+        grads[rec["bn"] + ".bn.weight"] = dgamma
+        grads[rec["bn"] + ".bn.bias"] = dbeta
+        K = W[rec["name"]][0].shape[0]
+        dw = ops.spconv_bwd_weight(rec["x"], rec["nbr"], dy, K)
+        kernel = self.get_submodule(rec["name"]).kernel
+        grads[rec["name"] + ".kernel"] = dw.view_as(kernel)
+        if not want_dx:
+            return None
+        return self._dgrad(rec["name"], dy, rec["nbr_t"], rec["x"].shape[0], W, residual=dx_residual)
+
+    def _block_train_fwd(self, tape, prefix, blk, x, nbr, W, out=None):
+        n, planes = x.shape[0], blk.conv1.cout
+        f32 = dict(dtype=torch.float32, device=x.device)
+        t = torch.empty((n, planes), **f32)
+        r1 = self._conv_bn_fwd(prefix + ".conv1", prefix + ".norm1", x, nbr, nbr, n, t, W, relu=True)
+        rd = None
+        if blk.downsample is not None:
+            res = torch.empty((n, planes), **f32)
+            rd = self._conv_bn_fwd(prefix + ".downsample.0", prefix + ".downsample.1", x, None, None, n, res, W,
+                                   relu=False)
+        else:
+            res = x
+        if out is None:
+            out = torch.empty((n, planes), **f32)
+        r2 = self._conv_bn_fwd(prefix + ".conv2", prefix + ".norm2", t, nbr, nbr, n, out, W, residual=res, relu=True)
+        tape.append(("block", (r1, r2, rd)))
+        return out
+
+    def _block_train_bwd(self, blk_rec, dout, W, grads):
+        r1, r2, rd = blk_rec
+        g2 = torch.empty_like(dout)                       # relu-masked dout = gradient of the residual operand
+        dt = self._conv_bn_bwd(r2, dout, W, grads, g_out=g2)
+        if rd is not None:
+            dxr = self._conv_bn_bwd(rd, g2, W, grads)
+        else:
+            dxr = g2
+        return self._conv_bn_bwd(r1, dt, W, grads, dx_residual=dxr)
+
+    @torch.no_grad()
+    def train_forward(self, st):
+        """-> (features [N0,96], [5 feature maps], maps, tape).  tape feeds train_backward."""
+        if st.maps is None:
+            st.maps = CoordinateMaps(st.C)
+        maps, W, dev = st.maps, self._train_weights(), st.F.device
+        N, P = maps.sizes, PLANES
+        f32 = dict(dtype=torch.float32, device=dev)
+        skip_c = (INIT_DIM, P[0], P[1], P[2])
+        up_c = (P[7], P[6], P[5], P[4])
+        cat = [torch.empty((N[l], up_c[l] + skip_c[l]), **f32) for l in range(4)]
+        tape = []
+        # stem: raw conv -> bn0 (batch statistics) -> relu
+        bn0 = self.bn0.bn
+        z0 = torch.empty((N[0], INIT_DIM), **f32)
+        ops.stem_conv_fwd(maps.coords[0], st.F, maps.tables[0], maps.caps[0], self.conv1_kernel_size,
+                          self.conv0p1s1.kernel.detach(), z0, None, None, relu=False)
+        mean, invstd = ops.bn_stats(z0, bn0.eps, bn0.momentum, bn0.running_mean, bn0.running_var)
+        bn0.num_batches_tracked += 1
+        y = cat[0][:, up_c[0]:]
+        ops.bn_apply(z0, mean, invstd, bn0.weight.detach(), bn0.bias.detach(), y, relu=True)
+        stem = dict(z=z0, y=y, mean=mean, invstd=invstd, feats=st.F)
+        for i, tag in enumerate(_ENC):
+            d = torch.empty((N[i + 1], getattr(self, f"conv{tag}s2").cout), **f32)
+            tape.append(("conv", self._conv_bn_fwd(f"conv{tag}s2", f"bn{i + 1}", y, maps.down[i], maps.up[i], N[i + 1],
+                                                   d, W)))
+            blocks = getattr(self, f"block{i + 1}")
+            for b, blk in enumerate(blocks):
+                last = b == len(blocks) - 1
+                d = self._block_train_fwd(tape, f"block{i + 1}.{b}", blk, d, maps.k3[i + 1], W,
+                                          out=cat[i + 1][:, up_c[i + 1]:] if (last and i < 3) else None)
+            y = d
+        fmaps = [y]
+        for j, tag in enumerate(_DEC):
+            lvl = 3 - j
+            tape.append(("conv", self._conv_bn_fwd(f"convtr{tag}s2", f"bntr{4 + j}", y, maps.up[lvl], maps.down[lvl],
+                                                   N[lvl], cat[lvl][:, :up_c[lvl]], W)))
+            y = cat[lvl]
+            for b, blk in enumerate(getattr(self, f"block{5 + j}")):
+                y = self._block_train_fwd(tape, f"block{5 + j}.{b}", blk, y, maps.k3[lvl], W)
+            fmaps.append(y)
+        return y, fmaps, maps, (tape, stem, up_c)
+
+    @torch.no_grad()
+    def train_backward(self, maps, saved, dy):
+        """dy: gradient of the backbone output [N0,96] (consumed).  -> {parameter name: gradient}."""
+        tape, stem, up_c = saved
+        W = self._train_weights()
+        grads = {}
+        tape = list(tape)
+        skip_grads = {}
+
+        def pop(kind):
+            k, rec = tape.pop()
+            assert k == kind, "tape walk out of step with the graph"
+            return rec
+
+        for j in reversed(range(4)):                               # decoder stages, level 0 first
+            lvl = 3 - j
+            for _ in range(len(getattr(self, f"block{5 + j}"))):
+                dy = self._block_train_bwd(pop("block"), dy, W, grads)
+            skip_grads[lvl] = dy[:, up_c[lvl]:]                    # gradient of the skip half of the concat
+            dy = self._conv_bn_bwd(pop("conv"), dy[:, :up_c[lvl]], W, grads)       # transposed conv -> coarser level
+        for e in reversed(range(4)):                               # encoder stages, deepest first
+            for _ in range(len(getattr(self, f"block{e + 1}"))):
+                dy = self._block_train_bwd(pop("block"), dy, W, grads)
+            # the stride-2 conv's input (level e) also feeds the level-e concat: add that gradient in the epilogue
+            dy = self._conv_bn_bwd(pop("conv"), dy, W, grads, dx_residual=skip_grads[e])
+        assert not tape, "tape walk out of step with the graph"
+        dp1 = dy                                                   # total gradient of the stem output
+        bn0 = self.bn0.bn
+        dgamma, dbeta = ops.bn_bwd(stem["z"], stem["y"], dp1, stem["mean"], stem["invstd"], bn0.weight.detach(), dp1,
+                                   relu=True)
+        grads["bn0.bn.weight"], grads["bn0.bn.bias"] = dgamma, dbeta
+        grads["conv0p1s1.kernel"] = ops.stem_bwd_weight(maps.coords[0], stem["feats"], maps.tables[0], maps.caps[0],
+                                                        self.conv1_kernel_size, dp1).view_as(self.conv0p1s1.kernel)
+        return grads

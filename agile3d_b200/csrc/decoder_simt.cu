@@ -204,7 +204,7 @@ c2s_partial_kernel(const float* __restrict__ x, const float* __restrict__ pos, l
 // grid heads*nq blocks of 128 threads: log-sum-exp merge of the per-CTA partials
 __global__ void c2s_merge_kernel(const float* __restrict__ part_m, const float* __restrict__ part_l,
                                  const float* __restrict__ part_acc, int n_cta, int HQP, int nq, int nqg,
-                                 float* __restrict__ ctx) {
+                                 float* __restrict__ ctx, float* __restrict__ lse_out) {
   const int row = blockIdx.x;             // h*nq + q
   const int h = row / nq, q = row % nq;
   const int g = q / nqg, ql = q % nqg;
@@ -225,6 +225,7 @@ __global__ void c2s_merge_kernel(const float* __restrict__ part_m, const float* 
     }
   }
   ctx[(long long)row * D + c] = (L > 0.f) ? a / L : 0.f;
+  if (lse_out && c == 0) lse_out[row] = (L > 0.f) ? M + logf(L) : INFINITY;   // +inf: exp(s - lse) = 0 in the backward
 }
 
 // ================================================================================================ s2c
@@ -505,7 +506,7 @@ size_t ag3d_c2s_workspace_bytes(int32_t nq, int32_t heads) {
 
 int ag3d_c2s_attn_fwd(const float* x, const float* pos, int64_t nv, const float* qfold, int32_t nq,
                       int32_t heads, const uint8_t* label, const int32_t* q_obj, const int32_t* obj_count,
-                      float* ctx, int32_t algo, void* ws, size_t ws_bytes, ag3d_stream_t stream) {
+                      float* ctx, float* lse, int32_t algo, void* ws, size_t ws_bytes, ag3d_stream_t stream) {
   AG3D_CHECK_ARG(nv > 0 && nq > 0, "empty problem");
   AG3D_CHECK_ARG(heads == 8, "heads must be 8 (hidden 128 = 8 x 16)");
   AG3D_CHECK_ARG(x && pos && qfold && ctx && aligned16(x) && aligned16(pos) && aligned16(qfold) && aligned16(ctx),
@@ -523,7 +524,7 @@ int ag3d_c2s_attn_fwd(const float* x, const float* pos, int64_t nv, const float*
     if (int rc = c2s_tc_launch(x, pos, nv, qfold, nq, heads, label, q_obj, obj_count, ws, ws_bytes, st, &pm, &pl, &pa,
                                &n_cta_tc, &nqg_tc))
       return rc;
-    c2s_merge_kernel<<<heads * nq, D, 0, st>>>(pm, pl, pa, n_cta_tc, 128, nq, nqg_tc, ctx);
+    c2s_merge_kernel<<<heads * nq, D, 0, st>>>(pm, pl, pa, n_cta_tc, 128, nq, nqg_tc, ctx, lse);
     AG3D_LAUNCH_CHECK("c2s_merge");
     return AG3D_OK;
   }
@@ -558,7 +559,7 @@ int ag3d_c2s_attn_fwd(const float* x, const float* pos, int64_t nv, const float*
   else { AG3D_CHECK_ARG(J == 5, "internal: query group too large"); LAUNCH_C2S(5); }
 #undef LAUNCH_C2S
   AG3D_LAUNCH_CHECK("c2s_partial");
-  c2s_merge_kernel<<<heads * nq, D, 0, st>>>(part_m, part_l, part_acc, n_cta, HQP, nq, nqg, ctx);
+  c2s_merge_kernel<<<heads * nq, D, 0, st>>>(part_m, part_l, part_acc, n_cta, HQP, nq, nqg, ctx, lse);
   AG3D_LAUNCH_CHECK("c2s_merge");
   return AG3D_OK;
 }

@@ -196,6 +196,15 @@ int ag3d_spconv_fwd(const float* in, int32_t in_ld, int32_t cin, const int32_t* 
   return AG3D_OK;
 }
 
+int ag3d_spconv_bwd_data(const float* dout, int32_t dout_ld, int32_t cout, const int32_t* nbr_t, int32_t K,
+                         int64_t n_in, const float* weight_t, const void* weight_t_tc, int32_t cin,
+                         const float* residual, int32_t res_ld, float* din, int32_t din_ld, int32_t algo, void* ws,
+                         size_t ws_bytes, ag3d_stream_t stream) {
+  // the data gradient of a sparse convolution is the sparse convolution over the transposed map with W[k]^T
+  return ag3d_spconv_fwd(dout, dout_ld, cout, nbr_t, K, n_in, weight_t, weight_t_tc, cin, nullptr, nullptr, residual,
+                         res_ld, din, din_ld, 0, algo, ws, ws_bytes, stream);
+}
+
 size_t ag3d_spconv_workspace_bytes(int64_t n_out, int32_t K, int32_t cin, int32_t cout) {
   (void)cin;
   if (n_out <= 0 || K < 1 || K > 32 || cout % 32 != 0 || cout < 32 || cout > 256) return 0;

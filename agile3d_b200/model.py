@@ -92,6 +92,116 @@ class BackboneFeatures:
         return self.F.device
 
 
+
+# ================================================================================================ autograd bridges
+# torch.autograd is the plumbing that routes gradients between the query-side glue (tiny torch ops) and the CUDA
+# kernels; every Function below is a pair of calls into the library (forward kernel, backward kernel).
+class _BackboneFn(torch.autograd.Function):
+    """Res16UNet34C + lin_squeeze_head in train mode: one node whose backward is Res16UNet34C.train_backward."""
+
+    @staticmethod
+    def forward(ctx, model, st, names, holder, *params):
+        bb, head = model.backbone, model.lin_squeeze_head
+        feats, fmaps, maps, saved = bb.train_forward(st)
+        holder["fmaps"] = fmaps
+        tc = bb.algo != ops.ALGO_SIMT
+        w = head.kernel.detach()
+        pcd = torch.empty((feats.shape[0], head.cout), dtype=torch.float32, device=feats.device)
+        ops.spconv_fwd(feats, None, w, pcd, None, head.bias.detach().reshape(-1).contiguous(), algo=bb.algo,
+                       weight_tc=ops.prepare_tc_weight(w) if tc else None)
+        ctx.model, ctx.maps, ctx.saved, ctx.feats, ctx.names = model, maps, saved, feats, names
+        return pcd
+
+    @staticmethod
+    def backward(ctx, dpcd):
+        model, feats = ctx.model, ctx.feats
+        bb, head = model.backbone, model.lin_squeeze_head
+        dpcd = dpcd.contiguous()
+        with torch.no_grad():
+            grads = {"lin_squeeze_head.kernel": ops.spconv_bwd_weight(feats, None, dpcd, 1).view_as(head.kernel),
+                     "lin_squeeze_head.bias": ops.col_sum(dpcd).view_as(head.bias)}
+            wt = head.kernel.detach().t().contiguous()
+            dfeats = torch.empty_like(feats)
+            ops.spconv_fwd(dpcd, None, wt, dfeats, algo=bb.algo,
+                           weight_tc=ops.prepare_tc_weight(wt) if bb.algo != ops.ALGO_SIMT else None)
+            for k, v in bb.train_backward(ctx.maps, ctx.saved, dfeats).items():
+                grads["backbone." + k] = v
+        ctx.saved = None
+        return (None, None, None, None) + tuple(grads[n] for n in ctx.names)
+
+
+def _pad_rows(t, rows):
+    out = torch.zeros((rows,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    out[:t.shape[0]] = t
+    return out
+
+
+class _C2sFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, pos, qfold, nq, H, label, q_obj, obj_count):
+        out = torch.empty((H * nq, x.shape[1]), dtype=torch.float32, device=x.device)
+        lse = torch.empty(H * nq, dtype=torch.float32, device=x.device)
+        qfold = qfold.contiguous()
+        ops.c2s_attn_fwd(x, pos, qfold, nq, H, label, q_obj, obj_count, out=out, lse=lse)
+        ctx.save_for_backward(x, pos, qfold, out, lse)
+        ctx.meta = (nq, H, label, q_obj, obj_count)
+        return out
+
+    @staticmethod
+    def backward(ctx, dctx):
+        x, pos, qfold, out, lse = ctx.saved_tensors
+        nq, H, label, q_obj, obj_count = ctx.meta
+        HQ, hqp = H * nq, ops.decoder_bwd_rows(nq, H)
+        with torch.no_grad():
+            dctx = dctx.contiguous()
+            qf, dc = _pad_rows(qfold, hqp), _pad_rows(dctx, hqp)
+            rowobj = torch.full((hqp,), -2, dtype=torch.int32, device=x.device)
+            if label is None:
+                ro = torch.full((HQ,), -1, dtype=torch.int32, device=x.device)
+            else:
+                o = q_obj.long()
+                ro = torch.where(obj_count[o] > 0, q_obj, torch.full_like(q_obj, -1)).repeat(H)     # rows are h-major
+            rowobj[:HQ] = torch.where(torch.isinf(lse), torch.full_like(ro, -2), ro)
+            lse_p = torch.full((hqp,), float("inf"), dtype=torch.float32, device=x.device)
+            lse_p[:HQ] = lse
+            dr = _pad_rows((dctx * out).sum(1), hqp)
+            dx, ds = ops.c2s_attn_bwd(x, pos, qf, qf.t().contiguous(), dc, dc.t().contiguous(), lse_p, dr, rowobj,
+                                      hqp, label)
+            dq = ops.spconv_bwd_weight(ds, None, x, 1)
+            ops.spconv_bwd_weight(ds, None, pos, 1, dweight=dq, accumulate=True)
+        return dx, None, dq[0, :HQ], None, None, None, None, None
+
+
+class _S2cFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, pos, A, c, U, bo, ln_w, ln_b, E, eps, q_obj, nq, H, n_obj):
+        A, c, U, E = A.contiguous(), c.contiguous(), U.contiguous(), E.contiguous()
+        x_out, logits, label, count = ops.s2c_mask_fwd(x, pos, A, c, U, bo, ln_w, ln_b, eps, E, q_obj, nq, H, n_obj)
+        ctx.save_for_backward(x, pos, A, c, U, bo, ln_w, ln_b, E, x_out)
+        ctx.meta = (eps, q_obj, nq, H, n_obj)
+        ctx.mark_non_differentiable(label, count)
+        ctx.set_materialize_grads(False)
+        return x_out, logits, label, count
+
+    @staticmethod
+    def backward(ctx, dxo, dlogits, _dl, _dc):
+        x, pos, A, c, U, bo, ln_w, ln_b, E, x_out = ctx.saved_tensors
+        eps, q_obj, nq, H, n_obj = ctx.meta
+        HQ, hqp = H * nq, ops.decoder_bwd_rows(nq, H)
+        with torch.no_grad():
+            Ap, Up, Ep = _pad_rows(A, hqp), _pad_rows(U, hqp), _pad_rows(E, 32)
+            dx, a, ds, dy, g, cols = ops.s2c_mask_bwd(
+                x, pos, Ap, Ap.t().contiguous(), _pad_rows(c, hqp), Up, Up.t().contiguous(), bo, ln_w, ln_b, eps, Ep,
+                Ep.t().contiguous(), q_obj, nq, H, n_obj, hqp,
+                None if dxo is None else dxo.contiguous(), None if dlogits is None else dlogits.contiguous())
+            dA = ops.spconv_bwd_weight(ds, None, x, 1)
+            ops.spconv_bwd_weight(ds, None, pos, 1, dweight=dA, accumulate=True)
+            dU = ops.spconv_bwd_weight(a, None, dy, 1)
+            dE = ops.spconv_bwd_weight(g, None, x_out, 1)
+        return (dx, None, dA[0, :HQ], cols[384:384 + HQ], dU[0, :HQ], cols[:128], cols[128:256], cols[256:384],
+                dE[0, :nq], None, None, None, None, None)
+
+
 class Agile3d(nn.Module):
     def __init__(self, backbone, hidden_dim, num_heads, dim_feedforward, shared_decoder, num_decoders,
                  num_bg_queries, dropout, pre_norm, positional_encoding_type, normalize_pos_enc, hlevels,
@@ -128,18 +238,34 @@ class Agile3d(nn.Module):
         self.time_encode = _time_table(d, 200)       # plain attribute, not in the state_dict (agile3d.py:138)
 
     # ------------------------------------------------------------------------------------------ backbone
-    @torch.no_grad()
     def forward_backbone(self, x: SparseTensor, raw_coordinates=None):
         if not isinstance(x, SparseTensor):
             raise TypeError("forward_backbone expects an agile3d_b200.SparseTensor")
-        feats, fmaps, maps = self.backbone(x)
         raw = raw_coordinates.to(device=x.F.device, dtype=torch.float32).contiguous()
         if raw.shape != (x.F.shape[0], 3):
             raise ValueError("raw_coordinates must be [N,3]")
         # scene row ranges (scenes are contiguous and ordered: SURVEY.md A.2)
         offsets = x.scene_offsets()
         n_scenes = len(offsets) - 1
-        pos, rng = ops.fourier_posenc(raw, offsets, self.pos_enc.gauss_B)
+        with torch.no_grad():
+            pos, rng = ops.fourier_posenc(raw, offsets, self.pos_enc.gauss_B)
+        if self.training:
+            # batch-statistics BatchNorm + recorded activations; one autograd node for backbone + head (engine.py:53)
+            named = [(n, p) for n, p in self.named_parameters()
+                     if n.startswith("backbone.") or n.startswith("lin_squeeze_head.")]
+            holder = {}
+            pcd = _BackboneFn.apply(self, x, tuple(n for n, _ in named), holder, *[p for _, p in named])
+            pcd_features = BackboneFeatures(pcd, offsets, x.C)
+            coordinates = BackboneFeatures(raw, offsets, x.C)
+            coordinates.range = rng
+            pos_encodings_pcd = [None, None, None, None, [[pos[offsets[b]:offsets[b + 1]] for b in range(n_scenes)]]]
+            return pcd_features, holder["fmaps"], coordinates, pos_encodings_pcd
+        with torch.no_grad():
+            return self._forward_backbone_eval(x, raw, offsets, pos, rng)
+
+    def _forward_backbone_eval(self, x, raw, offsets, pos, rng):
+        n_scenes = len(offsets) - 1
+        feats, fmaps, maps = self.backbone(x)
         pcd = torch.empty((feats.shape[0], self.hidden_dim), dtype=torch.float32, device=feats.device)
         head = self.lin_squeeze_head
         hkey = (self.backbone.algo, head.kernel.data_ptr(), head.kernel._version)
@@ -216,10 +342,18 @@ class Agile3d(nn.Module):
         return A, c, U
 
     # ------------------------------------------------------------------------------------------ forward_mask
-    @torch.no_grad()
     def forward_mask(self, pcd_features, aux, coordinates, pos_encodings_pcd, click_idx=None, click_time_idx=None):
-        if self.training:
-            raise NotImplementedError("train-mode forward_mask (autograd) is not built yet; call model.eval()")
+        """Same kernels with or without autograd: when gradients are enabled the two voxel-streaming kernels run as
+        autograd nodes (their backward is ag3d_c2s_attn_bwd / ag3d_s2c_mask_bwd) and the voxel features of every
+        layer are kept; otherwise layers > 0 update the features in place."""
+        grad = torch.is_grad_enabled() and (pcd_features.F.requires_grad or
+                                            any(p.requires_grad for p in self.decoder_norm.parameters()))
+        if not grad:
+            with torch.no_grad():
+                return self._forward_mask(pcd_features, coordinates, pos_encodings_pcd, click_idx, click_time_idx, False)
+        return self._forward_mask(pcd_features, coordinates, pos_encodings_pcd, click_idx, click_time_idx, True)
+
+    def _forward_mask(self, pcd_features, coordinates, pos_encodings_pcd, click_idx, click_time_idx, grad):
         H, d = self.num_heads, self.hidden_dim
         dev = pcd_features.F.device
         offsets = pcd_features.offsets
@@ -265,14 +399,26 @@ class Agile3d(nn.Module):
                 c2s, c2c = self.c2s_attention[li][0], self.c2c_attention[li][0]
                 ffn, s2c = self.ffn_attention[li][0], self.s2c_attention[li][0]
                 qfold = self._fold_c2s(c2s.multihead_attn, queries, qpos, H)
-                for i, b in enumerate(members):
-                    ops.c2s_attn_fwd(srcs[i], pos_list[b], qfold[i], nq, H, labels[i], q_obj[i], counts[i], out=ctx[i])
+                if grad:
+                    ctx = torch.stack([_C2sFn.apply(srcs[i], pos_list[b], qfold[i], nq, H, labels[i], q_obj[i], counts[i])
+                                       for i, b in enumerate(members)])
+                else:
+                    for i, b in enumerate(members):
+                        ops.c2s_attn_fwd(srcs[i], pos_list[b], qfold[i], nq, H, labels[i], q_obj[i], counts[i],
+                                         out=ctx[i])
                 q = self._finish_c2s(c2s, queries, ctx, H)
                 q = self._self_attn(c2c, q, qpos, H)
                 queries = self._ffn(ffn, q)
                 A, c, U = self._fold_s2c(s2c.multihead_attn, queries, qpos, H)
                 E = self.mask_embed_head(self.decoder_norm(queries)).contiguous()
                 for i, b in enumerate(members):
+                    if grad:
+                        p = s2c.multihead_attn
+                        srcs[i], logits, labels[i], counts[i] = _S2cFn.apply(
+                            srcs[i], pos_list[b], A[i], c[i], U[i], p.out_proj.bias, s2c.norm.weight, s2c.norm.bias,
+                            E[i], s2c.norm.eps, q_obj[i], nq, H, meta[b][0] + 1)
+                        outs[i].append(logits)
+                        continue
                     srcs[i], logits, labels[i], counts[i] = ops.s2c_mask_fwd(
                         srcs[i], pos_list[b], A[i], c[i], U[i], s2c.multihead_attn.out_proj.bias, s2c.norm.weight,
                         s2c.norm.bias, s2c.norm.eps, E[i], q_obj[i], nq, H, meta[b][0] + 1,

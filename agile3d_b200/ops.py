@@ -254,8 +254,8 @@ def fourier_posenc(xyz, scene_offsets, gauss_B):
 _c2s_ws = {}
 
 
-def c2s_attn_fwd(x, pos, qfold, nq, heads, label=None, q_obj=None, obj_count=None, algo=ALGO_AUTO, out=None):
-    """-> ctx f32 [heads*nq, 128]."""
+def c2s_attn_fwd(x, pos, qfold, nq, heads, label=None, q_obj=None, obj_count=None, algo=ALGO_AUTO, out=None, lse=None):
+    """-> ctx f32 [heads*nq, 128].  lse (optional f32 [heads*nq]) receives the rows' log-sum-exp (for the backward)."""
     _need_cuda(x, pos, qfold)
     for t in (x, pos, qfold):
         if not t.is_contiguous() or t.dtype != torch.float32:
@@ -273,7 +273,8 @@ def c2s_attn_fwd(x, pos, qfold, nq, heads, label=None, q_obj=None, obj_count=Non
     nbytes = 4 * nv * 128 * 2 + (nq * nv if label is not None else 0) + 4 * nq * 128 * 3
     with _Timed("c2s", nbytes, 2 * 2 * nv * 128 * heads * nq):
         check(lib().ag3d_c2s_attn_fwd(_p(x), _p(pos), nv, _p(qfold), nq, heads, _p(label), _p(q_obj),
-                                      _p(obj_count), _p(ctx), algo, _p(ws), ws.numel(), _stream()), "ag3d_c2s_attn_fwd")
+                                      _p(obj_count), _p(ctx), _p(lse), algo, _p(ws), ws.numel(), _stream()),
+              "ag3d_c2s_attn_fwd")
     return ctx
 
 
@@ -300,3 +301,187 @@ def s2c_mask_fwd(x, pos, A, c, U, bo, ln_w, ln_b, ln_eps, E, q_obj, nq, heads, n
                                       float(ln_eps), _p(E), _p(q_obj), nq, heads, n_obj, _p(x_out), _p(logits),
                                       _p(label), _p(obj_count), algo, _p(ws), wsb, _stream()), "ag3d_s2c_mask_fwd")
     return x_out, logits, label, obj_count
+
+
+# =============================================================================================== training step
+def _ws_for(tag, device, nbytes):
+    return _workspace(tag, device, max(int(nbytes), 16))
+
+
+def bn_stats(z, eps, momentum=0.0, running_mean=None, running_var=None):
+    """batch mean / inverse std of the rows of z [N,C] (+ running-stat update) -> (mean [C], invstd [C])."""
+    _need_cuda(z)
+    zp, z_ld = _rows2d(z)
+    n, c = z.shape
+    mean = torch.empty(c, dtype=torch.float32, device=z.device)
+    invstd = torch.empty(c, dtype=torch.float32, device=z.device)
+    wsb = lib().ag3d_colreduce_workspace_bytes(c)
+    ws = _ws_for("colreduce", z.device, wsb)
+    with _Timed("bn", 4 * n * c):
+        check(lib().ag3d_bn_stats(zp, z_ld, c, n, float(eps), float(momentum), _p(running_mean), _p(running_var),
+                                  _p(mean), _p(invstd), _p(ws), ws.numel(), _stream()), "ag3d_bn_stats")
+    return mean, invstd
+
+
+def bn_apply(z, mean, invstd, gamma, beta, out, residual=None, relu=False):
+    _need_cuda(z, out)
+    zp, z_ld = _rows2d(z)
+    op, o_ld = _rows2d(out)
+    rp, r_ld = (_rows2d(residual) if residual is not None else (C.c_void_p(0), 0))
+    n, c = z.shape
+    with _Timed("bn", 4 * n * c * (3 if residual is not None else 2)):
+        check(lib().ag3d_bn_apply(zp, z_ld, _p(mean), _p(invstd), _p(gamma), _p(beta), rp, r_ld, c, n,
+                                  RELU if relu else 0, op, o_ld, _stream()), "ag3d_bn_apply")
+    return out
+
+
+def bn_bwd(z, y, dy, mean, invstd, gamma, dz, relu=False, g_out=None):
+    """-> (dgamma [C], dbeta [C]); writes dz (may alias dy) and, when asked, the relu-masked dy into g_out."""
+    _need_cuda(z, dy, dz)
+    zp, z_ld = _rows2d(z)
+    yp, y_ld = (_rows2d(y) if y is not None else (C.c_void_p(0), 0))
+    dyp, dy_ld = _rows2d(dy)
+    dzp, dz_ld = _rows2d(dz)
+    gp, g_ld = (_rows2d(g_out) if g_out is not None else (C.c_void_p(0), 0))
+    n, c = z.shape
+    dgamma = torch.empty(c, dtype=torch.float32, device=z.device)
+    dbeta = torch.empty(c, dtype=torch.float32, device=z.device)
+    wsb = lib().ag3d_colreduce_workspace_bytes(c)
+    ws = _ws_for("colreduce", z.device, wsb)
+    with _Timed("bn", 4 * n * c * 6):
+        check(lib().ag3d_bn_bwd(zp, z_ld, yp, y_ld, dyp, dy_ld, _p(mean), _p(invstd), _p(gamma), c, n,
+                                RELU if relu else 0, dzp, dz_ld, gp, g_ld, _p(dgamma), _p(dbeta), _p(ws), ws.numel(),
+                                _stream()), "ag3d_bn_bwd")
+    return dgamma, dbeta
+
+
+def col_sum(z):
+    _need_cuda(z)
+    zp, z_ld = _rows2d(z)
+    n, c = z.shape
+    out = torch.empty(c, dtype=torch.float32, device=z.device)
+    wsb = lib().ag3d_colreduce_workspace_bytes(c)
+    ws = _ws_for("colreduce", z.device, wsb)
+    check(lib().ag3d_col_sum(zp, z_ld, c, n, _p(out), _p(ws), ws.numel(), _stream()), "ag3d_col_sum")
+    return out
+
+
+def spconv_bwd_weight(x, nbr, dout, K, dweight=None, accumulate=False):
+    """dW[k] (+)= x[nbr[k]]^T dout  -> f32 [K, cin, cout].  nbr None: K = 1 on the identity map (plain X^T dY)."""
+    _need_cuda(x, dout)
+    xp, x_ld = _rows2d(x)
+    dp, d_ld = _rows2d(dout)
+    n_out, cout = dout.shape
+    cin = x.shape[1]
+    if nbr is not None and (tuple(nbr.shape) != (K, n_out) or not nbr.is_contiguous()):
+        raise _lib.Ag3dError(f"neighbour table must be contiguous int32 [{K},{n_out}], got {tuple(nbr.shape)}")
+    if nbr is None and (K != 1 or x.shape[0] != n_out):
+        raise _lib.Ag3dError("identity-map weight gradient needs K == 1 and equal row counts")
+    if dweight is None:
+        dweight = torch.empty((K, cin, cout), dtype=torch.float32, device=x.device)
+        accumulate = False
+    if dweight.numel() != K * cin * cout or not dweight.is_contiguous():
+        raise _lib.Ag3dError("dweight must be contiguous [K,cin,cout]")
+    wsb = lib().ag3d_spconv_bwd_weight_workspace_bytes(n_out, K, cin, cout)
+    ws = _ws_for("wgrad", x.device, wsb)
+    with _Timed("spconv_wgrad", 4 * x.shape[0] * cin + 4 * n_out * cout + 4 * K * cin * cout, 0):
+        check(lib().ag3d_spconv_bwd_weight(xp, x_ld, cin, _p(nbr), K, n_out, dp, d_ld, cout, _p(dweight),
+                                           1 if accumulate else 0, _p(ws), ws.numel(), _stream()),
+              "ag3d_spconv_bwd_weight")
+    return dweight
+
+
+def stem_bwd_weight(coords, feats, table, cap, ksize, dz):
+    _need_cuda(coords, feats, dz)
+    dp, d_ld = _rows2d(dz)
+    n = coords.shape[0]
+    dw = torch.empty((ksize ** 3, 3, 32), dtype=torch.float32, device=dz.device)
+    wsb = lib().ag3d_stem_bwd_weight_workspace_bytes(ksize)
+    ws = _ws_for("stem_wgrad", dz.device, wsb)
+    with _Timed("stem_wgrad", 16 * n + 12 * n + 4 * n * 32 + 16 * ksize ** 3 * n):
+        check(lib().ag3d_stem_bwd_weight(_p(coords), _p(feats), n, _p(table), cap, ksize, dp, d_ld, _p(dw), 0, _p(ws),
+                                         ws.numel(), _stream()), "ag3d_stem_bwd_weight")
+    return dw
+
+
+def decoder_bwd_rows(nq, heads):
+    r = int(lib().ag3d_decoder_bwd_rows(nq, heads))
+    if r == 0:
+        raise _lib.Ag3dError("decoder backward handles at most 32 click queries per scene")
+    return r
+
+
+def c2s_attn_bwd(x, pos, qf, qft, dctx, dctxt, lse, dr, rowobj, hqp, label):
+    """-> (dx [Nv,128], dS [Nv,hqp])."""
+    _need_cuda(x, pos, qf)
+    nv = x.shape[0]
+    dx = torch.empty_like(x)
+    ds = torch.empty((nv, hqp), dtype=torch.float32, device=x.device)
+    with _Timed("c2s_bwd", 4 * nv * 128 * 3 + 4 * nv * hqp, 2 * 4 * nv * 128 * hqp):
+        check(lib().ag3d_c2s_attn_bwd(_p(x), _p(pos), nv, _p(qf), _p(qft), _p(dctx), _p(dctxt), _p(lse), _p(dr),
+                                      _p(rowobj), hqp, _p(label), _p(dx), _p(ds), _stream()), "ag3d_c2s_attn_bwd")
+    return dx, ds
+
+
+def s2c_mask_bwd(x, pos, A, At, c, U, Ut, bo, ln_w, ln_b, ln_eps, E, Et, q_obj, nq, heads, n_obj, hqp, dxo, dlogits):
+    """-> (dx, a [Nv,hqp], dS [Nv,hqp], dy [Nv,128], g [Nv,32], colsums [3*128+hqp])."""
+    _need_cuda(x, pos, A)
+    nv, dev = x.shape[0], x.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    dx = torch.empty_like(x)
+    a = torch.empty((nv, hqp), **f32)
+    ds = torch.empty((nv, hqp), **f32)
+    dy = torch.empty((nv, 128), **f32)
+    g = torch.empty((nv, 32), **f32)
+    cols = torch.empty(3 * 128 + hqp, **f32)
+    wsb = lib().ag3d_s2c_bwd_workspace_bytes(hqp)
+    ws = _ws_for("s2c_bwd", dev, wsb)
+    with _Timed("s2c_bwd", 4 * nv * 128 * 5 + 8 * nv * hqp, 2 * nv * 128 * (4 * hqp + 64)):
+        check(lib().ag3d_s2c_mask_bwd(_p(x), _p(pos), nv, _p(A), _p(At), _p(c), _p(U), _p(Ut), _p(bo), _p(ln_w),
+                                      _p(ln_b), float(ln_eps), _p(E), _p(Et), _p(q_obj), nq, heads, n_obj, hqp,
+                                      _p(dxo), _p(dlogits), _p(dx), _p(a), _p(ds), _p(dy), _p(g), _p(cols), _p(ws),
+                                      ws.numel(), _stream()), "ag3d_s2c_mask_bwd")
+    return dx, a, ds, dy, g, cols
+
+
+def loss_fwd(logits, target, w, eps=1e-6):
+    """-> f32 [2] = (sum_v w ce_v, sum_v w dice_v) for one scene."""
+    _need_cuda(logits, target, w)
+    n, c = logits.shape
+    sums = torch.empty(4, dtype=torch.float32, device=logits.device)
+    wsb = lib().ag3d_loss_workspace_bytes()
+    ws = _ws_for("loss", logits.device, wsb)
+    check(lib().ag3d_loss_fwd(_p(logits), c, n, _p(target), _p(w), float(eps), _p(sums), _p(ws), ws.numel(), _stream()),
+          "ag3d_loss_fwd")
+    return sums[0::2]
+
+
+def loss_bwd(logits, target, w, g, eps=1e-6):
+    n, c = logits.shape
+    d = torch.empty_like(logits)
+    check(lib().ag3d_loss_bwd(_p(logits), c, n, _p(target), _p(w), float(eps), _p(g), _p(d), _stream()), "ag3d_loss_bwd")
+    return d
+
+
+def click_loss_weights(xyz, clicks, alpha=0.8, beta=2.0, tita=0.3):
+    _need_cuda(xyz, clicks)
+    n = xyz.shape[0]
+    w = torch.empty(n, dtype=torch.float32, device=xyz.device)
+    check(lib().ag3d_click_loss_weights(_p(xyz), n, _p(clicks), clicks.shape[0], alpha, beta, tita, _p(w), _stream()),
+          "ag3d_click_loss_weights")
+    return w
+
+
+def grad_norm(flat):
+    _need_cuda(flat)
+    out = torch.empty(1, dtype=torch.float32, device=flat.device)
+    wsb = lib().ag3d_grad_norm_workspace_bytes()
+    ws = _ws_for("gnorm", flat.device, wsb)
+    check(lib().ag3d_grad_norm(_p(flat), flat.numel(), _p(out), _p(ws), ws.numel(), _stream()), "ag3d_grad_norm")
+    return out
+
+
+def adamw_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, norm=None, max_norm=0.0):
+    _need_cuda(p, g, m, v)
+    check(lib().ag3d_adamw_step(_p(p), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps, weight_decay, step,
+                                _p(norm), float(max_norm), _stream()), "ag3d_adamw_step")

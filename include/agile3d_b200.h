@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define AG3D_ABI_VERSION 5
+#define AG3D_ABI_VERSION 6
 
 #define AG3D_OK 0
 #define AG3D_E_INVALID (-1)   /* bad argument (shape, alignment, unsupported size) */
@@ -135,11 +135,13 @@ int ag3d_fourier_posenc(const float* xyz, const int32_t* scene_offsets_host, int
  * Mask (models/agile3d.py:365-380): query q of object q_obj[q] is blocked at voxel v iff label[v] != q_obj[q],
  * unless obj_count[q_obj[q]] == 0 (no voxel carries that label -> the row is un-masked).  label == NULL
  * means no mask (first decoder layer).  algo: AG3D_ALGO_SIMT = fp32 FFMA kernel, AG3D_ALGO_TC (= AUTO) = tcgen05
- * flash-decoding kernel (bf16x3, online softmax, context accumulators resident in TMEM).                      */
+ * flash-decoding kernel (bf16x3, online softmax, context accumulators resident in TMEM).
+ * lse (nullable, [heads*nq]) receives the log-sum-exp of every row's scores (+inf for a row with no admissible
+ * voxel) — what ag3d_c2s_attn_bwd needs to rebuild the probabilities.                                          */
 size_t ag3d_c2s_workspace_bytes(int32_t nq, int32_t heads);
 int ag3d_c2s_attn_fwd(const float* x, const float* pos, int64_t nv, const float* qfold, int32_t nq,
                       int32_t heads, const uint8_t* label, const int32_t* q_obj, const int32_t* obj_count,
-                      float* ctx, int32_t algo, void* ws, size_t ws_bytes, ag3d_stream_t stream);
+                      float* ctx, float* lse, int32_t algo, void* ws, size_t ws_bytes, ag3d_stream_t stream);
 
 /* ---- scene -> click cross-attention + LayerNorm + mask head (s2c) --------------------------------------
  * Replaces CrossAttentionLayer.forward_post as called at models/agile3d.py:305-312 plus
@@ -156,6 +158,96 @@ int ag3d_s2c_mask_fwd(const float* x, const float* pos, int64_t nv, const float*
                       const float* E, const int32_t* q_obj, int32_t nq, int32_t heads, int32_t n_obj,
                       float* x_out, float* logits, uint8_t* label, int32_t* obj_count, int32_t algo, void* ws,
                       size_t ws_bytes, ag3d_stream_t stream);
+
+/* ======================================================================================================
+ * Training step (e): what autograd + MinkowskiEngine's backward kernels + ATen do in
+ * the reference's engine.py:119-152 (`losses.backward()`, clip_grad_norm_, optimizer.step()).
+ * ====================================================================================================== */
+
+/* ---- BatchNorm with batch statistics (MinkowskiBatchNorm in train mode, models/modules/common.py:20-22) ----
+ * ag3d_bn_stats: per-channel mean / inverse std over the n rows (biased variance), and the running-stat update
+ *   running = (1 - momentum) * running + momentum * batch  (unbiased variance), running_* nullable.
+ * ag3d_bn_apply: y = act((z - mean) * invstd * gamma + beta (+ residual)).
+ * ag3d_bn_bwd:   g = dy * (y > 0 if AG3D_RELU);  dbeta = sum g;  dgamma = sum g * xhat;
+ *                dz = gamma * invstd * (g - dbeta / n - xhat * dgamma / n);  g_out (nullable) receives g — the
+ *                gradient of the residual operand.  dz may alias dy.
+ * ag3d_col_sum:  sum over rows (bias gradient of lin_squeeze_head).                                          */
+size_t ag3d_colreduce_workspace_bytes(int32_t C);
+int ag3d_bn_stats(const float* z, int32_t z_ld, int32_t C, int64_t n, float eps, float momentum, float* running_mean,
+                  float* running_var, float* mean, float* invstd, void* ws, size_t ws_bytes, ag3d_stream_t stream);
+int ag3d_bn_apply(const float* z, int32_t z_ld, const float* mean, const float* invstd, const float* gamma,
+                  const float* beta, const float* residual, int32_t res_ld, int32_t C, int64_t n, int32_t flags,
+                  float* y, int32_t y_ld, ag3d_stream_t stream);
+int ag3d_bn_bwd(const float* z, int32_t z_ld, const float* y, int32_t y_ld, const float* dy, int32_t dy_ld,
+                const float* mean, const float* invstd, const float* gamma, int32_t C, int64_t n, int32_t flags,
+                float* dz, int32_t dz_ld, float* g_out, int32_t g_ld, float* dgamma, float* dbeta, void* ws,
+                size_t ws_bytes, ag3d_stream_t stream);
+int ag3d_col_sum(const float* z, int32_t z_ld, int32_t C, int64_t n, float* sum, void* ws, size_t ws_bytes,
+                 ag3d_stream_t stream);
+
+/* ---- sparse convolution backward (MinkowskiEngine ConvolutionBackwardKernelGPU) ----------------------------
+ * Data gradient: din[i] = sum_k dout[nbr_t[k][i]] @ W[k]^T is itself a sparse convolution over the transposed
+ * map, so ag3d_spconv_bwd_data IS ag3d_spconv_fwd called with (dout, nbr_t, weight_t[k] = W[k_t(k)]^T); for a
+ * centred odd kernel nbr_t[k] = nbr[K-1-k] (the table is its own transpose with mirrored offsets), for the
+ * kernel-2/stride-2 pair the transposed table is the other one of (ag3d_kernel_map, ag3d_kernel_map_transposed).
+ * `residual` adds the gradient arriving over the skip branch in the same epilogue.
+ * Weight gradient: dW[k] (+)= sum_o in[nbr[k][o]]^T dout[o]   ([K, cin, cout], fp32 FFMA, deterministic
+ * split-row partial sums in the workspace).  nbr == NULL: K = 1, identity map — the plain "X^T dY" contraction,
+ * also used for the decoder's query-side gradients.  cin, cout multiples of 4.                               */
+int ag3d_spconv_bwd_data(const float* dout, int32_t dout_ld, int32_t cout, const int32_t* nbr_t, int32_t K,
+                         int64_t n_in, const float* weight_t, const void* weight_t_tc, int32_t cin,
+                         const float* residual, int32_t res_ld, float* din, int32_t din_ld, int32_t algo, void* ws,
+                         size_t ws_bytes, ag3d_stream_t stream);
+size_t ag3d_spconv_bwd_weight_workspace_bytes(int64_t n_out, int32_t K, int32_t cin, int32_t cout);
+int ag3d_spconv_bwd_weight(const float* in, int32_t in_ld, int32_t cin, const int32_t* nbr, int32_t K, int64_t n_out,
+                           const float* dout, int32_t dout_ld, int32_t cout, float* dweight, int32_t accumulate,
+                           void* ws, size_t ws_bytes, ag3d_stream_t stream);
+/* stem (3 -> 32, probes the hash table like ag3d_stem_conv_fwd): dW[k][ci][co] (+)= feats[src_k(v)][ci] dz[v][co] */
+size_t ag3d_stem_bwd_weight_workspace_bytes(int32_t ksize);
+int ag3d_stem_bwd_weight(const int32_t* coords, const float* feats, int64_t n, const void* table, int64_t cap,
+                         int32_t ksize, const float* dz, int32_t dz_ld, float* dweight, int32_t accumulate, void* ws,
+                         size_t ws_bytes, ag3d_stream_t stream);
+
+/* ---- decoder backward -------------------------------------------------------------------------------------
+ * Query-side matrices are row-padded with zeros to hqp = ag3d_decoder_bwd_rows(nq, heads) (head, query) rows
+ * and 32 queries; "t" suffix = transposed copy ([128, hqp] / [128, 32]).
+ * c2s: rowobj[r] = object a row is restricted to, -1 = unrestricted, -2 = padding / dead row;
+ *      dr[r] = dctx[r] . ctx[r].  Writes dx [nv,128] and ds_out [nv,hqp] (dS; dqfold = dS^T (x + pos)).
+ * s2c: dxo (nullable) = gradient of x_out, dlogits (nullable) = gradient of the logits [nv, n_obj] (routed to the
+ *      first maximal query of every object, as torch.max does).  Writes dx and the per-voxel factors a_out, ds_out
+ *      [nv,hqp], dy_out [nv,128], g_out [nv,32]; colsums = [dbo 128 | dln_w 128 | dln_b 128 | dc hqp].
+ *      dA = dS^T (x + pos), dU = a^T dy, dE = g^T x_out  via ag3d_spconv_bwd_weight.                          */
+int32_t ag3d_decoder_bwd_rows(int32_t nq, int32_t heads);
+int ag3d_c2s_attn_bwd(const float* x, const float* pos, int64_t nv, const float* qf, const float* qft,
+                      const float* dctx, const float* dctxt, const float* lse, const float* dr, const int32_t* rowobj,
+                      int32_t hqp, const uint8_t* label, float* dx, float* ds_out, ag3d_stream_t stream);
+size_t ag3d_s2c_bwd_workspace_bytes(int32_t hqp);
+int ag3d_s2c_mask_bwd(const float* x, const float* pos, int64_t nv, const float* A, const float* At, const float* c,
+                      const float* U, const float* Ut, const float* bo, const float* ln_w, const float* ln_b,
+                      float ln_eps, const float* E, const float* Et, const int32_t* q_obj, int32_t nq, int32_t heads,
+                      int32_t n_obj, int32_t hqp, const float* dxo, const float* dlogits, float* dx, float* a_out,
+                      float* ds_out, float* dy_out, float* g_out, float* colsums, void* ws, size_t ws_bytes,
+                      ag3d_stream_t stream);
+
+/* ---- loss (models/criterion.py:84-132) and click loss weights (utils/seg.py:62-89) --------------------------
+ * Per scene: sums[0] = sum_v w_v CE(logits_v, t_v), sums[2] = sum_v w_v dice_v (sums is float[4]; [1],[3] = 0);
+ * the caller divides by n.  ag3d_loss_bwd: dlogits = w_v / n * (g[0] dCE + g[1] ddice), g on the device.        */
+size_t ag3d_loss_workspace_bytes(void);
+int ag3d_loss_fwd(const float* logits, int32_t C, int64_t n, const int32_t* target, const float* w, float eps,
+                  float* sums, void* ws, size_t ws_bytes, ag3d_stream_t stream);
+int ag3d_loss_bwd(const float* logits, int32_t C, int64_t n, const int32_t* target, const float* w, float eps,
+                  const float* g, float* dlogits, ag3d_stream_t stream);
+int ag3d_click_loss_weights(const float* xyz, int64_t n, const float* clicks, int32_t n_clicks, float alpha, float beta,
+                            float tita, float* w, ag3d_stream_t stream);
+
+/* ---- clip_grad_norm_ + AdamW over flat fp32 buffers (engine.py:146-150) ---------------------------------------
+ * ag3d_grad_norm: norm_out[0] = ||g||_2.  ag3d_adamw_step: g is scaled by min(1, max_norm / (norm + 1e-6)) when
+ * grad_norm is given (device pointer), then the decoupled-weight-decay Adam update; `step` counts from 1.        */
+size_t ag3d_grad_norm_workspace_bytes(void);
+int ag3d_grad_norm(const float* g, int64_t n, float* norm_out, void* ws, size_t ws_bytes, ag3d_stream_t stream);
+int ag3d_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                    float eps, float weight_decay, int32_t step, const float* grad_norm, float max_norm,
+                    ag3d_stream_t stream);
 
 #ifdef __cplusplus
 }

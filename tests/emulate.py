@@ -104,13 +104,17 @@ def fourier_posenc(xyz, scene_offsets, gauss_B):
     return torch.cat(outs, 0), torch.stack(rng, 0)
 
 
-def c2s_attn_fwd(x, pos, qfold, nq, heads, label=None, q_obj=None, obj_count=None, algo=0, out=None):
+def c2s_attn_fwd(x, pos, qfold, nq, heads, label=None, q_obj=None, obj_count=None, algo=0, out=None, lse=None):
     s = qfold @ (x + pos).T                                   # [H*nq, Nv]
     if label is not None:
+        s = s.clone()
         for r in range(heads * nq):
             o = int(q_obj[r % nq])
             if int(obj_count[o]) > 0:
                 s[r, label != o] = float("-inf")
+    if lse is not None:
+        l = torch.logsumexp(s.detach(), dim=1)
+        lse.copy_(torch.where(torch.isinf(l), torch.full_like(l, float("inf")), l))
     r = torch.softmax(s, dim=1) @ x
     if out is not None:
         out.copy_(r)
@@ -123,10 +127,11 @@ def s2c_mask_fwd(x, pos, A, c, U, bo, ln_w, ln_b, ln_eps, E, q_obj, nq, heads, n
     a = torch.softmax(s.view(-1, heads, nq), dim=2).reshape(-1, heads * nq)
     y = torch.nn.functional.layer_norm(x + (a @ U + bo), (x.shape[1],), ln_w, ln_b, ln_eps)
     z = y @ E.T                                               # [Nv, nq]
-    logits = torch.full((x.shape[0], n_obj), float("-inf"))
-    for q in range(nq):
-        o = int(q_obj[q])
-        logits[:, o] = torch.maximum(logits[:, o], z[:, q])
+    cols = []
+    for o in range(n_obj):                                    # autograd-friendly: max over each object's queries
+        qs = [q for q in range(nq) if int(q_obj[q]) == o]
+        cols.append(z[:, qs].max(dim=1)[0] if qs else torch.full((x.shape[0],), float("-inf"), dtype=z.dtype))
+    logits = torch.stack(cols, 1)
     label = logits.argmax(1).to(torch.uint8)
     obj_count = torch.bincount(label.long(), minlength=n_obj).to(torch.int32)
     if x_out is not None:
@@ -135,7 +140,159 @@ def s2c_mask_fwd(x, pos, A, c, U, bo, ln_w, ln_b, ln_eps, E, q_obj, nq, heads, n
     return y, logits, label, obj_count
 
 
-ALL = ["prepare_tc_weight", "hash_build", "downsample", "kernel_map", "kernel_map_transposed", "spconv_fwd", "stem_conv_fwd",
+# ------------------------------------------------------------------------------------------------ training step
+def bn_stats(z, eps, momentum=0.0, running_mean=None, running_var=None):
+    n = z.shape[0]
+    mean = z.mean(0)
+    var = z.var(0, unbiased=False)
+    if running_mean is not None:
+        running_mean.mul_(1 - momentum).add_(momentum * mean)
+        running_var.mul_(1 - momentum).add_(momentum * var * (n / (n - 1) if n > 1 else 1.0))
+    return mean, torch.rsqrt(var + eps)
+
+
+def bn_apply(z, mean, invstd, gamma, beta, out, residual=None, relu=False):
+    y = (z - mean) * invstd * gamma + beta
+    if residual is not None:
+        y = y + residual
+    out.copy_(torch.relu(y) if relu else y)
+    return out
+
+
+def bn_bwd(z, y, dy, mean, invstd, gamma, dz, relu=False, g_out=None):
+    n = z.shape[0]
+    g = dy * (y > 0) if relu else dy.clone()
+    xhat = (z - mean) * invstd
+    dbeta, dgamma = g.sum(0), (g * xhat).sum(0)
+    res = gamma * invstd * (g - dbeta / n - xhat * dgamma / n)
+    if g_out is not None:
+        g_out.copy_(g)
+    dz.copy_(res)
+    return dgamma, dbeta
+
+
+def col_sum(z):
+    return z.sum(0)
+
+
+def spconv_bwd_weight(x, nbr, dout, K, dweight=None, accumulate=False):
+    dw = torch.zeros((K, x.shape[1], dout.shape[1]), dtype=x.dtype)
+    for k in range(K):
+        if nbr is None:
+            dw[k] = x.T @ dout
+        else:
+            sel = torch.nonzero(nbr[k] >= 0).squeeze(1)
+            dw[k] = x[nbr[k][sel].long()].T @ dout[sel]
+    if dweight is None:
+        return dw
+    if accumulate:
+        dweight += dw.view_as(dweight)
+    else:
+        dweight.copy_(dw.view_as(dweight))
+    return dweight
+
+
+def stem_bwd_weight(coords, feats, table, cap, ksize, dz):
+    nbr = kernel_map(coords, table, cap, ksize, 1)
+    return spconv_bwd_weight(feats, nbr, dz, ksize ** 3)
+
+
+def decoder_bwd_rows(nq, heads):
+    for J in (6, 8, 10, 12, 14, 16):
+        if nq * heads <= 16 * J:
+            return 16 * J
+    raise RuntimeError("too many queries")
+
+
+def c2s_attn_bwd(x, pos, qf, qft, dctx, dctxt, lse, dr, rowobj, hqp, label):
+    assert torch.equal(qft, qf.T) and torch.equal(dctxt, dctx.T) and qf.shape[0] == hqp
+    S = (x + pos) @ qf.T                                      # [Nv, hqp]
+    P = torch.exp(S - lse)
+    dead = (rowobj == -2).unsqueeze(0).expand_as(P).clone()
+    if label is not None:
+        dead |= (rowobj >= 0).unsqueeze(0) & (label.long().unsqueeze(1) != rowobj.long().unsqueeze(0))
+    P = torch.where(dead, torch.zeros_like(P), P)
+    dS = P * (x @ dctx.T - dr)
+    return P @ dctx + dS @ qf, dS
+
+
+def s2c_mask_bwd(x, pos, A, At, c, U, Ut, bo, ln_w, ln_b, ln_eps, E, Et, q_obj, nq, heads, n_obj, hqp, dxo, dlogits):
+    assert torch.equal(At, A.T) and torch.equal(Ut, U.T) and torch.equal(Et, E.T) and A.shape[0] == hqp
+    nv, HQ = x.shape[0], heads * nq
+    xp = x + pos
+    a = torch.zeros((nv, hqp), dtype=x.dtype)
+    a[:, :HQ] = torch.softmax((xp @ A[:HQ].T + c[:HQ]).view(nv, heads, nq), dim=2).reshape(nv, HQ)
+    y = x + a @ U + bo
+    mu, var = y.mean(1, keepdim=True), y.var(1, unbiased=False, keepdim=True)
+    rstd = torch.rsqrt(var + ln_eps)
+    n = (y - mu) * rstd
+    xo = n * ln_w + ln_b
+    prods = xo @ E[:nq].T
+    g = torch.zeros((nv, 32), dtype=x.dtype)
+    if dlogits is not None:
+        for o in range(n_obj):
+            cols = [q for q in range(nq) if int(q_obj[q]) == o]
+            if cols:
+                first = prods[:, cols].argmax(1)              # torch.argmax returns the first maximal index
+                g[torch.arange(nv), torch.tensor(cols)[first]] = dlogits[:, o]
+    t = g @ E
+    if dxo is not None:
+        t = t + dxo
+    dn = t * ln_w
+    dy = rstd * (dn - dn.mean(1, keepdim=True) - n * (dn * n).mean(1, keepdim=True))
+    da = dy @ U.T
+    ds = torch.zeros_like(a)
+    a3, da3 = a[:, :HQ].view(nv, heads, nq), da[:, :HQ].view(nv, heads, nq)
+    ds[:, :HQ] = (a3 * (da3 - (a3 * da3).sum(2, keepdim=True))).reshape(nv, HQ)
+    dx = dy + ds @ A
+    cols = torch.cat([dy.sum(0), (t * n).sum(0), t.sum(0), ds.sum(0)])
+    return dx, a, ds, dy, g, cols
+
+
+def loss_fwd(logits, target, w, eps=1e-6):
+    C = logits.shape[1]
+    lse = torch.logsumexp(logits, 1)
+    lt = logits.gather(1, target.long().unsqueeze(1)).squeeze(1)
+    pt = torch.exp(lt - lse)
+    num, den = 2 * pt / C, 2.0 / C
+    dice = torch.where(num > eps, 1 - (num + eps) / (den + eps), torch.zeros_like(num))
+    return torch.stack([(w * (lse - lt)).sum(), (w * dice).sum()])
+
+
+def loss_bwd(logits, target, w, g, eps=1e-6):
+    n, C = logits.shape
+    p = torch.softmax(logits, 1)
+    ind = torch.nn.functional.one_hot(target.long(), C).to(p.dtype)
+    pt = (p * ind).sum(1, keepdim=True)
+    den = 2.0 / C
+    kd = torch.where(2 * pt / C > eps, -(den / (den + eps)) * pt * g[1], torch.zeros_like(pt))
+    return (w / n).unsqueeze(1) * (g[0] * (p - ind) + kd * (ind - p))
+
+
+def click_loss_weights(xyz, clicks, alpha=0.8, beta=2.0, tita=0.3):
+    d = torch.cdist(xyz, clicks).min(1)[0]
+    return alpha + (beta - alpha) * (1 - torch.clamp(d, max=tita) / tita)
+
+
+def grad_norm(flat):
+    return flat.norm().reshape(1)
+
+
+def adamw_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, norm=None, max_norm=0.0):
+    coef = 1.0
+    if norm is not None and max_norm > 0:
+        coef = min(1.0, max_norm / (float(norm) + 1e-6))
+    gi = g * coef
+    p.mul_(1 - lr * weight_decay)
+    m.mul_(beta1).add_((1 - beta1) * gi)
+    v.mul_(beta2).add_((1 - beta2) * gi * gi)
+    bc1, bc2 = 1 - beta1 ** step, 1 - beta2 ** step
+    p.sub_((lr / bc1) * m / (v.sqrt() / math.sqrt(bc2) + eps))
+
+
+ALL = ["bn_stats", "bn_apply", "bn_bwd", "col_sum", "spconv_bwd_weight", "stem_bwd_weight", "decoder_bwd_rows",
+       "c2s_attn_bwd", "s2c_mask_bwd", "loss_fwd", "loss_bwd", "click_loss_weights", "grad_norm", "adamw_step",
+       "prepare_tc_weight", "hash_build", "downsample", "kernel_map", "kernel_map_transposed", "spconv_fwd", "stem_conv_fwd",
        "fourier_posenc", "c2s_attn_fwd", "s2c_mask_fwd"]
 
 

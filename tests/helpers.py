@@ -50,3 +50,30 @@ def rel_err(a, b):
     """max |a-b| / max |b|: the 'relative' in "within 1e-3 relative on fp32 mask logits"."""
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def oracle_train_step(model, coords, feats, raw, clicks, times, targets, dtype=torch.float32):
+    """One train-mode step of the CPU oracle: batch-statistics BatchNorm, SetCriterion with click loss weights, the
+    engine.py:128 weighted sum, backward.  targets: list of int arrays per scene.
+    -> (loss dict, total, {param name: grad}, per-scene loss weights, output dict)."""
+    from agile3d_b200.weights import default_args
+    from oracle import criterion_ref as CR
+    from oracle import me_ref as ME
+
+    args = default_args()
+    model.train()
+    model.zero_grad()
+    x = ME.SparseTensor(coordinates=torch.as_tensor(coords), features=torch.as_tensor(feats).to(dtype))
+    rawt = torch.as_tensor(raw).to(dtype)
+    pcd, aux, co, pos = model.forward_backbone(x, rawt)
+    out = model.forward_mask(pcd, aux, co, pos, clicks, times)
+    weights = []
+    for b, r in enumerate(co[1]):
+        ids = [int(i) for _, v in clicks[b].items() for i in v]
+        weights.append(CR.click_loss_weights(rawt[torch.from_numpy(r)], ids))
+    tg = [torch.as_tensor(t).long() for t in targets]
+    loss_dict = CR.criterion(out, tg, weights)
+    total = CR.total_loss(loss_dict, CR.weight_dict(args))
+    total.backward()
+    grads = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
+    return loss_dict, total, grads, weights, out

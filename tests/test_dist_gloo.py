@@ -58,3 +58,46 @@ def test_shard_and_balance_properties():
     loads = [sum(sizes[i] for i in o) for o in owned]
     assert max(loads) <= 500_000                                       # the largest scene bounds the makespan here
     assert agd.max_over_ranks(3.0) == 3.0 and agd.sum_over_ranks(2.0) == 2.0   # single process: identity
+
+
+def _dp_worker(rank, world, port, out):
+    """Data-parallel training exchange: every rank holds different gradients in FlatAdamW's flat
+    buffer; GradBuckets sums + averages them bucket by bucket; the clip + AdamW step (C-ABI ops replaced by their
+    contract emulation on CPU) then leaves identical parameters on every rank."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__))))
+    import emulate
+    import agile3d_b200.ops as ops
+    from agile3d_b200.optim import FlatAdamW, GradBuckets
+    for name in ("grad_norm", "adamw_step"):
+        setattr(ops, name, getattr(emulate, name))
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    agd.init_from_env(backend="gloo")
+    torch.manual_seed(0)                                     # same initial parameters everywhere
+    params = [torch.nn.Parameter(torch.randn(37, 5)), torch.nn.Parameter(torch.randn(101)), torch.nn.Parameter(torch.randn(3, 3, 3))]
+    opt = FlatAdamW(params, lr=1e-2, weight_decay=1e-2, max_norm=0.1)
+    buckets = GradBuckets(opt, n_buckets=4)
+    opt.zero_grad()
+    torch.manual_seed(100 + rank)                            # different data -> different gradients
+    loss = sum((p * torch.randn_like(p)).sum() for p in params)
+    loss.backward()
+    local = opt.flat_g.clone()
+    buckets.all_reduce()
+    norm = opt.step()
+    out[rank] = (local.numpy(), opt.flat_g.clone().numpy(), opt.flat_p.clone().numpy(), float(norm))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_all_reduce_and_step():
+    world = 2
+    port = _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_dp_worker, args=(world, port, out), nprocs=world, join=True)
+        res = dict(out)
+    mean = (res[0][0] + res[1][0]) / 2
+    for r in (0, 1):
+        assert abs(res[r][1] - mean).max() < 1e-6            # averaged gradients everywhere
+    assert abs(res[0][2] - res[1][2]).max() == 0.0           # identical parameters after the step
+    assert res[0][3] == res[1][3]
