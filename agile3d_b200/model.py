@@ -343,11 +343,10 @@ class Agile3d(nn.Module):
 
     # ------------------------------------------------------------------------------------------ forward_mask
     def forward_mask(self, pcd_features, aux, coordinates, pos_encodings_pcd, click_idx=None, click_time_idx=None):
-        """Same kernels with or without autograd: when gradients are enabled the two voxel-streaming kernels run as
+        """Same kernels with or without autograd: in train mode (engine.py:119-121) the two voxel-streaming kernels run as
         autograd nodes (their backward is ag3d_c2s_attn_bwd / ag3d_s2c_mask_bwd) and the voxel features of every
         layer are kept; otherwise layers > 0 update the features in place."""
-        grad = torch.is_grad_enabled() and (pcd_features.F.requires_grad or
-                                            any(p.requires_grad for p in self.decoder_norm.parameters()))
+        grad = torch.is_grad_enabled() and (self.training or pcd_features.F.requires_grad)
         if not grad:
             with torch.no_grad():
                 return self._forward_mask(pcd_features, coordinates, pos_encodings_pcd, click_idx, click_time_idx, False)
