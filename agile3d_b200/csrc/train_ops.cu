@@ -179,42 +179,73 @@ tn_gemm_kernel(const float* __restrict__ A, int lda, int M, const float* __restr
                int tiles_n, float* __restrict__ part) {
   __shared__ __align__(16) float As[TG_BK][TG_BM];
   __shared__ __align__(16) float Bs[TG_BK][TG_BN];
+  __shared__ int s_row[TG_THREADS], s_src[TG_THREADS], s_wcnt[TG_THREADS / 32];
   const int tm = blockIdx.x / tiles_n, tn = blockIdx.x % tiles_n;
   const int split = blockIdx.y, z = blockIdx.z;
   const int m0 = tm * TG_BM, n0 = tn * TG_BN;
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
   const int lr = tid >> 4, lc = (tid & 15) * 4;
+  const int warp = tid >> 5, lane = tid & 31;
   const int* idz = idx ? idx + (long long)z * idx_stride : nullptr;
   const long long r0 = (long long)split * rows_per_split;
   const long long r1 = min(rows, r0 + rows_per_split);
+  const bool a_ok = m0 + lc < M, b_ok = n0 + lc < N;
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (long long r = r0; r < r1; r += TG_BK) {
-    const long long row = r + lr;
+  for (long long r = r0; r < r1; r += TG_THREADS) {
+    // ---- compact the (output row, input row) pairs of this 256-row window: offsets without a neighbour cost nothing
+    const long long row = r + tid;
     int src = -1;
     if (row < r1) src = idz ? __ldg(idz + row) : (int)row;
-    if (!__syncthreads_or(src >= 0)) continue;
-    float4 av = make_float4(0.f, 0.f, 0.f, 0.f), bv = av;
-    if (src >= 0) {
-      if (m0 + lc < M) av = __ldg(reinterpret_cast<const float4*>(A + (long long)src * lda + m0 + lc));
-      if (n0 + lc < N) bv = __ldg(reinterpret_cast<const float4*>(B + row * ldb + n0 + lc));
+    const unsigned bal = __ballot_sync(0xffffffffu, src >= 0);
+    if (lane == 0) s_wcnt[warp] = __popc(bal);
+    __syncthreads();                       // also: the previous window's last chunk is fully consumed
+    int base = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < TG_THREADS / 32; ++w) {
+      const int c = s_wcnt[w];
+      if (w < warp) base += c;
+      total += c;
     }
-    *reinterpret_cast<float4*>(&As[lr][lc]) = av;
-    *reinterpret_cast<float4*>(&Bs[lr][lc]) = bv;
+    if (src >= 0) {
+      const int p = base + __popc(bal & ((1u << lane) - 1u));
+      s_row[p] = (int)(row - r);
+      s_src[p] = src;
+    }
     __syncthreads();
+    if (total == 0) continue;
+    // ---- 16 pairs per step, next step's rows prefetched into registers while the current one is multiplied
+    float4 av = make_float4(0.f, 0.f, 0.f, 0.f), bv = av;
+    if (lr < total) {
+      if (a_ok) av = __ldg(reinterpret_cast<const float4*>(A + (long long)s_src[lr] * lda + m0 + lc));
+      if (b_ok) bv = __ldg(reinterpret_cast<const float4*>(B + (r + s_row[lr]) * ldb + n0 + lc));
+    }
+    for (int c = 0; c < total; c += TG_BK) {
+      *reinterpret_cast<float4*>(&As[lr][lc]) = av;
+      *reinterpret_cast<float4*>(&Bs[lr][lc]) = bv;
+      __syncthreads();
+      av = make_float4(0.f, 0.f, 0.f, 0.f);
+      bv = av;
+      const int nx = c + TG_BK + lr;
+      if (nx < total) {
+        if (a_ok) av = __ldg(reinterpret_cast<const float4*>(A + (long long)s_src[nx] * lda + m0 + lc));
+        if (b_ok) bv = __ldg(reinterpret_cast<const float4*>(B + (r + s_row[nx]) * ldb + n0 + lc));
+      }
 #pragma unroll
-    for (int kk = 0; kk < TG_BK; ++kk) {
-      const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
-      const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
-      const float ar[4] = {a.x, a.y, a.z, a.w};
-      const float br[4] = {b.x, b.y, b.z, b.w};
+      for (int kk = 0; kk < TG_BK; ++kk) {
+        const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+        const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+        const float ar[4] = {a.x, a.y, a.z, a.w};
+        const float br[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+      }
+      __syncthreads();
     }
   }
   float* dst = part + ((long long)z * gridDim.y + split) * M * N;
@@ -260,7 +291,7 @@ static int tn_gemm_splits(long long rows, int M, int N, int nz, int* tiles_m, in
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   long long per = (rows + splits - 1) / splits;
-  per = (per + TG_BK - 1) / TG_BK * TG_BK;
+  per = (per + TG_THREADS - 1) / TG_THREADS * TG_THREADS;
   splits = (rows + per - 1) / per;
   *rps = per;
   return (int)splits;
