@@ -336,18 +336,23 @@ def test_train_step_batch_of_two_vs_fp64_oracle(algo):
     rl, rtotal, rgrads, _, rout = oracle_train_step(ref_m, coords, feats, raw, clicks, times, targets, torch.float64)
     m = _gpu_train_model(7, algo)
     loss_dict, total, grads, out = _gpu_train_step(m, coords, feats, raw, clicks, times, targets)
-    assert abs(float(total) - float(rtotal)) < 2e-3 * k * max(1.0, abs(float(rtotal)))
+    assert abs(float(total) - float(rtotal)) < 2e-3 * k * max(1.0, abs(float(rtotal))), (float(total), float(rtotal))
     for b in range(2):
-        assert rel_err(out["pred_masks"][b].detach().cpu().numpy(), rout["pred_masks"][b].detach().numpy()) < 1e-3 * k
+        e = rel_err(out["pred_masks"][b].detach().cpu().numpy(), rout["pred_masks"][b].detach().numpy())
+        assert e < 1e-3 * k, (b, e)
+    # all gradients as one vector: relative L2 error; per parameter: max error relative to that parameter's largest
+    # entry, floored at 1 % of the largest gradient entry of the model (parameters whose gradient is noise-level small
+    # against the rest cannot be compared entry-wise in fp32)
+    num = np.sqrt(sum(float((grads[n].double() - r).norm()) ** 2 for n, r in rgrads.items()))
+    den = np.sqrt(sum(float(r.double().norm()) ** 2 for r in rgrads.values()))
+    assert num / den < 2e-3 * k, f"global relative L2 gradient error {num / den:.3e}"
     gmax = max(float(v.abs().max()) for v in rgrads.values())
-    tot_r = np.sqrt(sum(float(v.double().norm()) ** 2 for v in rgrads.values()))
-    tot_g = np.sqrt(sum(float(v.double().norm()) ** 2 for v in grads.values()))
-    assert abs(tot_g - tot_r) / tot_r < 1e-3 * k
-    worst = 0.0
+    worst, worst_name = 0.0, ""
     for n, r in rgrads.items():
-        e = float((grads[n].double() - r).abs().max()) / max(float(r.abs().max()), 1e-3 * gmax)
-        worst = max(worst, e)
-    assert worst < 2e-2 * (1 if k == 1 else 10), worst
+        e = float((grads[n].double() - r).abs().max()) / max(float(r.abs().max()), 1e-2 * gmax)
+        if e > worst:
+            worst, worst_name = e, n
+    assert worst < 2e-2 * (1 if k == 1 else 10), (worst, worst_name)
 
 
 def test_training_reduces_the_loss():
