@@ -32,12 +32,15 @@ colreduce_kernel(const float* __restrict__ z, int z_ld, const float* __restrict_
       mu = __ldg(reinterpret_cast<const float4*>(mean) + c4);
       is = __ldg(reinterpret_cast<const float4*>(invstd) + c4);
     }
+    // MODE 0 sums z - z[0] (shifted data): E[(z-K)^2] - E[z-K]^2 has no cancellation when K is one of the samples
+    if (MODE == 0) mu = __ldg(reinterpret_cast<const float4*>(z) + c4);
     for (long long r = (long long)blockIdx.x * R + rl; r < n; r += (long long)gridDim.x * R) {
       const float4 zv = __ldg(reinterpret_cast<const float4*>(z + r * z_ld) + c4);
       if (MODE == 0) {
-        s0.x += zv.x; s0.y += zv.y; s0.z += zv.z; s0.w += zv.w;
-        s1.x = fmaf(zv.x, zv.x, s1.x); s1.y = fmaf(zv.y, zv.y, s1.y);
-        s1.z = fmaf(zv.z, zv.z, s1.z); s1.w = fmaf(zv.w, zv.w, s1.w);
+        const float dx = zv.x - mu.x, dy_ = zv.y - mu.y, dz_ = zv.z - mu.z, dw = zv.w - mu.w;
+        s0.x += dx; s0.y += dy_; s0.z += dz_; s0.w += dw;
+        s1.x = fmaf(dx, dx, s1.x); s1.y = fmaf(dy_, dy_, s1.y);
+        s1.z = fmaf(dz_, dz_, s1.z); s1.w = fmaf(dw, dw, s1.w);
       } else if (MODE == 2) {
         s0.x += zv.x; s0.y += zv.y; s0.z += zv.z; s0.w += zv.w;
       } else {
@@ -71,7 +74,8 @@ colreduce_kernel(const float* __restrict__ z, int z_ld, const float* __restrict_
 
 // one thread per channel: fp64 sum of the per-CTA partials
 __global__ void colreduce_final_kernel(const float* __restrict__ part, int n_cta, int C, long long n, int mode,
-                                       float eps, float momentum, float* __restrict__ running_mean,
+                                       const float* __restrict__ shift_row, float eps, float momentum,
+                                       float* __restrict__ running_mean,
                                        float* __restrict__ running_var, float* __restrict__ out0,
                                        float* __restrict__ out1) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -82,9 +86,10 @@ __global__ void colreduce_final_kernel(const float* __restrict__ part, int n_cta
     b += (double)part[((long long)i * 2 + 1) * C + c];
   }
   if (mode == 0) {
-    const double m = a / (double)n;
-    double var = b / (double)n - m * m;
+    const double ms = a / (double)n;                 // mean of the shifted data
+    double var = b / (double)n - ms * ms;
     if (var < 0.0) var = 0.0;
+    const double m = ms + (double)shift_row[c];
     out0[c] = (float)m;
     out1[c] = (float)(1.0 / sqrt(var + (double)eps));
     if (running_mean) {
@@ -531,7 +536,7 @@ static int colreduce_common(int mode, const float* z, int z_ld, const float* y, 
   else
     colreduce_kernel<2><<<n_cta, CR_THREADS, 0, st>>>(z, z_ld, y, y_ld, dy, dy_ld, mean, invstd, C, n, relu, part);
   AG3D_LAUNCH_CHECK("colreduce");
-  colreduce_final_kernel<<<(C + 127) / 128, 128, 0, st>>>(part, n_cta, C, n, mode, eps, momentum, rm, rv, out0, out1);
+  colreduce_final_kernel<<<(C + 127) / 128, 128, 0, st>>>(part, n_cta, C, n, mode, z, eps, momentum, rm, rv, out0, out1);
   AG3D_LAUNCH_CHECK("colreduce_final");
   return AG3D_OK;
 }
@@ -656,7 +661,7 @@ int ag3d_loss_fwd(const float* logits, int32_t C, int64_t n, const int32_t* targ
   loss_fwd_kernel<<<n_cta, 256, 0, st>>>(logits, C, n, target, w, eps, part);
   AG3D_LAUNCH_CHECK("loss_fwd");
   // partials are [cta][2][2]; the final kernel sums column c of row 0 / row 1 -> out0[c], out1[c]; only c = 0 is used
-  colreduce_final_kernel<<<1, 32, 0, st>>>(part, n_cta, 2, n, 2, 0.f, 0.f, nullptr, nullptr, sums, sums + 2);
+  colreduce_final_kernel<<<1, 32, 0, st>>>(part, n_cta, 2, n, 2, nullptr, 0.f, 0.f, nullptr, nullptr, sums, sums + 2);
   AG3D_LAUNCH_CHECK("loss_final");
   return AG3D_OK;
 }

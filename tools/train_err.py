@@ -29,32 +29,42 @@ for algo in (1, 0):
           f"{rel_err(out['pred_masks'][0].detach().cpu().numpy()[::4], g['logits_last']):.3e}")
 
 from agile3d_b200.scenes import make_clicks, make_scene  # noqa: E402
-for n_vox in (1300, 6000):
-    scs, clicks, times, targets = [], [], [], []
-    for s in (dict(n=n_vox, seed=21, k=2, cpo=2, bg=1), dict(n=int(n_vox * 0.7), seed=22, k=1, cpo=3, bg=0)):
-        sc = make_scene(s["n"], 0.02, seed=s["seed"], n_box=5)
-        c, tm, lab = make_clicks(sc, s["k"], s["cpo"], s["bg"], seed=s["seed"])
-        scs.append(sc); clicks.append(c); times.append(tm); targets.append(np.minimum(lab, len(c) - 1).astype(np.int32))
-    coords = np.concatenate([np.concatenate([np.full((sc["coords"].shape[0], 1), b, np.int32), sc["coords"]], 1)
-                             for b, sc in enumerate(scs)], 0)
-    feats = np.concatenate([sc["feats"] for sc in scs], 0)
-    raw = np.concatenate([sc["raw_coords"] for sc in scs], 0)
-    rl, rtotal, rgrads, _, rout = oracle_train_step(oracle_model(7, torch.float64), coords, feats, raw, clicks, times, targets, torch.float64)
-    r32 = oracle_train_step(oracle_model(7, torch.float32), coords, feats, raw, clicks, times, targets, torch.float32)
-    cands = {"oracle-fp32": (r32[1], r32[2], r32[4])}
-    for algo in (1, 0):
-        m = T._gpu_train_model(7, algo)
-        ld, total, grads, out = T._gpu_train_step(m, coords, feats, raw, clicks, times, targets)
-        cands[f"gpu algo={algo}"] = (total, grads, out)
-    for name, (total, grads, out) in cands.items():
-        num = np.sqrt(sum(float((grads[n].double().cpu() - r).norm()) ** 2 for n, r in rgrads.items()))
-        den = np.sqrt(sum(float(r.double().norm()) ** 2 for r in rgrads.values()))
-        gmax = max(float(v.abs().max()) for v in rgrads.values())
-        worst, wn = 0.0, ""
-        for n, r in rgrads.items():
-            e = float((grads[n].double().cpu() - r).abs().max()) / max(float(r.abs().max()), 1e-2 * gmax)
-            if e > worst:
-                worst, wn = e, n
-        le = max(rel_err(out["pred_masks"][b].detach().cpu().numpy(), rout["pred_masks"][b].detach().numpy()) for b in range(2))
-        print(f"batch2 N={coords.shape[0]} {name:14s}: total {float(total):.6f} vs {float(rtotal):.6f}  logits {le:.3e}  "
-              f"grad L2 rel {num / den:.3e}  worst param {worst:.3e} ({wn})")
+import agile3d_b200  # noqa: E402
+from oracle import me_ref as ME  # noqa: E402
+
+# backbone only (no discrete decisions): features and gradients against the fp64 oracle
+coords, feats, raw, clicks, times, targets = T._two_scenes()
+R = torch.randn((coords.shape[0], 128), generator=torch.Generator().manual_seed(3), dtype=torch.float64)
+for dt in (torch.float64, torch.float32):
+    ref = oracle_model(7, dt).train()
+    x = ME.SparseTensor(coordinates=torch.as_tensor(coords), features=torch.as_tensor(feats).to(dt))
+    pcd_r, *_ = ref.forward_backbone(x, torch.as_tensor(raw).to(dt))
+    (pcd_r.F * R.to(dt)).sum().backward()
+    gr = {n: p.grad for n, p in ref.named_parameters() if p.grad is not None}
+    if dt == torch.float64:
+        rgrads, pcd64 = gr, pcd_r.F.detach()
+    else:
+        print("backbone-only oracle-fp32:", rel_err(pcd_r.F.detach().numpy(), pcd64.numpy()), T._grad_errors(gr, rgrads))
+for algo in (1, 0):
+    m = T._gpu_train_model(7, algo)
+    xg = agile3d_b200.SparseTensor(coordinates=torch.as_tensor(coords), features=torch.as_tensor(feats), device="cuda")
+    pcd, *_ = m.forward_backbone(xg, torch.as_tensor(raw).cuda())
+    (pcd.F * R.float().cuda()).sum().backward()
+    grads = {n: p.grad for n, p in m.named_parameters() if p.grad is not None}
+    print(f"backbone-only gpu algo={algo}:", rel_err(pcd.F.detach().cpu().numpy(), pcd64.numpy()), T._grad_errors(grads, rgrads))
+
+# full-size scene: tensor-core (bf16x3) step against the exact-fp32 step, both on the GPU
+sc = make_scene(150000, 0.02, seed=2000)
+c, tm, lab = make_clicks(sc, 5, 2, 0, seed=2000)
+coords = np.concatenate([np.zeros((sc["coords"].shape[0], 1), np.int32), sc["coords"]], 1)
+res = {}
+for algo in (1, 0):
+    m = T._gpu_train_model(5, algo)
+    ld, total, grads, out = T._gpu_train_step(m, coords, sc["feats"], sc["raw_coords"], [c], [tm], [lab.astype(np.int32)])
+    res[algo] = (float(total), grads, out["pred_masks"][0].detach().cpu().numpy())
+    del m
+    torch.cuda.empty_cache()
+num = np.sqrt(sum(float((res[0][1][n].double() - r.double()).norm()) ** 2 for n, r in res[1][1].items()))
+den = np.sqrt(sum(float(r.double().norm()) ** 2 for r in res[1][1].values()))
+print(f"150k voxels, tensor-core vs fp32 on the GPU: total {res[0][0]:.6f} vs {res[1][0]:.6f}  logits {rel_err(res[0][2], res[1][2]):.3e}  "
+      f"grad L2 rel {num / den:.3e}")
