@@ -250,7 +250,8 @@ __global__ void __launch_bounds__(CT_THREADS, 1) c2s_tc_kernel(const C2sParams p
     }
   } else {
     // ======================================================================================= MMA issuer
-    if (lane == 0) {
+    // whole warp, warp-uniform state; one elected lane issues (see elect_one in tc_common.cuh)
+    {
       const uint32_t id1 = umma_idesc_bf16_major(CT_TV, 0, 0);   // S: N = 64, both operands K-major
       const uint32_t id2 = umma_idesc_bf16_major(CT_D, 0, 1);    // ctx: N = 128, B (= X tile) MN-major
       const uint32_t q_hi = smem_u32(Qs), q_lo = q_hi + Q_PIECE;
@@ -262,28 +263,34 @@ __global__ void __launch_bounds__(CT_THREADS, 1) c2s_tc_kernel(const C2sParams p
         const uint32_t ph = (uint32_t)it & 1u;
         mbar_wait(xp_ready, ph);
         tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {                            // K = 128 channels, 16 per step
-          const uint64_t a_h = umma_desc(q_hi + j * 2 * A_LBO, A_LBO, 128), a_l = umma_desc(q_lo + j * 2 * A_LBO, A_LBO, 128);
-          const uint64_t b_h = umma_desc(xp_hi + j * 2 * T_LBO, T_LBO, 128), b_l = umma_desc(xp_lo + j * 2 * T_LBO, T_LBO, 128);
-          umma_bf16(tmem_base + CT_TM_S, a_h, b_h, id1, j ? 1u : 0u);
-          umma_bf16(tmem_base + CT_TM_S, a_h, b_l, id1, 1u);
-          umma_bf16(tmem_base + CT_TM_S, a_l, b_h, id1, 1u);
+          for (int j = 0; j < 8; ++j) {                            // K = 128 channels, 16 per step
+            const uint64_t a_h = umma_desc(q_hi + j * 2 * A_LBO, A_LBO, 128), a_l = umma_desc(q_lo + j * 2 * A_LBO, A_LBO, 128);
+            const uint64_t b_h = umma_desc(xp_hi + j * 2 * T_LBO, T_LBO, 128), b_l = umma_desc(xp_lo + j * 2 * T_LBO, T_LBO, 128);
+            umma_bf16(tmem_base + CT_TM_S, a_h, b_h, id1, j ? 1u : 0u);
+            umma_bf16(tmem_base + CT_TM_S, a_h, b_l, id1, 1u);
+            umma_bf16(tmem_base + CT_TM_S, a_l, b_h, id1, 1u);
+          }
+          umma_commit(s_full);
         }
-        umma_commit(s_full);
+        __syncwarp();
         mbar_wait(p_ready, ph);
         mbar_wait(x_ready, ph);
         tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {                            // K = 64 voxels, 16 per step
-          const uint64_t a_h = umma_desc(p_hi + j * 2 * A_LBO, A_LBO, 128), a_l = umma_desc(p_lo + j * 2 * A_LBO, A_LBO, 128);
-          // MN-major B: K direction (voxel groups of 8) stride 128 B = "LBO", channel-chunk stride T_LBO = "SBO"
-          const uint64_t b_h = umma_desc(x_hi + j * 2 * 128, 128, T_LBO), b_l = umma_desc(x_lo + j * 2 * 128, 128, T_LBO);
-          umma_bf16(tmem_base + CT_TM_CTX, a_h, b_h, id2, (it | j) ? 1u : 0u);
-          umma_bf16(tmem_base + CT_TM_CTX, a_h, b_l, id2, 1u);
-          umma_bf16(tmem_base + CT_TM_CTX, a_l, b_h, id2, 1u);
+          for (int j = 0; j < 4; ++j) {                            // K = 64 voxels, 16 per step
+            const uint64_t a_h = umma_desc(p_hi + j * 2 * A_LBO, A_LBO, 128), a_l = umma_desc(p_lo + j * 2 * A_LBO, A_LBO, 128);
+            // MN-major B: K direction (voxel groups of 8) stride 128 B = "LBO", channel-chunk stride T_LBO = "SBO"
+            const uint64_t b_h = umma_desc(x_hi + j * 2 * 128, 128, T_LBO), b_l = umma_desc(x_lo + j * 2 * 128, 128, T_LBO);
+            umma_bf16(tmem_base + CT_TM_CTX, a_h, b_h, id2, (it | j) ? 1u : 0u);
+            umma_bf16(tmem_base + CT_TM_CTX, a_h, b_l, id2, 1u);
+            umma_bf16(tmem_base + CT_TM_CTX, a_l, b_h, id2, 1u);
+          }
+          umma_commit(g2_done);
         }
-        umma_commit(g2_done);
+        __syncwarp();
       }
     }
   }

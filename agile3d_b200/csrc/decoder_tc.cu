@@ -317,34 +317,41 @@ __global__ void __launch_bounds__(DT_THREADS, 1) s2c_tc_kernel(const S2cParams p
     }
   } else if (warp == 8) {
     // ======================================================================================= MMA issuer
-    if (lane == 0) {
+    // whole warp, warp-uniform state; one elected lane issues (see elect_one in tc_common.cuh)
+    {
       const uint32_t id_s = umma_idesc_bf16(HQP), id_o = umma_idesc_bf16(128), id_z = umma_idesc_bf16(DT_NQP);
-      const uint32_t r_base = smem_u32(R);
+      const uint32_t d_hi32 = umma_desc_hi32(128);
+      const uint32_t r_lo32 = umma_desc_lo32(smem_u32(R), A_LBO);
+      const uint32_t ring_u32 = smem_u32(ring);
       int nb = 0, it = 0;
       // one GEMM = `slabs` x (2 k-steps x 3 products); B operand of slab s at ring stage (b_off + s*b_slab)
       auto gemm = [&](int slabs, uint32_t d, uint32_t idesc, uint32_t b_lbo, bool stage_per_slab, uint32_t b_slab) {
-        uint32_t b_hi = 0;
+        uint32_t b_base = 0;
         for (int s = 0; s < slabs; ++s) {
           if (stage_per_slab || s == 0) {
             const int sb = nb % NBR;
             mbar_wait(b_full(sb), (uint32_t)(nb / NBR) & 1u);
             tc_fence_after();
-            b_hi = smem_u32(ring + (size_t)sb * B_STAGE);
+            b_base = umma_desc_lo32(ring_u32 + (uint32_t)sb * B_STAGE, b_lbo);
           }
-          const uint32_t bh = b_hi + (stage_per_slab ? 0u : (uint32_t)s * b_slab);
-          const uint32_t bl = bh + 4u * b_lbo;
-          const uint32_t a_hi = r_base + (uint32_t)s * A_STAGE, a_lo = a_hi + A_PIECE;
+          const uint32_t bh = b_base + ((stage_per_slab ? 0u : (uint32_t)s * b_slab) >> 4);
+          const uint32_t ah = r_lo32 + (uint32_t)s * (uint32_t)(A_STAGE >> 4);
+          const bool release = stage_per_slab || s == slabs - 1;
+          if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < 2; ++ks) {
-            const uint64_t da_hi = umma_desc(a_hi + ks * 2 * A_LBO, A_LBO, 128);
-            const uint64_t da_lo = umma_desc(a_lo + ks * 2 * A_LBO, A_LBO, 128);
-            const uint64_t db_hi = umma_desc(bh + ks * 2 * b_lbo, b_lbo, 128);
-            const uint64_t db_lo = umma_desc(bl + ks * 2 * b_lbo, b_lbo, 128);
-            umma_bf16(d, da_hi, db_hi, idesc, (s | ks) ? 1u : 0u);
-            umma_bf16(d, da_hi, db_lo, idesc, 1u);
-            umma_bf16(d, da_lo, db_hi, idesc, 1u);
+            for (int ks = 0; ks < 2; ++ks) {
+              const uint64_t da_hi = umma_desc_join(d_hi32, ah + ks * ((2 * A_LBO) >> 4));
+              const uint64_t da_lo = umma_desc_join(d_hi32, ah + ks * ((2 * A_LBO) >> 4) + (A_PIECE >> 4));
+              const uint64_t db_hi = umma_desc_join(d_hi32, bh + ks * ((2u * b_lbo) >> 4));
+              const uint64_t db_lo = umma_desc_join(d_hi32, bh + ks * ((2u * b_lbo) >> 4) + ((4u * b_lbo) >> 4));
+              umma_bf16(d, da_hi, db_hi, idesc, (s | ks) ? 1u : 0u);
+              umma_bf16(d, da_hi, db_lo, idesc, 1u);
+              umma_bf16(d, da_lo, db_hi, idesc, 1u);
+            }
+            if (release) umma_commit(b_empty(nb % NBR));
           }
-          if (stage_per_slab || s == slabs - 1) { umma_commit(b_empty(nb % NBR)); ++nb; }
+          __syncwarp();
+          if (release) ++nb;
         }
       };
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -352,20 +359,23 @@ __global__ void __launch_bounds__(DT_THREADS, 1) s2c_tc_kernel(const S2cParams p
         mbar_wait(xp_full, ph);
         tc_fence_after();
         gemm(4, tmem_base + TM_S, id_s, (uint32_t)HQP * 16u, true, 0);
-        umma_commit(s_full);
+        if (elect_one()) umma_commit(s_full);
+        __syncwarp();
         mbar_wait(p_full, ph);
         tc_fence_after();
         gemm(SLABS_P, tmem_base + TM_O, id_o, 128u * 16u, true, 0);
-        umma_commit(o_full);
+        if (elect_one()) umma_commit(o_full);
+        __syncwarp();
         mbar_wait(y_full, ph);
         tc_fence_after();
         gemm(4, tmem_base + TM_Z, id_z, (uint32_t)DT_NQP * 16u, false, 4096u);
-        umma_commit(z_full);
+        if (elect_one()) umma_commit(z_full);
+        __syncwarp();
       }
     }
   } else {
     // ======================================================================================= operand loader
-    if (lane == 0) {
+    {
       const unsigned char* img = reinterpret_cast<const unsigned char*>(p.img);
       int nb = 0;
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -374,8 +384,11 @@ __global__ void __launch_bounds__(DT_THREADS, 1) s2c_tc_kernel(const S2cParams p
           const uint32_t bytes = st < 4 ? (uint32_t)HQP * 128u : 16384u;
           const int sb = nb % NBR;
           mbar_wait(b_empty(sb), ((uint32_t)(nb / NBR) & 1u) ^ 1u);
-          mbar_arrive_expect_tx(b_full(sb), bytes);
-          bulk_g2s(smem_u32(ring + (size_t)sb * B_STAGE), img + off, bytes, b_full(sb));
+          if (elect_one()) {
+            mbar_arrive_expect_tx(b_full(sb), bytes);
+            bulk_g2s(smem_u32(ring + (size_t)sb * B_STAGE), img + off, bytes, b_full(sb));
+          }
+          __syncwarp();
           off += bytes;
           ++nb;
         }

@@ -27,7 +27,7 @@ namespace ag3d {
 constexpr int TC_BK = 32;                        // input channels per pipeline stage
 constexpr int TC_PROD_WARPS = 8;
 constexpr int TC_PROD_THREADS = TC_PROD_WARPS * 32;
-constexpr int TC_THREADS = TC_PROD_THREADS + 64; // + MMA warp + weight-loader warp
+constexpr int TC_THREADS = TC_PROD_THREADS + 96; // + MMA warp 0 + weight-loader warp + MMA warp 1
 constexpr int TC_MAX_T = 4;
 constexpr int TC_BAR_BYTES = 512;
 constexpr int TC_MAX_STAGES = 32 * 12 * TC_MAX_T;   // K <= 32 offsets, cin <= 384 (12 slabs), T tiles
@@ -106,6 +106,7 @@ struct TcParams {
   int na_log2, nb_log2;
   int k_per;        // kernel offsets per CTA row (split-K over gridDim.y); k range = [by*k_per, min(K, (by+1)*k_per))
   float* partial;   // split-K: raw accumulators [gridDim.y][n_out][cout]; NULL = fused epilogue
+  int NI;           // MMA-issuing warps (1 or 2): issuer w owns the stages of tiles j with (j & 1) == w
   int debug;        // profiling experiments only (AG3D_TC_DEBUG): 1 = skip MMAs, 2 = skip gather loads, 4 = one product
   int cpad;         // TMEM columns per tile (pow2 >= cout)
   int tmem_cols;    // allocation (pow2, 32..512)
@@ -147,8 +148,8 @@ __global__ void __launch_bounds__(TC_THREADS, SPLIT ? 2 : 1) spconv_tc_kernel(co
 
   if (tid == 0) {
     for (int s = 0; s < p.NA; ++s) { mbar_init(a_full(s), SPLIT ? 128 : TC_PROD_WARPS / 2); mbar_init(a_empty(s), 1); }
-    for (int s = 0; s < p.NB; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
-    mbar_init(acc_full, 1);
+    for (int s = 0; s < p.NB; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), p.NI); }
+    mbar_init(acc_full, p.NI);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (tid < TC_MAX_T) kmask_s[tid] = 0;
@@ -411,43 +412,54 @@ __global__ void __launch_bounds__(TC_THREADS, SPLIT ? 2 : 1) spconv_tc_kernel(co
         }
       }
     }
-  } else if (warp == TC_PROD_WARPS) {
-    // =========================================================================== MMA issuer (one thread)
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(p.cout);
-      const uint32_t b_lbo = (uint32_t)p.cout * 16u;
-      uint32_t started = 0;            // bit j: accumulator j has been written
-      int n_b = -1;                    // weight stage in use
-      uint32_t prev_kc = 0xFFFFFFFFu;
-      uint32_t b_hi = 0, b_lo = 0;
-      for (int n = 0; n < n_stage; ++n) {
-        const uint32_t e = stage_list[n];
-        const int j = (int)(e & 0xFFu);
-        if ((e >> 8) != prev_kc) {     // first tile of a new (k, slab): release the previous weight stage, take the next
-          if (n_b >= 0) umma_commit(b_empty(n_b & nb_mask));
-          ++n_b;
-          prev_kc = e >> 8;
-          const int sb = n_b & nb_mask;
-          mbar_wait(b_full(sb), ((uint32_t)n_b >> nb_shift) & 1u);
-          b_hi = smem_u32(b_smem + (size_t)sb * b_stage_bytes);
-          b_lo = b_hi + 4u * b_lbo;
-        }
-        const int s = n & na_mask;
-        mbar_wait(a_full(s), ((uint32_t)n >> na_shift) & 1u);
-        if constexpr (SPLIT) fence_proxy_async();   // cp.async (generic proxy) writes -> tensor core (async proxy) reads
-        tc_fence_after();
-        const uint32_t a_hi = smem_u32(a_smem + (size_t)s * A_STAGE);
-        const uint32_t a_lo = a_hi + A_PIECE;
-        const uint32_t d = tmem_base + (uint32_t)(j * p.cpad);
+  } else if (warp != TC_PROD_WARPS + 1) {
+    // =========================================================================== MMA issuers
+    // Issuing is the serial resource of this kernel (one instruction stream per issuer), so two warps share it:
+    // issuer w owns the stages of the tiles j with (j & 1) == w (disjoint accumulators), both walk every weight
+    // stage and both release it (b_empty counts NI arrivals).
+    const int issuer = warp == TC_PROD_WARPS ? 0 : 1;
+    if (issuer < p.NI) {
+    // The whole warp walks the stage list with warp-uniform state; one elected lane issues the six MMAs of a stage
+    // and the commit.  Descriptors of a ring slot are base + slot * stride in the low descriptor word.
+    const uint32_t idesc = umma_idesc_bf16(p.cout);
+    const uint32_t b_lbo = (uint32_t)p.cout * 16u;
+    const uint32_t d_hi32 = umma_desc_hi32(128);
+    const uint32_t a_lo32 = umma_desc_lo32(smem_u32(a_smem), A_LBO);
+    const uint32_t b_lo32 = umma_desc_lo32(smem_u32(b_smem), b_lbo);
+    const uint32_t b_lo_off = (4u * b_lbo) >> 4, b_ks_off = (2u * b_lbo) >> 4, b_slot = b_stage_bytes >> 4;
+    uint32_t started = 0;            // bit j: accumulator j has been written
+    int n_b = -1;                    // weight stage in use
+    uint32_t prev_kc = 0xFFFFFFFFu;
+    uint32_t b_cur = 0;
+    for (int n = 0; n < n_stage; ++n) {
+      const uint32_t e = stage_list[n];
+      const int j = (int)(e & 0xFFu);
+      if ((e >> 8) != prev_kc) {     // first tile of a new (k, slab): release the previous weight stage, take the next
+        if (n_b >= 0 && elect_one()) umma_commit(b_empty(n_b & nb_mask));
+        ++n_b;
+        prev_kc = e >> 8;
+        const int sb = n_b & nb_mask;
+        mbar_wait(b_full(sb), ((uint32_t)n_b >> nb_shift) & 1u);
+        b_cur = b_lo32 + (uint32_t)sb * b_slot;
+      }
+      if (p.NI == 2 && (j & 1) != issuer) continue;
+      const int s = n & na_mask;
+      mbar_wait(a_full(s), ((uint32_t)n >> na_shift) & 1u);
+      if constexpr (SPLIT) fence_proxy_async();   // cp.async (generic proxy) writes -> tensor core (async proxy) reads
+      tc_fence_after();
+      const uint32_t a_cur = a_lo32 + (uint32_t)s * (uint32_t)(A_STAGE >> 4);
+      const uint32_t d = tmem_base + (uint32_t)(j * p.cpad);
+      const uint32_t acc0 = (started >> j) & 1u;
+      started |= 1u << j;
+      if (elect_one()) {
+        if (!(p.debug & 1)) {
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {           // two 16-channel MMA steps per 32-channel slab
-          const uint64_t da_hi = umma_desc(a_hi + ks * 2 * A_LBO, A_LBO, 128);
-          const uint64_t da_lo = umma_desc(a_lo + ks * 2 * A_LBO, A_LBO, 128);
-          const uint64_t db_hi = umma_desc(b_hi + ks * 2 * b_lbo, b_lbo, 128);
-          const uint64_t db_lo = umma_desc(b_lo + ks * 2 * b_lbo, b_lbo, 128);
-          if (!(p.debug & 1)) {
-            umma_bf16(d, da_hi, db_hi, idesc, (started >> j) & 1u);
-            started |= 1u << j;
+          for (int ks = 0; ks < 2; ++ks) {           // two 16-channel MMA steps per 32-channel slab
+            const uint64_t da_hi = umma_desc_join(d_hi32, a_cur + ks * ((2 * A_LBO) >> 4));
+            const uint64_t da_lo = umma_desc_join(d_hi32, a_cur + ks * ((2 * A_LBO) >> 4) + (A_PIECE >> 4));
+            const uint64_t db_hi = umma_desc_join(d_hi32, b_cur + ks * b_ks_off);
+            const uint64_t db_lo = umma_desc_join(d_hi32, b_cur + ks * b_ks_off + b_lo_off);
+            umma_bf16(d, da_hi, db_hi, idesc, ks ? 1u : acc0);
             if (!(p.debug & 4)) {
               umma_bf16(d, da_hi, db_lo, idesc, 1u);
               umma_bf16(d, da_lo, db_hi, idesc, 1u);
@@ -456,20 +468,23 @@ __global__ void __launch_bounds__(TC_THREADS, SPLIT ? 2 : 1) spconv_tc_kernel(co
         }
         umma_commit(a_empty(s));       // stage s may be overwritten once these MMAs have read it
       }
-      umma_commit(acc_full);
+      __syncwarp();
+    }
+    if (elect_one()) umma_commit(acc_full);
+    __syncwarp();
     }
   } else {
     // =========================================================================== weight loader (TMA engine)
-    if (lane == 0) {
-      int n_b = 0;
-      uint32_t prev_kc = 0xFFFFFFFFu;
-      for (int n = 0; n < n_stage; ++n) {
-        const uint32_t e = stage_list[n];
-        if ((e >> 8) == prev_kc) continue;
-        prev_kc = e >> 8;
-        const int k = (int)(e >> 16), c = (int)((e >> 8) & 0xFFu);
-        const int sb = n_b & nb_mask;
-        mbar_wait(b_empty(sb), (((uint32_t)n_b >> nb_shift) & 1u) ^ 1u);
+    int n_b = 0;
+    uint32_t prev_kc = 0xFFFFFFFFu;
+    for (int n = 0; n < n_stage; ++n) {
+      const uint32_t e = stage_list[n];
+      if ((e >> 8) == prev_kc) continue;
+      prev_kc = e >> 8;
+      const int k = (int)(e >> 16), c = (int)((e >> 8) & 0xFFu);
+      const int sb = n_b & nb_mask;
+      mbar_wait(b_empty(sb), (((uint32_t)n_b >> nb_shift) & 1u) ^ 1u);
+      if (elect_one()) {
         if (p.debug & 32) {
           mbar_arrive(b_full(sb));
         } else {
@@ -478,8 +493,9 @@ __global__ void __launch_bounds__(TC_THREADS, SPLIT ? 2 : 1) spconv_tc_kernel(co
                                      ((size_t)k * n_slab + c) * (size_t)b_stage_bytes;
           bulk_g2s(smem_u32(b_smem + (size_t)sb * b_stage_bytes), src, b_stage_bytes, b_full(sb));
         }
-        ++n_b;
       }
+      __syncwarp();
+      ++n_b;
     }
   }
 
@@ -613,9 +629,11 @@ int spconv_tc_launch(const float* in, int in_ld, int cin, const int* nbr, int K,
   const long long tiles = (n_out + TC_BM - 1) / TC_BM;
   p.partial = nullptr;
   {
-    static int dbg = -1;
+    static int dbg = -1, ni = -1;
     if (dbg < 0) { const char* e = getenv("AG3D_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
+    if (ni < 0) { const char* e = getenv("AG3D_TC_ISSUERS"); ni = e ? atoi(e) : 2; }
     p.debug = dbg;
+    p.NI = (ni == 1 || plan.T == 1) ? 1 : 2;
   }
   if (plan.ksplit > 1) {
     AG3D_CHECK_ARG(ws && aligned16(ws) && ws_bytes >= (size_t)plan.ksplit * (size_t)n_out * cout * sizeof(float),

@@ -67,6 +67,29 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+// true in exactly one lane of a converged warp.  Code guarded by it is known by ptxas to run in a single thread, so
+// the uniform-register operands of tcgen05.mma / commit / bulk copies need no per-lane "waterfall" loops (a plain
+// `lane == 0` branch costs an ELECT + BRA.U.ANY loop around every such instruction).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// the two 32-bit halves of a no-swizzle K-major UMMA descriptor (see umma_desc): only the low half depends on
+// the shared-memory address, so a ring slot's descriptors are one add away from a precomputed base
+__device__ __forceinline__ uint32_t umma_desc_lo32(uint32_t saddr, uint32_t lbo) {
+  return ((saddr >> 4) & 0x3FFFu) | (((lbo >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ uint32_t umma_desc_hi32(uint32_t sbo) { return ((sbo >> 4) & 0x3FFFu) | (1u << 14); }
+__device__ __forceinline__ uint64_t umma_desc_join(uint32_t hi32, uint32_t lo32) {
+  return ((uint64_t)hi32 << 32) | (uint64_t)lo32;
+}
+
 // UMMA shared-memory matrix descriptor, K-major, no swizzle: 8-row x 16-byte core matrices (128 contiguous
 // bytes); LBO = byte distance between core matrices adjacent in K, SBO = between core matrices adjacent in M/N.
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {

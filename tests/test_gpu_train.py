@@ -368,15 +368,22 @@ def test_backbone_backward_vs_fp64_oracle(algo):
     pcd, *_ = m.forward_backbone(xg, torch.as_tensor(raw).to(DEV))
     (pcd.F * R.float().to(DEV)).sum().backward()
     grads = {n: p.grad for n, p in m.named_parameters() if p.grad is not None}
-    assert sorted(grads) == sorted(rgrads) and len(grads) == 186
+    # 63 conv kernels (62 backbone + lin_squeeze_head) + the head bias + 62 BatchNorms x (weight, bias)
+    assert sorted(grads) == sorted(rgrads) and len(grads) == 63 + 1 + 2 * 62
     fe = rel_err(pcd.F.detach().cpu().numpy(), pcd_r.F.detach().numpy())
     l2, worst, name = _grad_errors(grads, rgrads)
-    # measured on B200: fp32 ~1e-5 / 1e-4 / 1e-3; bf16x3 convolutions on these tiny scenes (4-18 rows at the two
-    # coarsest levels, batch statistics) ~1e-3 / 1e-2 / 1e-1 (tools/train_err.py)
-    lim = (1e-4, 2e-3, 2e-2) if algo == 1 else (5e-3, 5e-2, 5e-1)
+    # Yardstick: the same graph in the oracle's own fp32 arithmetic.  These tiny scenes (4-18 rows at the two coarsest
+    # levels, batch statistics) are ill-conditioned: fp32 torch autograd itself is ~5e-3 (L2) / ~5e-2 (worst) away from
+    # fp64, so the fp32 GPU path is held to a small multiple of that, the bf16x3 path to the looser measured bound.
+    ref32 = oracle_model(7, torch.float32).train()
+    x32 = ME.SparseTensor(coordinates=torch.as_tensor(coords), features=torch.as_tensor(feats))
+    pcd32, *_ = ref32.forward_backbone(x32, torch.as_tensor(raw))
+    (pcd32.F * R.float()).sum().backward()
+    l2_32, worst_32, _ = _grad_errors({n: p.grad for n, p in ref32.named_parameters() if p.grad is not None}, rgrads)
+    lim = (1e-4, max(3 * l2_32, 2e-3), max(3 * worst_32, 2e-2)) if algo == 1 else (5e-3, 5e-2, 5e-1)
     assert fe < lim[0], fe
-    assert l2 < lim[1], l2
-    assert worst < lim[2], (worst, name)
+    assert l2 < lim[1], (l2, l2_32)
+    assert worst < lim[2], (worst, worst_32, name)
 
 
 @pytest.mark.parametrize("algo", [1, 0], ids=["fp32", "tensor-core"])
