@@ -112,26 +112,44 @@ stem_conv_kernel(const int4* __restrict__ coords, const float* __restrict__ feat
   for (; row < n; row += step) {
     const int4 c = __ldg(coords + row);
     float acc = 0.f;
-    for (int kb = 0; kb < K; kb += 32) {
-      const int k = kb + lane;
-      int src = -1;
+    // All probes of the voxel are issued before any result is used (up to 4 independent hash chains per lane), then
+    // every lane fetches the 3 features of its own hits (independent loads), and only then the hits are folded in
+    // ascending offset order through shuffles: no global load sits on the serial accumulation chain.
+    int src[4];
+    float f0[4], f1[4], f2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = j * 32 + lane;
+      src[j] = -1;
       if (k < K) {
         int r = k;
         const int jx = r % ksize; r /= ksize;
         const int jy = r % ksize; r /= ksize;
         const int x = c.y + jx - half, y = c.z + jy - half, z = c.w + r - half;
-        if (coord_in_range(c.x, x, y, z)) src = table_find(table, mask, pack_key(c.x, x, y, z));
+        if (coord_in_range(c.x, x, y, z)) src[j] = table_find(table, mask, pack_key(c.x, x, y, z));
       }
-      unsigned hits = __ballot_sync(0xffffffffu, src >= 0);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      f0[j] = f1[j] = f2[j] = 0.f;
+      if (src[j] >= 0) {
+        const float* f = feats + (long long)src[j] * STEM_CIN;
+        f0[j] = __ldg(f + 0); f1[j] = __ldg(f + 1); f2[j] = __ldg(f + 2);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      unsigned hits = __ballot_sync(0xffffffffu, src[j] >= 0);
       while (hits) {
         const int b = __ffs(hits) - 1;
         hits &= hits - 1;
-        const int s = __shfl_sync(0xffffffffu, src, b);
-        const float* f = feats + (long long)s * STEM_CIN;
-        const float* w = w_s + (kb + b) * STEM_CIN * STEM_COUT + lane;
-        acc = fmaf(__ldg(f + 0), w[0], acc);
-        acc = fmaf(__ldg(f + 1), w[STEM_COUT], acc);
-        acc = fmaf(__ldg(f + 2), w[2 * STEM_COUT], acc);
+        const float a0 = __shfl_sync(0xffffffffu, f0[j], b);
+        const float a1 = __shfl_sync(0xffffffffu, f1[j], b);
+        const float a2 = __shfl_sync(0xffffffffu, f2[j], b);
+        const float* w = w_s + (j * 32 + b) * STEM_CIN * STEM_COUT + lane;
+        acc = fmaf(a0, w[0], acc);
+        acc = fmaf(a1, w[STEM_COUT], acc);
+        acc = fmaf(a2, w[2 * STEM_COUT], acc);
       }
     }
     float v = acc;

@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(TC_THREADS, SPLIT ? 2 : 1) spconv_tc_kernel(co
         const unsigned char* src = in_b + (size_t)c_cur * 128;
 #pragma unroll
         for (int i = 0; i < PR; ++i) {
-          const bool ok = idx_cur[i] >= 0;
+          const bool ok = idx_cur[i] >= 0 && !(p.debug & 2);
           const unsigned char* g = ok ? src + (size_t)idx_cur[i] * row_bytes : src;
           cp_async16_zfill(st + st_off[i], g, ok ? 16u : 0u);
           cp_async16_zfill(st + A_PIECE + st_off[i], g + 64, ok ? 16u : 0u);
@@ -587,6 +587,11 @@ static TcPlan tc_plan(long long n_out, int K, int cout, bool split = false) {
     const double cost = (double)waves * ((double)t + (double)cout / 128.0);
     if (cost < best_cost - 1e-9) { best_cost = cost; best_t = t; }
   }
+  {
+    static int force_t = -1;         // tuning experiments only (AG3D_TC_T)
+    if (force_t < 0) { const char* e = getenv("AG3D_TC_T"); force_t = e ? atoi(e) : 0; }
+    if (force_t > 0) best_t = std::min(force_t, t_max);
+  }
   pl.T = best_t;
   const long long ctas = (tiles + pl.T - 1) / pl.T;
   const long long slots = (long long)sms * (split ? 2 : 1);     // co-resident CTAs
@@ -635,6 +640,8 @@ int spconv_tc_launch(const float* in, int in_ld, int cin, const int* nbr, int K,
     p.debug = dbg;
     p.NI = (ni == 1 || plan.T == 1) ? 1 : 2;
   }
+  static int force_na = -1;          // tuning experiments only (AG3D_TC_NA = 2 | 4 | 8)
+  if (force_na < 0) { const char* e = getenv("AG3D_TC_NA"); force_na = e ? atoi(e) : 0; }
   if (plan.ksplit > 1) {
     AG3D_CHECK_ARG(ws && aligned16(ws) && ws_bytes >= (size_t)plan.ksplit * (size_t)n_out * cout * sizeof(float),
                    "split-K workspace too small (ag3d_spconv_workspace_bytes)");
@@ -647,6 +654,7 @@ int spconv_tc_launch(const float* in, int in_ld, int cin, const int* nbr, int K,
   const size_t budget = split ? 110 * 1024 : 200 * 1024;     // split: two CTAs per SM
   int na = (int)((budget - fixed) / A_STAGE);
   na = na >= 8 ? 8 : (na >= 4 ? 4 : 2);
+  if (force_na == 2 || force_na == 4 || force_na == 8) na = std::min(na, force_na);
   p.NA = na;
   p.na_log2 = na == 8 ? 3 : (na == 4 ? 2 : 1);
   p.nb_log2 = p.NB == 4 ? 2 : 1;

@@ -319,26 +319,43 @@ stem_wgrad_kernel(const int4* __restrict__ coords, const float* __restrict__ fea
   for (; row < n; row += step) {
     const int4 c = __ldg(coords + row);
     const float g = __ldg(dz + row * dz_ld + lane);
-    for (int kb = 0; kb < K; kb += 32) {
-      const int k = kb + lane;
-      int src = -1;
+    // probes and neighbour features of all (<= 4 x 32) offsets are fetched before the serial accumulation (as in
+    // stem_conv_kernel): no global load on the dependent chain
+    int src[4];
+    float f0[4], f1[4], f2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = j * 32 + lane;
+      src[j] = -1;
       if (k < K) {
         int r = k;
         const int jx = r % ksize; r /= ksize;
         const int jy = r % ksize; r /= ksize;
         const int x = c.y + jx - half, y = c.z + jy - half, zz = c.w + r - half;
-        if (coord_in_range(c.x, x, y, zz)) src = table_find(table, mask, pack_key(c.x, x, y, zz));
+        if (coord_in_range(c.x, x, y, zz)) src[j] = table_find(table, mask, pack_key(c.x, x, y, zz));
       }
-      unsigned hits = __ballot_sync(0xffffffffu, src >= 0);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      f0[j] = f1[j] = f2[j] = 0.f;
+      if (src[j] >= 0) {
+        const float* f = feats + (long long)src[j] * 3;
+        f0[j] = __ldg(f + 0); f1[j] = __ldg(f + 1); f2[j] = __ldg(f + 2);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      unsigned hits = __ballot_sync(0xffffffffu, src[j] >= 0);
       while (hits) {
         const int b = __ffs(hits) - 1;
         hits &= hits - 1;
-        const int s = __shfl_sync(0xffffffffu, src, b);
-        const float* f = feats + (long long)s * 3;
-        float* w = dw_s + (kb + b) * 96 + lane;
-        atomicAdd(w, __ldg(f + 0) * g);
-        atomicAdd(w + 32, __ldg(f + 1) * g);
-        atomicAdd(w + 64, __ldg(f + 2) * g);
+        const float a0 = __shfl_sync(0xffffffffu, f0[j], b);
+        const float a1 = __shfl_sync(0xffffffffu, f1[j], b);
+        const float a2 = __shfl_sync(0xffffffffu, f2[j], b);
+        float* w = dw_s + (j * 32 + b) * 96 + lane;
+        atomicAdd(w, a0 * g);
+        atomicAdd(w + 32, a1 * g);
+        atomicAdd(w + 64, a2 * g);
       }
     }
   }
