@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(TC_THREADS, SPLIT ? 2 : 1) spconv_tc_kernel(co
   const uint32_t acc_full = bar_base + 8u * 24;
 
   if (tid == 0) {
-    for (int s = 0; s < p.NA; ++s) { mbar_init(a_full(s), SPLIT ? 128 : TC_PROD_WARPS / 2); mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < p.NA; ++s) { mbar_init(a_full(s), SPLIT ? ((p.debug & 256) ? 4 : 128) : TC_PROD_WARPS / 2); mbar_init(a_empty(s), 1); }
     for (int s = 0; s < p.NB; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), p.NI); }
     mbar_init(acc_full, p.NI);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -247,37 +247,50 @@ __global__ void __launch_bounds__(TC_THREADS, SPLIT ? 2 : 1) spconv_tc_kernel(co
       const size_t row_bytes = (size_t)p.in_ld * 4;
       const long long rows_left = p.n_out - row0 - rbase;   // row (j, i) is real iff j*128 + 32*i < rows_left
       const int* nbr_r = p.nbr ? p.nbr + row0 + rbase : nullptr;
-      int idx_cur[PR], idx_nxt[PR];
-      uint32_t c_cur = 0, c_nxt = 0;
-      auto fetch_idx = [&](int n, int (&idx)[PR], uint32_t& cslab) {
+      // The neighbour indices of a stage come from global memory (L2 / HBM latency); they are fetched IDX_AHEAD own
+      // stages (= 2 * IDX_AHEAD stages of the CTA) before they are used, in a register ring, so that this latency
+      // never sits on the stage loop (with one stage of look-ahead the loop ran at one index round trip per stage).
+      constexpr int IDX_AHEAD = 4;
+      int idx[IDX_AHEAD][PR];
+      uint32_t cs[IDX_AHEAD];
+      auto fetch_idx = [&](int n, int (&ix)[PR], uint32_t& cslab) {
         const uint32_t e = stage_list[n];
         const int k = (int)(e >> 16), j = (int)(e & 0xFFu);
         cslab = (e >> 8) & 0xFFu;
 #pragma unroll
         for (int i = 0; i < PR; ++i) {
           const int off = j * TC_BM + 32 * i;
-          idx[i] = -1;
-          if (off < rows_left) idx[i] = nbr_r ? __ldg(nbr_r + (long long)k * p.n_out + off) : (int)(row0 + rbase + off);
+          ix[i] = -1;
+          if (off < rows_left) ix[i] = nbr_r ? __ldg(nbr_r + (long long)k * p.n_out + off) : (int)(row0 + rbase + off);
         }
       };
-      if (grp < n_stage) fetch_idx(grp, idx_cur, c_cur);
-      for (int n = grp; n < n_stage; n += PG) {
-        if (n + PG < n_stage) fetch_idx(n + PG, idx_nxt, c_nxt);
-        const int s = n & na_mask;
-        mbar_wait(a_empty(s), (((uint32_t)n >> na_shift) & 1u) ^ 1u);
-        const uint32_t st = smem_u32(a_smem + (size_t)s * A_STAGE);
-        const unsigned char* src = in_b + (size_t)c_cur * 128;
 #pragma unroll
-        for (int i = 0; i < PR; ++i) {
-          const bool ok = idx_cur[i] >= 0 && !(p.debug & 2);
-          const unsigned char* g = ok ? src + (size_t)idx_cur[i] * row_bytes : src;
-          cp_async16_zfill(st + st_off[i], g, ok ? 16u : 0u);
-          cp_async16_zfill(st + A_PIECE + st_off[i], g + 64, ok ? 16u : 0u);
+      for (int d = 0; d < IDX_AHEAD; ++d) {
+        cs[d] = 0;
+#pragma unroll
+        for (int i = 0; i < PR; ++i) idx[d][i] = -1;
+        if (grp + d * PG < n_stage) fetch_idx(grp + d * PG, idx[d], cs[d]);
+      }
+      for (int n = grp; n < n_stage;) {
+#pragma unroll
+        for (int d = 0; d < IDX_AHEAD; ++d) {
+          if (n < n_stage) {
+            const int s = n & na_mask;
+            mbar_wait(a_empty(s), (((uint32_t)n >> na_shift) & 1u) ^ 1u);
+            const uint32_t st = smem_u32(a_smem + (size_t)s * A_STAGE);
+            const unsigned char* src = in_b + (size_t)cs[d] * 128;
+#pragma unroll
+            for (int i = 0; i < PR; ++i) {
+              const bool ok = idx[d][i] >= 0 && !(p.debug & 2);
+              const unsigned char* g = ok ? src + (size_t)idx[d][i] * row_bytes : src;
+              cp_async16_zfill(st + st_off[i], g, ok ? 16u : 0u);
+              cp_async16_zfill(st + A_PIECE + st_off[i], g + 64, ok ? 16u : 0u);
+            }
+            if (!(p.debug & 256) || lane == 0) cp_async_mbar_arrive_noinc(a_full(s));
+            if (n + IDX_AHEAD * PG < n_stage) fetch_idx(n + IDX_AHEAD * PG, idx[d], cs[d]);
+            n += PG;
+          }
         }
-        cp_async_mbar_arrive_noinc(a_full(s));
-#pragma unroll
-        for (int i = 0; i < PR; ++i) idx_cur[i] = idx_nxt[i];
-        c_cur = c_nxt;
       }
     } else {
       int idx_ld[PR];                  // neighbour rows of stage n_issued (prefetched one own-stage ahead)
@@ -445,7 +458,7 @@ __global__ void __launch_bounds__(TC_THREADS, SPLIT ? 2 : 1) spconv_tc_kernel(co
       if (p.NI == 2 && (j & 1) != issuer) continue;
       const int s = n & na_mask;
       mbar_wait(a_full(s), ((uint32_t)n >> na_shift) & 1u);
-      if constexpr (SPLIT) fence_proxy_async();   // cp.async (generic proxy) writes -> tensor core (async proxy) reads
+      if constexpr (SPLIT) { if (!(p.debug & 128)) fence_proxy_async(); }   // cp.async (generic proxy) writes -> tensor core (async proxy) reads
       tc_fence_after();
       const uint32_t a_cur = a_lo32 + (uint32_t)s * (uint32_t)(A_STAGE >> 4);
       const uint32_t d = tmem_base + (uint32_t)(j * p.cpad);
@@ -572,7 +585,17 @@ struct TcPlan { int cpad, T, ksplit, k_per; };
 
 // tiles per CTA: minimise waves * (T gathers + one weight stage); weight stage cost relative to a gather = cout/128.
 // Small levels (few tiles) are weight-streaming bound on a handful of SMs: split the kernel offsets over gridDim.y.
-static TcPlan tc_plan(long long n_out, int K, int cout, bool split = false) {
+// CTAs per SM of the split-row variant (AG3D_TC_SPLIT_OCC = 1 | 2).  Two CTAs hide each other's latencies but leave
+// each only two weight stages and T <= 2; one CTA gets four weight stages shared by up to four tiles and an
+// eight-deep gather ring.
+static int split_occ() {
+  static int occ = -1;
+  if (occ < 0) { const char* e = getenv("AG3D_TC_SPLIT_OCC"); occ = (e && atoi(e) == 2) ? 2 : 1; }
+  return occ;
+}
+
+static TcPlan tc_plan(long long n_out, int K, int cout, bool split2 = false) {
+  const bool split = split2;       // true: two co-resident CTAs per SM
   TcPlan pl;
   pl.cpad = pow2_at_least(cout, 32);
   // split mode runs two CTAs per SM: each may hold 256 TMEM columns
@@ -604,7 +627,7 @@ static TcPlan tc_plan(long long n_out, int K, int cout, bool split = false) {
 
 size_t spconv_tc_workspace_bytes(long long n_out, int K, int cout) {
   const TcPlan pl = tc_plan(n_out, K, cout, false);
-  const TcPlan ps = tc_plan(n_out, K, cout, true);
+  const TcPlan ps = tc_plan(n_out, K, cout, split_occ() == 2);
   if (ps.ksplit > pl.ksplit) return (size_t)ps.ksplit * (size_t)n_out * cout * sizeof(float);
   return pl.ksplit > 1 ? (size_t)pl.ksplit * (size_t)n_out * cout * sizeof(float) : 0;
 }
@@ -627,7 +650,8 @@ int spconv_tc_launch(const float* in, int in_ld, int cin, const int* nbr, int K,
   p.out_split = (flags & AG3D_OUT_SPLIT) ? 1 : 0;
   p.res_split = (flags & AG3D_RES_SPLIT) ? 1 : 0;
   const bool split = p.in_split != 0;
-  const TcPlan plan = tc_plan(n_out, K, cout, split);
+  const bool two = split && split_occ() == 2;     // two CTAs per SM
+  const TcPlan plan = tc_plan(n_out, K, cout, two);
   p.cpad = plan.cpad;
   p.T = plan.T;
   p.k_per = plan.k_per;
@@ -636,9 +660,9 @@ int spconv_tc_launch(const float* in, int in_ld, int cin, const int* nbr, int K,
   {
     static int dbg = -1, ni = -1;
     if (dbg < 0) { const char* e = getenv("AG3D_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
-    if (ni < 0) { const char* e = getenv("AG3D_TC_ISSUERS"); ni = e ? atoi(e) : 2; }
+    if (ni < 0) { const char* e = getenv("AG3D_TC_ISSUERS"); ni = e ? atoi(e) : 1; }
     p.debug = dbg;
-    p.NI = (ni == 1 || plan.T == 1) ? 1 : 2;
+    p.NI = (ni == 2 && plan.T > 1) ? 2 : 1;   // measured: a second issuing warp does not pay (tools/tc_probe.sh)
   }
   static int force_na = -1;          // tuning experiments only (AG3D_TC_NA = 2 | 4 | 8)
   if (force_na < 0) { const char* e = getenv("AG3D_TC_NA"); force_na = e ? atoi(e) : 0; }
@@ -648,21 +672,22 @@ int spconv_tc_launch(const float* in, int in_ld, int cin, const int* nbr, int K,
     p.partial = static_cast<float*>(ws);
   }
   p.tmem_cols = pow2_at_least(p.T * p.cpad, 32);
-  p.NB = (cout <= 128 && !split) ? 4 : 2;
+  p.NB = (cout <= 128 && !two) ? 4 : 2;
   const size_t fixed = TC_BAR_BYTES + TC_LIST_BYTES + (split ? 0 : (size_t)p.k_per * p.T * TC_BM * 4) +
                        (size_t)p.NB * (size_t)cout * 128;
-  const size_t budget = split ? 110 * 1024 : 200 * 1024;     // split: two CTAs per SM
+  const size_t budget = two ? 110 * 1024 : (split ? 224 * 1024 : 200 * 1024);
   int na = (int)((budget - fixed) / A_STAGE);
   na = na >= 8 ? 8 : (na >= 4 ? 4 : 2);
   if (force_na == 2 || force_na == 4 || force_na == 8) na = std::min(na, force_na);
   p.NA = na;
   p.na_log2 = na == 8 ? 3 : (na == 4 ? 2 : 1);
   p.nb_log2 = p.NB == 4 ? 2 : 1;
-  const size_t smem = fixed + (size_t)na * A_STAGE;
+  size_t smem = fixed + (size_t)na * A_STAGE;
+  if (!two) smem = std::max(smem, (size_t)116 * 1024);   // one CTA per SM: it may allocate all 512 TMEM columns
   static bool attr = false;
   if (!attr) {
     AG3D_CUDA(cudaFuncSetAttribute(spconv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    AG3D_CUDA(cudaFuncSetAttribute(spconv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+    AG3D_CUDA(cudaFuncSetAttribute(spconv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr = true;
   }
   const dim3 grid((unsigned)((tiles + p.T - 1) / p.T), (unsigned)plan.ksplit);

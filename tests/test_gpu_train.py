@@ -372,18 +372,92 @@ def test_backbone_backward_vs_fp64_oracle(algo):
     assert sorted(grads) == sorted(rgrads) and len(grads) == 63 + 1 + 2 * 62
     fe = rel_err(pcd.F.detach().cpu().numpy(), pcd_r.F.detach().numpy())
     l2, worst, name = _grad_errors(grads, rgrads)
-    # Yardstick: the same graph in the oracle's own fp32 arithmetic.  These tiny scenes (4-18 rows at the two coarsest
-    # levels, batch statistics) are ill-conditioned: fp32 torch autograd itself is ~5e-3 (L2) / ~5e-2 (worst) away from
-    # fp64, so the fp32 GPU path is held to a small multiple of that, the bf16x3 path to the looser measured bound.
-    ref32 = oracle_model(7, torch.float32).train()
-    x32 = ME.SparseTensor(coordinates=torch.as_tensor(coords), features=torch.as_tensor(feats))
-    pcd32, *_ = ref32.forward_backbone(x32, torch.as_tensor(raw))
-    (pcd32.F * R.float()).sum().backward()
-    l2_32, worst_32, _ = _grad_errors({n: p.grad for n, p in ref32.named_parameters() if p.grad is not None}, rgrads)
-    lim = (1e-4, max(3 * l2_32, 2e-3), max(3 * worst_32, 2e-2)) if algo == 1 else (5e-3, 5e-2, 5e-1)
+    # The loss <features, R> with a random R makes every gradient a random-sign sum, so ONE ReLU decision that differs
+    # (a pre-activation within rounding of zero) moves all gradients upstream of it by ~5e-3 (L2) / ~1e-1 (worst).
+    # Measured with tools/grad_diag2.py on B200: block by block the fp32 path is 2e-7 .. 7e-7 away from the fp64 oracle
+    # until block8.0, where a single element (|pre-activation| = 3.5e-6) falls on the other side of the ReLU; the fp32
+    # torch oracle shows the same effect on some hosts.  So: tight where no ReLU decision is involved (the head, fed by
+    # dL/dpcd and the forward features only), bounded by "a few flips" elsewhere.
+    head = {n: g for n, g in grads.items() if n.startswith("lin_squeeze_head.")}
+    hl2, hworst, _ = _grad_errors(head, {n: rgrads[n] for n in head})
+    head_tol = 1e-4 if algo == 1 else 2e-3
+    assert len(head) == 2 and hl2 < head_tol and hworst < 10 * head_tol, (hl2, hworst)
+    lim = (1e-4, 3e-2, 3e-1) if algo == 1 else (5e-3, 5e-2, 5e-1)
     assert fe < lim[0], fe
-    assert l2 < lim[1], (l2, l2_32)
-    assert worst < lim[2], (worst, worst_32, name)
+    assert l2 < lim[1], l2
+    assert worst < lim[2], (worst, name)
+
+
+def test_backbone_backward_block_by_block_fp32():
+    """The gradient entering and leaving every BasicBlock against torch.autograd on the fp64 oracle, in backward order.
+    Blocks are held to 1e-4 until the first block in which a ReLU decision differs from the oracle's (after that, all
+    upstream gradients differ legitimately, see test_backbone_backward_vs_fp64_oracle); at least the first block must
+    be reached, and in practice (B200) the first flip sits in the second block processed."""
+    import agile3d_b200
+    from agile3d_b200.backbone import Res16UNet34C
+    from oracle import me_ref as ME
+    from oracle.agile3d_ref import RefBasicBlock
+    coords, feats, raw, *_ = _two_scenes()
+    R = torch.randn((coords.shape[0], 128), generator=torch.Generator().manual_seed(3), dtype=torch.float64)
+    ref = oracle_model(7, torch.float64).train()
+    cap, relus = {}, {}
+
+    def block_hook(name):
+        def f(mod, inp, out):
+            inp[0].F.retain_grad()
+            out.F.retain_grad()
+            cap[name] = (inp[0].F, out.F)
+        return f
+
+    def relu_hook(name):
+        def f(mod, inp, out):
+            relus.setdefault(name, []).append(out.F.detach())
+        return f
+
+    for n, mod in ref.named_modules():
+        if isinstance(mod, RefBasicBlock):
+            mod.register_forward_hook(block_hook(n.replace("backbone.", "")))
+            mod.relu.register_forward_hook(relu_hook(n.replace("backbone.", "")))
+    x = ME.SparseTensor(coordinates=torch.as_tensor(coords), features=torch.as_tensor(feats).double())
+    pcd_r, *_ = ref.forward_backbone(x, torch.as_tensor(raw).double())
+    (pcd_r.F * R).sum().backward()
+    order = []
+    for stage in (8, 7, 6, 5, 4, 3, 2, 1):
+        nb = len(getattr(ref.backbone, f"block{stage}"))
+        order += [f"block{stage}.{b}" for b in reversed(range(nb))]
+    rec = []
+    orig = Res16UNet34C._block_train_bwd
+
+    def patched(self, blk_rec, dout, W, grads):
+        d_in = dout.detach().clone()
+        masks = (blk_rec[0]["y"].detach() > 0).cpu(), (blk_rec[1]["y"].detach() > 0).cpu()
+        dx = orig(self, blk_rec, dout, W, grads)
+        rec.append((d_in.double().cpu(), dx.detach().double().cpu(), masks))
+        return dx
+
+    Res16UNet34C._block_train_bwd = patched
+    try:
+        m = _gpu_train_model(7, 1)
+        xg = agile3d_b200.SparseTensor(coordinates=torch.as_tensor(coords), features=torch.as_tensor(feats), device=DEV)
+        pcd, *_ = m.forward_backbone(xg, torch.as_tensor(raw).to(DEV))
+        (pcd.F * R.float().to(DEV)).sum().backward()
+    finally:
+        Res16UNet34C._block_train_bwd = orig
+    assert len(rec) == len(order) == 23
+
+    def rel(a, b):
+        return float((a - b).norm() / max(float(b.norm()), 1e-30))
+
+    tight = 0
+    for name, (d_in, dx, masks) in zip(order, rec):
+        xin, yout = cap[name]
+        flips = sum(int((mg != (mo > 0)).sum()) for mg, mo in zip(masks, relus[name]))
+        assert rel(d_in, yout.grad) < 1e-4, (name, "dout", rel(d_in, yout.grad))
+        if flips:
+            break
+        assert rel(dx, xin.grad) < 1e-4, (name, "dx", rel(dx, xin.grad))
+        tight += 1
+    assert tight >= 1, "a ReLU decision already differs in the last block"
 
 
 @pytest.mark.parametrize("algo", [1, 0], ids=["fp32", "tensor-core"])

@@ -1,0 +1,14 @@
+#!/bin/bash
+mkdir -p gpurun_out
+python -m agile3d_b200.build > gpurun_out/build.log 2>&1
+bash tools/tc_probe.sh > gpurun_out/tc_probe3.txt 2>&1
+cat gpurun_out/tc_probe3.txt
+timeout 600 python -m pytest tests -m gpu -q -x --no-header -k "not train" 2>&1 | tail -3
+for occ in 1 2; do
+AG3D_TC_SPLIT_OCC=$occ timeout 300 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_occ$occ.json 2> gpurun_out/bench_occ$occ.err
+python - $occ <<'PY'
+import json,sys
+d=json.loads(open(f"gpurun_out/bench_occ{sys.argv[1]}.json").read().strip().splitlines()[-1])
+print("occ",sys.argv[1],round(d["value"],1), "scenes/s e2e", round(d["e2e"]["value"],1), {k:v["ms_per_step"] for k,v in d["roofline"]["families"].items()})
+PY
+done
