@@ -409,12 +409,13 @@ def run_train(args, rank, world, local_rank):
     step_e2e(0)
     ms_e2e = timed(step_e2e, args.steps)
     clocks = sampler.stop() if sampler else None
+    # per-family pass: every rank runs the step (it contains the gradient all-reduce), rank 0 records it
     fam = None
+    prof = ops.Profiler() if rank == 0 else None
+    ops.set_profiler(prof)
+    step_resident(0)
+    ops.set_profiler(None)
     if rank == 0:
-        prof = ops.Profiler()
-        ops.set_profiler(prof)
-        step_resident(0)
-        ops.set_profiler(None)
         fam = prof.summary()
     agd.barrier()
     if rank != 0:
