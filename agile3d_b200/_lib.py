@@ -35,6 +35,8 @@ SIGNATURES = {
     "ag3d_spconv_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32]),
     "ag3d_spconv_fwd": (_i32, [_vp, _i32, _i32, _vp, _i32, _i64, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _i32, _i32,
                                _i32, _vp, _sz, _vp]),
+    "ag3d_spconv_fwd_rows": (_i32, [_vp, _i64, _i32, _i32, _vp, _i32, _i64, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _i32,
+                                    _i32, _i32, _vp, _sz, _vp]),
     "ag3d_stem_conv_fwd": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
     "ag3d_posenc_workspace_bytes": (_sz, [_i32]),
     "ag3d_fourier_posenc": (_i32, [_vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _sz, _vp]),

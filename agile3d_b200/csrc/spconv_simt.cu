@@ -168,7 +168,7 @@ stem_conv_kernel(const int4* __restrict__ coords, const float* __restrict__ feat
   }
 }
 
-int spconv_tc_launch(const float* in, int in_ld, int cin, const int* nbr, int K, long long n_out,
+int spconv_tc_launch(const float* in, long long n_in, int in_ld, int cin, const int* nbr, int K, long long n_out,
                      const void* wprep, int cout, const float* scale, const float* shift, const float* residual,
                      int res_ld, float* out, int out_ld, int flags, void* ws, size_t ws_bytes, cudaStream_t st);
 bool spconv_tc_supported(int cin, int cout);
@@ -180,11 +180,12 @@ using namespace ag3d;
 
 extern "C" {
 
-int ag3d_spconv_fwd(const float* in, int32_t in_ld, int32_t cin, const int32_t* nbr, int32_t K, int64_t n_out,
-                    const float* weight, const void* weight_tc, int32_t cout, const float* scale, const float* shift,
-                    const float* residual, int32_t res_ld, float* out, int32_t out_ld, int32_t flags,
-                    int32_t algo, void* ws, size_t ws_bytes, ag3d_stream_t stream) {
+int ag3d_spconv_fwd_rows(const float* in, int64_t n_in, int32_t in_ld, int32_t cin, const int32_t* nbr, int32_t K,
+                         int64_t n_out, const float* weight, const void* weight_tc, int32_t cout, const float* scale,
+                         const float* shift, const float* residual, int32_t res_ld, float* out, int32_t out_ld,
+                         int32_t flags, int32_t algo, void* ws, size_t ws_bytes, ag3d_stream_t stream) {
   AG3D_CHECK_ARG(n_out > 0 && n_out < 2147483647LL, "row count out of range");
+  AG3D_CHECK_ARG(n_in >= 0 && n_in < 2147483647LL && (nbr || n_in == 0 || n_in == n_out), "input row count");
   AG3D_CHECK_ARG(cin > 0 && cin % 32 == 0 && cout > 0 && cout % 32 == 0, "cin and cout must be multiples of 32");
   AG3D_CHECK_ARG(K >= 1 && (nbr || K == 1), "K > 1 needs a neighbour table");
   AG3D_CHECK_ARG(in && out && aligned16(in) && aligned16(out), "bad pointers");
@@ -196,7 +197,7 @@ int ag3d_spconv_fwd(const float* in, int32_t in_ld, int32_t cin, const int32_t* 
     algo = (weight_tc && K <= 32 && spconv_tc_supported(cin, cout)) ? AG3D_ALGO_TC : AG3D_ALGO_SIMT;
   if (algo == AG3D_ALGO_TC) {
     AG3D_CHECK_ARG(spconv_tc_supported(cin, cout), "shape not supported by the tcgen05 path");
-    return spconv_tc_launch(in, in_ld, cin, nbr, K, n_out, weight_tc, cout, scale, shift, residual, res_ld, out,
+    return spconv_tc_launch(in, n_in, in_ld, cin, nbr, K, n_out, weight_tc, cout, scale, shift, residual, res_ld, out,
                             out_ld, flags, ws, ws_bytes, st);
   }
   AG3D_CHECK_ARG(algo == AG3D_ALGO_SIMT, "unknown algo");
@@ -212,6 +213,15 @@ int ag3d_spconv_fwd(const float* in, int32_t in_ld, int32_t cin, const int32_t* 
   }
   AG3D_LAUNCH_CHECK("spconv_simt");
   return AG3D_OK;
+}
+
+int ag3d_spconv_fwd(const float* in, int32_t in_ld, int32_t cin, const int32_t* nbr, int32_t K, int64_t n_out,
+                    const float* weight, const void* weight_tc, int32_t cout, const float* scale, const float* shift,
+                    const float* residual, int32_t res_ld, float* out, int32_t out_ld, int32_t flags,
+                    int32_t algo, void* ws, size_t ws_bytes, ag3d_stream_t stream) {
+  // input row count unknown (0): the tensor-core path then gathers with cp.async instead of the TMA engine
+  return ag3d_spconv_fwd_rows(in, nbr ? 0 : n_out, in_ld, cin, nbr, K, n_out, weight, weight_tc, cout, scale, shift,
+                              residual, res_ld, out, out_ld, flags, algo, ws, ws_bytes, stream);
 }
 
 int ag3d_spconv_bwd_data(const float* dout, int32_t dout_ld, int32_t cout, const int32_t* nbr_t, int32_t K,

@@ -17,8 +17,11 @@
 //   * the 8 producer warps then become the epilogue: tcgen05.ld the accumulators, apply folded BatchNorm /
 //     bias, residual, ReLU and write the channel slice of the output buffer.
 // (tile, k) pairs in which no row of the tile has a neighbour are skipped by all roles.
+#include <cuda.h>
+
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 
 #include "tc_common.cuh"
 
@@ -112,10 +115,29 @@ struct TcParams {
   int tmem_cols;    // allocation (pow2, 32..512)
 };
 
-// SPLIT = input rows are bf16 hi/lo pairs: cp.async gather, few registers, two CTAs per SM
-template <bool SPLIT>
-__global__ void __launch_bounds__(TC_THREADS, SPLIT ? 2 : 1) spconv_tc_kernel(const TcParams p) {
-  extern __shared__ __align__(128) unsigned char smem[];
+constexpr uint32_t TMA_STAGE = 16384;   // [128 rows x 128 B] gathered slab, SWIZZLE_128B, 1024-byte aligned
+
+// four rows of a 2-D tensor (row = 128 B here) -> four consecutive 128-byte lines of shared memory; a negative or
+// out-of-range row index yields zeros and still counts its bytes on the mbarrier (measured, profiles/r01_e_tma_*).
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int col, int r0, int r1,
+                                            int r2, int r3) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+      "l"(tm), "r"(bar), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+      : "memory");
+}
+
+// MODE 0: fp32 input rows, gathered through registers and split in the kernel, one CTA per SM
+// MODE 1: input rows are bf16 hi/lo pairs ("split"): cp.async gather, few registers, two CTAs per SM
+// MODE 2: split rows gathered by the TMA engine (tile::gather4, SWIZZLE_128B operand tiles): one producer WARP per
+//         ring slot issues a whole stage with a single instruction (lane l = rows 4l..4l+3)
+template <int MODE>
+__global__ void __launch_bounds__(TC_THREADS, MODE ? 2 : 1)
+spconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const TcParams p) {
+  constexpr bool SPLIT = MODE != 0;
+  constexpr bool TMA = MODE == 2;
+  extern __shared__ __align__(1024) unsigned char smem[];
   // barrier block: bars[0..7] a_full, [8..15] a_empty, [16..19] b_full, [20..23] b_empty, [24] acc_full
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 256);
@@ -127,6 +149,7 @@ __global__ void __launch_bounds__(TC_THREADS, SPLIT ? 2 : 1) spconv_tc_kernel(co
   const int TR = p.T * TC_BM;
   unsigned char* b_smem = smem + TC_BAR_BYTES + TC_LIST_BYTES + (SPLIT ? (size_t)0 : (size_t)p.k_per * TR * 4);
   unsigned char* a_smem = b_smem + (size_t)p.NB * b_stage_bytes;
+  if constexpr (TMA) a_smem += (1024u - (smem_u32(a_smem) & 1023u)) & 1023u;   // swizzle atoms are 1024-byte aligned
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long tiles_total = (p.n_out + TC_BM - 1) / TC_BM;
@@ -147,7 +170,7 @@ __global__ void __launch_bounds__(TC_THREADS, SPLIT ? 2 : 1) spconv_tc_kernel(co
   const uint32_t acc_full = bar_base + 8u * 24;
 
   if (tid == 0) {
-    for (int s = 0; s < p.NA; ++s) { mbar_init(a_full(s), SPLIT ? ((p.debug & 256) ? 4 : 128) : TC_PROD_WARPS / 2); mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < p.NA; ++s) { mbar_init(a_full(s), TMA ? 1 : (SPLIT ? ((p.debug & 256) ? 4 : 128) : TC_PROD_WARPS / 2)); mbar_init(a_empty(s), 1); }
     for (int s = 0; s < p.NB; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), p.NI); }
     mbar_init(acc_full, p.NI);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -239,7 +262,56 @@ __global__ void __launch_bounds__(TC_THREADS, SPLIT ? 2 : 1) spconv_tc_kernel(co
     }
     const float* in_kc = p.in + kc * 8;
 
-    if constexpr (SPLIT) {
+    if constexpr (TMA) {
+      // ---- TMA gather: producer warp w owns ring slot w (NA <= 8 warps take part).  Per stage: the lane's four
+      //      neighbour rows (fetched IDX_AHEAD own stages ahead), wait for the slot, one expect_tx, one gather4 per lane.
+      if (warp < p.NA) {
+        constexpr int IDX_AHEAD = 4;
+        const uint32_t slot = smem_u32(a_smem) + (uint32_t)warp * TMA_STAGE + (uint32_t)lane * 512u;
+        const uint32_t full = a_full(warp), empty = a_empty(warp);
+        const long long rows_here = p.n_out - row0;            // rows of this CTA that exist
+        int4 ring[IDX_AHEAD];
+        uint32_t cs[IDX_AHEAD];
+        auto fetch = [&](int n, int4& r, uint32_t& cslab) {
+          const uint32_t e = stage_list[n];
+          const int k = (int)(e >> 16), j = (int)(e & 0xFFu);
+          cslab = (e >> 8) & 0xFFu;
+          const int off = j * TC_BM + 4 * lane;
+          int v[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            v[i] = -1;
+            if (off + i < rows_here)
+              v[i] = p.nbr ? __ldg(p.nbr + (long long)k * p.n_out + row0 + off + i) : (int)(row0 + off + i);
+          }
+          r = make_int4(v[0], v[1], v[2], v[3]);
+        };
+#pragma unroll
+        for (int d = 0; d < IDX_AHEAD; ++d) {
+          ring[d] = make_int4(-1, -1, -1, -1);
+          cs[d] = 0;
+          if (warp + d * p.NA < n_stage) fetch(warp + d * p.NA, ring[d], cs[d]);
+        }
+        int it = 0;                                            // stages this warp has issued (slot phase)
+        for (int n = warp; n < n_stage;) {
+#pragma unroll
+          for (int d = 0; d < IDX_AHEAD; ++d) {
+            if (n < n_stage) {
+              const int4 r = ring[d];
+              const int col = (int)cs[d] * 64;
+              if (n + IDX_AHEAD * p.NA < n_stage) fetch(n + IDX_AHEAD * p.NA, ring[d], cs[d]);
+              mbar_wait(empty, ((uint32_t)it & 1u) ^ 1u);
+              if (lane == 0) mbar_arrive_expect_tx(full, TMA_STAGE);
+              __syncwarp();
+              if (!(p.debug & 2)) tma_gather4(slot, &tm_in, full, col, r.x, r.y, r.z, r.w);
+              else if (lane == 0) asm volatile("mbarrier.complete_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(full), "r"(TMA_STAGE) : "memory");
+              n += p.NA;
+              ++it;
+            }
+          }
+        }
+      }
+    } else if constexpr (SPLIT) {
       // ---- input already stored as bf16 hi/lo pairs: the gather is a pure byte copy, done by cp.async straight
       //      into the operand stage (no registers, no ALU); completion is tracked by the stage's mbarrier, so up to
       //      NA stages of gathers are in flight per group.
@@ -437,7 +509,14 @@ __global__ void __launch_bounds__(TC_THREADS, SPLIT ? 2 : 1) spconv_tc_kernel(co
     const uint32_t idesc = umma_idesc_bf16(p.cout);
     const uint32_t b_lbo = (uint32_t)p.cout * 16u;
     const uint32_t d_hi32 = umma_desc_hi32(128);
-    const uint32_t a_lo32 = umma_desc_lo32(smem_u32(a_smem), A_LBO);
+    // A operand: MODE 0/1 canonical no-swizzle tiles (A_STAGE bytes, hi piece | lo piece); MODE 2 one SWIZZLE_128B
+    // tile per stage whose 128-byte rows are [hi ch 0-31 | lo ch 0-31]: k-step ks of the hi (lo) product starts
+    // 32 ks (64 + 32 ks) bytes into the row, SBO = 1024 (eight rows), layout type 2.
+    const uint32_t a_hi32 = TMA ? (umma_desc_hi32(1024) | (2u << 29)) : umma_desc_hi32(128);
+    const uint32_t a_lo32 = TMA ? umma_desc_lo32(smem_u32(a_smem), 16) : umma_desc_lo32(smem_u32(a_smem), A_LBO);
+    constexpr uint32_t A_SLOT16 = TMA ? (TMA_STAGE >> 4) : (uint32_t)(A_STAGE >> 4);
+    constexpr uint32_t A_KS16 = TMA ? 2u : (uint32_t)((2 * A_LBO) >> 4);      // one 16-channel k-step
+    constexpr uint32_t A_LO16 = TMA ? 4u : (uint32_t)(A_PIECE >> 4);          // hi piece -> lo piece
     const uint32_t b_lo32 = umma_desc_lo32(smem_u32(b_smem), b_lbo);
     const uint32_t b_lo_off = (4u * b_lbo) >> 4, b_ks_off = (2u * b_lbo) >> 4, b_slot = b_stage_bytes >> 4;
     uint32_t started = 0;            // bit j: accumulator j has been written
@@ -458,9 +537,9 @@ __global__ void __launch_bounds__(TC_THREADS, SPLIT ? 2 : 1) spconv_tc_kernel(co
       if (p.NI == 2 && (j & 1) != issuer) continue;
       const int s = n & na_mask;
       mbar_wait(a_full(s), ((uint32_t)n >> na_shift) & 1u);
-      if constexpr (SPLIT) { if (!(p.debug & 128)) fence_proxy_async(); }   // cp.async (generic proxy) writes -> tensor core (async proxy) reads
+      if constexpr (SPLIT && !TMA) { if (!(p.debug & 128)) fence_proxy_async(); }   // cp.async (generic proxy) writes -> tensor core (async proxy) reads
       tc_fence_after();
-      const uint32_t a_cur = a_lo32 + (uint32_t)s * (uint32_t)(A_STAGE >> 4);
+      const uint32_t a_cur = a_lo32 + (uint32_t)s * A_SLOT16;
       const uint32_t d = tmem_base + (uint32_t)(j * p.cpad);
       const uint32_t acc0 = (started >> j) & 1u;
       started |= 1u << j;
@@ -468,8 +547,8 @@ __global__ void __launch_bounds__(TC_THREADS, SPLIT ? 2 : 1) spconv_tc_kernel(co
         if (!(p.debug & 1)) {
 #pragma unroll
           for (int ks = 0; ks < 2; ++ks) {           // two 16-channel MMA steps per 32-channel slab
-            const uint64_t da_hi = umma_desc_join(d_hi32, a_cur + ks * ((2 * A_LBO) >> 4));
-            const uint64_t da_lo = umma_desc_join(d_hi32, a_cur + ks * ((2 * A_LBO) >> 4) + (A_PIECE >> 4));
+            const uint64_t da_hi = umma_desc_join(a_hi32, a_cur + ks * A_KS16);
+            const uint64_t da_lo = umma_desc_join(a_hi32, a_cur + ks * A_KS16 + A_LO16);
             const uint64_t db_hi = umma_desc_join(d_hi32, b_cur + ks * b_ks_off);
             const uint64_t db_lo = umma_desc_join(d_hi32, b_cur + ks * b_ks_off + b_lo_off);
             umma_bf16(d, da_hi, db_hi, idesc, ks ? 1u : acc0);
@@ -636,7 +715,42 @@ bool spconv_tc_supported(int cin, int cout) {
   return cin % TC_BK == 0 && cin >= 32 && cin <= 384 && cout % 32 == 0 && cout >= 32 && cout <= 256;
 }
 
-int spconv_tc_launch(const float* in, int in_ld, int cin, const int* nbr, int K, long long n_out,
+// ---- tensor map of the split input rows for MODE 2: bf16 [rows, 2*cin] with row pitch 4*in_ld bytes, box = one
+// 128-byte slab row, SWIZZLE_128B.  The driver entry point is resolved once through the runtime (no libcuda link).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    (void)cudaGetLastError();
+  }
+  return fn;
+}
+static bool make_row_map(CUtensorMap* tm, const float* in, int in_ld, int cin, long long n_in) {
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) return false;
+  // The map must carry the TRUE row count: with an oversized row extent (the neighbour table never names a row
+  // outside the buffer, so 2^31 - 1 looked harmless) the TMA unit raised sporadic illegal-address faults on small
+  // levels (measured on B200, tools/tma_model_diag.py); absent neighbours (-1) are out of range and read as zeros.
+  if (n_in <= 0) return false;
+  cuuint64_t strides[1] = {(cuuint64_t)in_ld * 4};
+  cuuint64_t dims[2] = {(cuuint64_t)cin * 2, (cuuint64_t)n_in};
+  cuuint32_t box[2] = {64, 1};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<float*>(in), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int spconv_tc_launch(const float* in, long long n_in, int in_ld, int cin, const int* nbr, int K, long long n_out,
                      const void* wprep, int cout, const float* scale, const float* shift, const float* residual,
                      int res_ld, float* out, int out_ld, int flags, void* ws, size_t ws_bytes, cudaStream_t st) {
   AG3D_CHECK_ARG(K <= 32, "the tensor-core path handles at most 32 kernel offsets");
@@ -673,26 +787,35 @@ int spconv_tc_launch(const float* in, int in_ld, int cin, const int* nbr, int K,
   }
   p.tmem_cols = pow2_at_least(p.T * p.cpad, 32);
   p.NB = (cout <= 128 && !two) ? 4 : 2;
+  // gather engine of the split-row variant: TMA tile::gather4 (default) or per-thread cp.async (AG3D_TC_GATHER=cpasync)
+  static int want_tma = -1;
+  if (want_tma < 0) { const char* e = getenv("AG3D_TC_GATHER"); want_tma = (e && e[0] == 'c') ? 0 : 1; }
+  alignas(64) CUtensorMap tm_in;
+  memset(&tm_in, 0, sizeof(tm_in));
+  const bool tma = split && want_tma && make_row_map(&tm_in, in, in_ld, cin, n_in);
+  const size_t a_stage = tma ? (size_t)TMA_STAGE : (size_t)A_STAGE;
   const size_t fixed = TC_BAR_BYTES + TC_LIST_BYTES + (split ? 0 : (size_t)p.k_per * p.T * TC_BM * 4) +
-                       (size_t)p.NB * (size_t)cout * 128;
+                       (size_t)p.NB * (size_t)cout * 128 + (tma ? 1024 : 0);
   const size_t budget = two ? 110 * 1024 : (split ? 224 * 1024 : 200 * 1024);
-  int na = (int)((budget - fixed) / A_STAGE);
+  int na = (int)((budget - fixed) / a_stage);
   na = na >= 8 ? 8 : (na >= 4 ? 4 : 2);
   if (force_na == 2 || force_na == 4 || force_na == 8) na = std::min(na, force_na);
   p.NA = na;
   p.na_log2 = na == 8 ? 3 : (na == 4 ? 2 : 1);
   p.nb_log2 = p.NB == 4 ? 2 : 1;
-  size_t smem = fixed + (size_t)na * A_STAGE;
+  size_t smem = fixed + (size_t)na * a_stage;
   if (!two) smem = std::max(smem, (size_t)116 * 1024);   // one CTA per SM: it may allocate all 512 TMEM columns
   static bool attr = false;
   if (!attr) {
-    AG3D_CUDA(cudaFuncSetAttribute(spconv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    AG3D_CUDA(cudaFuncSetAttribute(spconv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    AG3D_CUDA(cudaFuncSetAttribute(spconv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    AG3D_CUDA(cudaFuncSetAttribute(spconv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    AG3D_CUDA(cudaFuncSetAttribute(spconv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr = true;
   }
   const dim3 grid((unsigned)((tiles + p.T - 1) / p.T), (unsigned)plan.ksplit);
-  if (split) spconv_tc_kernel<true><<<grid, TC_THREADS, smem, st>>>(p);
-  else spconv_tc_kernel<false><<<grid, TC_THREADS, smem, st>>>(p);
+  if (tma) spconv_tc_kernel<2><<<grid, TC_THREADS, smem, st>>>(tm_in, p);
+  else if (split) spconv_tc_kernel<1><<<grid, TC_THREADS, smem, st>>>(tm_in, p);
+  else spconv_tc_kernel<0><<<grid, TC_THREADS, smem, st>>>(tm_in, p);
   AG3D_LAUNCH_CHECK("spconv_tc");
   if (plan.ksplit > 1) {
     const long long total = n_out * (cout / 16);

@@ -213,9 +213,12 @@ def spconv_fwd(x, nbr, weight, out, scale=None, shift=None, residual=None, relu=
         if wsb:
             ws = _workspace("spconv", x.device, wsb)
     with _Timed("spconv", nbytes, 2 * pairs * cin * cout):
-        check(lib().ag3d_spconv_fwd(xp, x_ld, cin, _p(nbr), K, n_out, _p(w), _p(weight_tc), cout, _p(scale), _p(shift),
-                                    rp, r_ld, op, o_ld, flags, algo, _p(ws), wsb, _stream()),
-              "ag3d_spconv_fwd")
+        rc = lib().ag3d_spconv_fwd_rows(xp, x.shape[0], x_ld, cin, _p(nbr), K, n_out, _p(w), _p(weight_tc), cout,
+                                        _p(scale), _p(shift), rp, r_ld, op, o_ld, flags, algo, _p(ws), wsb, _stream())
+        if rc:
+            check(rc, f"ag3d_spconv_fwd_rows(x {tuple(x.shape)} ld {x_ld} @{x.data_ptr():#x}, K {K}, out {tuple(out.shape)} ld {o_ld} "
+                      f"@{out.data_ptr():#x}, residual {None if residual is None else hex(residual.data_ptr())}, flags {flags}, "
+                      f"algo {algo}, ws {wsb})")
     return out
 
 

@@ -110,6 +110,13 @@ int ag3d_spconv_fwd(const float* in, int32_t in_ld, int32_t cin, const int32_t* 
                     const float* weight, const void* weight_tc, int32_t cout, const float* scale, const float* shift,
                     const float* residual, int32_t res_ld, float* out, int32_t out_ld, int32_t flags,
                     int32_t algo, void* ws, size_t ws_bytes, ag3d_stream_t stream);
+/* Same operator with the number of rows of `in` stated (n_in; with nbr == NULL it equals n_out).  Knowing the extent
+ * of the input lets the tensor-core path describe it to the TMA engine (tensor map) and gather the neighbour rows
+ * with tile::gather4 instead of per-thread cp.async; n_in == 0 means "unknown" and is what ag3d_spconv_fwd passes. */
+int ag3d_spconv_fwd_rows(const float* in, int64_t n_in, int32_t in_ld, int32_t cin, const int32_t* nbr, int32_t K,
+                         int64_t n_out, const float* weight, const void* weight_tc, int32_t cout, const float* scale,
+                         const float* shift, const float* residual, int32_t res_ld, float* out, int32_t out_ld,
+                         int32_t flags, int32_t algo, void* ws, size_t ws_bytes, ag3d_stream_t stream);
 /* Stem: conv0p1s1 (3 -> 32 channels, kernel 5, models/res16unet.py:39-47) evaluated directly against the
  * hash table (no 125-column neighbour table is materialised) with folded bn0 + ReLU.                        */
 int ag3d_stem_conv_fwd(const int32_t* coords, const float* feats, int64_t n, const void* table, int64_t cap,

@@ -96,5 +96,26 @@ int main() {
         }
       }
     }
+  // ---- does an absent row (index -1) touch memory below the tensor base?  Put the tensor at the start of its own
+  //      large allocation (the virtual addresses below it are not mapped) and gather {-1, 0, -1, 1}.
+  {
+    uint16_t* big;
+    cudaMalloc(&big, (size_t)64 << 20);
+    cudaMemset(big, 0x11, (size_t)64 << 20);
+    CUtensorMap tm;
+    cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)0x7FFFFFFF};
+    cuuint64_t strides[1] = {(cuuint64_t)C * 2};
+    cuuint32_t box[2] = {64, 1};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult rc = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, big, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    printf("== tensor at the start of a 64 MB allocation %p, rows {-1,0,-1,1}: encode rc %d\n", (void*)big, (int)rc);
+    for (int rep = 0; rep < 3; ++rep) {
+      probe<<<1, 32, 8192>>>(tm, -1, 0, -1 - rep * 1000, 1, 0, o, 4 * 128);
+      cudaError_t e = cudaDeviceSynchronize();
+      printf("   rep %d: %s\n", rep, cudaGetErrorString(e));
+      if (e != cudaSuccess) return 3;
+    }
+  }
   return 0;
 }

@@ -1,9 +1,8 @@
 #!/bin/bash
-# one full-size tensor-core conv (tools/tc_time.py) under the kernel's experiment switches: where does a stage's time go?
-run() { echo "== $*"; env "$@" python tools/tc_time.py 2>&1 | grep split=1; }
-run AG3D_TC_SPLIT_OCC=2 AG3D_TC_DEBUG=35        # barriers only
-run AG3D_TC_SPLIT_OCC=2 AG3D_TC_DEBUG=163       # + no proxy fence
-run AG3D_TC_SPLIT_OCC=2 AG3D_TC_DEBUG=291       # + 4 arrivals instead of 128
-run AG3D_TC_SPLIT_OCC=2 AG3D_TC_DEBUG=419       # + both
-run AG3D_TC_SPLIT_OCC=2 AG3D_TC_DEBUG=99        # barriers only, no epilogue
-run AG3D_TC_SPLIT_OCC=2 AG3D_TC_DEBUG=128       # full work, no proxy fence (wrong results possible)
+# one full-size tensor-core conv (tools/tc_time.py) under the kernel's experiment switches
+run() { echo "== $*"; env "$@" timeout 120 python tools/tc_time.py 2>&1 | grep -E "split=1|Error|error" | head -3; }
+run AG3D_TC_GATHER=cpasync
+run AG3D_TC_GATHER=tma
+run AG3D_TC_GATHER=tma AG3D_TC_DEBUG=1          # no MMAs
+run AG3D_TC_GATHER=tma AG3D_TC_DEBUG=2          # no gathers
+run AG3D_TC_GATHER=tma AG3D_TC_DEBUG=3
