@@ -263,12 +263,20 @@ spconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const TcParams p) {
     const float* in_kc = p.in + kc * 8;
 
     if constexpr (TMA) {
-      // ---- TMA gather: producer warp w owns ring slot w (NA <= 8 warps take part).  Per stage: the lane's four
-      //      neighbour rows (fetched IDX_AHEAD own stages ahead), wait for the slot, one expect_tx, one gather4 per lane.
-      if (warp < p.NA) {
+      // ---- TMA gather.  The eight producer warps share the NA ring slots: slot = warp % NA, and the 8 / NA warps of
+      //      a slot each issue their share of the stage's 32 gather4 instructions (row group g = rows 4g..4g+3).
+      //      ptxas serialises a warp's gather4s (one instruction per active lane), so spreading a stage over more
+      //      warps raises the issue rate (measured: profiles/r01_e_tma_gather4_bandwidth.txt).  Per stage: the lane's
+      //      four neighbour rows (fetched IDX_AHEAD own stages ahead), wait for the slot, one expect_tx, the gathers.
+      {
         constexpr int IDX_AHEAD = 4;
-        const uint32_t slot = smem_u32(a_smem) + (uint32_t)warp * TMA_STAGE + (uint32_t)lane * 512u;
-        const uint32_t full = a_full(warp), empty = a_empty(warp);
+        const int slot_id = warp & na_mask, part = warp >> na_shift;
+        const int lanes_per = (32 * p.NA) / TC_PROD_WARPS;        // active lanes per warp: 8 (NA = 2), 16, 32
+        const bool active = lane < lanes_per;
+        const int g = part * lanes_per + lane;                    // row group of this lane
+        const uint32_t slot = smem_u32(a_smem) + (uint32_t)slot_id * TMA_STAGE + (uint32_t)g * 512u;
+        const uint32_t full = a_full(slot_id), empty = a_empty(slot_id);
+        const bool leader = part == 0 && lane == 0;
         const long long rows_here = p.n_out - row0;            // rows of this CTA that exist
         int4 ring[IDX_AHEAD];
         uint32_t cs[IDX_AHEAD];
@@ -276,12 +284,12 @@ spconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const TcParams p) {
           const uint32_t e = stage_list[n];
           const int k = (int)(e >> 16), j = (int)(e & 0xFFu);
           cslab = (e >> 8) & 0xFFu;
-          const int off = j * TC_BM + 4 * lane;
+          const int off = j * TC_BM + 4 * g;
           int v[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             v[i] = -1;
-            if (off + i < rows_here)
+            if (active && off + i < rows_here)
               v[i] = p.nbr ? __ldg(p.nbr + (long long)k * p.n_out + row0 + off + i) : (int)(row0 + off + i);
           }
           r = make_int4(v[0], v[1], v[2], v[3]);
@@ -290,10 +298,10 @@ spconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const TcParams p) {
         for (int d = 0; d < IDX_AHEAD; ++d) {
           ring[d] = make_int4(-1, -1, -1, -1);
           cs[d] = 0;
-          if (warp + d * p.NA < n_stage) fetch(warp + d * p.NA, ring[d], cs[d]);
+          if (slot_id + d * p.NA < n_stage) fetch(slot_id + d * p.NA, ring[d], cs[d]);
         }
         int it = 0;                                            // stages this warp has issued (slot phase)
-        for (int n = warp; n < n_stage;) {
+        for (int n = slot_id; n < n_stage;) {
 #pragma unroll
           for (int d = 0; d < IDX_AHEAD; ++d) {
             if (n < n_stage) {
@@ -301,10 +309,13 @@ spconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const TcParams p) {
               const int col = (int)cs[d] * 64;
               if (n + IDX_AHEAD * p.NA < n_stage) fetch(n + IDX_AHEAD * p.NA, ring[d], cs[d]);
               mbar_wait(empty, ((uint32_t)it & 1u) ^ 1u);
-              if (lane == 0) mbar_arrive_expect_tx(full, TMA_STAGE);
+              if (leader) mbar_arrive_expect_tx(full, TMA_STAGE);
               __syncwarp();
-              if (!(p.debug & 2)) tma_gather4(slot, &tm_in, full, col, r.x, r.y, r.z, r.w);
-              else if (lane == 0) asm volatile("mbarrier.complete_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(full), "r"(TMA_STAGE) : "memory");
+              if (!(p.debug & 2)) {
+                if (active) tma_gather4(slot, &tm_in, full, col, r.x, r.y, r.z, r.w);
+              } else if (leader) {
+                asm volatile("mbarrier.complete_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(full), "r"(TMA_STAGE) : "memory");
+              }
               n += p.NA;
               ++it;
             }
