@@ -56,6 +56,10 @@ SIGNATURES = {
                                     _sz, _vp]),
     "ag3d_spconv_bwd_weight_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32]),
     "ag3d_spconv_bwd_weight": (_i32, [_vp, _i32, _i32, _vp, _i32, _i64, _vp, _i32, _i32, _vp, _i32, _vp, _sz, _vp]),
+    "ag3d_pack_split": (_i32, [_vp, _i32, _i32, _i64, _vp, _i32, _vp]),
+    "ag3d_spconv_bwd_weight_tc_supported": (_i32, [_i32, _i32, _i32]),
+    "ag3d_spconv_bwd_weight_tc_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32]),
+    "ag3d_spconv_bwd_weight_tc": (_i32, [_vp, _i64, _i32, _i32, _vp, _i32, _i64, _vp, _i32, _i32, _vp, _i32, _vp, _sz, _vp]),
     "ag3d_stem_bwd_weight_workspace_bytes": (_sz, [_i32]),
     "ag3d_stem_bwd_weight": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, _vp, _i32, _vp, _i32, _vp, _sz, _vp]),
     "ag3d_decoder_bwd_rows": (_i32, [_i32, _i32]),

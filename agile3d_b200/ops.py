@@ -369,6 +369,46 @@ def col_sum(z):
     return out
 
 
+def pack_split_rows(x):
+    """fp32 rows [N,C] (C % 32 == 0, a channel slice is fine) -> new contiguous tensor of "split" rows (one kernel)."""
+    _need_cuda(x)
+    xp, x_ld = _rows2d(x)
+    n, c = x.shape
+    out = torch.empty((n, c), dtype=torch.float32, device=x.device)
+    check(lib().ag3d_pack_split(xp, x_ld, c, n, _p(out), c, _stream()), "ag3d_pack_split")
+    return out
+
+
+def wgrad_tc_supported(K, cin, cout):
+    return bool(lib().ag3d_spconv_bwd_weight_tc_supported(K, cin, cout))
+
+
+def spconv_bwd_weight_tc(x_split, nbr, dout_split, K, dweight=None, accumulate=False):
+    """Tensor-core weight gradient: both operands are split rows (pack_split_rows).  -> f32 [K, cin, cout]."""
+    _need_cuda(x_split, dout_split)
+    xp, x_ld = _rows2d(x_split)
+    dp, d_ld = _rows2d(dout_split)
+    n_out, cout = dout_split.shape
+    n_in, cin = x_split.shape
+    if nbr is not None and (tuple(nbr.shape) != (K, n_out) or not nbr.is_contiguous()):
+        raise _lib.Ag3dError(f"neighbour table must be contiguous int32 [{K},{n_out}], got {tuple(nbr.shape)}")
+    if nbr is None and (K != 1 or n_in != n_out):
+        raise _lib.Ag3dError("identity-map weight gradient needs K == 1 and equal row counts")
+    if dweight is None:
+        dweight = torch.empty((K, cin, cout), dtype=torch.float32, device=x_split.device)
+        accumulate = False
+    wsb = lib().ag3d_spconv_bwd_weight_tc_workspace_bytes(n_out, K, cin, cout)
+    ws = _ws_for("wgrad_tc", x_split.device, wsb)
+    pairs = n_out
+    if _prof is not None and nbr is not None:
+        pairs = int((nbr >= 0).sum().item())
+    with _Timed("spconv_wgrad", 4 * n_in * cin + 4 * n_out * cout + 4 * K * cin * cout + 4 * pairs, 2 * pairs * cin * cout):
+        check(lib().ag3d_spconv_bwd_weight_tc(xp, n_in, x_ld, cin, _p(nbr), K, n_out, dp, d_ld, cout, _p(dweight),
+                                              1 if accumulate else 0, _p(ws), ws.numel(), _stream()),
+              "ag3d_spconv_bwd_weight_tc")
+    return dweight
+
+
 def spconv_bwd_weight(x, nbr, dout, K, dweight=None, accumulate=False):
     """dW[k] (+)= x[nbr[k]]^T dout  -> f32 [K, cin, cout].  nbr None: K = 1 on the identity map (plain X^T dY)."""
     _need_cuda(x, dout)

@@ -209,6 +209,17 @@ size_t ag3d_spconv_bwd_weight_workspace_bytes(int64_t n_out, int32_t K, int32_t 
 int ag3d_spconv_bwd_weight(const float* in, int32_t in_ld, int32_t cin, const int32_t* nbr, int32_t K, int64_t n_out,
                            const float* dout, int32_t dout_ld, int32_t cout, float* dweight, int32_t accumulate,
                            void* ws, size_t ws_bytes, ag3d_stream_t stream);
+/* The same gradient on the tensor cores (tcgen05, "bf16x4": all four hi/lo products).  Both operands are "split" rows
+ * (AG3D_IN_SPLIT format: 64 B bf16 hi | 64 B bf16 lo per 32-channel slab; ag3d_pack_split converts fp32 rows); the
+ * neighbour rows of `in_split` and the rows of `dout_split` are gathered by the TMA engine, so the true row counts of
+ * both buffers are part of the call.  cin, cout multiples of 32.                                                    */
+int ag3d_pack_split(const float* in, int32_t in_ld, int32_t C, int64_t n, float* out, int32_t out_ld,
+                    ag3d_stream_t stream);
+int32_t ag3d_spconv_bwd_weight_tc_supported(int32_t K, int32_t cin, int32_t cout);
+size_t ag3d_spconv_bwd_weight_tc_workspace_bytes(int64_t n_out, int32_t K, int32_t cin, int32_t cout);
+int ag3d_spconv_bwd_weight_tc(const float* in_split, int64_t n_in, int32_t in_ld, int32_t cin, const int32_t* nbr,
+                              int32_t K, int64_t n_out, const float* dout_split, int32_t dout_ld, int32_t cout,
+                              float* dweight, int32_t accumulate, void* ws, size_t ws_bytes, ag3d_stream_t stream);
 /* stem (3 -> 32, probes the hash table like ag3d_stem_conv_fwd): dW[k][ci][co] (+)= feats[src_k(v)][ci] dz[v][co] */
 size_t ag3d_stem_bwd_weight_workspace_bytes(int32_t ksize);
 int ag3d_stem_bwd_weight(const int32_t* coords, const float* feats, int64_t n, const void* table, int64_t cap,
