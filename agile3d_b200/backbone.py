@@ -285,6 +285,22 @@ class Res16UNet34C(nn.Module):
                            weight_tc=wt_tc[i] if wt_tc is not None else None)
         return din
 
+    def _wgrad(self, x, nbr, dy, K):
+        """dW = x[nbr]^T dy: tcgen05 kernel on split (bf16 hi/lo) copies of both operands in tensor-core mode (the copy
+        of a layer input is shared by the convolutions that read it, e.g. conv1 and the block's downsample)."""
+        cin, cout = x.shape[1], dy.shape[1]
+        if self.algo == ops.ALGO_SIMT or not ops.wgrad_tc_supported(K, cin, cout):
+            return ops.spconv_bwd_weight(x, nbr, dy, K)
+        cache = getattr(self, "_split_cache", None)
+        key = (x.data_ptr(), tuple(x.shape), tuple(x.stride()))
+        xs = cache.get(key) if cache is not None else None
+        if xs is None:
+            xs = ops.pack_split_rows(x)
+            if cache is not None:
+                cache.clear()                      # inputs are consumed block by block: keep only the latest
+                cache[key] = xs
+        return ops.spconv_bwd_weight_tc(xs, nbr, ops.pack_split_rows(dy), K)
+
     def _conv_bn_fwd(self, name, bn_name, x, nbr, nbr_t, n_out, out, W, residual=None, relu=True):
         w3, wtc = W[name][0], W[name][1]
         bn = self.get_submodule(bn_name).bn
@@ -303,7 +319,7 @@ class Res16UNet34C(nn.Module):
         grads[rec["bn"] + ".bn.weight"] = dgamma
         grads[rec["bn"] + ".bn.bias"] = dbeta
         K = W[rec["name"]][0].shape[0]
-        dw = ops.spconv_bwd_weight(rec["x"], rec["nbr"], dy, K)
+        dw = self._wgrad(rec["x"], rec["nbr"], dy, K)
         kernel = self.get_submodule(rec["name"]).kernel
         grads[rec["name"] + ".kernel"] = dw.view_as(kernel)
         if not want_dx:
@@ -386,6 +402,7 @@ class Res16UNet34C(nn.Module):
         """dy: gradient of the backbone output [N0,96] (consumed).  -> {parameter name: gradient}."""
         tape, stem, up_c = saved
         W = self._train_weights()
+        self._split_cache = {}
         grads = {}
         tape = list(tape)
         skip_grads = {}
@@ -412,6 +429,7 @@ class Res16UNet34C(nn.Module):
         dgamma, dbeta = ops.bn_bwd(stem["z"], stem["y"], dp1, stem["mean"], stem["invstd"], bn0.weight.detach(), dp1,
                                    relu=True)
         grads["bn0.bn.weight"], grads["bn0.bn.bias"] = dgamma, dbeta
+        self._split_cache = None
         grads["conv0p1s1.kernel"] = ops.stem_bwd_weight(maps.coords[0], stem["feats"], maps.tables[0], maps.caps[0],
                                                         self.conv1_kernel_size, dp1).view_as(self.conv0p1s1.kernel)
         return grads

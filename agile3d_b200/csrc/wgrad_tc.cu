@@ -93,25 +93,28 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < WG_PROD_WARPS) {
-    // =========================================================================== producers: warp t issues tile t
-    if (warp < n_tiles && n_stage > 0) {
-      const bool is_a = warp < 2;
-      const int q = q0 + warp;                                    // combo of an A tile
-      const bool q_ok = is_a && q < combos;
+    // =========================================================================== producers
+    // ptxas serialises a warp's TMA instructions (one per active lane, ~74 cycles each), so the 64 gather4s of the two
+    // A tiles are spread over all eight warps (tile = warp & 1, eight row groups per warp, lanes 0..7), and every
+    // B tile - 128 CONSECUTIVE rows - is one ordinary 2-D tile load (box 64 x 128) issued by lane 8 of warp b.
+    if (n_stage > 0) {
+      const int t = warp & 1;                                     // A tile / combo of this warp
+      const int q = q0 + t;
+      const bool q_ok = q < combos;
       const int k = q_ok ? q / p.n_slab_in : 0;
-      const int col = is_a ? (q_ok ? (q % p.n_slab_in) * 64 : 0) : ((c_lo >> 5) + (warp - 2)) * 64;
-      const CUtensorMap* tm = is_a ? &tm_x : &tm_dy;
+      const int col_a = q_ok ? (q % p.n_slab_in) * 64 : 0;
+      const bool a_lane = lane < 8;
+      const int g = (warp >> 1) * 8 + lane;                       // row group (rows 4g .. 4g+3 of the stage)
+      const bool b_lane = lane == 8 && warp < nb;
+      const int col_b = ((c_lo >> 5) + warp) * 64;
       const int* nbr_k = p.nbr ? p.nbr + (long long)k * p.n_out : nullptr;
       auto rows_of = [&](int it) {
-        const long long o = r_lo + (long long)it * WG_ROWS + 4 * lane;
+        const long long o = r_lo + (long long)it * WG_ROWS + 4 * g;
         int v[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           v[i] = -1;
-          if (o + i < r_hi) {
-            if (!is_a) v[i] = (int)(o + i);
-            else if (q_ok) v[i] = nbr_k ? __ldg(nbr_k + o + i) : (int)(o + i);
-          }
+          if (a_lane && q_ok && o + i < r_hi) v[i] = nbr_k ? __ldg(nbr_k + o + i) : (int)(o + i);
         }
         return make_int4(v[0], v[1], v[2], v[3]);
       };
@@ -129,8 +132,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             mbar_wait(empty(s), (((uint32_t)(it / p.NS)) & 1u) ^ 1u);
             if (warp == 0 && lane == 0) mbar_arrive_expect_tx(full(s), stage_bytes);
             __syncwarp();
-            wg_gather4(tiles0 + (uint32_t)s * stage_bytes + (uint32_t)warp * WG_TILE + (uint32_t)lane * 512u, tm, full(s), col,
-                       r.x, r.y, r.z, r.w);
+            const uint32_t st = tiles0 + (uint32_t)s * stage_bytes;
+            if (a_lane) wg_gather4(st + (uint32_t)t * WG_TILE + (uint32_t)g * 512u, &tm_x, full(s), col_a, r.x, r.y, r.z, r.w);
+            if (b_lane) {
+              const int row = (int)(r_lo + (long long)it * WG_ROWS);
+              asm volatile(
+                  "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                      st + (uint32_t)(2 + warp) * WG_TILE),
+                  "l"(&tm_dy), "r"(full(s)), "r"(col_b), "r"(row)
+                  : "memory");
+            }
             ++it;
           }
         }
@@ -234,12 +245,12 @@ static WgEncodeFn wg_encode() {
   }
   return fn;
 }
-static bool wg_row_map(CUtensorMap* tm, const float* base, int ld, int channels, long long rows) {
+static bool wg_row_map(CUtensorMap* tm, const float* base, int ld, int channels, long long rows, int box_rows) {
   WgEncodeFn enc = wg_encode();
   if (!enc || rows <= 0) return false;
   cuuint64_t dims[2] = {(cuuint64_t)channels * 2, (cuuint64_t)rows};       // true extents (see spconv_tc.cu)
   cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {64, 1};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<float*>(base), dims, strides, box, estr,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
@@ -304,7 +315,7 @@ int ag3d_spconv_bwd_weight_tc(const float* in_split, int64_t n_in, int32_t in_ld
   AG3D_CHECK_ARG(ws && aligned16(ws) && ws_bytes >= (size_t)2 * pl.splits * K * cin * cout * sizeof(float),
                  "bwd_weight_tc: workspace too small (ag3d_spconv_bwd_weight_tc_workspace_bytes)");
   alignas(64) CUtensorMap tm_x, tm_dy;
-  AG3D_CHECK_ARG(wg_row_map(&tm_x, in_split, in_ld, cin, n_in) && wg_row_map(&tm_dy, dout_split, dout_ld, cout, n_out),
+  AG3D_CHECK_ARG(wg_row_map(&tm_x, in_split, in_ld, cin, n_in, 1) && wg_row_map(&tm_dy, dout_split, dout_ld, cout, n_out, WG_ROWS),
                  "bwd_weight_tc: cuTensorMapEncodeTiled failed");
   WgParams p;
   p.nbr = nbr; p.K = K; p.n_out = n_out; p.cin = cin; p.cout = cout; p.n_slab_in = cin / 32;

@@ -118,7 +118,7 @@ class _BackboneFn(torch.autograd.Function):
         bb, head = model.backbone, model.lin_squeeze_head
         dpcd = dpcd.contiguous()
         with torch.no_grad():
-            grads = {"lin_squeeze_head.kernel": ops.spconv_bwd_weight(feats, None, dpcd, 1).view_as(head.kernel),
+            grads = {"lin_squeeze_head.kernel": bb._wgrad(feats, None, dpcd, 1).view_as(head.kernel),
                      "lin_squeeze_head.bias": ops.col_sum(dpcd).view_as(head.bias)}
             wt = head.kernel.detach().t().contiguous()
             dfeats = torch.empty_like(feats)
@@ -128,6 +128,27 @@ class _BackboneFn(torch.autograd.Function):
                 grads["backbone." + k] = v
         ctx.saved = None
         return (None, None, None, None) + tuple(grads[n] for n in ctx.names)
+
+
+# X^T dY contractions over the voxels of the decoder backward (query-side gradients): tcgen05 weight-gradient kernel on
+# split copies of both operands when the model runs in tensor-core mode (set by Agile3d._forward_mask), else fp32 SIMT
+_WGRAD_TC = [False]
+
+
+def _xt_dy(xs, dys):
+    """sum over xs of x^T dy -> [1, cin, cout]; xs is a list of [Nv, cin] operands sharing one dy [Nv, cout]."""
+    dy = dys
+    cin, cout = xs[0].shape[1], dy.shape[1]
+    if _WGRAD_TC[0] and ops.wgrad_tc_supported(1, cin, cout):
+        dsplit = ops.pack_split_rows(dy)
+        out = None
+        for x in xs:
+            out = ops.spconv_bwd_weight_tc(ops.pack_split_rows(x), None, dsplit, 1, dweight=out, accumulate=out is not None)
+        return out
+    out = None
+    for x in xs:
+        out = ops.spconv_bwd_weight(x, None, dy, 1, dweight=out, accumulate=out is not None)
+    return out
 
 
 def _pad_rows(t, rows):
@@ -167,8 +188,7 @@ class _C2sFn(torch.autograd.Function):
             dr = _pad_rows((dctx * out).sum(1), hqp)
             dx, ds = ops.c2s_attn_bwd(x, pos, qf, qf.t().contiguous(), dc, dc.t().contiguous(), lse_p, dr, rowobj,
                                       hqp, label)
-            dq = ops.spconv_bwd_weight(ds, None, x, 1)
-            ops.spconv_bwd_weight(ds, None, pos, 1, dweight=dq, accumulate=True)
+            dq = _xt_dy([ds], x + pos)                       # dS^T x + dS^T pos
         return dx, None, dq[0, :HQ], None, None, None, None, None
 
 
@@ -194,10 +214,9 @@ class _S2cFn(torch.autograd.Function):
                 x, pos, Ap, Ap.t().contiguous(), _pad_rows(c, hqp), Up, Up.t().contiguous(), bo, ln_w, ln_b, eps, Ep,
                 Ep.t().contiguous(), q_obj, nq, H, n_obj, hqp,
                 None if dxo is None else dxo.contiguous(), None if dlogits is None else dlogits.contiguous())
-            dA = ops.spconv_bwd_weight(ds, None, x, 1)
-            ops.spconv_bwd_weight(ds, None, pos, 1, dweight=dA, accumulate=True)
-            dU = ops.spconv_bwd_weight(a, None, dy, 1)
-            dE = ops.spconv_bwd_weight(g, None, x_out, 1)
+            dA = _xt_dy([ds], x + pos)                       # dS^T x + dS^T pos
+            dU = _xt_dy([a], dy)
+            dE = _xt_dy([g], x_out)
         return (dx, None, dA[0, :HQ], cols[384:384 + HQ], dU[0, :HQ], cols[:128], cols[128:256], cols[256:384],
                 dE[0, :nq], None, None, None, None, None)
 
@@ -357,6 +376,7 @@ class Agile3d(nn.Module):
         dev = pcd_features.F.device
         offsets = pcd_features.offsets
         n_scenes = len(offsets) - 1
+        _WGRAD_TC[0] = self.backbone.algo != ops.ALGO_SIMT
         tt = self.time_encode.to(dev) if self.time_encode.device != dev else self.time_encode
         self.time_encode = tt
         # ---- host side: flatten the click dictionaries (query order per scene: [fg clicks by object id then click
