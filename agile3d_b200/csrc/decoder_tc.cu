@@ -106,8 +106,13 @@ struct S2cCfg {
   static constexpr int HQP = 8 * NQ16;
   static constexpr int SLABS_P = HQP / 32;
   static constexpr int R_SLABS = SLABS_P > 4 ? SLABS_P : 4;
-  static constexpr int B_STAGE = HQP * 128 > 16384 ? HQP * 128 : 16384;
-  static constexpr int NBR = (HQP <= 128) ? 3 : 2;
+  // operand ring: 16-KB slots.  A G1 slab image (hi piece | lo piece, HQP * 128 bytes) of the 32-query variant is two
+  // slots (hi, lo), so four slots are in flight instead of two 32-KB stages: the ring round trip, not the MMAs, is
+  // what a tile waits for (the three GEMMs stream 17 slots per tile)
+  static constexpr int B_STAGE = 16384;
+  static constexpr int G1_CHUNKS = HQP * 128 > 16384 ? 2 : 1;          // slots per G1 slab
+  static constexpr int G1_BYTES = HQP * 128 / G1_CHUNKS;               // bytes per G1 slot
+  static constexpr int NBR = (HQP <= 128) ? 6 : 4;
   static constexpr size_t SMEM = DT_MISC_BYTES + (size_t)R_SLABS * A_STAGE + (size_t)NBR * B_STAGE;
 };
 
@@ -117,7 +122,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) s2c_tc_kernel(const S2cParams p
   constexpr int HQP = Cfg::HQP, SLABS_P = Cfg::SLABS_P, NBR = Cfg::NBR;
   constexpr uint32_t B_STAGE = Cfg::B_STAGE;
   extern __shared__ __align__(128) unsigned char smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);            // [0..5] phase barriers, [8..] ring
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);            // [0..5] phase barriers, [8..15] ring full, [16..23] ring empty
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 192);
   int* hist_s = reinterpret_cast<int*>(smem + 256);              // [32]
   int* qobj_s = reinterpret_cast<int*>(smem + 384);              // [32]
@@ -132,7 +137,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) s2c_tc_kernel(const S2cParams p
   const uint32_t xp_full = bar_base, s_full = bar_base + 8, p_full = bar_base + 16, o_full = bar_base + 24,
                  y_full = bar_base + 32, z_full = bar_base + 40;
   auto b_full = [&](int s) { return bar_base + 8u * (8 + s); };
-  auto b_empty = [&](int s) { return bar_base + 8u * (12 + s); };
+  auto b_empty = [&](int s) { return bar_base + 8u * (16 + s); };   // up to 8 ring slots: barriers 8..15 / 16..23
 
   if (tid == 0) {
     mbar_init(xp_full, 8); mbar_init(p_full, 8); mbar_init(y_full, 8);
@@ -324,51 +329,61 @@ __global__ void __launch_bounds__(DT_THREADS, 1) s2c_tc_kernel(const S2cParams p
       const uint32_t r_lo32 = umma_desc_lo32(smem_u32(R), A_LBO);
       const uint32_t ring_u32 = smem_u32(ring);
       int nb = 0, it = 0;
-      // one GEMM = `slabs` x (2 k-steps x 3 products); B operand of slab s at ring stage (b_off + s*b_slab)
-      auto gemm = [&](int slabs, uint32_t d, uint32_t idesc, uint32_t b_lbo, bool stage_per_slab, uint32_t b_slab) {
-        uint32_t b_base = 0;
+      // one GEMM = `slabs` x (2 k-steps x 3 products).  chunks = ring slots per slab (2: hi piece and lo piece in
+      // separate slots, G1 of the 32-query variant; 1: whole slab image in one slot; 0: all slabs in ONE slot, G3)
+      auto gemm = [&](int slabs, uint32_t d, uint32_t idesc, uint32_t b_lbo, int chunks, uint32_t b_slab) {
+        uint32_t b_hi = 0, b_lo = 0;
         for (int s = 0; s < slabs; ++s) {
-          if (stage_per_slab || s == 0) {
+          if (chunks || s == 0) {
             const int sb = nb % NBR;
             mbar_wait(b_full(sb), (uint32_t)(nb / NBR) & 1u);
+            b_hi = umma_desc_lo32(ring_u32 + (uint32_t)sb * B_STAGE, b_lbo);
+            b_lo = b_hi + ((4u * b_lbo) >> 4);
+            if (chunks == 2) {
+              const int sb2 = (nb + 1) % NBR;
+              mbar_wait(b_full(sb2), (uint32_t)((nb + 1) / NBR) & 1u);
+              b_lo = umma_desc_lo32(ring_u32 + (uint32_t)sb2 * B_STAGE, b_lbo);
+            }
             tc_fence_after();
-            b_base = umma_desc_lo32(ring_u32 + (uint32_t)sb * B_STAGE, b_lbo);
           }
-          const uint32_t bh = b_base + ((stage_per_slab ? 0u : (uint32_t)s * b_slab) >> 4);
+          const uint32_t off = chunks ? 0u : ((uint32_t)s * b_slab) >> 4;
           const uint32_t ah = r_lo32 + (uint32_t)s * (uint32_t)(A_STAGE >> 4);
-          const bool release = stage_per_slab || s == slabs - 1;
+          const bool release = chunks || s == slabs - 1;
           if (elect_one()) {
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
               const uint64_t da_hi = umma_desc_join(d_hi32, ah + ks * ((2 * A_LBO) >> 4));
               const uint64_t da_lo = umma_desc_join(d_hi32, ah + ks * ((2 * A_LBO) >> 4) + (A_PIECE >> 4));
-              const uint64_t db_hi = umma_desc_join(d_hi32, bh + ks * ((2u * b_lbo) >> 4));
-              const uint64_t db_lo = umma_desc_join(d_hi32, bh + ks * ((2u * b_lbo) >> 4) + ((4u * b_lbo) >> 4));
+              const uint64_t db_hi = umma_desc_join(d_hi32, b_hi + off + ks * ((2u * b_lbo) >> 4));
+              const uint64_t db_lo = umma_desc_join(d_hi32, b_lo + off + ks * ((2u * b_lbo) >> 4));
               umma_bf16(d, da_hi, db_hi, idesc, (s | ks) ? 1u : 0u);
               umma_bf16(d, da_hi, db_lo, idesc, 1u);
               umma_bf16(d, da_lo, db_hi, idesc, 1u);
             }
-            if (release) umma_commit(b_empty(nb % NBR));
+            if (release) {
+              umma_commit(b_empty(nb % NBR));
+              if (chunks == 2) umma_commit(b_empty((nb + 1) % NBR));
+            }
           }
           __syncwarp();
-          if (release) ++nb;
+          if (release) nb += chunks == 2 ? 2 : 1;
         }
       };
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         const uint32_t ph = (uint32_t)it & 1u;
         mbar_wait(xp_full, ph);
         tc_fence_after();
-        gemm(4, tmem_base + TM_S, id_s, (uint32_t)HQP * 16u, true, 0);
+        gemm(4, tmem_base + TM_S, id_s, (uint32_t)HQP * 16u, Cfg::G1_CHUNKS, 0);
         if (elect_one()) umma_commit(s_full);
         __syncwarp();
         mbar_wait(p_full, ph);
         tc_fence_after();
-        gemm(SLABS_P, tmem_base + TM_O, id_o, 128u * 16u, true, 0);
+        gemm(SLABS_P, tmem_base + TM_O, id_o, 128u * 16u, 1, 0);
         if (elect_one()) umma_commit(o_full);
         __syncwarp();
         mbar_wait(y_full, ph);
         tc_fence_after();
-        gemm(4, tmem_base + TM_Z, id_z, (uint32_t)DT_NQP * 16u, false, 4096u);
+        gemm(4, tmem_base + TM_Z, id_z, (uint32_t)DT_NQP * 16u, 0, 4096u);
         if (elect_one()) umma_commit(z_full);
         __syncwarp();
       }
@@ -380,8 +395,8 @@ __global__ void __launch_bounds__(DT_THREADS, 1) s2c_tc_kernel(const S2cParams p
       int nb = 0;
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         size_t off = 0;
-        for (int st = 0; st < 4 + SLABS_P + 1; ++st) {
-          const uint32_t bytes = st < 4 ? (uint32_t)HQP * 128u : 16384u;
+        for (int st = 0; st < 4 * Cfg::G1_CHUNKS + SLABS_P + 1; ++st) {
+          const uint32_t bytes = st < 4 * Cfg::G1_CHUNKS ? (uint32_t)Cfg::G1_BYTES : 16384u;
           const int sb = nb % NBR;
           mbar_wait(b_empty(sb), ((uint32_t)(nb / NBR) & 1u) ^ 1u);
           if (elect_one()) {

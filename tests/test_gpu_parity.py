@@ -289,6 +289,22 @@ def test_end_to_end_vs_fp64_oracle_batched():
             assert e < 1e-3, f"layer {l} scene {b}: rel err {e}"
 
 
+def test_many_click_queries_vs_fp64_oracle():
+    """The tail of the iterative-click protocol (eval_multi_obj.py:116-167): more than 32 queries per scene.  c2s runs
+    its query groups, s2c takes the many-query path (ops._s2c_mask_many_queries); same 1e-3 criterion."""
+    from agile3d_b200.scenes import make_clicks, make_scene
+    sc = make_scene(5000, 0.02, seed=31, n_box=8)
+    clicks, times, _ = make_clicks(sc, 4, 11, 3, seed=5)                     # 44 fg + 3 bg clicks + 10 learned = 57 queries
+    coords = np.concatenate([np.zeros((sc["coords"].shape[0], 1), np.int32), sc["coords"]], 1)
+    ref_m = oracle_model(7, torch.float64)
+    _, _, _, ref_layers = oracle_forward(ref_m, coords, sc["feats"], sc["raw_coords"], [clicks], [times], dtype=torch.float64)
+    m = _gpu_model(7)
+    _, layers = _run_gpu(m, coords, sc["feats"], sc["raw_coords"], [clicks], [times])
+    for l in range(3):
+        e = rel_err(layers[l][0].cpu().numpy(), ref_layers[l][0].numpy())
+        assert e < 1e-3, f"layer {l}: rel err {e}"
+
+
 def test_forward_mask_is_repeatable_and_handles_unmutated():
     g = load_golden("g3000_k3")
     m = _gpu_model(g["wseed"])
