@@ -2,21 +2,25 @@
 //
 //   out[o, :] = act( scale * sum_k in[nbr[k][o], :] @ W[k] + shift (+ residual[o, :]) )
 //
-// Structure (one CTA, 1 per SM, 320 threads):
-//   * the CTA owns T consecutive 128-row output tiles; their fp32 accumulators [128 x Cout] live in TMEM
-//     (T * pow2(Cout) <= 512 columns) for the whole kernel;
+// Structure (352 threads: 8 producer/epilogue warps, MMA issuer, weight loader, optional second issuer):
+//   * the CTA owns T consecutive 128-row output tiles; their fp32 accumulators [128 x Cout] live in TMEM for the whole
+//     kernel (two CTAs per SM with T <= 2 in the split-row modes, one CTA with T <= 4 on fp32 rows);
 //   * the weight operand is *stationary*: for every (kernel offset k, 32-channel slab c) the pre-split weight
-//     slab is brought into shared memory ONCE by the TMA engine (cp.async.bulk, one elected thread) and reused by
-//     all T tiles, which divides the weight traffic from L2 by T;
-//   * 8 producer warps gather the 32-channel slab of the neighbour rows (coalesced 128-bit loads through the
-//     offset-major neighbour table), split every fp32 value into two bf16 pieces (hi = rn(x), lo = rn(x - hi)) and
-//     store both pieces into a ring of shared-memory stages in the UMMA canonical K-major layout;
+//     slab is brought into shared memory ONCE by the TMA engine (cp.async.bulk) and reused by all T tiles;
+//   * the A operand is the 32-channel slab of the 128 neighbour rows of (tile, k), one ring stage per (k, slab, tile):
+//       MODE 2 (default for split rows): the TMA engine gathers it - tile::gather4 pulls four rows per instruction
+//               into a SWIZZLE_128B tile, absent neighbours (-1) are out-of-range rows = zeros, completion through the
+//               stage's mbarrier; the producer warps only issue (slot = warp % NA, 32 / (8/NA) gathers per warp);
+//       MODE 1: every thread cp.async-copies its 16-byte pieces of the split rows (row count of the input unknown);
+//       MODE 0: fp32 rows through registers, split into bf16 hi/lo there, canonical no-swizzle K-major tiles;
 //   * one elected thread issues tcgen05.mma (kind::f16, bf16 inputs, fp32 accumulate): per 16-channel step the three
 //     products hi*hi + hi*lo + lo*hi ("bf16x3", relative error <= ~1e-5) accumulate into TMEM;
 //   * tcgen05.commit hands shared-memory stages back to the producers and finally signals the epilogue;
 //   * the 8 producer warps then become the epilogue: tcgen05.ld the accumulators, apply folded BatchNorm /
-//     bias, residual, ReLU and write the channel slice of the output buffer.
-// (tile, k) pairs in which no row of the tile has a neighbour are skipped by all roles.
+//     bias, residual, ReLU and write the channel slice of the output buffer (fp32 or split rows).
+// (tile, k) pairs in which no row of the tile has a neighbour are skipped by all roles; levels with few rows split
+// the kernel offsets over gridDim.y (deterministic reduction in splitk_reduce_kernel).
+// AG3D_TC_* environment switches are measurement aids (tools/tc_probe.sh), not configuration.
 #include <cuda.h>
 
 #include <algorithm>
