@@ -273,8 +273,8 @@ class Res16UNet34C(nn.Module):
     def _prep_t(self, wt):
         return [ops.prepare_tc_weight(wt[:, :, a:b].contiguous()) for a, b in self._chunks(wt.shape[2])]
 
-    def _dgrad(self, name, dz, nbr_t, n_in, W, residual=None):
-        """din [n_in, cin] = sum_k dz[nbr_t[k]] @ W_t[k] (+ residual)."""
+    def _dgrad(self, name, dz, nbr_t, n_in, W, residual=None, in_split=False):
+        """din [n_in, cin] = sum_k dz[nbr_t[k]] @ W_t[k] (+ residual).  in_split: dz holds split (bf16 hi/lo) rows."""
         _, _, wt, wt_tc = W[name]
         cin = wt.shape[2]
         din = torch.empty((n_in, cin), dtype=torch.float32, device=dz.device)
@@ -282,15 +282,17 @@ class Res16UNet34C(nn.Module):
             whole = (a, b) == (0, cin)
             ops.spconv_fwd(dz, nbr_t, wt if whole else wt[:, :, a:b].contiguous(), din[:, a:b],
                            residual=None if residual is None else residual[:, a:b], algo=self.algo,
-                           weight_tc=wt_tc[i] if wt_tc is not None else None)
+                           weight_tc=wt_tc[i] if wt_tc is not None else None, in_split=in_split)
         return din
 
-    def _wgrad(self, x, nbr, dy, K):
-        """dW = x[nbr]^T dy: tcgen05 kernel on split (bf16 hi/lo) copies of both operands in tensor-core mode (the copy
-        of a layer input is shared by the convolutions that read it, e.g. conv1 and the block's downsample)."""
-        cin, cout = x.shape[1], dy.shape[1]
-        if self.algo == ops.ALGO_SIMT or not ops.wgrad_tc_supported(K, cin, cout):
-            return ops.spconv_bwd_weight(x, nbr, dy, K)
+    def _tc_rows(self, cin, cout, K=1):
+        """tensor-core mode and shapes the tcgen05 kernels take: layer inputs and output gradients then travel as
+        split (bf16 hi/lo) copies, gathered by the TMA engine in the forward, data-gradient and weight-gradient kernels"""
+        return self.algo != ops.ALGO_SIMT and cin % 32 == 0 and cout % 32 == 0 and ops.wgrad_tc_supported(K, cin, cout)
+
+    def _split_of(self, x):
+        """split copy of a layer input, shared by the convolutions that read the same tensor (conv1 and the block's
+        downsample; forward and weight gradient)"""
         cache = getattr(self, "_split_cache", None)
         key = (x.data_ptr(), tuple(x.shape), tuple(x.stride()))
         xs = cache.get(key) if cache is not None else None
@@ -299,17 +301,26 @@ class Res16UNet34C(nn.Module):
             if cache is not None:
                 cache.clear()                      # inputs are consumed block by block: keep only the latest
                 cache[key] = xs
-        return ops.spconv_bwd_weight_tc(xs, nbr, ops.pack_split_rows(dy), K)
+        return xs
+
+    def _wgrad(self, x, nbr, dy, K, xs=None, dys=None):
+        """dW = x[nbr]^T dy: tcgen05 kernel on split copies of both operands in tensor-core mode, else fp32 SIMT."""
+        cin, cout = x.shape[1], dy.shape[1]
+        if not self._tc_rows(cin, cout, K):
+            return ops.spconv_bwd_weight(x, nbr, dy, K)
+        return ops.spconv_bwd_weight_tc(xs if xs is not None else self._split_of(x), nbr,
+                                        dys if dys is not None else ops.pack_split_rows(dy), K)
 
     def _conv_bn_fwd(self, name, bn_name, x, nbr, nbr_t, n_out, out, W, residual=None, relu=True):
         w3, wtc = W[name][0], W[name][1]
         bn = self.get_submodule(bn_name).bn
         z = torch.empty((n_out, w3.shape[2]), dtype=torch.float32, device=x.device)
-        ops.spconv_fwd(x, nbr, w3, z, algo=self.algo, weight_tc=wtc)
+        xs = self._split_of(x) if (wtc is not None and self._tc_rows(w3.shape[1], w3.shape[2], w3.shape[0])) else None
+        ops.spconv_fwd(x if xs is None else xs, nbr, w3, z, algo=self.algo, weight_tc=wtc, in_split=xs is not None)
         mean, invstd = ops.bn_stats(z, bn.eps, bn.momentum, bn.running_mean, bn.running_var)
         bn.num_batches_tracked += 1
         ops.bn_apply(z, mean, invstd, bn.weight.detach(), bn.bias.detach(), out, residual=residual, relu=relu)
-        return dict(name=name, bn=bn_name, x=x, nbr=nbr, nbr_t=nbr_t, z=z, y=out, mean=mean, invstd=invstd, relu=relu)
+        return dict(name=name, bn=bn_name, x=x, xs=xs, nbr=nbr, nbr_t=nbr_t, z=z, y=out, mean=mean, invstd=invstd, relu=relu)
 
     def _conv_bn_bwd(self, rec, dy, W, grads, g_out=None, want_dx=True, dx_residual=None):
         """dy: gradient of the layer's output y (overwritten with dz).  -> din (or None)."""
@@ -319,12 +330,14 @@ class Res16UNet34C(nn.Module):
         grads[rec["bn"] + ".bn.weight"] = dgamma
         grads[rec["bn"] + ".bn.bias"] = dbeta
         K = W[rec["name"]][0].shape[0]
-        dw = self._wgrad(rec["x"], rec["nbr"], dy, K)
+        dys = ops.pack_split_rows(dy) if self._tc_rows(rec["x"].shape[1], dy.shape[1], K) else None
+        dw = self._wgrad(rec["x"], rec["nbr"], dy, K, xs=rec.get("xs"), dys=dys)
         kernel = self.get_submodule(rec["name"]).kernel
         grads[rec["name"] + ".kernel"] = dw.view_as(kernel)
         if not want_dx:
             return None
-        return self._dgrad(rec["name"], dy, rec["nbr_t"], rec["x"].shape[0], W, residual=dx_residual)
+        return self._dgrad(rec["name"], dy if dys is None else dys, rec["nbr_t"], rec["x"].shape[0], W,
+                           residual=dx_residual, in_split=dys is not None)
 
     def _block_train_fwd(self, tape, prefix, blk, x, nbr, W, out=None):
         n, planes = x.shape[0], blk.conv1.cout
@@ -366,6 +379,7 @@ class Res16UNet34C(nn.Module):
         up_c = (P[7], P[6], P[5], P[4])
         cat = [torch.empty((N[l], up_c[l] + skip_c[l]), **f32) for l in range(4)]
         tape = []
+        self._split_cache = {}
         # stem: raw conv -> bn0 (batch statistics) -> relu
         bn0 = self.bn0.bn
         z0 = torch.empty((N[0], INIT_DIM), **f32)
@@ -395,6 +409,7 @@ class Res16UNet34C(nn.Module):
             for b, blk in enumerate(getattr(self, f"block{5 + j}")):
                 y = self._block_train_fwd(tape, f"block{5 + j}.{b}", blk, y, maps.k3[lvl], W)
             fmaps.append(y)
+        self._split_cache = None
         return y, fmaps, maps, (tape, stem, up_c)
 
     @torch.no_grad()
