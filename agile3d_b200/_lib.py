@@ -64,6 +64,13 @@ SIGNATURES = {
     "ag3d_stem_bwd_weight": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, _vp, _i32, _vp, _i32, _vp, _sz, _vp]),
     "ag3d_decoder_bwd_rows": (_i32, [_i32, _i32]),
     "ag3d_c2s_attn_bwd": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "ag3d_c2s_bwd_pointwise": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
+    "ag3d_s2c_softmax_heads": (_i32, [_vp, _i64, _i32, _i32, _i32, _vp]),
+    "ag3d_s2c_ds": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _vp]),
+    "ag3d_ln_fwd_stats": (_i32, [_vp, _i64, _f32, _vp, _vp, _vp]),
+    "ag3d_ln_bwd_workspace_bytes": (_sz, []),
+    "ag3d_ln_bwd": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "ag3d_s2c_route": (_i32, [_vp, _vp, _vp, _i32, _i32, _i64, _vp, _vp]),
     "ag3d_s2c_bwd_workspace_bytes": (_sz, [_i32]),
     "ag3d_s2c_mask_bwd": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _i32, _i32,
                                  _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

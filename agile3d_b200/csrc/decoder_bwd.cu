@@ -409,6 +409,208 @@ static int bwd_ctas(long long nv) {
   return (int)(t < 1 ? 1 : t);
 }
 
+// Point-wise middle of the click -> scene attention backward when its four GEMMs run on the tensor cores
+// (ops.c2s_attn_bwd_tc):  P = masked exp(S - lse),  dS = P * (dP - dr), in place (S -> P, dP -> dS).
+// Same masking rule as c2s_bwd_kernel: a (row j, voxel v) pair is dead when row j is padding (rowobj -2) or restricted
+// to an object other than the voxel's label.
+__global__ void __launch_bounds__(256)
+c2s_bwd_pointwise_kernel(float* __restrict__ s_p, float* __restrict__ dp_ds, const float* __restrict__ lse,
+                         const float* __restrict__ dr, const int* __restrict__ rowobj,
+                         const unsigned char* __restrict__ label, long long nv, int hq) {
+  const int c4n = hq >> 2;
+  const long long total = nv * c4n;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long v = t / c4n;
+    const int c = (int)(t % c4n) * 4;
+    const int lab = label ? (int)label[v] : 0;
+    float4 s4 = *reinterpret_cast<const float4*>(s_p + v * hq + c);
+    float4 d4 = *reinterpret_cast<const float4*>(dp_ds + v * hq + c);
+    float sv[4] = {s4.x, s4.y, s4.z, s4.w}, dv[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int ro = __ldg(rowobj + c + e);
+      const bool dead = (ro == -2) || (ro >= 0 && lab != ro);
+      const float pv = dead ? 0.f : __expf(sv[e] - __ldg(lse + c + e));
+      sv[e] = pv;
+      dv[e] = pv * (dv[e] - __ldg(dr + c + e));
+    }
+    *reinterpret_cast<float4*>(s_p + v * hq + c) = make_float4(sv[0], sv[1], sv[2], sv[3]);
+    *reinterpret_cast<float4*>(dp_ds + v * hq + c) = make_float4(dv[0], dv[1], dv[2], dv[3]);
+  }
+}
+
+// ---- point-wise / row-wise pieces of the scene -> click backward when its GEMMs run as 1x1 tensor-core convolutions
+// (ops.s2c_mask_bwd_tc).  Same formulas as s2c_bwd_kernel.
+
+// Per-(voxel, head) row operations on [nv, hqp] matrices, staged through shared memory so that global traffic is
+// coalesced (a thread owns one (voxel, head) segment of nq values; rows are padded by one float against bank conflicts):
+//   DS = false: softmax over the nq queries, in place on S
+//   DS = true : dS = a * (da - sum_q a da), in place on da
+// padding columns [heads*nq, hqp) are zeroed.
+constexpr int ROWS_TV = 32;
+template <bool DS>
+__global__ void __launch_bounds__(256)
+s2c_rows_kernel(const float* __restrict__ a, float* __restrict__ io, long long nv, int heads, int nq, int hqp) {
+  extern __shared__ float sm[];
+  const int ld = hqp + 1;
+  float* t_io = sm;                       // [ROWS_TV][ld]
+  float* t_a = sm + ROWS_TV * ld;         // [ROWS_TV][ld] (DS only)
+  const int hq = heads * nq;
+  const long long n_tiles = (nv + ROWS_TV - 1) / ROWS_TV;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long v0 = tile * ROWS_TV;
+    const int rows = (int)min((long long)ROWS_TV, nv - v0);
+    const int n4 = rows * hqp / 4;        // hqp % 4 == 0: the tile is one contiguous, 16-byte aligned span
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+      const float4 v = *(reinterpret_cast<const float4*>(io + v0 * hqp) + i);
+      const int r = (i * 4) / hqp, c = (i * 4) % hqp;
+      float* d = t_io + r * ld + c;
+      d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+      if (DS) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(a + v0 * hqp) + i);
+        float* e = t_a + r * ld + c;
+        e[0] = w.x; e[1] = w.y; e[2] = w.z; e[3] = w.w;
+      }
+    }
+    __syncthreads();
+    for (int pidx = threadIdx.x; pidx < rows * heads; pidx += blockDim.x) {
+      const int r = pidx / heads, h = pidx % heads;
+      float* row = t_io + r * ld + h * nq;
+      if (DS) {
+        const float* ar = t_a + r * ld + h * nq;
+        float dot = 0.f;
+        for (int q = 0; q < nq; ++q) dot = fmaf(ar[q], row[q], dot);
+        for (int q = 0; q < nq; ++q) row[q] = ar[q] * (row[q] - dot);
+      } else {
+        float mx = -INFINITY;
+        for (int q = 0; q < nq; ++q) mx = fmaxf(mx, row[q]);
+        float sum = 0.f;
+        for (int q = 0; q < nq; ++q) {
+          const float e = __expf(row[q] - mx);
+          row[q] = e;
+          sum += e;
+        }
+        const float inv = 1.f / sum;
+        for (int q = 0; q < nq; ++q) row[q] *= inv;
+      }
+      if (h == 0)
+        for (int c = hq; c < hqp; ++c) t_io[r * ld + c] = 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+      const int r = (i * 4) / hqp, c = (i * 4) % hqp;
+      const float* d = t_io + r * ld + c;
+      *(reinterpret_cast<float4*>(io + v0 * hqp) + i) = make_float4(d[0], d[1], d[2], d[3]);
+    }
+    __syncthreads();
+  }
+}
+
+// LayerNorm statistics of y [nv, 128]: n = (y - mean) * rstd (written), rstd (written); warp per row, 4 channels per lane
+__global__ void __launch_bounds__(256)
+ln_fwd_stats_kernel(const float* __restrict__ y, long long nv, float eps, float* __restrict__ n_out,
+                    float* __restrict__ rstd_out) {
+  const int lane = threadIdx.x & 31;
+  long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long step = (long long)gridDim.x * (blockDim.x >> 5);
+  for (; row < nv; row += step) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(y + row * BD) + lane);
+    float sum = (v.x + v.y) + (v.z + v.w);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * (1.f / BD);
+    const float4 d = make_float4(v.x - mean, v.y - mean, v.z - mean, v.w - mean);
+    float sq = fmaf(d.x, d.x, fmaf(d.y, d.y, fmaf(d.z, d.z, d.w * d.w)));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq * (1.f / BD) + eps);
+    *(reinterpret_cast<float4*>(n_out + row * BD) + lane) = make_float4(d.x * rstd, d.y * rstd, d.z * rstd, d.w * rstd);
+    if (lane == 0) rstd_out[row] = rstd;
+  }
+}
+
+// LayerNorm backward: t = d x' (total), n, rstd -> dy = rstd * (t*lw - mean(t*lw) - n * mean(t*lw*n)); per-CTA column
+// partials [dbo = sum dy | dln_w = sum t*n | dln_b = sum t] (lane l owns channels 4l..4l+3 of every row it visits)
+__global__ void __launch_bounds__(256)
+ln_bwd_kernel(const float* __restrict__ t, const float* __restrict__ n, const float* __restrict__ rstd,
+              const float* __restrict__ lw, long long nv, float* __restrict__ dy, float* __restrict__ colpart) {
+  __shared__ float red[8][3 * BD];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float4 w4 = __ldg(reinterpret_cast<const float4*>(lw) + lane);
+  float s_bo[4] = {0.f, 0.f, 0.f, 0.f}, s_w[4] = {0.f, 0.f, 0.f, 0.f}, s_b[4] = {0.f, 0.f, 0.f, 0.f};
+  long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  const long long step = (long long)gridDim.x * (blockDim.x >> 5);
+  for (; row < nv; row += step) {
+    const float4 tv = __ldg(reinterpret_cast<const float4*>(t + row * BD) + lane);
+    const float4 nv4 = __ldg(reinterpret_cast<const float4*>(n + row * BD) + lane);
+    const float r = __ldg(rstd + row);
+    const float tt[4] = {tv.x, tv.y, tv.z, tv.w}, nn[4] = {nv4.x, nv4.y, nv4.z, nv4.w}, ww[4] = {w4.x, w4.y, w4.z, w4.w};
+    float tw[4], m1 = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      s_b[e] += tt[e];
+      s_w[e] = fmaf(tt[e], nn[e], s_w[e]);
+      tw[e] = tt[e] * ww[e];
+      m1 += tw[e];
+      m2 = fmaf(tw[e], nn[e], m2);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      m1 += __shfl_xor_sync(0xffffffffu, m1, o);
+      m2 += __shfl_xor_sync(0xffffffffu, m2, o);
+    }
+    m1 *= (1.f / BD);
+    m2 *= (1.f / BD);
+    float d[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      d[e] = r * (tw[e] - m1 - nn[e] * m2);
+      s_bo[e] += d[e];
+    }
+    *(reinterpret_cast<float4*>(dy + row * BD) + lane) = make_float4(d[0], d[1], d[2], d[3]);
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    red[warp][4 * lane + e] = s_bo[e];
+    red[warp][BD + 4 * lane + e] = s_w[e];
+    red[warp][2 * BD + 4 * lane + e] = s_b[e];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 3 * BD; c += blockDim.x) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += red[w][c];
+    colpart[(long long)blockIdx.x * (3 * BD) + c] = s;
+  }
+}
+
+// first-maximum routing of the logit gradients: g[v][q] = dlogits[v][obj(q)] iff q is the first query of its object
+// that attains the object's maximum of G[v][.] (models/agile3d.py:348-361 take the max over an object's clicks)
+__global__ void __launch_bounds__(256)
+s2c_route_kernel(const float* __restrict__ G, const float* __restrict__ dlogits, const int* __restrict__ q_obj, int nq,
+                 int n_obj, long long nv, float* __restrict__ g_out) {
+  __shared__ int qobj_s[NQP];
+  if (threadIdx.x < NQP) qobj_s[threadIdx.x] = threadIdx.x < nq ? q_obj[threadIdx.x] : -1;
+  __syncthreads();
+  const long long total = nv * NQP;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long v = t / NQP;
+    const int q = (int)(t % NQP);
+    float g = 0.f;
+    if (q < nq && dlogits) {
+      const int o = qobj_s[q];
+      const float mine = __ldg(G + v * NQP + q);
+      bool first_max = true;
+      for (int q2 = 0; q2 < nq; ++q2) {
+        if (qobj_s[q2] != o || q2 == q) continue;
+        const float other = __ldg(G + v * NQP + q2);
+        if (other > mine || (other == mine && q2 < q)) first_max = false;
+      }
+      if (first_max) g = __ldg(dlogits + v * n_obj + o);
+    }
+    g_out[t] = g;
+  }
+}
+
 }  // namespace ag3d
 
 using namespace ag3d;
@@ -420,6 +622,80 @@ int32_t ag3d_decoder_bwd_rows(int32_t nq, int32_t heads) {
   for (int J : {6, 8, 10, 12, 14, 16})
     if (hq <= 16 * J) return 16 * J;
   return 0;
+}
+
+static unsigned pw_blocks(long long work) {
+  long long b = (work + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  return (unsigned)(b > cap ? cap : (b < 1 ? 1 : b));
+}
+
+int ag3d_s2c_softmax_heads(float* s_a, int64_t nv, int32_t heads, int32_t nq, int32_t hqp, ag3d_stream_t stream) {
+  AG3D_CHECK_ARG(s_a && nv > 0 && heads > 0 && nq > 0 && heads * nq <= hqp, "s2c_softmax_heads: arguments");
+  AG3D_CHECK_ARG(hqp % 4 == 0 && hqp <= 256 && aligned16(s_a), "s2c_softmax_heads: hqp");
+  const size_t smem = (size_t)ROWS_TV * (hqp + 1) * sizeof(float);
+  s2c_rows_kernel<false><<<pw_blocks((nv + ROWS_TV - 1) / ROWS_TV * 256), 256, smem, as_stream(stream)>>>(nullptr, s_a, nv, heads,
+                                                                                                       nq, hqp);
+  AG3D_LAUNCH_CHECK("s2c_softmax_heads");
+  return AG3D_OK;
+}
+
+int ag3d_s2c_ds(const float* a, float* da_ds, int64_t nv, int32_t heads, int32_t nq, int32_t hqp, ag3d_stream_t stream) {
+  AG3D_CHECK_ARG(a && da_ds && nv > 0 && heads > 0 && nq > 0 && heads * nq <= hqp, "s2c_ds: arguments");
+  AG3D_CHECK_ARG(hqp % 4 == 0 && hqp <= 256 && aligned16(a) && aligned16(da_ds), "s2c_ds: hqp");
+  const size_t smem = (size_t)2 * ROWS_TV * (hqp + 1) * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    AG3D_CUDA(cudaFuncSetAttribute(s2c_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * ROWS_TV * 257 * 4));
+    attr = true;
+  }
+  s2c_rows_kernel<true><<<pw_blocks((nv + ROWS_TV - 1) / ROWS_TV * 256), 256, smem, as_stream(stream)>>>(a, da_ds, nv, heads, nq,
+                                                                                                      hqp);
+  AG3D_LAUNCH_CHECK("s2c_ds");
+  return AG3D_OK;
+}
+
+int ag3d_ln_fwd_stats(const float* y, int64_t nv, float eps, float* n_out, float* rstd_out, ag3d_stream_t stream) {
+  AG3D_CHECK_ARG(y && n_out && rstd_out && nv > 0 && aligned16(y) && aligned16(n_out), "ln_fwd_stats: arguments");
+  ln_fwd_stats_kernel<<<pw_blocks(nv * 32), 256, 0, as_stream(stream)>>>(y, nv, eps, n_out, rstd_out);
+  AG3D_LAUNCH_CHECK("ln_fwd_stats");
+  return AG3D_OK;
+}
+
+size_t ag3d_ln_bwd_workspace_bytes(void) { return (size_t)sm_count() * 4 * 3 * BD * sizeof(float); }
+
+/* colsums: [dbo 128 | dln_w 128 | dln_b 128] */
+int ag3d_ln_bwd(const float* t, const float* n, const float* rstd, const float* ln_w, int64_t nv, float* dy,
+                float* colsums, void* ws, size_t ws_bytes, ag3d_stream_t stream) {
+  AG3D_CHECK_ARG(t && n && rstd && ln_w && dy && colsums && nv > 0, "ln_bwd: arguments");
+  AG3D_CHECK_ARG(aligned16(t) && aligned16(n) && aligned16(dy) && aligned16(ln_w), "ln_bwd: alignment");
+  long long blocks = (nv + 7) / 8;
+  if (blocks > (long long)sm_count() * 4) blocks = (long long)sm_count() * 4;
+  AG3D_CHECK_ARG(ws && ws_bytes >= (size_t)blocks * 3 * BD * sizeof(float), "ln_bwd: workspace");
+  cudaStream_t st = as_stream(stream);
+  ln_bwd_kernel<<<(unsigned)blocks, 256, 0, st>>>(t, n, rstd, ln_w, nv, dy, static_cast<float*>(ws));
+  AG3D_LAUNCH_CHECK("ln_bwd");
+  return launch_split_reduce(static_cast<const float*>(ws), (int)blocks, 3 * BD, 3 * BD, 0, colsums, st);
+}
+
+int ag3d_s2c_route(const float* G, const float* dlogits, const int32_t* q_obj, int32_t nq, int32_t n_obj, int64_t nv,
+                   float* g_out, ag3d_stream_t stream) {
+  AG3D_CHECK_ARG(G && q_obj && g_out && nv > 0 && nq > 0 && nq <= NQP, "s2c_route: arguments");
+  s2c_route_kernel<<<pw_blocks(nv * NQP), 256, 0, as_stream(stream)>>>(G, dlogits, q_obj, nq, n_obj, nv, g_out);
+  AG3D_LAUNCH_CHECK("s2c_route");
+  return AG3D_OK;
+}
+
+int ag3d_c2s_bwd_pointwise(float* s_p, float* dp_ds, const float* lse, const float* dr, const int32_t* rowobj,
+                           const uint8_t* label, int64_t nv, int32_t hq, ag3d_stream_t stream) {
+  AG3D_CHECK_ARG(nv > 0 && hq >= 4 && hq % 4 == 0, "c2s_bwd_pointwise: shape");
+  AG3D_CHECK_ARG(s_p && dp_ds && lse && dr && rowobj && aligned16(s_p) && aligned16(dp_ds), "c2s_bwd_pointwise: pointers");
+  const long long total = nv * (hq / 4);
+  long long blocks = (total + 255) / 256;
+  if (blocks > (long long)sm_count() * 16) blocks = (long long)sm_count() * 16;
+  c2s_bwd_pointwise_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(s_p, dp_ds, lse, dr, rowobj, label, nv, hq);
+  AG3D_LAUNCH_CHECK("c2s_bwd_pointwise");
+  return AG3D_OK;
 }
 
 int ag3d_c2s_attn_bwd(const float* x, const float* pos, int64_t nv, const float* qf, const float* qft,

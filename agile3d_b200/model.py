@@ -186,8 +186,11 @@ class _C2sFn(torch.autograd.Function):
             lse_p = torch.full((hqp,), float("inf"), dtype=torch.float32, device=x.device)
             lse_p[:HQ] = lse
             dr = _pad_rows((dctx * out).sum(1), hqp)
-            dx, ds = ops.c2s_attn_bwd(x, pos, qf, qf.t().contiguous(), dc, dc.t().contiguous(), lse_p, dr, rowobj,
-                                      hqp, label)
+            if _WGRAD_TC[0]:      # tensor-core mode: the four GEMMs as 1x1 tcgen05 convolutions
+                dx, ds = ops.c2s_attn_bwd_tc(x, pos, qf, dc, lse_p, dr, rowobj, hqp, label)
+            else:
+                dx, ds = ops.c2s_attn_bwd(x, pos, qf, qf.t().contiguous(), dc, dc.t().contiguous(), lse_p, dr, rowobj,
+                                          hqp, label)
             dq = _xt_dy([ds], x + pos)                       # dS^T x + dS^T pos
         return dx, None, dq[0, :HQ], None, None, None, None, None
 
@@ -210,10 +213,15 @@ class _S2cFn(torch.autograd.Function):
         HQ, hqp = H * nq, ops.decoder_bwd_rows(nq, H)
         with torch.no_grad():
             Ap, Up, Ep = _pad_rows(A, hqp), _pad_rows(U, hqp), _pad_rows(E, 32)
-            dx, a, ds, dy, g, cols = ops.s2c_mask_bwd(
-                x, pos, Ap, Ap.t().contiguous(), _pad_rows(c, hqp), Up, Up.t().contiguous(), bo, ln_w, ln_b, eps, Ep,
-                Ep.t().contiguous(), q_obj, nq, H, n_obj, hqp,
-                None if dxo is None else dxo.contiguous(), None if dlogits is None else dlogits.contiguous())
+            dxo_c = None if dxo is None else dxo.contiguous()
+            dlg_c = None if dlogits is None else dlogits.contiguous()
+            if _WGRAD_TC[0]:      # tensor-core mode: the six GEMMs as 1x1 tcgen05 convolutions
+                dx, a, ds, dy, g, cols = ops.s2c_mask_bwd_tc(x, pos, Ap, _pad_rows(c, hqp), Up, bo, ln_w, ln_b, eps, Ep,
+                                                             q_obj, nq, H, n_obj, hqp, dxo_c, dlg_c, x_out)
+            else:
+                dx, a, ds, dy, g, cols = ops.s2c_mask_bwd(
+                    x, pos, Ap, Ap.t().contiguous(), _pad_rows(c, hqp), Up, Up.t().contiguous(), bo, ln_w, ln_b, eps, Ep,
+                    Ep.t().contiguous(), q_obj, nq, H, n_obj, hqp, dxo_c, dlg_c)
             dA = _xt_dy([ds], x + pos)                       # dS^T x + dS^T pos
             dU = _xt_dy([a], dy)
             dE = _xt_dy([g], x_out)

@@ -500,6 +500,28 @@ def c2s_attn_bwd(x, pos, qf, qft, dctx, dctxt, lse, dr, rowobj, hqp, label):
     return dx, ds
 
 
+def c2s_attn_bwd_tc(x, pos, qf, dctx, lse, dr, rowobj, hqp, label):
+    """Same contract as c2s_attn_bwd (-> dx [Nv,128], dS [Nv,hqp]) with the four GEMMs of the backward as 1x1
+    tensor-core convolutions (bf16x3) and one point-wise kernel in between:
+        S = (x+pos) qf^T,  dP = x dctx^T,  P = masked exp(S - lse),  dS = P (dP - dr),  dx = P dctx + dS qf.
+    qf, dctx: [hqp, 128] (rows padded to hqp, a multiple of 32)."""
+    _need_cuda(x, pos, qf, dctx)
+    nv, d = x.shape
+    f32 = dict(dtype=torch.float32, device=x.device)
+    xp = x + pos
+    qft, dct = qf.t().contiguous(), dctx.t().contiguous()
+    s_p, dp_ds = torch.empty((nv, hqp), **f32), torch.empty((nv, hqp), **f32)
+    spconv_fwd(xp, None, qft, s_p, algo=ALGO_TC, weight_tc=prepare_tc_weight(qft))
+    spconv_fwd(x, None, dct, dp_ds, algo=ALGO_TC, weight_tc=prepare_tc_weight(dct))
+    with _Timed("c2s_bwd", 4 * nv * hqp * 4):
+        check(lib().ag3d_c2s_bwd_pointwise(_p(s_p), _p(dp_ds), _p(lse), _p(dr), _p(rowobj), _p(label), nv, hqp, _stream()),
+              "ag3d_c2s_bwd_pointwise")
+    dx0, dx = torch.empty((nv, d), **f32), torch.empty((nv, d), **f32)
+    spconv_fwd(s_p, None, dctx, dx0, algo=ALGO_TC, weight_tc=prepare_tc_weight(dctx))
+    spconv_fwd(dp_ds, None, qf, dx, residual=dx0, algo=ALGO_TC, weight_tc=prepare_tc_weight(qf))
+    return dx, dp_ds
+
+
 def s2c_mask_bwd(x, pos, A, At, c, U, Ut, bo, ln_w, ln_b, ln_eps, E, Et, q_obj, nq, heads, n_obj, hqp, dxo, dlogits):
     """-> (dx, a [Nv,hqp], dS [Nv,hqp], dy [Nv,128], g [Nv,32], colsums [3*128+hqp])."""
     _need_cuda(x, pos, A)
@@ -518,6 +540,52 @@ def s2c_mask_bwd(x, pos, A, At, c, U, Ut, bo, ln_w, ln_b, ln_eps, E, Et, q_obj, 
                                       _p(ln_b), float(ln_eps), _p(E), _p(Et), _p(q_obj), nq, heads, n_obj, hqp,
                                       _p(dxo), _p(dlogits), _p(dx), _p(a), _p(ds), _p(dy), _p(g), _p(cols), _p(ws),
                                       ws.numel(), _stream()), "ag3d_s2c_mask_bwd")
+    return dx, a, ds, dy, g, cols
+
+
+def s2c_mask_bwd_tc(x, pos, A, c, U, bo, ln_w, ln_b, ln_eps, E, q_obj, nq, heads, n_obj, hqp, dxo, dlogits, x_out):
+    """Same contract as s2c_mask_bwd (-> dx, a [Nv,hqp], dS [Nv,hqp], dy [Nv,128], g [Nv,32], colsums) with the six
+    GEMMs of the backward as 1x1 tensor-core convolutions (bf16x3) and row-wise kernels in between:
+        S = (x+pos) A^T + c -> a = per-head softmax        y = x + a U + bo -> n, rstd (LayerNorm statistics)
+        G = x' E^T -> g = first-maximum routing of dlogits  t = g E + dxo -> dy = LayerNorm backward (+ column sums)
+        da = dy U^T -> dS = a (da - <a, da>)                dx = dy + dS A
+    A, U: [hqp, 128] and c: [hqp] (rows padded to hqp), E: [32, 128]; x_out = x' saved by the forward."""
+    _need_cuda(x, pos, A, U, E)
+    nv, d = x.shape
+    f32 = dict(dtype=torch.float32, device=x.device)
+    st = _stream()
+    conv = lambda inp, w, out, **kw: spconv_fwd(inp, None, w, out, algo=ALGO_TC, weight_tc=prepare_tc_weight(w), **kw)
+    At, Ut, Et = A.t().contiguous(), U.t().contiguous(), E.t().contiguous()
+    a = torch.empty((nv, hqp), **f32)
+    conv(x + pos, At, a, shift=c.contiguous())
+    with _Timed("s2c_bwd", 8 * nv * hqp):
+        check(lib().ag3d_s2c_softmax_heads(_p(a), nv, heads, nq, hqp, st), "ag3d_s2c_softmax_heads")
+    y = torch.empty((nv, d), **f32)
+    conv(a, U, y, shift=bo, residual=x)
+    n, rstd = torch.empty((nv, d), **f32), torch.empty(nv, **f32)
+    with _Timed("s2c_bwd", 8 * nv * d):
+        check(lib().ag3d_ln_fwd_stats(_p(y), nv, float(ln_eps), _p(n), _p(rstd), st), "ag3d_ln_fwd_stats")
+    G, g = torch.empty((nv, 32), **f32), torch.empty((nv, 32), **f32)
+    conv(x_out, Et, G)
+    check(lib().ag3d_s2c_route(_p(G), _p(dlogits), _p(q_obj), nq, n_obj, nv, _p(g), st), "ag3d_s2c_route")
+    t = y                                                         # reuse: y is no longer needed
+    if dxo is not None:
+        conv(g, E, t, residual=dxo)
+    else:
+        conv(g, E, t)
+    dy = torch.empty((nv, d), **f32)
+    cols = torch.empty(3 * d + hqp, **f32)
+    wsb = lib().ag3d_ln_bwd_workspace_bytes()
+    ws = _ws_for("ln_bwd", x.device, wsb)
+    with _Timed("s2c_bwd", 16 * nv * d):
+        check(lib().ag3d_ln_bwd(_p(t), _p(n), _p(rstd), _p(ln_w), nv, _p(dy), _p(cols), _p(ws), ws.numel(), st), "ag3d_ln_bwd")
+    ds = torch.empty((nv, hqp), **f32)
+    conv(dy, Ut, ds)
+    with _Timed("s2c_bwd", 12 * nv * hqp):
+        check(lib().ag3d_s2c_ds(_p(a), _p(ds), nv, heads, nq, hqp, st), "ag3d_s2c_ds")
+    cols[3 * d:] = col_sum(ds)
+    dx = torch.empty((nv, d), **f32)
+    conv(ds, A, dx, residual=dy)
     return dx, a, ds, dy, g, cols
 
 

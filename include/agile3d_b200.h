@@ -239,6 +239,23 @@ int32_t ag3d_decoder_bwd_rows(int32_t nq, int32_t heads);
 int ag3d_c2s_attn_bwd(const float* x, const float* pos, int64_t nv, const float* qf, const float* qft,
                       const float* dctx, const float* dctxt, const float* lse, const float* dr, const int32_t* rowobj,
                       int32_t hqp, const uint8_t* label, float* dx, float* ds_out, ag3d_stream_t stream);
+/* Point-wise middle of the same backward when its four GEMMs (S = (x+pos) qf^T, dP = x dctx^T, dx = P dctx + dS qf)
+ * run as 1x1 tensor-core convolutions (ag3d_spconv_fwd_rows): P = masked exp(S - lse) and dS = P * (dP - dr), in
+ * place (s_p: S -> P, dp_ds: dP -> dS; both f32 [nv, hq], hq % 4 == 0).                                            */
+int ag3d_c2s_bwd_pointwise(float* s_p, float* dp_ds, const float* lse, const float* dr, const int32_t* rowobj,
+                           const uint8_t* label, int64_t nv, int32_t hq, ag3d_stream_t stream);
+/* Row-wise pieces of the scene -> click backward (ag3d_s2c_mask_bwd) for the variant whose GEMMs run as 1x1
+ * tensor-core convolutions (agile3d_b200/ops.py::s2c_mask_bwd_tc): per-head softmax over the queries (in place on
+ * S [nv, hqp]), dS = a (da - <a, da>) per head (in place on da), LayerNorm statistics (n = normalised rows, rstd),
+ * LayerNorm backward with the column sums [dbo | dln_w | dln_b], and the first-maximum routing of dlogits.          */
+int ag3d_s2c_softmax_heads(float* s_a, int64_t nv, int32_t heads, int32_t nq, int32_t hqp, ag3d_stream_t stream);
+int ag3d_s2c_ds(const float* a, float* da_ds, int64_t nv, int32_t heads, int32_t nq, int32_t hqp, ag3d_stream_t stream);
+int ag3d_ln_fwd_stats(const float* y, int64_t nv, float eps, float* n_out, float* rstd_out, ag3d_stream_t stream);
+size_t ag3d_ln_bwd_workspace_bytes(void);
+int ag3d_ln_bwd(const float* t, const float* n, const float* rstd, const float* ln_w, int64_t nv, float* dy,
+                float* colsums, void* ws, size_t ws_bytes, ag3d_stream_t stream);
+int ag3d_s2c_route(const float* G, const float* dlogits, const int32_t* q_obj, int32_t nq, int32_t n_obj, int64_t nv,
+                   float* g_out, ag3d_stream_t stream);
 size_t ag3d_s2c_bwd_workspace_bytes(int32_t hqp);
 int ag3d_s2c_mask_bwd(const float* x, const float* pos, int64_t nv, const float* A, const float* At, const float* c,
                       const float* U, const float* Ut, const float* bo, const float* ln_w, const float* ln_b,

@@ -211,6 +211,10 @@ def test_c2s_bwd_vs_emulation(nv, nq, n_obj):
         dq = ops.spconv_bwd_weight(ds, None, t(x), 1)
         ops.spconv_bwd_weight(ds, None, t(pos), 1, dweight=dq, accumulate=True)
         assert rel_err(dq[0].cpu(), ds_r.T @ (d(x) + d(pos))) < 2e-4
+        # the same backward with its four GEMMs as 1x1 tcgen05 convolutions (bf16x3) + the point-wise kernel
+        dx_t, ds_t = ops.c2s_attn_bwd_tc(t(x), t(pos), t(qp), t(dp), t(lse_p.float()), t(dr.float()), t(rowobj), hqp, t(lab))
+        assert rel_err(dx_t.cpu(), dx_r) < 1e-3
+        assert rel_err(ds_t.cpu(), ds_r) < 1e-3
 
 
 @pytest.mark.parametrize("nv,nq,n_obj", [(1000, 11, 2), (5003, 15, 3), (20000, 20, 6), (4100, 25, 9), (129, 32, 12)])
@@ -246,6 +250,18 @@ def test_s2c_bwd_vs_emulation(nv, nq, n_obj):
             assert rel_err(a_.cpu()[same], b_[same]) < 3e-4, name
         if bool(same.all()):
             assert rel_err(got[5].cpu(), ref[5]) < 1e-3
+        # the same backward with its six GEMMs as 1x1 tcgen05 convolutions (bf16x3) + row-wise kernels
+        s64 = ((d(x) + d(pos)) @ d(A).T + d(c)).view(nv, H, nq)
+        y64 = d(x) + torch.softmax(s64, dim=2).view(nv, H * nq) @ d(U) + d(bo)
+        xo = torch.nn.functional.layer_norm(y64, (128,), d(lw), d(lb), 1e-5).float()
+        got_tc = ops.s2c_mask_bwd_tc(t(x), t(pos), t(Ap), t(cp), t(Up), t(bo), t(lw), t(lb), 1e-5, t(Ep), t(q_obj), nq, H,
+                                     n_obj, hqp, t(dxo) if use_dxo else None, t(dlg), t(xo))
+        same = (got_tc[4].cpu().double() != 0).eq(ref[4] != 0).all(1)
+        assert float(same.float().mean()) > 0.99
+        for name, a_, b_ in zip(("dx", "a", "ds", "dy", "g"), got_tc[:5], ref[:5]):
+            assert rel_err(a_.cpu()[same], b_[same]) < 1e-3, ("tensor-core", name)
+        if bool(same.all()):
+            assert rel_err(got_tc[5].cpu(), ref[5]) < 2e-3
 
 
 # ------------------------------------------------------------------------------------------------ loss / optimizer
