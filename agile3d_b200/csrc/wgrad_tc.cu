@@ -10,10 +10,10 @@
 //   dW = D[hi,hi] + D[hi,lo] + D[lo,hi] + D[lo,lo]                                      (all four products: "bf16x4")
 //
 // A CTA owns two combos (offset k, 32-channel input slab) = M 128, an output-channel chunk of <= 128 channels
-// (N = 2 * chunk <= 256) and a range of rows.  Per 128-row stage the TMA engine gathers the two A tiles through the
+// (N = 2 * chunk <= 256) and a range of rows.  Per WG_ROWS-row stage the TMA engine gathers the two A tiles through the
 // neighbour table and the B tiles from consecutive rows (tile::gather4, SWIZZLE_128B: the [rows x 128 B] tiles are
-// exactly the MN-major canonical layout, SBO = 1024 between 8-row groups, LBO = 16384 between 64-element atoms), one
-// elected thread issues 8 MMAs (K = 16 rows each), and the epilogue adds the two column halves in registers and writes
+// exactly the MN-major canonical layout, SBO = 1024 between 8-row groups, LBO = one tile between 64-element atoms), one
+// elected thread issues WG_ROWS / 16 MMAs (K = 16 rows each), and the epilogue adds the two column halves in registers and writes
 // the hi-row / lo-row partial sums, which the deterministic split reduction folds together with the row splits.
 #include <cuda.h>
 
@@ -30,8 +30,11 @@ int launch_split_reduce(const float* part, int splits, long long count, long lon
 
 constexpr int WG_PROD_WARPS = 8;
 constexpr int WG_THREADS = WG_PROD_WARPS * 32 + 32;     // + MMA warp
-constexpr uint32_t WG_TILE = 16384;                      // [128 rows x 128 B]
-constexpr int WG_ROWS = 128;
+constexpr int WG_ROWS = 128;                              // rows (= GEMM K) per stage.  Measured on 150k-row layers: 64-row
+                                                          // stages with a deeper ring are 1.4x SLOWER (per-stage signalling)
+constexpr uint32_t WG_TILE = WG_ROWS * 128;               // [WG_ROWS x 128 B]
+constexpr int WG_GROUPS = WG_ROWS / 4;                    // gather4 instructions per A tile
+constexpr int WG_LANES = 2 * WG_GROUPS / WG_PROD_WARPS;   // ... spread over the warps: active lanes per warp
 
 struct WgParams {
   const int* nbr; int K; long long n_out;
@@ -95,17 +98,17 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
   if (warp < WG_PROD_WARPS) {
     // =========================================================================== producers
     // ptxas serialises a warp's TMA instructions (one per active lane, ~74 cycles each), so the 64 gather4s of the two
-    // A tiles are spread over all eight warps (tile = warp & 1, eight row groups per warp, lanes 0..7), and every
-    // B tile - 128 CONSECUTIVE rows - is one ordinary 2-D tile load (box 64 x 128) issued by lane 8 of warp b.
+    // A tiles are spread over all eight warps (tile = warp & 1, WG_LANES row groups per warp), and every B tile -
+    // WG_ROWS CONSECUTIVE rows - is one ordinary 2-D tile load (box 64 x WG_ROWS) issued by the next lane of warp b.
     if (n_stage > 0) {
       const int t = warp & 1;                                     // A tile / combo of this warp
       const int q = q0 + t;
       const bool q_ok = q < combos;
       const int k = q_ok ? q / p.n_slab_in : 0;
       const int col_a = q_ok ? (q % p.n_slab_in) * 64 : 0;
-      const bool a_lane = lane < 8;
-      const int g = (warp >> 1) * 8 + lane;                       // row group (rows 4g .. 4g+3 of the stage)
-      const bool b_lane = lane == 8 && warp < nb;
+      const bool a_lane = lane < WG_LANES;
+      const int g = (warp >> 1) * WG_LANES + lane;                // row group (rows 4g .. 4g+3 of the stage)
+      const bool b_lane = lane == WG_LANES && warp < nb;
       const int col_b = ((c_lo >> 5) + warp) * 64;
       const int* nbr_k = p.nbr ? p.nbr + (long long)k * p.n_out : nullptr;
       auto rows_of = [&](int it) {
@@ -187,7 +190,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
       const uint32_t a0 = tiles0 + (uint32_t)s * stage_bytes, b0 = a0 + 2u * WG_TILE;
       if (elect_one()) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {                              // 16 rows per step = two 8-row groups = 2048 B
+        for (int j = 0; j < WG_ROWS / 16; ++j) {                   // 16 rows per step = two 8-row groups = 2048 B
           const uint64_t da = umma_desc_join(hi32, umma_desc_lo32(a0 + j * 2048u, WG_TILE));
           const uint64_t db = umma_desc_join(hi32, umma_desc_lo32(b0 + j * 2048u, WG_TILE));
           umma_bf16(tmem_base, da, db, idesc, (it | j) ? 1u : 0u);
