@@ -72,18 +72,32 @@ colreduce_kernel(const float* __restrict__ z, int z_ld, const float* __restrict_
   }
 }
 
-// one thread per channel: fp64 sum of the per-CTA partials
-__global__ void colreduce_final_kernel(const float* __restrict__ part, int n_cta, int C, long long n, int mode,
-                                       const float* __restrict__ shift_row, float eps, float momentum,
-                                       float* __restrict__ running_mean,
-                                       float* __restrict__ running_var, float* __restrict__ out0,
-                                       float* __restrict__ out1) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+// fp64 sum of the per-CTA partials, deterministic: a CTA owns 32 channels, thread (g, c) adds the partials g, g + 16,
+// ... of its channel (coalesced over c), and the 16 group sums are folded in a fixed order by the first 32 threads
+constexpr int CF_GROUPS = 16;
+__global__ void __launch_bounds__(32 * CF_GROUPS)
+colreduce_final_kernel(const float* __restrict__ part, int n_cta, int C, long long n, int mode,
+                       const float* __restrict__ shift_row, float eps, float momentum,
+                       float* __restrict__ running_mean, float* __restrict__ running_var,
+                       float* __restrict__ out0, float* __restrict__ out1) {
+  __shared__ double sa[CF_GROUPS][32], sb[CF_GROUPS][32];
+  const int cl = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
   double a = 0.0, b = 0.0;
-  for (int i = 0; i < n_cta; ++i) {
-    a += (double)part[((long long)i * 2 + 0) * C + c];
-    b += (double)part[((long long)i * 2 + 1) * C + c];
+  if (c < C)
+    for (int i = grp; i < n_cta; i += CF_GROUPS) {
+      a += (double)part[((long long)i * 2 + 0) * C + c];
+      b += (double)part[((long long)i * 2 + 1) * C + c];
+    }
+  sa[grp][cl] = a;
+  sb[grp][cl] = b;
+  __syncthreads();
+  if (grp != 0 || c >= C) return;
+  a = 0.0;
+  b = 0.0;
+  for (int g2 = 0; g2 < CF_GROUPS; ++g2) {
+    a += sa[g2][cl];
+    b += sb[g2][cl];
   }
   if (mode == 0) {
     const double ms = a / (double)n;                 // mean of the shifted data
@@ -553,7 +567,7 @@ static int colreduce_common(int mode, const float* z, int z_ld, const float* y, 
   else
     colreduce_kernel<2><<<n_cta, CR_THREADS, 0, st>>>(z, z_ld, y, y_ld, dy, dy_ld, mean, invstd, C, n, relu, part);
   AG3D_LAUNCH_CHECK("colreduce");
-  colreduce_final_kernel<<<(C + 127) / 128, 128, 0, st>>>(part, n_cta, C, n, mode, z, eps, momentum, rm, rv, out0, out1);
+  colreduce_final_kernel<<<(C + 31) / 32, 32 * CF_GROUPS, 0, st>>>(part, n_cta, C, n, mode, z, eps, momentum, rm, rv, out0, out1);
   AG3D_LAUNCH_CHECK("colreduce_final");
   return AG3D_OK;
 }
@@ -678,7 +692,7 @@ int ag3d_loss_fwd(const float* logits, int32_t C, int64_t n, const int32_t* targ
   loss_fwd_kernel<<<n_cta, 256, 0, st>>>(logits, C, n, target, w, eps, part);
   AG3D_LAUNCH_CHECK("loss_fwd");
   // partials are [cta][2][2]; the final kernel sums column c of row 0 / row 1 -> out0[c], out1[c]; only c = 0 is used
-  colreduce_final_kernel<<<1, 32, 0, st>>>(part, n_cta, 2, n, 2, nullptr, 0.f, 0.f, nullptr, nullptr, sums, sums + 2);
+  colreduce_final_kernel<<<1, 32 * CF_GROUPS, 0, st>>>(part, n_cta, 2, n, 2, nullptr, 0.f, 0.f, nullptr, nullptr, sums, sums + 2);
   AG3D_LAUNCH_CHECK("loss_final");
   return AG3D_OK;
 }

@@ -135,11 +135,11 @@ class _BackboneFn(torch.autograd.Function):
 _WGRAD_TC = [False]
 
 
-def _xt_dy(xs, dys):
+def _xt_dy(xs, dys, tc):
     """sum over xs of x^T dy -> [1, cin, cout]; xs is a list of [Nv, cin] operands sharing one dy [Nv, cout]."""
     dy = dys
     cin, cout = xs[0].shape[1], dy.shape[1]
-    if _WGRAD_TC[0] and ops.wgrad_tc_supported(1, cin, cout):
+    if tc and ops.wgrad_tc_supported(1, cin, cout):
         dsplit = ops.pack_split_rows(dy)
         out = None
         for x in xs:
@@ -166,6 +166,7 @@ class _C2sFn(torch.autograd.Function):
         ops.c2s_attn_fwd(x, pos, qfold, nq, H, label, q_obj, obj_count, out=out, lse=lse)
         ctx.save_for_backward(x, pos, qfold, out, lse)
         ctx.meta = (nq, H, label, q_obj, obj_count)
+        ctx.tc = _WGRAD_TC[0]                      # the mode of the model that ran this forward
         return out
 
     @staticmethod
@@ -186,12 +187,12 @@ class _C2sFn(torch.autograd.Function):
             lse_p = torch.full((hqp,), float("inf"), dtype=torch.float32, device=x.device)
             lse_p[:HQ] = lse
             dr = _pad_rows((dctx * out).sum(1), hqp)
-            if _WGRAD_TC[0]:      # tensor-core mode: the four GEMMs as 1x1 tcgen05 convolutions
+            if ctx.tc:            # tensor-core mode: the four GEMMs as 1x1 tcgen05 convolutions
                 dx, ds = ops.c2s_attn_bwd_tc(x, pos, qf, dc, lse_p, dr, rowobj, hqp, label)
             else:
                 dx, ds = ops.c2s_attn_bwd(x, pos, qf, qf.t().contiguous(), dc, dc.t().contiguous(), lse_p, dr, rowobj,
                                           hqp, label)
-            dq = _xt_dy([ds], x + pos)                       # dS^T x + dS^T pos
+            dq = _xt_dy([ds], x + pos, ctx.tc)               # dS^T x + dS^T pos
         return dx, None, dq[0, :HQ], None, None, None, None, None
 
 
@@ -202,6 +203,7 @@ class _S2cFn(torch.autograd.Function):
         x_out, logits, label, count = ops.s2c_mask_fwd(x, pos, A, c, U, bo, ln_w, ln_b, eps, E, q_obj, nq, H, n_obj)
         ctx.save_for_backward(x, pos, A, c, U, bo, ln_w, ln_b, E, x_out)
         ctx.meta = (eps, q_obj, nq, H, n_obj)
+        ctx.tc = _WGRAD_TC[0]                      # the mode of the model that ran this forward
         ctx.mark_non_differentiable(label, count)
         ctx.set_materialize_grads(False)
         return x_out, logits, label, count
@@ -215,16 +217,16 @@ class _S2cFn(torch.autograd.Function):
             Ap, Up, Ep = _pad_rows(A, hqp), _pad_rows(U, hqp), _pad_rows(E, 32)
             dxo_c = None if dxo is None else dxo.contiguous()
             dlg_c = None if dlogits is None else dlogits.contiguous()
-            if _WGRAD_TC[0]:      # tensor-core mode: the six GEMMs as 1x1 tcgen05 convolutions
+            if ctx.tc:            # tensor-core mode: the six GEMMs as 1x1 tcgen05 convolutions
                 dx, a, ds, dy, g, cols = ops.s2c_mask_bwd_tc(x, pos, Ap, _pad_rows(c, hqp), Up, bo, ln_w, ln_b, eps, Ep,
                                                              q_obj, nq, H, n_obj, hqp, dxo_c, dlg_c, x_out)
             else:
                 dx, a, ds, dy, g, cols = ops.s2c_mask_bwd(
                     x, pos, Ap, Ap.t().contiguous(), _pad_rows(c, hqp), Up, Up.t().contiguous(), bo, ln_w, ln_b, eps, Ep,
                     Ep.t().contiguous(), q_obj, nq, H, n_obj, hqp, dxo_c, dlg_c)
-            dA = _xt_dy([ds], x + pos)                       # dS^T x + dS^T pos
-            dU = _xt_dy([a], dy)
-            dE = _xt_dy([g], x_out)
+            dA = _xt_dy([ds], x + pos, ctx.tc)               # dS^T x + dS^T pos
+            dU = _xt_dy([a], dy, ctx.tc)
+            dE = _xt_dy([g], x_out, ctx.tc)
         return (dx, None, dA[0, :HQ], cols[384:384 + HQ], dU[0, :HQ], cols[:128], cols[128:256], cols[256:384],
                 dE[0, :nq], None, None, None, None, None)
 

@@ -290,7 +290,23 @@ def adamw_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, norm=None,
     p.sub_((lr / bc1) * m / (v.sqrt() / math.sqrt(bc2) + eps))
 
 
-ALL = ["bn_stats", "bn_apply", "bn_bwd", "col_sum", "spconv_bwd_weight", "stem_bwd_weight", "decoder_bwd_rows",
+def wgrad_tc_supported(K, cin, cout):
+    return False          # the emulation has one weight-gradient path (the host logic then never asks for split rows)
+
+
+def c2s_attn_bwd_tc(x, pos, qf, dctx, lse, dr, rowobj, hqp, label):
+    """same contract as c2s_attn_bwd (ops.c2s_attn_bwd_tc only differs in how the GPU evaluates it)"""
+    return c2s_attn_bwd(x, pos, qf, qf.t().contiguous(), dctx, dctx.t().contiguous(), lse, dr, rowobj, hqp, label)
+
+
+def s2c_mask_bwd_tc(x, pos, A, c, U, bo, ln_w, ln_b, ln_eps, E, q_obj, nq, heads, n_obj, hqp, dxo, dlogits, x_out):
+    """same contract as s2c_mask_bwd (x_out, the forward's output, is only a shortcut for the GPU variant)"""
+    return s2c_mask_bwd(x, pos, A, A.t().contiguous(), c, U, U.t().contiguous(), bo, ln_w, ln_b, ln_eps, E,
+                        E.t().contiguous(), q_obj, nq, heads, n_obj, hqp, dxo, dlogits)
+
+
+ALL = ["wgrad_tc_supported", "c2s_attn_bwd_tc", "s2c_mask_bwd_tc",
+       "bn_stats", "bn_apply", "bn_bwd", "col_sum", "spconv_bwd_weight", "stem_bwd_weight", "decoder_bwd_rows",
        "c2s_attn_bwd", "s2c_mask_bwd", "loss_fwd", "loss_bwd", "click_loss_weights", "grad_norm", "adamw_step",
        "prepare_tc_weight", "hash_build", "downsample", "kernel_map", "kernel_map_transposed", "spconv_fwd", "stem_conv_fwd",
        "fourier_posenc", "c2s_attn_fwd", "s2c_mask_fwd"]
