@@ -114,7 +114,7 @@ struct TcParams {
   int k_per;        // kernel offsets per CTA row (split-K over gridDim.y); k range = [by*k_per, min(K, (by+1)*k_per))
   float* partial;   // split-K: raw accumulators [gridDim.y][n_out][cout]; NULL = fused epilogue
   int NI;           // MMA-issuing warps (1 or 2): issuer w owns the stages of tiles j with (j & 1) == w
-  int debug;        // profiling experiments only (AG3D_TC_DEBUG): 1 = skip MMAs, 2 = skip gather loads, 4 = one product
+  int debug;        // profiling experiments only (AG3D_TC_DEBUG): 1 = skip MMAs, 2 = skip gather loads (MODE 0/1), 4 = one product
   int cpad;         // TMEM columns per tile (pow2 >= cout)
   int tmem_cols;    // allocation (pow2, 32..512)
 };
@@ -315,11 +315,7 @@ spconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const TcParams p) {
               mbar_wait(empty, ((uint32_t)it & 1u) ^ 1u);
               if (leader) mbar_arrive_expect_tx(full, TMA_STAGE);
               __syncwarp();
-              if (!(p.debug & 2)) {
-                if (active) tma_gather4(slot, &tm_in, full, col, r.x, r.y, r.z, r.w);
-              } else if (leader) {
-                asm volatile("mbarrier.complete_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(full), "r"(TMA_STAGE) : "memory");
-              }
+              if (active) tma_gather4(slot, &tm_in, full, col, r.x, r.y, r.z, r.w);
               n += p.NA;
               ++it;
             }
