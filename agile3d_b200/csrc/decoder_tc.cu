@@ -5,13 +5,14 @@
 //   Z = Y . E^T                  [128 x 32]    (bf16x3)      -> per-object max -> logits, label, histogram
 // The three small right-hand operands (A, U^T, E; <= 176 KB as bf16 hi/lo images, L2 resident) are streamed per
 // tile through a ring of shared-memory stages by the TMA engine (cp.async.bulk); the voxel tile itself is read
-// from HBM exactly once.  Column layout of S/P: head-major with every head padded to NQ16 (16 or 32) columns so
+// from HBM exactly once.  Column layout of S/P: head-major with every head padded to NQ16 (16, 24 or 32) columns so
 // that a 16-column TMEM load never straddles heads; padded columns carry a bias of -inf (probability 0).
 // Roles: 8 compute warps (tile load + split, softmax, LayerNorm, mask head), 1 MMA-issuer thread, 1 loader thread.
 #include <float.h>
 #include <math.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "tc_common.cuh"
 
@@ -217,7 +218,13 @@ __global__ void __launch_bounds__(DT_THREADS, 1) s2c_tc_kernel(const S2cParams p
         const int col0 = (4 * g + hh) * NQ16;
         float sc[NQ16];
 #pragma unroll
-        for (int ch = 0; ch < NQ16 / 16; ++ch) tmem_ld16(t_lane + TM_S + col0 + ch * 16, sc + ch * 16);
+        if constexpr (NQ16 % 16 == 0) {
+#pragma unroll
+          for (int ch = 0; ch < NQ16 / 16; ++ch) tmem_ld16(t_lane + TM_S + col0 + ch * 16, sc + ch * 16);
+        } else {
+#pragma unroll
+          for (int ch = 0; ch < NQ16 / 8; ++ch) tmem_ld8(t_lane + TM_S + col0 + ch * 8, sc + ch * 8);
+        }
         float mx = -INFINITY;
 #pragma unroll
         for (int i = 0; i < NQ16; ++i) { sc[i] += cpad_s[col0 + i]; mx = fmaxf(mx, sc[i]); }
@@ -447,8 +454,16 @@ static int s2c_tc_launch_t(const float* x, const float* pos, long long nv, const
   return AG3D_OK;
 }
 
+// heads are padded to 16, 24 or 32 query columns (AG3D_S2C_PACK=0 disables the 24-column variant: measurement aid)
+static int s2c_pad(int nq) {
+  static int pack = -1;
+  if (pack < 0) { const char* e = getenv("AG3D_S2C_PACK"); pack = (e && e[0] == '0') ? 0 : 1; }
+  return nq <= 16 ? 16 : ((nq <= 24 && pack) ? 24 : 32);
+}
+
 size_t s2c_tc_workspace_bytes(int nq) {
-  return (nq <= 16 ? s2c_img_bytes<16>() + 128 * 4 : s2c_img_bytes<32>() + 256 * 4) + 256;
+  (void)nq;
+  return s2c_img_bytes<32>() + 256 * 4 + 256;      // the largest variant
 }
 
 int s2c_tc_launch(const float* x, const float* pos, long long nv, const float* A, const float* c, const float* U,
@@ -457,8 +472,12 @@ int s2c_tc_launch(const float* x, const float* pos, long long nv, const float* A
                   int* obj_count, void* ws, size_t ws_bytes, cudaStream_t st) {
   AG3D_CHECK_ARG(heads == 8 && nq <= 32, "tensor-core s2c handles 8 heads and at most 32 queries");
   AG3D_CHECK_ARG(ws && aligned16(ws) && ws_bytes >= s2c_tc_workspace_bytes(nq), "s2c workspace too small");
-  if (nq <= 16)
+  const int pad = s2c_pad(nq);
+  if (pad == 16)
     return s2c_tc_launch_t<16>(x, pos, nv, A, c, U, bo, ln_w, ln_b, ln_eps, E, q_obj, nq, heads, n_obj, x_out, logits,
+                               label, obj_count, ws, st);
+  if (pad == 24)
+    return s2c_tc_launch_t<24>(x, pos, nv, A, c, U, bo, ln_w, ln_b, ln_eps, E, q_obj, nq, heads, n_obj, x_out, logits,
                                label, obj_count, ws, st);
   return s2c_tc_launch_t<32>(x, pos, nv, A, c, U, bo, ln_w, ln_b, ln_eps, E, q_obj, nq, heads, n_obj, x_out, logits,
                              label, obj_count, ws, st);
