@@ -231,3 +231,45 @@ def test_many_query_scene_to_click_path_matches_the_restatement():
     xin = x.clone()
     again = ops._s2c_mask_many_queries(xin, pos, A, c, U, bo, lw, lb, 1e-5, E, q_obj, nq, H, n_obj, xin)   # in place
     assert again[0].data_ptr() == xin.data_ptr() and rel_err(xin.numpy(), ref[0].numpy()) < 1e-5
+
+
+def test_train_step_host_logic_with_split_row_plumbing(monkeypatch):
+    """The tensor-core-mode plumbing of the training step (split copies of layer inputs / output gradients shared
+    between the forward, data-gradient and weight-gradient calls, the per-step copy cache, the X^T dY helper of the
+    decoder) with identity "split" copies and the emulated kernels: a stale or mis-keyed cached copy would show up as
+    wrong gradients against the reference's golden vector."""
+    import agile3d_b200
+    import agile3d_b200.ops as ops
+    from agile3d_b200.weights import default_args
+    emulate.patch_ops(monkeypatch)
+    packs = []
+
+    def pack(x):
+        packs.append(tuple(x.shape))
+        return x.clone().contiguous()
+
+    monkeypatch.setattr(ops, "prepare_tc_weight", lambda w: torch.zeros(1))       # "prepared weights exist": tensor-core mode
+    monkeypatch.setattr(ops, "wgrad_tc_supported", lambda K, cin, cout: cin % 32 == 0 and cout % 32 == 0, raising=False)
+    monkeypatch.setattr(ops, "pack_split_rows", pack, raising=False)
+    monkeypatch.setattr(ops, "spconv_bwd_weight_tc",
+                        lambda xs, nbr, ds, K, dweight=None, accumulate=False:
+                        emulate.spconv_bwd_weight(xs, nbr, ds, K, dweight=dweight, accumulate=accumulate), raising=False)
+    g = _train_golden()
+    m = _model(g["wseed"]).train()
+    criterion = agile3d_b200.build_criterion(default_args())
+    coords = torch.from_numpy(g["coords"])
+    x = agile3d_b200.SparseTensor(coordinates=coords, features=torch.from_numpy(g["feats"]))
+    raw = torch.from_numpy(g["raw_coords"])
+    out = m.forward_mask(*m.forward_backbone(x, raw), g["clicks"], g["times"])
+    targets = [torch.from_numpy(g["targets"])]
+    weights = agile3d_b200.cal_click_loss_weights(coords[:, 0], raw, torch.cat(targets), g["clicks"])
+    loss_dict = criterion(out, targets, weights)
+    total = sum(loss_dict[k] * criterion.weight_dict[k] for k in loss_dict if k in criterion.weight_dict)
+    n_fwd = len(packs)
+    total.backward()
+    assert n_fwd > 50 and len(packs) > n_fwd + 60, (n_fwd, len(packs))     # the split-row branches really ran
+    params = dict(m.named_parameters())
+    gn = np.array([float(params[n].grad.double().norm()) for n in g["grad_names"]])
+    assert np.abs(gn - g["grad_norms"]).max() / g["grad_norms"].max() < 2e-3
+    worst = max(abs(a - b) / max(b, 1e-3 * g["grad_norms"].max()) for a, b in zip(gn, g["grad_norms"]))
+    assert worst < 2e-2, worst
