@@ -265,6 +265,12 @@ class Agile3d(nn.Module):
         self.ffn_attention = stack(lambda: _FFNLayer(d, dim_feedforward))
         self.decoder_norm = nn.LayerNorm(d)
         self.time_encode = _time_table(d, 200)       # plain attribute, not in the state_dict (agile3d.py:138)
+        # derived weight images (folded BatchNorm, tensor-core images) are cached per parameter generation
+        self.register_load_state_dict_post_hook(lambda module, incompatible: ops.bump_param_generation())
+
+    def _apply(self, fn, *a, **kw):
+        ops.bump_param_generation()
+        return super()._apply(fn, *a, **kw)
 
     # ------------------------------------------------------------------------------------------ backbone
     def forward_backbone(self, x: SparseTensor, raw_coordinates=None):
@@ -297,7 +303,7 @@ class Agile3d(nn.Module):
         feats, fmaps, maps = self.backbone(x)
         pcd = torch.empty((feats.shape[0], self.hidden_dim), dtype=torch.float32, device=feats.device)
         head = self.lin_squeeze_head
-        hkey = (self.backbone.algo, head.kernel.data_ptr(), head.kernel._version)
+        hkey = (self.backbone.algo, ops.param_generation(), head.kernel.data_ptr(), head.kernel._version)
         if getattr(self, "_head_tc", (None, None))[0] != hkey:
             wtc = ops.prepare_tc_weight(head.kernel) if self.backbone.algo != ops.ALGO_SIMT else None
             self._head_tc = (hkey, wtc)

@@ -60,6 +60,19 @@ class _Timed:
 
 _ws_cache = {}
 
+# Generation counter of the model parameters: bumped by every writer that changes parameter VALUES without going
+# through torch's version counter (FlatAdamW.step's raw kernel, load_state_dict, .to()).  Caches of derived weight
+# images (folded BatchNorm, bf16 hi/lo tensor-core images, transposed kernels) key on it.
+_param_generation = [0]
+
+
+def bump_param_generation():
+    _param_generation[0] += 1
+
+
+def param_generation():
+    return _param_generation[0]
+
 
 def _workspace(tag, device, nbytes):
     """Grow-only scratch buffer per (purpose, device, stream); stream-ordered reuse is safe on one stream."""

@@ -38,6 +38,7 @@ class FlatAdamW:
         self.lr, self.betas, self.eps, self.weight_decay, self.max_norm = lr, betas, eps, weight_decay, max_norm
         self.step_count = 0
         self.last_norm = None
+        ops.bump_param_generation()        # parameters were re-seated onto the flat buffer
 
     def zero_grad(self, set_to_none=False):
         self.flat_g.zero_()
@@ -51,6 +52,9 @@ class FlatAdamW:
         self.last_norm = ops.grad_norm(self.flat_g)
         ops.adamw_step(self.flat_p, self.flat_g, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps,
                        self.weight_decay, self.step_count, self.last_norm if self.max_norm > 0 else None, self.max_norm)
+        # the kernel wrote the parameters behind torch's back (no ._version bump): invalidate every derived weight
+        # image (Res16UNet34C._train_weights/_folded, Agile3d head image)
+        ops.bump_param_generation()
         return self.last_norm
 
 

@@ -349,3 +349,67 @@ def test_full_size_properties_150k():
     assert torch.equal(layers2[2][0], layers[2][0])
     # clicked voxels of object j carry the object's own click feature: the scene is consistent row-wise
     assert h[0].F.shape == (n, 128)
+
+
+# ------------------------------------------------------------------------------------------------ BASELINE shapes
+# BASELINE.json configs at their FULL sizes against the CPU oracle (the largest oracle-compared scene
+# was 9 000 voxels, so the split-K plans, multi-tile CTAs and 4 000+-CTA grids of the real shapes were unpinned).
+#   headline : 150k voxels @2cm, 5 objects x 2 clicks (Nq = 20)           SURVEY.md §8(d) "headline" / configs[2] scene
+#   c2       : 150k voxels @2cm, 1 object, 3 fg + 2 bg clicks (Nq = 15)   configs[1]
+#   c5_nq30  : 80k voxels @5cm outdoor, 10 objects x 2 clicks (Nq = 30)   configs[4], the 20-click point
+#   c5_nq210 : same scene, 10 objects x 20 clicks (Nq = 210)              configs[4], the end of the click loop
+BASELINE_SHAPES = {
+    "headline": dict(target=150000, voxel=0.02, seed=2000, outdoor=False, k=5, cpo=2, bg=0),
+    "c2": dict(target=150000, voxel=0.02, seed=2001, outdoor=False, k=1, cpo=3, bg=2),
+    "c5_nq30": dict(target=80000, voxel=0.05, seed=5000, outdoor=True, k=10, cpo=2, bg=0),
+    "c5_nq210": dict(target=80000, voxel=0.05, seed=5000, outdoor=True, k=10, cpo=20, bg=0),
+}
+
+
+def _baseline_scene(cfg):
+    from agile3d_b200.scenes import make_clicks, make_scene
+    sc = make_scene(cfg["target"], cfg["voxel"], seed=cfg["seed"], outdoor=cfg["outdoor"])
+    clicks, times, _ = make_clicks(sc, cfg["k"], cfg["cpo"], cfg["bg"], seed=cfg["seed"])
+    coords = np.concatenate([np.zeros((sc["coords"].shape[0], 1), np.int32), sc["coords"]], 1)
+    return sc, coords, clicks, times
+
+
+@pytest.mark.parametrize("shape", ["headline", "c5_nq30"])
+def test_baseline_shape_maps_bit_exact(shape):
+    """Coordinate levels, parents and every kernel map of the U-Net at the full BASELINE size, bit-exact."""
+    from agile3d_b200.backbone import CoordinateMaps
+    _, coords, _, _ = _baseline_scene(BASELINE_SHAPES[shape])
+    maps = CoordinateMaps(torch.from_numpy(coords).to(DEV))
+    levels, parents = [torch.from_numpy(coords)], []
+    for lvl in range(4):
+        c, _, _, par = emulate.downsample(levels[-1], 2 << lvl)
+        levels.append(c)
+        parents.append(par)
+    for lvl in range(5):
+        assert torch.equal(maps.coords[lvl].cpu(), levels[lvl]), f"coords level {lvl}"
+        assert torch.equal(maps.k3[lvl].cpu(), emulate.kernel_map(levels[lvl], levels[lvl], 0, 3, 1 << lvl)), f"k3 {lvl}"
+    for lvl in range(4):
+        assert torch.equal(maps.parents[lvl].cpu(), parents[lvl]), f"parents level {lvl}"
+        assert torch.equal(maps.down[lvl].cpu(), emulate.kernel_map(levels[lvl + 1], levels[lvl], 0, 2, 1 << lvl))
+        assert torch.equal(maps.up[lvl].cpu(), emulate.kernel_map_transposed(levels[lvl], parents[lvl], 1 << lvl))
+
+
+@pytest.mark.parametrize("shape", list(BASELINE_SHAPES))
+def test_baseline_shape_logits_vs_fp64_oracle(shape):
+    """Mask logits of all three decoder layers within 1e-3 (max|a-b| / max|b|) of the fp64 CPU oracle at the full
+    BASELINE sizes, default (tensor-core) mode; backbone features likewise."""
+    cfg = BASELINE_SHAPES[shape]
+    sc, coords, clicks, times = _baseline_scene(cfg)
+    nq = 10 + cfg["k"] * cfg["cpo"] + cfg["bg"]
+    ref_m = oracle_model(5, torch.float64)
+    pcd_r, _, _, ref_layers = oracle_forward(ref_m, coords, sc["feats"], sc["raw_coords"], [clicks], [times],
+                                             dtype=torch.float64)
+    m = _gpu_model(5)
+    h, layers = _run_gpu(m, coords, sc["feats"], sc["raw_coords"], [clicks], [times])
+    assert layers[2][0].shape == (coords.shape[0], 1 + cfg["k"])
+    e = rel_err(h[0].F.cpu().numpy(), pcd_r.F.numpy())
+    assert e < 1e-3, f"{shape}: backbone features rel err {e}"
+    errs = [rel_err(layers[l][0].cpu().numpy(), ref_layers[l][0].numpy()) for l in range(3)]
+    flips = [int((layers[l][0].cpu().argmax(1) != ref_layers[l][0].argmax(1)).sum()) for l in range(3)]
+    print(f"{shape}: Nv={coords.shape[0]} Nq={nq} rel err per layer {['%.2e' % v for v in errs]} label flips {flips}")
+    assert max(errs) < 1e-3, (shape, errs, flips)

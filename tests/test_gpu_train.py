@@ -353,7 +353,7 @@ def test_train_step_vs_reference_golden(algo):
     m = _gpu_train_model(g["wseed"], algo)
     loss_dict, total, grads, out = _gpu_train_step(m, g["coords"], g["feats"], g["raw_coords"], g["clicks"], g["times"],
                                                    [g["targets"]])
-    tight = 1e-4 if algo == 1 else 2e-3     # before the first discrete decision; bf16x3 on a 4-row coarsest level
+    tight = 1e-4 if algo == 1 else 1e-3     # before the first discrete decision (levels under 256 rows run in exact fp32)
     loose = 5e-2                            # after it (see the module docstring)
     ref = dict(zip(loss_names, g["loss_values"]))
     for key in ("loss_bce_0", "loss_dice_0"):
@@ -426,9 +426,9 @@ def test_backbone_backward_vs_fp64_oracle(algo):
     # dL/dpcd and the forward features only), bounded by "a few flips" elsewhere.
     head = {n: g for n, g in grads.items() if n.startswith("lin_squeeze_head.")}
     hl2, hworst, _ = _grad_errors(head, {n: rgrads[n] for n in head})
-    head_tol = 1e-4 if algo == 1 else 2e-3
+    head_tol = 1e-4 if algo == 1 else 1e-3
     assert len(head) == 2 and hl2 < head_tol and hworst < 10 * head_tol, (hl2, hworst)
-    lim = (1e-4, 3e-2, 3e-1) if algo == 1 else (5e-3, 5e-2, 5e-1)
+    lim = (1e-4, 3e-2, 3e-1) if algo == 1 else (1e-3, 5e-2, 5e-1)    # features: the north-star 1e-3
     assert fe < lim[0], fe
     assert l2 < lim[1], l2
     assert worst < lim[2], (worst, name)

@@ -273,3 +273,48 @@ def test_train_step_host_logic_with_split_row_plumbing(monkeypatch):
     assert np.abs(gn - g["grad_norms"]).max() / g["grad_norms"].max() < 2e-3
     worst = max(abs(a - b) / max(b, 1e-3 * g["grad_norms"].max()) for a, b in zip(gn, g["grad_norms"]))
     assert worst < 2e-2, worst
+
+
+def test_cached_weight_images_follow_the_optimizer(monkeypatch):
+    """FlatAdamW updates the parameters through a raw kernel that never bumps torch's version
+    counters, so every derived weight image (transposed kernels of the data gradient, tensor-core images, folded
+    BatchNorm, the head's image) must be re-derived after opt.step().  Two steps; after each the cached copies equal
+    the current parameters, and an eval forward after training uses the trained weights."""
+    import agile3d_b200
+    import agile3d_b200.ops as ops
+    from agile3d_b200.optim import FlatAdamW
+    from agile3d_b200.weights import default_args
+    emulate.patch_ops(monkeypatch)
+    g = _train_golden()
+    m = _model(g["wseed"]).train()
+    criterion = agile3d_b200.build_criterion(default_args())
+    opt = FlatAdamW(m.parameters(), lr=1e-2, weight_decay=0.0, max_norm=0.1)
+    coords = torch.from_numpy(g["coords"])
+    x = agile3d_b200.SparseTensor(coordinates=coords, features=torch.from_numpy(g["feats"]))
+    raw = torch.from_numpy(g["raw_coords"])
+    targets = [torch.from_numpy(g["targets"])]
+    weights = agile3d_b200.cal_click_loss_weights(coords[:, 0], raw, torch.cat(targets), g["clicks"])
+    name = "block1.0.conv1"
+    kernel = m.backbone.get_submodule(name).kernel
+    before = kernel.detach().clone()
+    for step in range(2):
+        opt.zero_grad()
+        out = m.forward_mask(*m.forward_backbone(x, raw), g["clicks"], g["times"])
+        ld = criterion(out, targets, weights)
+        sum(ld[k] * criterion.weight_dict[k] for k in ld if k in criterion.weight_dict).backward()
+        opt.step()
+        assert float((kernel.detach() - before).abs().max()) > 1e-4 * (step + 1)          # the step moved the weights
+        w3, _, wt, _ = m.backbone._train_weights()[name]
+        assert torch.equal(w3, kernel.detach())
+        assert torch.equal(wt, kernel.detach().flip(0).transpose(1, 2))
+    # eval after training: folded constants and the head image are re-derived too
+    m.eval()
+    gen = ops.param_generation()
+    f1 = m.backbone._folded()
+    assert m.backbone._folded() is f1 and ops.param_generation() == gen                   # cached while nothing changes
+    with torch.no_grad():
+        m.backbone.bn0.bn.running_var.mul_(2.0)                                           # torch writer: version counter
+    assert m.backbone._folded() is not f1
+    f2 = m.backbone._folded()
+    ops.bump_param_generation()                                                           # raw-kernel writer
+    assert m.backbone._folded() is not f2
