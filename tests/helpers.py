@@ -46,10 +46,7 @@ def oracle_forward(model, coords, feats, raw, clicks, times, dtype=torch.float32
     return pcd, aux, pos, per_layer
 
 
-def rel_err(a, b):
-    """max |a-b| / max |b|: the 'relative' in "within 1e-3 relative on fp32 mask logits"."""
-    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
-    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+from oracle.compare import decision_forced_errors, rel_err  # noqa: E402,F401  (re-exported for the tests)
 
 
 def oracle_train_step(model, coords, feats, raw, clicks, times, targets, dtype=torch.float32):

@@ -256,6 +256,7 @@ def test_train_step_host_logic_with_split_row_plumbing(monkeypatch):
                         emulate.spconv_bwd_weight(xs, nbr, ds, K, dweight=dweight, accumulate=accumulate), raising=False)
     g = _train_golden()
     m = _model(g["wseed"]).train()
+    m.backbone.SMALL_LEVEL_ROWS = 0          # this 1200-voxel scene: keep every level on the split-row branches
     criterion = agile3d_b200.build_criterion(default_args())
     coords = torch.from_numpy(g["coords"])
     x = agile3d_b200.SparseTensor(coordinates=coords, features=torch.from_numpy(g["feats"]))
