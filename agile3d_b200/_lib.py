@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libagile3d_b200.so")
 
 RELU = 1
-ALGO_AUTO, ALGO_SIMT, ALGO_TC = 0, 1, 2
+ALGO_AUTO, ALGO_SIMT, ALGO_TC, ALGO_TC_PACKED = 0, 1, 2, 3
 
 _lib = None
 

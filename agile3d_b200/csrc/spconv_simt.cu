@@ -172,6 +172,11 @@ int spconv_tc_launch(const float* in, long long n_in, int in_ld, int cin, const 
                      const void* wprep, int cout, const float* scale, const float* shift, const float* residual,
                      int res_ld, float* out, int out_ld, int flags, void* ws, size_t ws_bytes, cudaStream_t st);
 bool spconv_tc_supported(int cin, int cout);
+int spconv_pk_launch(const float* in, long long n_in, int in_ld, int cin, const int* nbr, int K, long long n_out,
+                     const void* wprep, int cout, const float* scale, const float* shift, const float* residual,
+                     int res_ld, float* out, int out_ld, int flags, cudaStream_t st);
+bool spconv_pk_supported(int cin, int cout, int K);
+bool spconv_pk_preferred(long long n_out);
 size_t spconv_tc_workspace_bytes(long long n_out, int K, int cout);
 
 }  // namespace ag3d
@@ -193,8 +198,15 @@ int ag3d_spconv_fwd_rows(const float* in, int64_t n_in, int32_t in_ld, int32_t c
   AG3D_CHECK_ARG(in_ld % 4 == 0 && out_ld % 4 == 0 && in_ld >= cin && out_ld >= cout, "leading dims");
   AG3D_CHECK_ARG(!residual || (res_ld >= cout && aligned16(residual) && res_ld % 4 == 0), "residual leading dim");
   cudaStream_t st = as_stream(stream);
-  if (algo == AG3D_ALGO_AUTO)
+  if (algo == AG3D_ALGO_AUTO) {
     algo = (weight_tc && K <= 32 && spconv_tc_supported(cin, cout)) ? AG3D_ALGO_TC : AG3D_ALGO_SIMT;
+    if (algo == AG3D_ALGO_TC && nbr && n_in > 0 && (flags & AG3D_IN_SPLIT) && spconv_pk_supported(cin, cout, K) &&
+        spconv_pk_preferred(n_out))
+      algo = AG3D_ALGO_TC_PACKED;
+  }
+  if (algo == AG3D_ALGO_TC_PACKED)
+    return spconv_pk_launch(in, n_in, in_ld, cin, nbr, K, n_out, weight_tc, cout, scale, shift, residual, res_ld, out,
+                            out_ld, flags, st);
   if (algo == AG3D_ALGO_TC) {
     AG3D_CHECK_ARG(spconv_tc_supported(cin, cout), "shape not supported by the tcgen05 path");
     return spconv_tc_launch(in, n_in, in_ld, cin, nbr, K, n_out, weight_tc, cout, scale, shift, residual, res_ld, out,

@@ -745,7 +745,7 @@ static EncodeTiledFn encode_tiled() {
   }
   return fn;
 }
-static bool make_row_map(CUtensorMap* tm, const float* in, int in_ld, int cin, long long n_in) {
+bool make_row_map(CUtensorMap* tm, const float* in, int in_ld, int cin, long long n_in) {
   EncodeTiledFn enc = encode_tiled();
   if (!enc) return false;
   // The map must carry the TRUE row count: with an oversized row extent (the neighbour table never names a row

@@ -7,7 +7,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import ALGO_AUTO, ALGO_SIMT, ALGO_TC, RELU, check, lib  # noqa: F401
+from ._lib import ALGO_AUTO, ALGO_SIMT, ALGO_TC, ALGO_TC_PACKED, RELU, check, lib  # noqa: F401
 
 SLOT_BYTES = 16
 

@@ -48,6 +48,9 @@ extern "C" {
 #define AG3D_ALGO_AUTO 0
 #define AG3D_ALGO_SIMT 1 /* exact fp32 FFMA implicit GEMM */
 #define AG3D_ALGO_TC 2   /* tcgen05 bf16x3 (hi*hi + hi*lo + lo*hi, fp32 accumulate in TMEM) implicit GEMM */
+#define AG3D_ALGO_TC_PACKED 3 /* same arithmetic, MMA rows = the present (input,output) pairs of a 256-row super tile
+                                 (csrc/spconv_pk.cu); split input rows, K >= 2, cout in {32,64,96,128}.  AUTO picks
+                                 it for levels with enough rows, AG3D_ALGO_TC always means the dense-tile kernel */
 
 typedef void* ag3d_stream_t; /* cudaStream_t */
 
