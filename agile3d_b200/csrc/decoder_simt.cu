@@ -490,6 +490,12 @@ int s2c_tc_launch(const float* x, const float* pos, long long nv, const float* A
                   const int* q_obj, int nq, int heads, int n_obj, float* x_out, float* logits, unsigned char* label,
                   int* obj_count, void* ws, size_t ws_bytes, cudaStream_t st);
 
+size_t s2c_mq_workspace_bytes(int nq);
+int s2c_mq_launch(const float* x, const float* pos, long long nv, const float* A, const float* c, const float* U,
+                  const float* bo, const float* ln_w, const float* ln_b, float ln_eps, const float* E,
+                  const int* q_obj, int nq, int heads, int n_obj, float* x_out, float* logits, unsigned char* label,
+                  int* obj_count, void* ws, size_t ws_bytes, cudaStream_t st);
+
 }  // namespace ag3d
 
 using namespace ag3d;
@@ -564,7 +570,10 @@ int ag3d_c2s_attn_fwd(const float* x, const float* pos, int64_t nv, const float*
   return AG3D_OK;
 }
 
-size_t ag3d_s2c_workspace_bytes(int32_t nq) { return (nq >= 1 && nq <= 32) ? s2c_tc_workspace_bytes(nq) : 0; }
+size_t ag3d_s2c_workspace_bytes(int32_t nq) {
+  if (nq < 1 || nq > 256) return 0;
+  return nq <= 32 ? s2c_tc_workspace_bytes(nq) : s2c_mq_workspace_bytes(nq);
+}
 
 int ag3d_s2c_mask_fwd(const float* x, const float* pos, int64_t nv, const float* A, const float* c,
                       const float* U, const float* bo, const float* ln_w, const float* ln_b, float ln_eps,
@@ -573,7 +582,7 @@ int ag3d_s2c_mask_fwd(const float* x, const float* pos, int64_t nv, const float*
                       size_t ws_bytes, ag3d_stream_t stream) {
   AG3D_CHECK_ARG(nv > 0 && nq > 0, "empty problem");
   AG3D_CHECK_ARG(heads == 8, "heads must be 8 (hidden 128 = 8 x 16)");
-  AG3D_CHECK_ARG(nq <= 32, "this version handles at most 32 click queries per scene in s2c");
+  AG3D_CHECK_ARG(nq <= 256, "at most 256 click queries per scene");
   AG3D_CHECK_ARG(n_obj >= 1 && n_obj <= 32, "n_obj must be 1..32");
   AG3D_CHECK_ARG(x && pos && A && c && U && bo && ln_w && ln_b && E && q_obj && x_out && logits && label && obj_count,
                  "bad pointers");
@@ -581,6 +590,11 @@ int ag3d_s2c_mask_fwd(const float* x, const float* pos, int64_t nv, const float*
                  "pointers must be 16-byte aligned");
   cudaStream_t st = as_stream(stream);
   if (algo == AG3D_ALGO_AUTO) algo = ws ? AG3D_ALGO_TC : AG3D_ALGO_SIMT;
+  if (nq > 32) {      // query groups of 16 with two-pass softmax statistics (decoder_mq.cu); tensor-core path only
+    AG3D_CHECK_ARG(algo == AG3D_ALGO_TC, "more than 32 click queries need the tensor-core path (pass the workspace)");
+    return s2c_mq_launch(x, pos, nv, A, c, U, bo, ln_w, ln_b, ln_eps, E, q_obj, nq, heads, n_obj, x_out, logits, label,
+                         obj_count, ws, ws_bytes, st);
+  }
   if (algo == AG3D_ALGO_TC)
     return s2c_tc_launch(x, pos, nv, A, c, U, bo, ln_w, ln_b, ln_eps, E, q_obj, nq, heads, n_obj, x_out, logits,
                          label, obj_count, ws, ws_bytes, st);

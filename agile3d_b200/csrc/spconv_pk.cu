@@ -46,7 +46,7 @@ constexpr int PK_ND = 4;                  // accumulator buffers (groups in flig
 constexpr int PK_MAX_NA = 8, PK_MAX_NB = 4;
 constexpr uint32_t PK_STAGE = 16384;      // [128 pair rows x 128 B] gathered slab, SWIZZLE_128B
 constexpr int PK_BAR_BYTES = 512;
-constexpr int PK_REGS_E = 192, PK_REGS_P = 40, PK_REGS_M = 48;    // 256*192 + 256*40 + 128*48 = 65536
+constexpr int PK_REGS_E = 176, PK_REGS_P = 40, PK_REGS_M = 48;    // 256*176 + 256*40 + 128*48 = 61440 = 640 threads x the 96 registers the CTA is launched with (setmaxnreg only redistributes that pool)
 
 struct PkParams {
   const int* nbr; int K; long long n_out;

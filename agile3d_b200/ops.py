@@ -294,36 +294,7 @@ def c2s_attn_fwd(x, pos, qfold, nq, heads, label=None, q_obj=None, obj_count=Non
     return ctx
 
 
-S2C_KERNEL_MAX_QUERIES = 32
-
-
-def _s2c_mask_many_queries(x, pos, A, c, U, bo, ln_w, ln_b, ln_eps, E, q_obj, nq, heads, n_obj, x_out):
-    """Scene -> click attention + mask head for MORE than 32 click queries per scene (the tail of the reference's
-    iterative-click protocol, eval_multi_obj.py:116-167, where Nq grows to 10 + 20 K).  The fused kernel keeps all
-    (head, query) columns of a voxel tile in TMEM and stops at 32 queries; beyond that this functional path runs the
-    same algebra with library GEMMs in voxel chunks on the GPU (eval only, not the measured configuration)."""
-    nv = x.shape[0]
-    if x_out is None:
-        x_out = torch.empty_like(x)
-    logits = torch.empty((nv, n_obj), dtype=torch.float32, device=x.device)
-    label = torch.empty(nv, dtype=torch.uint8, device=x.device)
-    qo = q_obj.to(torch.int64)
-    At, Et = A.t().contiguous(), E.t().contiguous()
-    chunk = max(4096, (256 << 20) // (4 * heads * nq))
-    for v0 in range(0, nv, chunk):
-        xs = x[v0:v0 + chunk]
-        n = xs.shape[0]
-        s = torch.addmm(c, xs + pos[v0:v0 + chunk], At).view(n, heads, nq)
-        p = torch.softmax(s, dim=2).view(n, heads * nq)
-        y = torch.nn.functional.layer_norm(xs + torch.addmm(bo, p, U), (xs.shape[1],), ln_w, ln_b, ln_eps)
-        z = y @ Et                                                         # [n, nq]
-        lg = torch.full((n, n_obj), float("-inf"), dtype=torch.float32, device=x.device)
-        lg.scatter_reduce_(1, qo.unsqueeze(0).expand(n, nq), z, reduce="amax", include_self=True)
-        x_out[v0:v0 + chunk] = y
-        logits[v0:v0 + chunk] = lg
-        label[v0:v0 + chunk] = lg.argmax(1).to(torch.uint8)
-    obj_count = torch.bincount(label.to(torch.int64), minlength=n_obj)[:n_obj].to(torch.int32)
-    return x_out, logits, label, obj_count
+S2C_MAX_QUERIES = 256       # per scene: 10 learned background queries + clicks (eval_multi_obj.py:116-167 reaches 210)
 
 
 def s2c_mask_fwd(x, pos, A, c, U, bo, ln_w, ln_b, ln_eps, E, q_obj, nq, heads, n_obj, x_out=None, algo=ALGO_AUTO):
@@ -332,8 +303,8 @@ def s2c_mask_fwd(x, pos, A, c, U, bo, ln_w, ln_b, ln_eps, E, q_obj, nq, heads, n
     for t in (x, pos, A, c, U, bo, ln_w, ln_b, E):
         if not t.is_contiguous() or t.dtype != torch.float32:
             raise _lib.Ag3dError("s2c inputs must be contiguous fp32")
-    if nq > S2C_KERNEL_MAX_QUERIES:
-        return _s2c_mask_many_queries(x, pos, A, c, U, bo, ln_w, ln_b, ln_eps, E, q_obj, nq, heads, n_obj, x_out)
+    if nq > S2C_MAX_QUERIES:
+        raise _lib.Ag3dError(f"at most {S2C_MAX_QUERIES} click queries per scene, got {nq}")
     nv = x.shape[0]
     if x_out is None:
         x_out = torch.empty_like(x)

@@ -160,7 +160,9 @@ int ag3d_c2s_attn_fwd(const float* x, const float* pos, int64_t nv, const float*
  *   y_v = LayerNorm(x_v + sum_{h,q} a[v,(h,q)] U[(h,q)] + bo)              -> x_out
  *   logits[v, o] = max_{q : q_obj[q] == o} y_v . E[q]  (o = 0 background)    -> logits [nv, n_obj]
  *   label[v] = argmax_o logits[v, o] (first maximum);  obj_count[o] += #voxels labelled o (caller zeroes).
- * x_out may alias x.  nq <= 32 in this version.  algo: AG3D_ALGO_SIMT = fp32 FFMA kernel; AG3D_ALGO_TC = three
+ * x_out may alias x.  nq <= 256: up to 32 queries all score columns of a voxel tile live in TMEM at once
+ * (decoder_tc.cu); beyond that the queries are walked in groups of 16 with two-pass softmax statistics
+ * (decoder_mq.cu, tensor-core path only).  algo: AG3D_ALGO_SIMT = fp32 FFMA kernel; AG3D_ALGO_TC = three
  * chained tcgen05 GEMMs (bf16x3, fp32 accumulate in TMEM), needs the workspace; AUTO = TC when ws is given.      */
 size_t ag3d_s2c_workspace_bytes(int32_t nq);
 int ag3d_s2c_mask_fwd(const float* x, const float* pos, int64_t nv, const float* A, const float* c,

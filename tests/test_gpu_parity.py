@@ -233,6 +233,42 @@ def test_s2c_mask_vs_oracle(nv, nq, n_obj, algo):
     assert torch.equal(y2, y) and torch.equal(lg2, lg)
 
 
+@pytest.mark.parametrize("nv,nq,n_obj", [(3000, 33, 4), (5003, 45, 7), (4100, 57, 5), (9000, 100, 11), (20000, 210, 11),
+                                         (777, 256, 12), (129, 64, 3), (2000, 48, 32)])
+def test_s2c_mask_many_queries_vs_oracle(nv, nq, n_obj):
+    """More than 32 click queries per scene (the tail of eval_multi_obj.py:116-167): query groups of 16 with two-pass
+    softmax statistics (csrc/decoder_mq.cu).  One object (the last) has no query: its logit column is -inf."""
+    from agile3d_b200 import ops
+    g = torch.Generator().manual_seed(nv * 5 + nq)
+    x = torch.randn((nv, 128), generator=g)
+    pos = torch.randn((nv, 128), generator=g) * 0.7
+    q_obj = torch.randint(0, n_obj - 1, (nq,), generator=g, dtype=torch.int32)      # NOT sorted: the kernel sorts
+    q_obj[:n_obj - 1] = torch.arange(n_obj - 1, dtype=torch.int32)                  # every other object has a query
+    A = torch.randn((8 * nq, 128), generator=g) * 0.05
+    c = torch.randn(8 * nq, generator=g) * 0.1
+    U = torch.randn((8 * nq, 128), generator=g) * 0.3
+    bo, lw, lb = torch.randn(128, generator=g) * 0.1, torch.rand(128, generator=g) + 0.5, torch.randn(128, generator=g) * 0.1
+    E = torch.randn((nq, 128), generator=g) * 0.2
+    d = lambda t: t.double()
+    ry, rl, rlab, rcnt = emulate.s2c_mask_fwd(d(x), d(pos), d(A), d(c), d(U), d(bo), d(lw), d(lb), 1e-5, d(E), q_obj,
+                                              nq, 8, n_obj)
+    t = lambda v: v.to(DEV)
+    y, lg, lab, cnt = ops.s2c_mask_fwd(t(x), t(pos), t(A), t(c), t(U), t(bo), t(lw), t(lb), 1e-5, t(E), t(q_obj), nq,
+                                       8, n_obj)
+    assert rel_err(y.cpu().numpy(), ry.numpy()) < 1e-4
+    finite = torch.isfinite(rl)
+    assert torch.equal(torch.isfinite(lg.cpu()), finite)
+    assert rel_err(lg.cpu()[finite].numpy(), rl[finite].numpy()) < 1e-4
+    top2 = torch.topk(rl, 2, dim=1)[0]
+    safe = (top2[:, 0] - top2[:, 1]) > 1e-3
+    assert torch.equal(lab.cpu()[safe], rlab[safe])
+    assert int(cnt.sum()) == nv and torch.equal(cnt.cpu(), torch.bincount(lab.cpu().long(), minlength=n_obj).int())
+    xd = t(x).clone()                                                               # in place
+    y2, lg2, _, _ = ops.s2c_mask_fwd(xd, t(pos), t(A), t(c), t(U), t(bo), t(lw), t(lb), 1e-5, t(E), t(q_obj), nq, 8,
+                                     n_obj, x_out=xd)
+    assert torch.equal(y2, y) and torch.equal(lg2, lg)
+
+
 # ------------------------------------------------------------------------------------------------ end to end
 def _gpu_model(wseed, algo=None):
     import agile3d_b200
@@ -291,7 +327,7 @@ def test_end_to_end_vs_fp64_oracle_batched():
 
 def test_many_click_queries_vs_fp64_oracle():
     """The tail of the iterative-click protocol (eval_multi_obj.py:116-167): more than 32 queries per scene.  c2s runs
-    its query groups, s2c takes the many-query path (ops._s2c_mask_many_queries); same 1e-3 criterion."""
+    its query groups, s2c its many-query kernel (csrc/decoder_mq.cu); same 1e-3 criterion."""
     from agile3d_b200.scenes import make_clicks, make_scene
     sc = make_scene(5000, 0.02, seed=31, n_box=8)
     clicks, times, _ = make_clicks(sc, 4, 11, 3, seed=5)                     # 44 fg + 3 bg clicks + 10 learned = 57 queries

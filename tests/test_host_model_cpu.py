@@ -208,31 +208,6 @@ def test_flat_adamw_matches_torch(monkeypatch):
             assert torch.allclose(p, q, atol=1e-6)
 
 
-def test_many_query_scene_to_click_path_matches_the_restatement():
-    """ops._s2c_mask_many_queries (the > 32 click-query path of scene -> click attention + mask head, library GEMMs in
-    voxel chunks) against the plain restatement, with and without in-place update of the voxel features."""
-    from agile3d_b200 import ops
-    g = torch.Generator().manual_seed(4)
-    nv, nq, H, n_obj = 9001, 45, 8, 7
-    x, pos = torch.randn((nv, 128), generator=g), torch.randn((nv, 128), generator=g)
-    A = torch.randn((H * nq, 128), generator=g) * 0.05
-    c = torch.randn(H * nq, generator=g) * 0.1
-    U = torch.randn((H * nq, 128), generator=g) * 0.3
-    bo, lw, lb = torch.randn(128, generator=g) * 0.1, torch.rand(128, generator=g) + 0.5, torch.randn(128, generator=g) * 0.1
-    E = torch.randn((nq, 128), generator=g) * 0.2
-    q_obj = torch.randint(0, n_obj - 1, (nq,), generator=g, dtype=torch.int32)          # the last object has no query
-    ref = emulate.s2c_mask_fwd(x, pos, A, c, U, bo, lw, lb, 1e-5, E, q_obj, nq, H, n_obj)
-    got = ops._s2c_mask_many_queries(x, pos, A, c, U, bo, lw, lb, 1e-5, E, q_obj, nq, H, n_obj, None)
-    assert rel_err(got[0].numpy(), ref[0].numpy()) < 1e-5
-    finite = torch.isfinite(ref[1])
-    assert torch.equal(torch.isfinite(got[1]), finite)                                  # -inf for the object without queries
-    assert rel_err(got[1][finite].numpy(), ref[1][finite].numpy()) < 1e-5
-    assert float((got[2] != ref[2]).float().mean()) < 1e-3 and int(got[3].sum()) == nv
-    xin = x.clone()
-    again = ops._s2c_mask_many_queries(xin, pos, A, c, U, bo, lw, lb, 1e-5, E, q_obj, nq, H, n_obj, xin)   # in place
-    assert again[0].data_ptr() == xin.data_ptr() and rel_err(xin.numpy(), ref[0].numpy()) < 1e-5
-
-
 def test_train_step_host_logic_with_split_row_plumbing(monkeypatch):
     """The tensor-core-mode plumbing of the training step (split copies of layer inputs / output gradients shared
     between the forward, data-gradient and weight-gradient calls, the per-step copy cache, the X^T dY helper of the
