@@ -45,6 +45,11 @@ SIGNATURES = {
     "ag3d_s2c_workspace_bytes": (_sz, [_i32]),
     "ag3d_s2c_mask_fwd": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _i32, _i32, _i32,
                                  _vp, _vp, _vp, _vp, _i32, _vp, _sz, _vp]),
+    "ag3d_query_blob_floats": (_i64, []),
+    "ag3d_query_init": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ag3d_query_fold_c2s": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp, _vp]),
+    "ag3d_query_update_a": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp]),
+    "ag3d_query_update_b": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp]),
     # ---- training step
     "ag3d_colreduce_workspace_bytes": (_sz, [_i32]),
     "ag3d_bn_stats": (_i32, [_vp, _i32, _i32, _i64, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

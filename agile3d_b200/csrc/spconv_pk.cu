@@ -43,7 +43,7 @@ constexpr int PK_P_WARPS = 8;
 constexpr int PK_WARP_MMA = 16, PK_WARP_W = 17, PK_WARP_PLAN = 18;
 constexpr int PK_THREADS = 20 * 32;
 constexpr int PK_ND = 4;                  // accumulator buffers (groups in flight between the MMA issuer and the owners)
-constexpr int PK_MAX_NA = 8, PK_MAX_NB = 4;
+constexpr int PK_MAX_NA = 8, PK_MAX_NB = 8;
 constexpr uint32_t PK_STAGE = 16384;      // [128 pair rows x 128 B] gathered slab, SWIZZLE_128B
 constexpr int PK_BAR_BYTES = 512;
 constexpr int PK_REGS_E = 176, PK_REGS_P = 40, PK_REGS_M = 48;    // 256*176 + 256*40 + 128*48 = 61440 = 640 threads x the 96 registers the CTA is launched with (setmaxnreg only redistributes that pool)
@@ -55,6 +55,7 @@ struct PkParams {
   float* out; int out_ld; int flags; int out_split, res_split;
   int NA, NB;
   int n_super;
+  int debug;        // measurement aid (AG3D_PK_DEBUG): 1 no gathers, 2 no weight copies, 4 no MMAs, 8 no accumulator read-out, 16 no stores, 32 no accumulator hand-shake, 64 no weight ring, 128 synthetic plan (no neighbour-table loads)
   uint32_t plan_bytes;     // one plan buffer: lists [K][4][64] i32 | cnt [K][4] i32 (512 B) | npass [K] i32 (128 B) | mask [256] u32
   uint32_t off_b, off_a;   // shared-memory offsets of the weight ring and (before 1024-byte alignment) the A ring
 };
@@ -148,16 +149,16 @@ __global__ void __launch_bounds__(PK_THREADS, 1) spconv_pk_kernel(const __grid_c
   constexpr int NCH = HALF / 16;          // 16-column chunks per owner warp
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 320);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 384);
   const uint32_t bar_base = smem_u32(bars);
   auto a_full = [&](int s) { return bar_base + 8u * s; };
   auto a_empty = [&](int s) { return bar_base + 8u * (8 + s); };
   auto b_full = [&](int s) { return bar_base + 8u * (16 + s); };
-  auto b_empty = [&](int s) { return bar_base + 8u * (20 + s); };
-  auto d_full = [&](int s) { return bar_base + 8u * (24 + s); };
-  auto d_empty = [&](int s) { return bar_base + 8u * (28 + s); };
-  auto plan_full = [&](int s) { return bar_base + 8u * (32 + s); };
-  auto plan_empty = [&](int s) { return bar_base + 8u * (34 + s); };
+  auto b_empty = [&](int s) { return bar_base + 8u * (24 + s); };
+  auto d_full = [&](int s) { return bar_base + 8u * (32 + s); };
+  auto d_empty = [&](int s) { return bar_base + 8u * (36 + s); };
+  auto plan_full = [&](int s) { return bar_base + 8u * (40 + s); };
+  auto plan_empty = [&](int s) { return bar_base + 8u * (42 + s); };
   unsigned char* plan0 = smem + PK_BAR_BYTES;
   auto plan_list = [&](int buf) { return reinterpret_cast<int*>(plan0 + (size_t)buf * p.plan_bytes); };
   auto plan_cnt = [&](int buf) { return reinterpret_cast<int*>(plan0 + (size_t)buf * p.plan_bytes + (size_t)p.K * 1024); };
@@ -213,12 +214,13 @@ __global__ void __launch_bounds__(PK_THREADS, 1) spconv_pk_kernel(const __grid_c
         const int rank0 = __popc(b0 & lt), rank1 = __popc(b0) + __popc(b1 & lt);
         for (int pass = 0; pass < np; ++pass) {
           const int db = (int)(dn % PK_ND);
+          if (p.debug & 32) continue;
           pk_wait(d_full(db), (dn / PK_ND) & 1u);
           ++dn;
           tc_fence_after();
           const int s0 = rank0 - 32 * pass, s1 = rank1 - 32 * pass;
           const bool ok0 = p0 && (unsigned)s0 < 32u, ok1 = p1 && (unsigned)s1 < 32u;
-          if (__ballot_sync(0xffffffffu, ok0 || ok1)) {
+          if (__ballot_sync(0xffffffffu, ok0 || ok1) && !(p.debug & 8)) {
             const uint32_t taddr = t_lane + (uint32_t)(db * COUT);
             // the next 16-column chunk is in flight while this one is routed (registers permitting: not at Cout = 128)
             constexpr int NBUF = COUT >= 128 ? 1 : 2;
@@ -249,8 +251,8 @@ __global__ void __launch_bounds__(PK_THREADS, 1) spconv_pk_kernel(const __grid_c
       const long long row_a = (long long)t * PK_R + q * PK_SEG + lane, row_b = row_a + 32;
 #pragma unroll
       for (int ch = 0; ch < NCH; ++ch) {
-        if (row_a < p.n_out) pk_store16(p, row_a, h * HALF + ch * 16, acc0 + ch * 16);
-        if (row_b < p.n_out) pk_store16(p, row_b, h * HALF + ch * 16, acc1 + ch * 16);
+        if (row_a < p.n_out && !(p.debug & 16)) pk_store16(p, row_a, h * HALF + ch * 16, acc0 + ch * 16);
+        if (row_b < p.n_out && !(p.debug & 16)) pk_store16(p, row_b, h * HALF + ch * 16, acc1 + ch * 16);
       }
     }
   } else if (warp < PK_E_WARPS + PK_P_WARPS) {
@@ -283,6 +285,10 @@ __global__ void __launch_bounds__(PK_THREADS, 1) spconv_pk_kernel(const __grid_c
             int4 rows = make_int4(-1, -1, -1, -1);
             if (issue) rows = *reinterpret_cast<const int4*>(list + (k * 4 + q) * PK_SEG + pos);
             pk_wait(a_empty(slot), ((n / (uint32_t)NA) & 1u) ^ 1u);
+            if (p.debug & 1) {
+              if (part == 0 && lane == 0) mbar_arrive(a_full(slot));
+              continue;
+            }
             if (part == 0 && lane == 0) {
               int tot = 0;
               tot += min(8, (max(0, c4.x - 32 * pass) + 3) >> 2);
@@ -321,12 +327,12 @@ __global__ void __launch_bounds__(PK_THREADS, 1) spconv_pk_kernel(const __grid_c
           int db[2] = {0, 0};
           for (int c = 0; c < n_slab; ++c, ++nb) {
             const int sb = (int)(nb % (uint32_t)NB);
-            pk_wait(b_full(sb), (nb / (uint32_t)NB) & 1u);
+            if (!(p.debug & 64)) pk_wait(b_full(sb), (nb / (uint32_t)NB) & 1u);
             const uint32_t b_cur = b_lo32 + (uint32_t)sb * b_slot;
             for (int pass = 0; pass < np; ++pass, ++n) {
               if (c == 0) {
                 db[pass] = (int)(dn % PK_ND);
-                pk_wait(d_empty(db[pass]), ((dn / PK_ND) & 1u) ^ 1u);
+                if (!(p.debug & 32)) pk_wait(d_empty(db[pass]), ((dn / PK_ND) & 1u) ^ 1u);
                 ++dn;
               }
               const int slot = (int)(n % (uint32_t)NA);
@@ -336,7 +342,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) spconv_pk_kernel(const __grid_c
               const uint32_t d = tmem_base + (uint32_t)(db[pass] * COUT);
               if (elect_one()) {
 #pragma unroll
-                for (int ks = 0; ks < 2; ++ks) {         // two 16-channel steps per 32-channel slab, three products each
+                for (int ks = 0; ks < ((p.debug & 4) ? 0 : 2); ++ks) {   // two 16-channel steps per 32-channel slab, three products each
                   const uint64_t da_hi = umma_desc_join(a_hi32, a_cur + ks * 2u);
                   const uint64_t da_lo = umma_desc_join(a_hi32, a_cur + ks * 2u + 4u);
                   const uint64_t db_hi = umma_desc_join(d_hi32, b_cur + ks * b_ks_off);
@@ -346,11 +352,11 @@ __global__ void __launch_bounds__(PK_THREADS, 1) spconv_pk_kernel(const __grid_c
                   umma_bf16(d, da_lo, db_hi, idesc, 1u);
                 }
                 umma_commit(a_empty(slot));
-                if (c == n_slab - 1) umma_commit(d_full(db[pass]));
+                if (c == n_slab - 1 && !(p.debug & 32)) umma_commit(d_full(db[pass]));
               }
               __syncwarp();
             }
-            if (elect_one()) umma_commit(b_empty(sb));   // all passes of this (k, slab) have read the weight stage
+            if (!(p.debug & 64) && elect_one()) umma_commit(b_empty(sb));   // all passes of this (k, slab) have read the weight stage
             __syncwarp();
           }
         }
@@ -360,11 +366,16 @@ __global__ void __launch_bounds__(PK_THREADS, 1) spconv_pk_kernel(const __grid_c
     } else if (warp == PK_WARP_W) {
       // =========================================================================== weight stages
       uint32_t nb = 0;
-      for (int t = blockIdx.x; t < p.n_super; t += gridDim.x) {
+      for (int t = blockIdx.x; t < p.n_super && !(p.debug & 64); t += gridDim.x) {
         for (int k = 0; k < K; ++k) {
           for (int c = 0; c < n_slab; ++c, ++nb) {
             const int sb = (int)(nb % (uint32_t)NB);
             pk_wait(b_empty(sb), ((nb / (uint32_t)NB) & 1u) ^ 1u);
+            if (p.debug & 2) {
+              if (elect_one()) mbar_arrive(b_full(sb));
+              __syncwarp();
+              continue;
+            }
             if (elect_one()) {
               mbar_arrive_expect_tx(b_full(sb), b_stage_bytes);
               const unsigned char* src = reinterpret_cast<const unsigned char*>(p.wp) + ((size_t)k * n_slab + c) * (size_t)b_stage_bytes;
@@ -397,8 +408,13 @@ __global__ void __launch_bounds__(PK_THREADS, 1) spconv_pk_kernel(const __grid_c
               va[j] = vb[j] = -1;
               if (k0 + j < K) {
                 const int* col = p.nbr + (long long)(k0 + j) * p.n_out;
-                if (in_a) va[j] = __ldg(col + row_a);
-                if (in_b) vb[j] = __ldg(col + row_b);
+                if (p.debug & 128) {
+                  va[j] = (lane % 3 == 0 && in_a) ? (int)row_a : -1;
+                  vb[j] = (lane % 3 == 1 && in_b) ? (int)row_b : -1;
+                } else {
+                  if (in_a) va[j] = __ldg(col + row_a);
+                  if (in_b) vb[j] = __ldg(col + row_b);
+                }
               }
             }
 #pragma unroll
@@ -479,6 +495,11 @@ int spconv_pk_launch(const float* in, long long n_in, int in_ld, int cin, const 
   if (force_na < 0) { const char* e = getenv("AG3D_PK_NA"); force_na = e ? atoi(e) : 0; }
   if (force_nb < 0) { const char* e = getenv("AG3D_PK_NB"); force_nb = e ? atoi(e) : 0; }
   p.NB = force_nb >= 2 && force_nb <= PK_MAX_NB ? force_nb : 3;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("AG3D_PK_DEBUG"); dbg = e ? atoi(e) : 0; }
+    p.debug = dbg;
+  }
   p.off_a = p.off_b + (uint32_t)p.NB * b_stage;
   const size_t budget = 227 * 1024;
   int na = (int)((budget - p.off_a - 1024) / PK_STAGE);

@@ -265,6 +265,7 @@ class Agile3d(nn.Module):
         self.ffn_attention = stack(lambda: _FFNLayer(d, dim_feedforward))
         self.decoder_norm = nn.LayerNorm(d)
         self.time_encode = _time_table(d, 200)       # plain attribute, not in the state_dict (agile3d.py:138)
+        self.fused_queries = True                    # eval: click-query side in fused kernels (csrc/query_ops.cu)
         # derived weight images (folded BatchNorm, tensor-core images) are cached per parameter generation
         self.register_load_state_dict_post_hook(lambda module, incompatible: ops.bump_param_generation())
 
@@ -384,8 +385,121 @@ class Agile3d(nn.Module):
         grad = torch.is_grad_enabled() and (self.training or pcd_features.F.requires_grad)
         if not grad:
             with torch.no_grad():
+                if self.fused_queries:
+                    return self._forward_mask_fused(pcd_features, coordinates, pos_encodings_pcd, click_idx, click_time_idx)
                 return self._forward_mask(pcd_features, coordinates, pos_encodings_pcd, click_idx, click_time_idx, False)
         return self._forward_mask(pcd_features, coordinates, pos_encodings_pcd, click_idx, click_time_idx, True)
+
+    # ---- eval path: the click-query side of every layer in three fused kernels (csrc/query_ops.cu) - no torch op
+    #      touches the data between the C-ABI calls; train mode keeps the torch glue below for autograd
+    def _layer_blob(self, li):
+        """per-layer weight blob of ag3d_query_* (pre-transposed matrices, layout in csrc/query_ops.cu)"""
+        key = (ops.param_generation(), sum(p._version for p in self._dec_params()))
+        cache = getattr(self, "_blob_cache", None)
+        if cache is None or cache[0] != key:
+            cache = self._blob_cache = (key, {})
+        if li not in cache[1]:
+            d = self.hidden_dim
+            c2s, c2c = self.c2s_attention[li][0], self.c2c_attention[li][0]
+            ffn, s2c = self.ffn_attention[li][0], self.s2c_attention[li][0]
+            parts = []
+            p = c2s.multihead_attn
+            W, b = p.in_proj_weight, p.in_proj_bias
+            parts += [W[:d].t(), b[:d], W[d:2 * d], W[2 * d:].t(), b[2 * d:], p.out_proj.weight.t(), p.out_proj.bias,
+                      c2s.norm.weight, c2s.norm.bias]
+            p = c2c.self_attn
+            W, b = p.in_proj_weight, p.in_proj_bias
+            parts += [W[:d].t(), b[:d], W[d:2 * d].t(), b[d:2 * d], W[2 * d:].t(), b[2 * d:], p.out_proj.weight.t(),
+                      p.out_proj.bias, c2c.norm.weight, c2c.norm.bias]
+            parts += [ffn.linear1.weight.t(), ffn.linear1.bias, ffn.linear2.weight.t(), ffn.linear2.bias, ffn.norm.weight,
+                      ffn.norm.bias]
+            p = s2c.multihead_attn
+            W, b = p.in_proj_weight, p.in_proj_bias
+            parts += [W[d:2 * d].t(), b[d:2 * d], W[2 * d:].t(), b[2 * d:], W[:d], b[:d], p.out_proj.weight.t()]
+            m = self.mask_embed_head
+            parts += [self.decoder_norm.weight, self.decoder_norm.bias, m[0].weight.t(), m[0].bias, m[2].weight.t(), m[2].bias]
+            blob = torch.cat([t.detach().float().contiguous().reshape(-1) for t in parts])
+            if blob.numel() != ops.query_blob_floats():
+                raise RuntimeError("query weight blob does not match csrc/query_ops.cu")
+            cache[1][li] = blob
+        return cache[1][li]
+
+    def _dec_params(self):
+        ps = getattr(self, "_dec_param_list", None)
+        if ps is None:
+            ps = self._dec_param_list = [p for n, p in self.named_parameters() if not n.startswith("backbone.")]
+        return ps
+
+    @staticmethod
+    def _staged_ints(rows, dev):
+        """python ints -> device int32 tensor through pinned memory of torch's caching host allocator (an async copy: no
+        pageable-copy synchronisation; the allocator keeps the block alive until the copy has run)"""
+        t = torch.tensor(rows, dtype=torch.int32)
+        if dev.type != "cuda":
+            return t.to(dev)
+        return t.pin_memory().to(dev, non_blocking=True)
+
+    def _forward_mask_fused(self, pcd_features, coordinates, pos_encodings_pcd, click_idx, click_time_idx):
+        H = self.num_heads
+        dev = pcd_features.F.device
+        offsets = pcd_features.offsets
+        n_scenes = len(offsets) - 1
+        tt = self.time_encode.to(dev) if self.time_encode.device != dev else self.time_encode
+        self.time_encode = tt
+        nbg = self.num_bg_queries
+        meta, groups = [], {}
+        for b in range(n_scenes):
+            ck, ct = click_idx[b], click_time_idx[b]
+            K = len(ck) - 1
+            split = [len(ck[str(i)]) for i in range(1, K + 1)]
+            if min(split, default=1) < 1:
+                raise ValueError("every foreground object needs at least one click (agile3d.py:214)")
+            n_fg, n_bgc = sum(split), len(ck["0"])
+            # query order of a scene: [fg clicks by object id then click order | learned bg | bg clicks] (agile3d.py:249-264)
+            src = [offsets[b] + i for o in range(1, K + 1) for i in ck[str(o)]] + [-(k + 1) for k in range(nbg)] \
+                + [offsets[b] + i for i in ck["0"]]
+            tix = [t for o in range(1, K + 1) for t in ct[str(o)]] + [0] * nbg + list(ct["0"])
+            q_obj = [o for o, n in enumerate(split, start=1) for _ in range(n)] + [0] * (nbg + n_bgc)
+            meta.append((K, src, tix, q_obj))
+            groups.setdefault(n_fg + nbg + n_bgc, []).append(b)
+        results = [None] * n_scenes
+        pos_list = pos_encodings_pcd[self.hlevels[0]][0]
+        for nq, members in groups.items():
+            B = len(members)
+            if nq > ops.S2C_MAX_QUERIES:
+                raise ValueError(f"at most {ops.S2C_MAX_QUERIES} click queries per scene, got {nq}")
+            ints = self._staged_ints([v for b in members for v in meta[b][1]] + [v for b in members for v in meta[b][2]]
+                                     + [b for b in members for _ in range(nq)] + [v for b in members for v in meta[b][3]], dev)
+            src_row, time_idx, scene_of_row, q_obj = ints[:B * nq], ints[B * nq:2 * B * nq], ints[2 * B * nq:3 * B * nq], \
+                ints[3 * B * nq:].view(B, nq)
+            queries, qpos = ops.query_init(pcd_features.F, coordinates.F, coordinates.range, src_row, time_idx, scene_of_row,
+                                           self.pos_enc.gauss_B, tt, self.bg_query_feat.weight, self.bg_query_pos.weight)
+            srcs = [pcd_features.F[offsets[b]:offsets[b + 1]] for b in members]
+            labels, counts = [None] * B, [None] * B
+            outs = [[] for _ in members]
+            ctx = torch.empty((B, H * nq, self.hidden_dim), dtype=torch.float32, device=dev)
+            for layer in range(self.num_decoders):
+                li = 0 if self.shared_decoder else layer
+                s2c = self.s2c_attention[li][0]
+                blob = self._layer_blob(li)
+                qfold = ops.query_fold_c2s(queries, qpos, blob, B, nq, H)
+                for i, b in enumerate(members):
+                    ops.c2s_attn_fwd(srcs[i], pos_list[b], qfold[i], nq, H, labels[i], q_obj[i], counts[i], out=ctx[i])
+                q1, qh, kh, vh = ops.query_update_a(ctx, queries, qpos, blob, B, nq, s2c.norm.eps)
+                queries, A, c, U, E = ops.query_update_b(q1, qh, kh, vh, qpos, blob, B, nq, H, s2c.norm.eps)
+                for i, b in enumerate(members):
+                    srcs[i], logits, labels[i], counts[i] = ops.s2c_mask_fwd(
+                        srcs[i], pos_list[b], A[i], c[i], U[i], s2c.multihead_attn.out_proj.bias, s2c.norm.weight,
+                        s2c.norm.bias, s2c.norm.eps, E[i], q_obj[i], nq, H, meta[b][0] + 1,
+                        x_out=None if layer == 0 else srcs[i])      # never overwrite the caller's backbone features
+                    outs[i].append(logits)
+            for i, b in enumerate(members):
+                results[b] = outs[i]
+        per_layer = [list(p) for p in zip(*results)]
+        out = {"pred_masks": per_layer[-1], "backbone_features": pcd_features}
+        if self.aux:
+            out["aux_outputs"] = [{"pred_masks": p} for p in per_layer[:-1]]
+        return out
 
     def _forward_mask(self, pcd_features, coordinates, pos_encodings_pcd, click_idx, click_time_idx, grad):
         H, d = self.num_heads, self.hidden_dim

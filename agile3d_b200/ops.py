@@ -324,6 +324,52 @@ def s2c_mask_fwd(x, pos, A, c, U, bo, ln_w, ln_b, ln_eps, E, q_obj, nq, heads, n
     return x_out, logits, label, obj_count
 
 
+# =============================================================================================== click-query side (K11)
+def query_blob_floats():
+    return int(lib().ag3d_query_blob_floats())
+
+
+def query_init(feats, xyz, rng, src_row, time_idx, scene_of_row, gauss_B, time_table, bg_feat, bg_pos):
+    """-> (queries, qpos) f32 [rows, 128]; src_row int32 [rows] (>= 0: clicked voxel row, -(k+1): learned bg query k)."""
+    _need_cuda(feats, xyz, rng, src_row)
+    n = src_row.shape[0]
+    q = torch.empty((n, 128), dtype=torch.float32, device=feats.device)
+    qp = torch.empty_like(q)
+    check(lib().ag3d_query_init(_p(feats), _p(xyz), _p(rng), _p(src_row), _p(time_idx), _p(scene_of_row), n, _p(gauss_B),
+                                _p(time_table), _p(bg_feat), _p(bg_pos), _p(q), _p(qp), _stream()), "ag3d_query_init")
+    return q, qp
+
+
+def query_fold_c2s(queries, qpos, blob, B, nq, heads=8):
+    _need_cuda(queries, qpos, blob)
+    qfold = torch.empty((B, heads * nq, 128), dtype=torch.float32, device=queries.device)
+    check(lib().ag3d_query_fold_c2s(_p(queries), _p(qpos), _p(blob), B, nq, _p(qfold), _stream()), "ag3d_query_fold_c2s")
+    return qfold
+
+
+def query_update_a(ctx, queries, qpos, blob, B, nq, ln_eps=1e-5):
+    """tail of c2s + the c2c projections -> (q1, qh, kh, vh), each f32 [B, nq, 128]."""
+    _need_cuda(ctx, queries, qpos, blob)
+    out = torch.empty((4, B, nq, 128), dtype=torch.float32, device=queries.device)
+    check(lib().ag3d_query_update_a(_p(ctx), _p(queries), _p(qpos), _p(blob), B, nq, float(ln_eps), _p(out[0]), _p(out[1]),
+                                    _p(out[2]), _p(out[3]), _stream()), "ag3d_query_update_a")
+    return out[0], out[1], out[2], out[3]
+
+
+def query_update_b(q1, qh, kh, vh, qpos, blob, B, nq, heads=8, ln_eps=1e-5):
+    """c2c attention + FFN + s2c folds + mask embeddings -> (q3 [B,nq,128], A [B,8nq,128], c [B,8nq], U [B,8nq,128], E [B,nq,128])."""
+    _need_cuda(q1, qh, kh, vh, qpos, blob)
+    dev, f32 = q1.device, torch.float32
+    q3 = torch.empty((B, nq, 128), dtype=f32, device=dev)
+    A = torch.empty((B, heads * nq, 128), dtype=f32, device=dev)
+    c = torch.empty((B, heads * nq), dtype=f32, device=dev)
+    U = torch.empty((B, heads * nq, 128), dtype=f32, device=dev)
+    E = torch.empty((B, nq, 128), dtype=f32, device=dev)
+    check(lib().ag3d_query_update_b(_p(q1), _p(qh), _p(kh), _p(vh), _p(qpos), _p(blob), B, nq, float(ln_eps), _p(q3), _p(A),
+                                    _p(c), _p(U), _p(E), _stream()), "ag3d_query_update_b")
+    return q3, A, c, U, E
+
+
 # =============================================================================================== training step
 def _ws_for(tag, device, nbytes):
     return _workspace(tag, device, max(int(nbytes), 16))

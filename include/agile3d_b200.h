@@ -137,6 +137,33 @@ int ag3d_fourier_posenc(const float* xyz, const int32_t* scene_offsets_host, int
                         const float* gauss_B, int32_t d_pos, float* out, float* range_out, void* ws,
                         size_t ws_bytes, ag3d_stream_t stream);
 
+/* ---- click-query side of a decoder layer (K11) -------------------------------------------------------------
+ * Replaces the O(Nq) torch calls between the two voxel-streaming kernels of a layer (models/agile3d.py:273-325):
+ * the q/k/v/out projections of CrossAttentionLayer / SelfAttentionLayer (models/modules/attention_block.py:28-38,
+ * 86-98), FFNLayer (:151-155), decoder_norm + mask_embed_head (models/agile3d.py:342-347) and the query assembly of
+ * a click round (models/agile3d.py:202-264).  All matrices [n_scenes, nq, 128] fp32 row-major; `blob` is the
+ * per-layer weight blob of ag3d_query_blob_floats() floats (layout: csrc/query_ops.cu, built by
+ * agile3d_b200/model.py::_layer_blob from the state_dict); nq <= 256.
+ *   ag3d_query_init:     row r of (queries, qpos): src_row[r] >= 0 -> feats[src_row[r]] and fourier(xyz[src_row[r]];
+ *                        range of scene scene_of_row[r]) + time_table[time_idx[r]];  src_row[r] = -(k+1) -> learned
+ *                        background query k (bg_feat[k], bg_pos[k]).
+ *   ag3d_query_fold_c2s: qfold[(h,q),:] = Wk_h^T ((Wq_h (Q+qpos) + bq_h) / 4)            [n_scenes, 8 nq, 128]
+ *   ag3d_query_update_a: q1 = LN(Q + out_proj(per-head Wv ctx + bv)) (tail of c2s);  qh/kh/vh = c2c projections
+ *   ag3d_query_update_b: q2 = LN(q1 + c2c attention), q3 = LN(q2 + FFN(q2)) -> queries of the next layer;
+ *                        A, c, U = folds for ag3d_s2c_mask_fwd;  E = mask_embed_head(decoder_norm(q3))               */
+int64_t ag3d_query_blob_floats(void);
+int ag3d_query_init(const float* feats, const float* xyz, const float* range, const int32_t* src_row,
+                    const int32_t* time_idx, const int32_t* scene_of_row, int32_t n_rows, const float* gauss_B,
+                    const float* time_table, const float* bg_feat, const float* bg_pos, float* queries, float* qpos,
+                    ag3d_stream_t stream);
+int ag3d_query_fold_c2s(const float* queries, const float* qpos, const float* blob, int32_t n_scenes, int32_t nq,
+                        float* qfold, ag3d_stream_t stream);
+int ag3d_query_update_a(const float* ctx, const float* queries, const float* qpos, const float* blob, int32_t n_scenes,
+                        int32_t nq, float ln_eps, float* q1, float* qh, float* kh, float* vh, ag3d_stream_t stream);
+int ag3d_query_update_b(const float* q1, const float* qh, const float* kh, const float* vh, const float* qpos,
+                        const float* blob, int32_t n_scenes, int32_t nq, float ln_eps, float* q3, float* A, float* c,
+                        float* U, float* E, ag3d_stream_t stream);
+
 /* ---- click -> scene cross-attention (c2s) -------------------------------------------------------------
  * Replaces nn.MultiheadAttention inside CrossAttentionLayer.forward_post as called at
  * models/agile3d.py:283-290 (models/modules/attention_block.py:86-98), with the key/value projections

@@ -305,11 +305,95 @@ def s2c_mask_bwd_tc(x, pos, A, c, U, bo, ln_w, ln_b, ln_eps, E, q_obj, nq, heads
                         E.t().contiguous(), q_obj, nq, heads, n_obj, hqp, dxo, dlogits)
 
 
+# ------------------------------------------------------------------------------------------------ click-query side (K11)
+# Contract emulations of ag3d_query_* (include/agile3d_b200.h).  The weight blob is decoded here from the layout
+# documented in csrc/query_ops.cu, independently of agile3d_b200/model.py::_layer_blob that builds it.
+_QD, _QF = 128, 1024
+_BLOB_FIELDS = [("c2s_WqT", (128, 128)), ("c2s_bq", (128,)), ("c2s_Wk", (128, 128)), ("c2s_WvT", (128, 128)), ("c2s_bv", (128,)),
+                ("c2s_WoT", (128, 128)), ("c2s_bo", (128,)), ("c2s_lnw", (128,)), ("c2s_lnb", (128,)),
+                ("c2c_WqT", (128, 128)), ("c2c_bq", (128,)), ("c2c_WkT", (128, 128)), ("c2c_bk", (128,)), ("c2c_WvT", (128, 128)),
+                ("c2c_bv", (128,)), ("c2c_WoT", (128, 128)), ("c2c_bo", (128,)), ("c2c_lnw", (128,)), ("c2c_lnb", (128,)),
+                ("ffn_W1T", (128, 1024)), ("ffn_b1", (1024,)), ("ffn_W2T", (1024, 128)), ("ffn_b2", (128,)), ("ffn_lnw", (128,)),
+                ("ffn_lnb", (128,)),
+                ("s2c_WkT", (128, 128)), ("s2c_bk", (128,)), ("s2c_WvT", (128, 128)), ("s2c_bv", (128,)), ("s2c_Wq", (128, 128)),
+                ("s2c_bq", (128,)), ("s2c_WoT", (128, 128)),
+                ("dec_lnw", (128,)), ("dec_lnb", (128,)), ("M1T", (128, 128)), ("m1b", (128,)), ("M2T", (128, 128)), ("m2b", (128,))]
+
+
+def query_blob_floats():
+    return sum(int(np.prod(sh)) for _, sh in _BLOB_FIELDS)
+
+
+def _blob(blob):
+    out, off = {}, 0
+    for name, sh in _BLOB_FIELDS:
+        n = int(np.prod(sh))
+        out[name] = blob[off:off + n].view(*sh)
+        off += n
+    assert off == blob.numel()
+    return out
+
+
+def _ln(x, w, b, eps):
+    return torch.nn.functional.layer_norm(x, (x.shape[-1],), w, b, eps)
+
+
+def query_init(feats, xyz, rng, src_row, time_idx, scene_of_row, gauss_B, time_table, bg_feat, bg_pos):
+    n = src_row.shape[0]
+    q = torch.empty((n, _QD), dtype=feats.dtype)
+    qp = torch.empty_like(q)
+    for r in range(n):
+        s = int(src_row[r])
+        if s < 0:
+            q[r], qp[r] = bg_feat[-(s + 1)], bg_pos[-(s + 1)]
+        else:
+            lo, hi = rng[int(scene_of_row[r]), :3], rng[int(scene_of_row[r]), 3:]
+            t = (((xyz[s] - lo) / (hi - lo)) * (2 * math.pi)) @ gauss_B
+            q[r], qp[r] = feats[s], torch.cat([t.sin(), t.cos()]) + time_table[int(time_idx[r])]
+    return q, qp
+
+
+def query_fold_c2s(queries, qpos, blob, B, nq, heads=8):
+    w = _blob(blob)
+    qp = (((queries + qpos).view(B, nq, _QD) @ w["c2s_WqT"]) + w["c2s_bq"]) * 0.25
+    return torch.einsum("bqhd,hdc->bhqc", qp.view(B, nq, heads, 16), w["c2s_Wk"].view(heads, 16, _QD)).reshape(B, heads * nq, _QD).contiguous()
+
+
+def query_update_a(ctx, queries, qpos, blob, B, nq, ln_eps=1e-5):
+    w = _blob(blob)
+    H = 8
+    Q, P = queries.view(B, nq, _QD), qpos.view(B, nq, _QD)
+    WvT = w["c2s_WvT"].view(_QD, H, 16)                                            # [c, h, d]
+    heads = torch.einsum("bhqc,chd->bqhd", ctx.view(B, H, nq, _QD), WvT).reshape(B, nq, _QD) + w["c2s_bv"]
+    q1 = _ln(Q + (heads @ w["c2s_WoT"] + w["c2s_bo"]), w["c2s_lnw"], w["c2s_lnb"], ln_eps)
+    x = q1 + P
+    return q1, x @ w["c2c_WqT"] + w["c2c_bq"], x @ w["c2c_WkT"] + w["c2c_bk"], q1 @ w["c2c_WvT"] + w["c2c_bv"]
+
+
+def query_update_b(q1, qh, kh, vh, qpos, blob, B, nq, heads=8, ln_eps=1e-5):
+    w = _blob(blob)
+    H = heads
+    P = qpos.view(B, nq, _QD)
+    sp = lambda t: t.reshape(B, nq, H, 16).transpose(1, 2)                          # [B, H, nq, 16]
+    a = torch.softmax((sp(qh) * 0.25) @ sp(kh).transpose(2, 3), dim=-1)
+    o = (a @ sp(vh)).transpose(1, 2).reshape(B, nq, _QD)
+    q2 = _ln(q1 + (o @ w["c2c_WoT"] + w["c2c_bo"]), w["c2c_lnw"], w["c2c_lnb"], ln_eps)
+    q3 = _ln(q2 + (torch.relu(q2 @ w["ffn_W1T"] + w["ffn_b1"]) @ w["ffn_W2T"] + w["ffn_b2"]), w["ffn_lnw"], w["ffn_lnb"], ln_eps)
+    kp = ((q3 + P) @ w["s2c_WkT"] + w["s2c_bk"]).view(B, nq, H, 16)
+    vp = (q3 @ w["s2c_WvT"] + w["s2c_bv"]).view(B, nq, H, 16)
+    A = (torch.einsum("bqhd,hdc->bhqc", kp, w["s2c_Wq"].view(H, 16, _QD)) * 0.25).reshape(B, H * nq, _QD).contiguous()
+    c = (torch.einsum("bqhd,hd->bhq", kp, w["s2c_bq"].view(H, 16)) * 0.25).reshape(B, H * nq).contiguous()
+    U = torch.einsum("bqhd,hdc->bhqc", vp, w["s2c_WoT"].view(H, 16, _QD)).reshape(B, H * nq, _QD).contiguous()
+    E = torch.relu(_ln(q3, w["dec_lnw"], w["dec_lnb"], ln_eps) @ w["M1T"] + w["m1b"]) @ w["M2T"] + w["m2b"]
+    return q3, A, c, U, E
+
+
 ALL = ["wgrad_tc_supported", "c2s_attn_bwd_tc", "s2c_mask_bwd_tc",
        "bn_stats", "bn_apply", "bn_bwd", "col_sum", "spconv_bwd_weight", "stem_bwd_weight", "decoder_bwd_rows",
        "c2s_attn_bwd", "s2c_mask_bwd", "loss_fwd", "loss_bwd", "click_loss_weights", "grad_norm", "adamw_step",
        "prepare_tc_weight", "hash_build", "downsample", "kernel_map", "kernel_map_transposed", "spconv_fwd", "stem_conv_fwd",
-       "fourier_posenc", "c2s_attn_fwd", "s2c_mask_fwd"]
+       "fourier_posenc", "c2s_attn_fwd", "s2c_mask_fwd", "query_blob_floats", "query_init", "query_fold_c2s",
+       "query_update_a", "query_update_b"]
 
 
 def patch_ops(monkeypatch):

@@ -36,6 +36,7 @@ def test_argument_validation_without_gpu():
     assert L.ag3d_hash_capacity(1000) == 2048 and L.ag3d_hash_capacity(150000) == 524288
     rc = L.ag3d_spconv_fwd(None, 32, 33, None, 1, 10, None, None, 32, None, None, None, 0, None, 32, 0, 1, None, 0, None)
     assert rc == -1 and b"multiples of 32" in L.ag3d_last_error()
-    rc = L.ag3d_s2c_mask_fwd(None, None, 10, None, None, None, None, None, None, 1e-5, None, None, 40, 8, 3, None,
+    rc = L.ag3d_s2c_mask_fwd(None, None, 10, None, None, None, None, None, None, 1e-5, None, None, 300, 8, 3, None,
                              None, None, None, 0, None, 0, None)
-    assert rc == -1 and b"32 click queries" in L.ag3d_last_error()
+    assert rc == -1 and b"256 click queries" in L.ag3d_last_error()
+    assert L.ag3d_query_blob_floats() == 14 * 128 * 128 + 2 * 128 * 1024 + 1024 + 21 * 128

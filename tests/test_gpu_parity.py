@@ -269,6 +269,60 @@ def test_s2c_mask_many_queries_vs_oracle(nv, nq, n_obj):
     assert torch.equal(y2, y) and torch.equal(lg2, lg)
 
 
+@pytest.mark.parametrize("B,nq", [(1, 12), (3, 20), (2, 45), (1, 210), (1, 256), (8, 16)])
+def test_query_kernels_vs_emulation(B, nq):
+    """K11 (csrc/query_ops.cu): query assembly, c2s fold, c2s tail + c2c projections, c2c attention + FFN + s2c folds +
+    mask embeddings against the fp64 contract emulation, with the weight blob of a real model."""
+    from agile3d_b200 import ops
+    m = _gpu_model(9)
+    blob = m._layer_blob(1)
+    assert blob.numel() == emulate.query_blob_floats()
+    g = torch.Generator().manual_seed(B * 1000 + nq)
+    rn = lambda *sh: torch.randn(sh, generator=g)
+    # ---- query assembly
+    nv = 500
+    feats, xyz = rn(nv, 128), torch.rand((nv, 3), generator=g) * 5
+    rng = torch.tensor([[0.0, 0.0, 0.0, 5.0, 5.0, 5.0]]).repeat(B, 1) + torch.rand((B, 6), generator=g) * 0.1
+    src = torch.randint(0, nv, (B * nq,), generator=g, dtype=torch.int32)
+    src[::3] = -(torch.randint(0, 10, (len(src[::3]),), generator=g, dtype=torch.int32) + 1)
+    tix = torch.randint(0, 200, (B * nq,), generator=g, dtype=torch.int32)
+    sor = torch.arange(B, dtype=torch.int32).repeat_interleave(nq)
+    gB, ttab, bgf, bgp = m.pos_enc.gauss_B.cpu(), m.time_encode.cpu(), m.bg_query_feat.weight.detach().cpu(), m.bg_query_pos.weight.detach().cpu()
+    t = lambda v: v.to(DEV)
+    q_ref, qp_ref = emulate.query_init(feats.double(), xyz.double(), rng.double(), src, tix, sor, gB.double(), ttab.double(),
+                                       bgf.double(), bgp.double())
+    q, qp = ops.query_init(t(feats), t(xyz), t(rng), t(src), t(tix), t(sor), t(gB), t(ttab), t(bgf), t(bgp))
+    assert torch.equal(q.cpu(), q_ref.float())
+    assert float((qp.cpu() - qp_ref).abs().max()) < 3e-5
+    # ---- the three per-layer kernels
+    Q, P = rn(B, nq, 128), rn(B, nq, 128) * 0.7
+    ctx = rn(B, 8 * nq, 128)
+    bd = blob.detach().cpu().double()
+    ref_fold = emulate.query_fold_c2s(Q.double(), P.double(), bd, B, nq)
+    got_fold = ops.query_fold_c2s(t(Q), t(P), blob, B, nq)
+    assert rel_err(got_fold.cpu().numpy(), ref_fold.numpy()) < 1e-5
+    ref_a = emulate.query_update_a(ctx.double(), Q.double(), P.double(), bd, B, nq)
+    got_a = ops.query_update_a(t(ctx), t(Q), t(P), blob, B, nq)
+    for name, a_, b_ in zip(("q1", "qh", "kh", "vh"), got_a, ref_a):
+        assert rel_err(a_.cpu().numpy(), b_.numpy()) < 1e-5, name
+    ref_b = emulate.query_update_b(*ref_a, P.double(), bd, B, nq)
+    got_b = ops.query_update_b(*[v.float().to(DEV) for v in ref_a], t(P), blob, B, nq)
+    for name, a_, b_ in zip(("q3", "A", "c", "U", "E"), got_b, ref_b):
+        assert rel_err(a_.cpu().numpy(), b_.numpy()) < 2e-5, name
+
+
+def test_fused_query_path_equals_torch_glue():
+    """eval forward_mask with the fused click-query kernels against the same model running the torch glue."""
+    g = load_golden("g3000_k3")
+    m = _gpu_model(g["wseed"])
+    h, layers = _run_gpu(m, g["coords"], g["feats"], g["raw_coords"], [g["clicks"]], [g["times"]])
+    m.fused_queries = False
+    out = m.forward_mask(*h, [g["clicks"]], [g["times"]])
+    ref = [a["pred_masks"] for a in out["aux_outputs"]] + [out["pred_masks"]]
+    for l in range(3):
+        assert rel_err(layers[l][0].cpu().numpy(), ref[l][0].cpu().numpy()) < 2e-5
+
+
 # ------------------------------------------------------------------------------------------------ end to end
 def _gpu_model(wseed, algo=None):
     import agile3d_b200

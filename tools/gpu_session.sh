@@ -2,12 +2,9 @@
 # Current GPU session (overwritten per call; results land in gpurun_out/ and the kept ones are copied to profiles/).
 cd "$GRAFT_REPO_ROOT" || exit 1
 mkdir -p gpurun_out
-timeout 300 python tools/pk_shapes.py 700 20000 > gpurun_out/s4_pk_small.txt 2>&1
-if grep -q FAILED gpurun_out/s4_pk_small.txt; then
-  AG3D_PK_REPS=1 timeout 600 compute-sanitizer --tool memcheck --print-limit 20 python tools/pk_shapes.py 700 > gpurun_out/s4_pk_sanitizer.txt 2>&1
-else
-  timeout 600 python tools/pk_shapes.py 150000 > gpurun_out/s4_pk_150k.txt 2>&1
-fi
-timeout 900 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "many" -s > gpurun_out/s4_pytest_many.log 2>&1
-AG3D_PK_MIN_ROWS=100000000 timeout 1500 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "baseline_shape" -s > gpurun_out/s4_pytest_baseline.log 2>&1
-tail -n 12 gpurun_out/s4_pk_small.txt gpurun_out/s4_pk_150k.txt; tail -n 30 gpurun_out/s4_pk_sanitizer.txt; tail -n 8 gpurun_out/s4_pytest_many.log gpurun_out/s4_pytest_baseline.log
+tools/probes/bin/commit_probe > gpurun_out/s6_commit_probe.txt 2>&1
+O=gpurun_out/s6_pk_probe.txt
+: > $O
+for d in 31 63 95 127 159 255 223; do AG3D_PK_NA=6 AG3D_PK_NB=6 AG3D_PK_DEBUG=$d timeout 120 python tools/pk_probe.py 96 96 >> $O 2>&1; done
+timeout 900 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "query or fused or golden or many" > gpurun_out/s6_pytest_query.log 2>&1
+cat gpurun_out/s6_commit_probe.txt; grep -v Warn $O; tail -n 15 gpurun_out/s6_pytest_query.log
