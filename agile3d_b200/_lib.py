@@ -28,6 +28,8 @@ SIGNATURES = {
     "ag3d_hash_build": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp]),
     "ag3d_downsample_workspace_bytes": (_sz, [_i64]),
     "ag3d_downsample": (_i32, [_vp, _i64, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ag3d_downsample_dev": (_i32, [_vp, _i64, _vp, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ag3d_scene_offsets": (_i32, [_vp, _i64, _i32, _vp, _vp]),
     "ag3d_kernel_map": (_i32, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp]),
     "ag3d_kernel_map_transposed": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp]),
     "ag3d_spconv_tc_weight_bytes": (_sz, [_i32, _i32, _i32]),
@@ -76,6 +78,7 @@ SIGNATURES = {
     "ag3d_ln_bwd_workspace_bytes": (_sz, []),
     "ag3d_ln_bwd": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
     "ag3d_s2c_route": (_i32, [_vp, _vp, _vp, _i32, _i32, _i64, _vp, _vp]),
+    "ag3d_s2c_route_ld": (_i32, [_vp, _i32, _vp, _vp, _i32, _i32, _i64, _vp, _vp, _vp]),
     "ag3d_s2c_bwd_workspace_bytes": (_sz, [_i32]),
     "ag3d_s2c_mask_bwd": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _i32, _i32,
                                  _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -30,21 +30,13 @@ class CoordinateMaps:
     hash tables, and the kernel maps of every (level, kernel) pair the U-Net uses.  Built once per
     SparseTensor on the GPU and cached on it."""
 
-    def __init__(self, coords: torch.Tensor, count_pairs: bool = False):
+    def __init__(self, coords: torch.Tensor, count_pairs: bool = False, want_offsets: bool = False):
         if coords.dtype != torch.int32 or coords.dim() != 2 or coords.shape[1] != 4 or not coords.is_contiguous():
             raise ValueError("coords must be a contiguous int32 [N,4] tensor")
-        self.coords = [coords]
-        table, cap, status = ops.hash_build(coords)
-        self.tables, self.caps, self.parents = [table], [cap], []
-        self._status = status
-        for lvl in range(4):                                        # tensor strides 2, 4, 8, 16
-            c, t, cp, par = ops.downsample(self.coords[lvl], 2 << lvl)
-            self.coords.append(c)
-            self.tables.append(t)
-            self.caps.append(cp)
-            self.parents.append(par)
-        # the downsample calls synchronised, so the status words are ready
-        dup, oor = (int(v) for v in status.tolist())
+        # 5 coordinate levels (tensor strides 1 .. 16), their hash tables and the scene row ranges: the level sizes stay
+        # on the device between the levels, the host reads everything back once (ops.build_levels)
+        self.coords, self.tables, self.caps, self.parents, (dup, oor), self.offsets = \
+            ops.build_levels(coords, 4, want_offsets)
         if dup or oor:
             raise ValueError(f"SparseTensor coordinates: {dup} duplicate rows, {oor} rows outside +-32767 "
                              "(run sparse_quantize first)")

@@ -69,8 +69,11 @@ __global__ void hash_build_kernel(const int4* __restrict__ coords, long long n, 
 }
 
 // --- downsample: pass 1 inserts the coarse key of every fine row, remembering the slot.
-__global__ void coarse_insert_kernel(const int4* __restrict__ coords, long long n, int new_stride, Slot* table,
-                                     unsigned long long mask, int* __restrict__ slot_of_row) {
+// n_dev (nullable): the row count lives on the device (the previous level's count of a chained downsample, not yet
+// known to the host); n is then only the upper bound that sized the grid.
+__global__ void coarse_insert_kernel(const int4* __restrict__ coords, long long n, const int* __restrict__ n_dev,
+                                     int new_stride, Slot* table, unsigned long long mask, int* __restrict__ slot_of_row) {
+  if (n_dev) n = *n_dev;
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long step = (long long)gridDim.x * blockDim.x;
   for (; i < n; i += step) {
@@ -93,7 +96,8 @@ __device__ __forceinline__ int is_rep(const Slot* table, const int* slot_of_row,
 }
 
 __global__ void rep_count_kernel(const Slot* __restrict__ table, const int* __restrict__ slot_of_row, long long n,
-                                 int* __restrict__ block_sums) {
+                                 const int* __restrict__ n_dev, int* __restrict__ block_sums) {
+  if (n_dev) n = *n_dev;
   __shared__ int warp_sums[SCAN_THREADS / 32];
   const long long base = (long long)blockIdx.x * SCAN_TILE;
   int cnt = 0;
@@ -138,9 +142,10 @@ __global__ void block_scan_kernel(int* block_sums, int n_blocks, int* out_total)
   if (threadIdx.x == 0) *out_total = carry;
 }
 
-__global__ void rep_assign_kernel(const int4* __restrict__ coords, long long n, int new_stride, Slot* table,
-                                  const int* __restrict__ slot_of_row, const int* __restrict__ block_offsets,
-                                  int4* __restrict__ out_coords) {
+__global__ void rep_assign_kernel(const int4* __restrict__ coords, long long n, const int* __restrict__ n_dev,
+                                  int new_stride, Slot* table, const int* __restrict__ slot_of_row,
+                                  const int* __restrict__ block_offsets, int4* __restrict__ out_coords) {
+  if (n_dev) n = *n_dev;
   // rows are assigned to threads in *blocked* order inside the tile so that the scan preserves row order
   __shared__ int warp_sums[SCAN_THREADS / 32];
   const long long base = (long long)blockIdx.x * SCAN_TILE + (long long)threadIdx.x * SCAN_ITEMS;
@@ -182,7 +187,8 @@ __global__ void rep_assign_kernel(const int4* __restrict__ coords, long long n, 
 }
 
 __global__ void parent_kernel(const Slot* __restrict__ table, const int* __restrict__ slot_of_row, long long n,
-                              int* __restrict__ parent) {
+                              const int* __restrict__ n_dev, int* __restrict__ parent) {
+  if (n_dev) n = *n_dev;
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long step = (long long)gridDim.x * blockDim.x;
   for (; i < n; i += step) parent[i] = table[slot_of_row[i]].row;
@@ -231,6 +237,27 @@ __global__ void kernel_map_transposed_kernel(const int4* __restrict__ fine, cons
 #pragma unroll
     for (int k = 0; k < 8; ++k) nbr[(long long)k * n + i] = (k == kk) ? p : -1;
   }
+}
+
+// offsets[b] = first row whose scene index is >= b (b = 0 .. max_scenes); offsets[max_scenes + 1] = number of rows whose
+// scene index is smaller than their predecessor's (scenes must be contiguous and in batch order)
+__global__ void scene_offsets_kernel(const int4* __restrict__ coords, long long n, int max_scenes, int* __restrict__ offsets) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b <= max_scenes) {
+    long long lo = 0, hi = n;                       // lower bound of b in the (sorted) scene column
+    while (lo < hi) {
+      const long long mid = (lo + hi) >> 1;
+      if (__ldg(&coords[mid].x) < b) lo = mid + 1; else hi = mid;
+    }
+    offsets[b] = (int)lo;
+  }
+}
+__global__ void scene_order_kernel(const int4* __restrict__ coords, long long n, int* __restrict__ bad) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x + 1;
+  const long long step = (long long)gridDim.x * blockDim.x;
+  int c = 0;
+  for (; i < n; i += step) c += __ldg(&coords[i].x) < __ldg(&coords[i - 1].x);
+  if (c) atomicAdd(bad, c);
 }
 
 static inline int grid_for(long long n, int threads) {
@@ -297,9 +324,9 @@ size_t ag3d_downsample_workspace_bytes(int64_t n) {
   return (size_t)(n + blocks + 8) * sizeof(int32_t);
 }
 
-int ag3d_downsample(const int32_t* coords, int64_t n, int32_t new_stride, void* coarse_table, int64_t cap,
-                    int32_t* parent, int32_t* out_coords, int32_t* out_n, void* ws, size_t ws_bytes,
-                    ag3d_stream_t stream) {
+static int downsample_impl(const int32_t* coords, int64_t n, const int32_t* n_dev, int32_t new_stride, void* coarse_table,
+                           int64_t cap, int32_t* parent, int32_t* out_coords, int32_t* out_n, void* ws, size_t ws_bytes,
+                           ag3d_stream_t stream) {
   AG3D_CHECK_ARG(n > 0 && n < INT_MAX, "row count out of range");
   AG3D_CHECK_ARG(new_stride >= 2, "new_stride must be >= 2");
   if (int rc = check_table(coarse_table, cap, n)) return rc;
@@ -318,17 +345,42 @@ int ag3d_downsample(const int32_t* coords, int64_t n, int32_t new_stride, void* 
   const int4* c4 = reinterpret_cast<const int4*>(coords);
   table_clear_kernel<<<grid_for(cap, 256), 256, 0, st>>>(table, cap);
   AG3D_LAUNCH_CHECK("table_clear");
-  coarse_insert_kernel<<<grid_for(n, 256), 256, 0, st>>>(c4, n, new_stride, table, mask, slot_of_row);
+  coarse_insert_kernel<<<grid_for(n, 256), 256, 0, st>>>(c4, n, n_dev, new_stride, table, mask, slot_of_row);
   AG3D_LAUNCH_CHECK("coarse_insert");
-  rep_count_kernel<<<n_blocks, SCAN_THREADS, 0, st>>>(table, slot_of_row, n, block_sums);
+  rep_count_kernel<<<n_blocks, SCAN_THREADS, 0, st>>>(table, slot_of_row, n, n_dev, block_sums);
   AG3D_LAUNCH_CHECK("rep_count");
   block_scan_kernel<<<1, 1024, 0, st>>>(block_sums, n_blocks, out_n);
   AG3D_LAUNCH_CHECK("block_scan");
-  rep_assign_kernel<<<n_blocks, SCAN_THREADS, 0, st>>>(c4, n, new_stride, table, slot_of_row, block_sums,
+  rep_assign_kernel<<<n_blocks, SCAN_THREADS, 0, st>>>(c4, n, n_dev, new_stride, table, slot_of_row, block_sums,
                                                        reinterpret_cast<int4*>(out_coords));
   AG3D_LAUNCH_CHECK("rep_assign");
-  parent_kernel<<<grid_for(n, 256), 256, 0, st>>>(table, slot_of_row, n, parent);
+  parent_kernel<<<grid_for(n, 256), 256, 0, st>>>(table, slot_of_row, n, n_dev, parent);
   AG3D_LAUNCH_CHECK("parent");
+  return AG3D_OK;
+}
+
+int ag3d_downsample(const int32_t* coords, int64_t n, int32_t new_stride, void* coarse_table, int64_t cap,
+                    int32_t* parent, int32_t* out_coords, int32_t* out_n, void* ws, size_t ws_bytes,
+                    ag3d_stream_t stream) {
+  return downsample_impl(coords, n, nullptr, new_stride, coarse_table, cap, parent, out_coords, out_n, ws, ws_bytes, stream);
+}
+
+int ag3d_downsample_dev(const int32_t* coords, int64_t n_max, const int32_t* n_dev, int32_t new_stride, void* coarse_table,
+                        int64_t cap, int32_t* parent, int32_t* out_coords, int32_t* out_n, void* ws, size_t ws_bytes,
+                        ag3d_stream_t stream) {
+  AG3D_CHECK_ARG(n_dev, "n_dev missing");
+  return downsample_impl(coords, n_max, n_dev, new_stride, coarse_table, cap, parent, out_coords, out_n, ws, ws_bytes, stream);
+}
+
+int ag3d_scene_offsets(const int32_t* coords, int64_t n, int32_t max_scenes, int32_t* offsets, ag3d_stream_t stream) {
+  AG3D_CHECK_ARG(n > 0 && n < INT_MAX && max_scenes >= 1 && max_scenes <= 65534, "row / scene count out of range");
+  AG3D_CHECK_ARG(coords && aligned16(coords) && offsets, "bad pointers");
+  cudaStream_t st = as_stream(stream);
+  AG3D_CUDA(cudaMemsetAsync(offsets + max_scenes + 1, 0, sizeof(int32_t), st));
+  scene_offsets_kernel<<<(max_scenes + 1 + 127) / 128, 128, 0, st>>>(reinterpret_cast<const int4*>(coords), n, max_scenes, offsets);
+  AG3D_LAUNCH_CHECK("scene_offsets");
+  scene_order_kernel<<<grid_for(n, 256), 256, 0, st>>>(reinterpret_cast<const int4*>(coords), n, offsets + max_scenes + 1);
+  AG3D_LAUNCH_CHECK("scene_order");
   return AG3D_OK;
 }
 

@@ -611,6 +611,44 @@ s2c_route_kernel(const float* __restrict__ G, const float* __restrict__ dlogits,
   }
 }
 
+// ---- the same routing for up to 256 queries per scene (training at the tail of the click protocol, engine.py:78-115):
+// pass 1: arg[v][o] = first query of object o attaining max_q G[v][q]; pass 2: g[v][q] = dlogits[v][o(q)] iff q == arg[v][o(q)]
+__global__ void __launch_bounds__(256)
+s2c_route_arg_kernel(const float* __restrict__ G, int ld, const int* __restrict__ q_obj, int nq, int n_obj, long long nv,
+                     int* __restrict__ arg) {
+  __shared__ int qobj_s[256];
+  if (threadIdx.x < 256) qobj_s[threadIdx.x] = threadIdx.x < nq ? q_obj[threadIdx.x] : -1;
+  __syncthreads();
+  const long long total = nv * n_obj;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long v = t / n_obj;
+    const int o = (int)(t % n_obj);
+    float best = -INFINITY;
+    int a = -1;
+    for (int q = 0; q < nq; ++q) {
+      if (qobj_s[q] != o) continue;
+      const float z = __ldg(G + v * ld + q);
+      if (a < 0 || z > best) { best = z; a = q; }
+    }
+    arg[t] = a;
+  }
+}
+__global__ void __launch_bounds__(256)
+s2c_route_scatter_kernel(const int* __restrict__ arg, const float* __restrict__ dlogits, const int* __restrict__ q_obj, int nq,
+                         int n_obj, long long nv, int ld, float* __restrict__ g_out) {
+  const long long total = nv * ld;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long v = t / ld;
+    const int q = (int)(t % ld);
+    float g = 0.f;
+    if (q < nq && dlogits) {
+      const int o = __ldg(q_obj + q);
+      if (__ldg(arg + v * n_obj + o) == q) g = __ldg(dlogits + v * n_obj + o);
+    }
+    g_out[t] = g;
+  }
+}
+
 }  // namespace ag3d
 
 using namespace ag3d;
@@ -683,6 +721,17 @@ int ag3d_s2c_route(const float* G, const float* dlogits, const int32_t* q_obj, i
   AG3D_CHECK_ARG(G && q_obj && g_out && nv > 0 && nq > 0 && nq <= NQP, "s2c_route: arguments");
   s2c_route_kernel<<<pw_blocks(nv * NQP), 256, 0, as_stream(stream)>>>(G, dlogits, q_obj, nq, n_obj, nv, g_out);
   AG3D_LAUNCH_CHECK("s2c_route");
+  return AG3D_OK;
+}
+
+int ag3d_s2c_route_ld(const float* G, int32_t ld, const float* dlogits, const int32_t* q_obj, int32_t nq, int32_t n_obj,
+                      int64_t nv, int32_t* arg_ws, float* g_out, ag3d_stream_t stream) {
+  AG3D_CHECK_ARG(G && q_obj && g_out && arg_ws && nv > 0 && nq > 0 && nq <= 256 && ld >= nq && n_obj >= 1 && n_obj <= 32,
+                 "s2c_route_ld: arguments");
+  s2c_route_arg_kernel<<<pw_blocks(nv * n_obj), 256, 0, as_stream(stream)>>>(G, ld, q_obj, nq, n_obj, nv, arg_ws);
+  AG3D_LAUNCH_CHECK("s2c_route_arg");
+  s2c_route_scatter_kernel<<<pw_blocks(nv * ld), 256, 0, as_stream(stream)>>>(arg_ws, dlogits, q_obj, nq, n_obj, nv, ld, g_out);
+  AG3D_LAUNCH_CHECK("s2c_route_scatter");
   return AG3D_OK;
 }
 

@@ -27,6 +27,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -35,6 +36,7 @@
 namespace ag3d {
 
 bool make_row_map(CUtensorMap* tm, const float* in, int in_ld, int cin, long long n_in);   // spconv_tc.cu
+extern int g_last_tmap_rc;
 
 constexpr int PK_R = 256;                 // output rows per super tile
 constexpr int PK_SEG = 64;                // rows per segment (one TMEM lane quarter)
@@ -55,6 +57,7 @@ struct PkParams {
   float* out; int out_ld; int flags; int out_split, res_split;
   int NA, NB;
   int n_super;
+  long long* prof;  // measurement aid (AG3D_PK_PROF): per-role wait cycles of CTA 0, [role 4][slot 8]
   int debug;        // measurement aid (AG3D_PK_DEBUG): 1 no gathers, 2 no weight copies, 4 no MMAs, 8 no accumulator read-out, 16 no stores, 32 no accumulator hand-shake, 64 no weight ring, 128 synthetic plan (no neighbour-table loads)
   uint32_t plan_bytes;     // one plan buffer: lists [K][4][64] i32 | cnt [K][4] i32 (512 B) | npass [K] i32 (128 B) | mask [256] u32
   uint32_t off_b, off_a;   // shared-memory offsets of the weight ring and (before 1024-byte alignment) the A ring
@@ -80,6 +83,12 @@ __device__ __forceinline__ void pk_wait(uint32_t bar, uint32_t parity) {
   unsigned spins = 0;
   while (!mbar_try(bar, parity))
     if (++spins > SPIN_LIMIT) __trap();
+}
+// wait that adds the cycles it blocked to acc (profiling builds of the roles pass their counters; cheap otherwise)
+__device__ __forceinline__ void pk_wait_t(uint32_t bar, uint32_t parity, long long& acc) {
+  const long long t0 = clock64();          // try_wait itself may block up to a hardware time limit: time the whole wait
+  pk_wait(bar, parity);
+  acc += clock64() - t0;
 }
 __device__ __forceinline__ void pk_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void pk_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -200,9 +209,11 @@ __global__ void __launch_bounds__(PK_THREADS, 1) spconv_pk_kernel(const __grid_c
     float acc0[HALF], acc1[HALF];
     uint32_t dn = 0;
     int it = 0;
+    long long w_plan = 0, w_d = 0;
+    const long long t_begin = clock64();
     for (int t = blockIdx.x; t < p.n_super; t += gridDim.x, ++it) {
       const int buf = it & 1;
-      pk_wait(plan_full(buf), (uint32_t)(it >> 1) & 1u);
+      pk_wait_t(plan_full(buf), (uint32_t)(it >> 1) & 1u, w_plan);
       const uint32_t mask0 = plan_mask(buf)[q * PK_SEG + lane], mask1 = plan_mask(buf)[q * PK_SEG + 32 + lane];
       const int* npass = plan_npass(buf);
 #pragma unroll
@@ -215,7 +226,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) spconv_pk_kernel(const __grid_c
         for (int pass = 0; pass < np; ++pass) {
           const int db = (int)(dn % PK_ND);
           if (p.debug & 32) continue;
-          pk_wait(d_full(db), (dn / PK_ND) & 1u);
+          pk_wait_t(d_full(db), (dn / PK_ND) & 1u, w_d);
           ++dn;
           tc_fence_after();
           const int s0 = rank0 - 32 * pass, s1 = rank1 - 32 * pass;
@@ -255,6 +266,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) spconv_pk_kernel(const __grid_c
         if (row_b < p.n_out && !(p.debug & 16)) pk_store16(p, row_b, h * HALF + ch * 16, acc1 + ch * 16);
       }
     }
+    if (p.prof && blockIdx.x == 0 && tid == 0) { p.prof[0] = clock64() - t_begin; p.prof[1] = w_plan; p.prof[2] = w_d; }
   } else if (warp < PK_E_WARPS + PK_P_WARPS) {
     // =========================================================================== TMA gather producers
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PK_REGS_P));
@@ -265,9 +277,11 @@ __global__ void __launch_bounds__(PK_THREADS, 1) spconv_pk_kernel(const __grid_c
     const uint32_t a_base = smem_u32(a_smem) + (uint32_t)g * 512u;
     uint32_t n = 0;
     int it = 0;
+    long long w_plan = 0, w_a = 0;
+    const long long t_begin = clock64();
     for (int t = blockIdx.x; t < p.n_super; t += gridDim.x, ++it) {
       const int buf = it & 1;
-      pk_wait(plan_full(buf), (uint32_t)(it >> 1) & 1u);
+      pk_wait_t(plan_full(buf), (uint32_t)(it >> 1) & 1u, w_plan);
       const int* list = plan_list(buf);
       const int* cnt = plan_cnt(buf);
       const int* npass = plan_npass(buf);
@@ -284,7 +298,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) spconv_pk_kernel(const __grid_c
             const bool issue = active && pos < cq;
             int4 rows = make_int4(-1, -1, -1, -1);
             if (issue) rows = *reinterpret_cast<const int4*>(list + (k * 4 + q) * PK_SEG + pos);
-            pk_wait(a_empty(slot), ((n / (uint32_t)NA) & 1u) ^ 1u);
+            pk_wait_t(a_empty(slot), ((n / (uint32_t)NA) & 1u) ^ 1u, w_a);
             if (p.debug & 1) {
               if (part == 0 && lane == 0) mbar_arrive(a_full(slot));
               continue;
@@ -305,6 +319,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) spconv_pk_kernel(const __grid_c
       __syncwarp();
       if (lane == 0) mbar_arrive(plan_empty(buf));
     }
+    if (p.prof && blockIdx.x == 0 && pw == 0 && lane == 0) { p.prof[8] = clock64() - t_begin; p.prof[9] = w_plan; p.prof[10] = w_a; }
   } else {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PK_REGS_M));
     if (warp == PK_WARP_MMA) {
@@ -318,25 +333,27 @@ __global__ void __launch_bounds__(PK_THREADS, 1) spconv_pk_kernel(const __grid_c
       const uint32_t b_lo_off = (4u * b_lbo) >> 4, b_ks_off = (2u * b_lbo) >> 4, b_slot = b_stage_bytes >> 4;
       uint32_t n = 0, nb = 0, dn = 0;
       int it = 0;
+      long long w_plan = 0, w_a = 0, w_b = 0, w_d = 0;
+      const long long t_begin = clock64();
       for (int t = blockIdx.x; t < p.n_super; t += gridDim.x, ++it) {
         const int buf = it & 1;
-        pk_wait(plan_full(buf), (uint32_t)(it >> 1) & 1u);
+        pk_wait_t(plan_full(buf), (uint32_t)(it >> 1) & 1u, w_plan);
         const int* npass = plan_npass(buf);
         for (int k = 0; k < K; ++k) {
           const int np = npass[k];
           int db[2] = {0, 0};
           for (int c = 0; c < n_slab; ++c, ++nb) {
             const int sb = (int)(nb % (uint32_t)NB);
-            if (!(p.debug & 64)) pk_wait(b_full(sb), (nb / (uint32_t)NB) & 1u);
+            if (!(p.debug & 64)) pk_wait_t(b_full(sb), (nb / (uint32_t)NB) & 1u, w_b);
             const uint32_t b_cur = b_lo32 + (uint32_t)sb * b_slot;
             for (int pass = 0; pass < np; ++pass, ++n) {
               if (c == 0) {
                 db[pass] = (int)(dn % PK_ND);
-                if (!(p.debug & 32)) pk_wait(d_empty(db[pass]), ((dn / PK_ND) & 1u) ^ 1u);
+                if (!(p.debug & 32)) pk_wait_t(d_empty(db[pass]), ((dn / PK_ND) & 1u) ^ 1u, w_d);
                 ++dn;
               }
               const int slot = (int)(n % (uint32_t)NA);
-              pk_wait(a_full(slot), (n / (uint32_t)NA) & 1u);
+              pk_wait_t(a_full(slot), (n / (uint32_t)NA) & 1u, w_a);
               tc_fence_after();
               const uint32_t a_cur = a_lo32 + (uint32_t)slot * (PK_STAGE >> 4);
               const uint32_t d = tmem_base + (uint32_t)(db[pass] * COUT);
@@ -362,6 +379,9 @@ __global__ void __launch_bounds__(PK_THREADS, 1) spconv_pk_kernel(const __grid_c
         }
         if (lane == 0) mbar_arrive(plan_empty(buf));
         __syncwarp();
+      }
+      if (p.prof && blockIdx.x == 0 && lane == 0) {
+        p.prof[16] = clock64() - t_begin; p.prof[17] = w_plan; p.prof[18] = w_a; p.prof[19] = w_b; p.prof[20] = w_d; p.prof[21] = n;
       }
     } else if (warp == PK_WARP_W) {
       // =========================================================================== weight stages
@@ -390,9 +410,11 @@ __global__ void __launch_bounds__(PK_THREADS, 1) spconv_pk_kernel(const __grid_c
       const int pw = warp - PK_WARP_PLAN;
       const uint32_t lt = (1u << lane) - 1u;
       int it = 0;
+      long long w_plan = 0;
+      const long long t_begin = clock64();
       for (int t = blockIdx.x; t < p.n_super; t += gridDim.x, ++it) {
         const int buf = it & 1;
-        if (it >= 2) pk_wait(plan_empty(buf), (uint32_t)((it >> 1) - 1) & 1u);
+        if (it >= 2) pk_wait_t(plan_empty(buf), (uint32_t)((it >> 1) - 1) & 1u, w_plan);
         int* list = plan_list(buf);
         int* cnt = plan_cnt(buf);
 #pragma unroll 1
@@ -447,6 +469,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) spconv_pk_kernel(const __grid_c
         }
         pk_bar_sync(1, 64);                                   // keep the pair in step (cnt is read above)
       }
+      if (p.prof && blockIdx.x == 0 && pw == 0 && lane == 0) { p.prof[24] = clock64() - t_begin; p.prof[25] = w_plan; p.prof[26] = it; }
     }
   }
 
@@ -499,6 +522,11 @@ int spconv_pk_launch(const float* in, long long n_in, int in_ld, int cin, const 
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("AG3D_PK_DEBUG"); dbg = e ? atoi(e) : 0; }
     p.debug = dbg;
+    static long long* prof = nullptr;
+    static int want_prof = -1;
+    if (want_prof < 0) { const char* e = getenv("AG3D_PK_PROF"); want_prof = e ? atoi(e) : 0; }
+    if (want_prof && !prof) { cudaMallocManaged(&prof, 32 * sizeof(long long)); }
+    p.prof = want_prof ? prof : nullptr;
   }
   p.off_a = p.off_b + (uint32_t)p.NB * b_stage;
   const size_t budget = 227 * 1024;
@@ -510,7 +538,11 @@ int spconv_pk_launch(const float* in, long long n_in, int in_ld, int cin, const 
   const size_t smem = (size_t)p.off_a + 1024 + (size_t)na * PK_STAGE;
   alignas(64) CUtensorMap tm_in;
   memset(&tm_in, 0, sizeof(tm_in));
-  AG3D_CHECK_ARG(make_row_map(&tm_in, in, in_ld, cin, n_in), "cuTensorMapEncodeTiled failed");
+  if (!make_row_map(&tm_in, in, in_ld, cin, n_in)) {
+    set_error("cuTensorMapEncodeTiled failed (CUresult " + std::to_string(g_last_tmap_rc) + ", rows " + std::to_string(n_in) +
+              ", ld " + std::to_string(in_ld) + ", cin " + std::to_string(cin) + ")");
+    return AG3D_E_INVALID;
+  }
   static bool attr = false;
   if (!attr) {
     AG3D_CUDA(cudaFuncSetAttribute(spconv_pk_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -527,6 +559,16 @@ int spconv_pk_launch(const float* in, long long n_in, int in_ld, int cin, const 
     default: spconv_pk_kernel<128><<<grid, PK_THREADS, smem, st>>>(tm_in, p); break;
   }
   AG3D_LAUNCH_CHECK("spconv_pk");
+  if (p.prof) {      // measurement aid only: synchronises
+    cudaStreamSynchronize(st);
+    static int printed = 0;
+    if (printed++ % 13 == 12) {
+      const long long* q = p.prof;
+      fprintf(stderr, "pk prof (cycles, CTA 0): owners total %lld wait plan %lld d_full %lld | producers total %lld plan %lld a_empty %lld | "
+              "mma total %lld plan %lld a_full %lld b_full %lld d_empty %lld stages %lld | planner total %lld wait %lld tiles %lld\n",
+              q[0], q[1], q[2], q[8], q[9], q[10], q[16], q[17], q[18], q[19], q[20], q[21], q[24], q[25], q[26]);
+    }
+  }
   return AG3D_OK;
 }
 

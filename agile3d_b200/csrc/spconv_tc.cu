@@ -731,11 +731,10 @@ bool spconv_tc_supported(int cin, int cout) {
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int g_last_tmap_rc = 0;     // CUresult of the last cuTensorMapEncodeTiled (diagnostics)
 static EncodeTiledFn encode_tiled() {
   static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
+  if (!fn) {                              // a failed lookup is retried on the next call, never cached
     void* p = nullptr;
     cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
@@ -747,7 +746,7 @@ static EncodeTiledFn encode_tiled() {
 }
 bool make_row_map(CUtensorMap* tm, const float* in, int in_ld, int cin, long long n_in) {
   EncodeTiledFn enc = encode_tiled();
-  if (!enc) return false;
+  if (!enc) { g_last_tmap_rc = -1; return false; }
   // The map must carry the TRUE row count: with an oversized row extent (the neighbour table never names a row
   // outside the buffer, so 2^31 - 1 looked harmless) the TMA unit raised sporadic illegal-address faults on small
   // levels (measured on B200, tools/tma_model_diag.py); absent neighbours (-1) are out of range and read as zeros.
@@ -756,9 +755,11 @@ bool make_row_map(CUtensorMap* tm, const float* in, int in_ld, int cin, long lon
   cuuint64_t dims[2] = {(cuuint64_t)cin * 2, (cuuint64_t)n_in};
   cuuint32_t box[2] = {64, 1};
   cuuint32_t estr[2] = {1, 1};
-  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<float*>(in), dims, strides, box, estr,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  const CUresult rc = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<float*>(in), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  g_last_tmap_rc = (int)rc;
+  return rc == CUDA_SUCCESS;
 }
 
 int spconv_tc_launch(const float* in, long long n_in, int in_ld, int cin, const int* nbr, int K, long long n_out,

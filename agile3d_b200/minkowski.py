@@ -122,7 +122,14 @@ class SparseTensor:
     def scene_offsets(self):
         """Row ranges of the scenes: offsets[b] .. offsets[b+1] (scenes are contiguous)."""
         if self._offsets is None:
-            self._offsets = self._offsets_from(self.C[:, 0].cpu())
+            if self.C.is_cuda:
+                # coordinates arrived on the GPU (eval_multi_obj.py:88-98): the row ranges come out of the same single
+                # read-back as the level sizes of the coordinate maps (no 16 B/voxel copy to the host)
+                from .backbone import CoordinateMaps
+                self.maps = CoordinateMaps(self.C, want_offsets=True)
+                self._offsets = self.maps.offsets
+            else:
+                self._offsets = self._offsets_from(self.C[:, 0])
         return self._offsets
 
     @property

@@ -173,7 +173,10 @@ class _C2sFn(torch.autograd.Function):
     def backward(ctx, dctx):
         x, pos, qfold, out, lse = ctx.saved_tensors
         nq, H, label, q_obj, obj_count = ctx.meta
-        HQ, hqp = H * nq, ops.decoder_bwd_rows(nq, H)
+        HQ = H * nq
+        # tensor-core mode takes any number of queries (rows padded to a multiple of 32, processed in chunks of 256);
+        # the exact-fp32 kernels hold all (head, query) rows of a voxel tile at once: at most 32 queries
+        hqp = ops._pad32(HQ) if (ctx.tc and HQ > 256) else ops.decoder_bwd_rows(nq, H)
         with torch.no_grad():
             dctx = dctx.contiguous()
             qf, dc = _pad_rows(qfold, hqp), _pad_rows(dctx, hqp)
@@ -188,12 +191,14 @@ class _C2sFn(torch.autograd.Function):
             lse_p[:HQ] = lse
             dr = _pad_rows((dctx * out).sum(1), hqp)
             if ctx.tc:            # tensor-core mode: the four GEMMs as 1x1 tcgen05 convolutions
-                dx, ds = ops.c2s_attn_bwd_tc(x, pos, qf, dc, lse_p, dr, rowobj, hqp, label)
+                dx, ds_chunks = ops.c2s_attn_bwd_tc(x, pos, qf, dc, lse_p, dr, rowobj, hqp, label)
+                xp = x + pos
+                dq = torch.cat([_xt_dy([ds], xp, True)[0] for ds in ds_chunks], 0)       # dS^T x + dS^T pos
             else:
                 dx, ds = ops.c2s_attn_bwd(x, pos, qf, qf.t().contiguous(), dc, dc.t().contiguous(), lse_p, dr, rowobj,
                                           hqp, label)
-            dq = _xt_dy([ds], x + pos, ctx.tc)               # dS^T x + dS^T pos
-        return dx, None, dq[0, :HQ], None, None, None, None, None
+                dq = _xt_dy([ds], x + pos, False)[0]
+        return dx, None, dq[:HQ], None, None, None, None, None
 
 
 class _S2cFn(torch.autograd.Function):
@@ -212,21 +217,23 @@ class _S2cFn(torch.autograd.Function):
     def backward(ctx, dxo, dlogits, _dl, _dc):
         x, pos, A, c, U, bo, ln_w, ln_b, E, x_out = ctx.saved_tensors
         eps, q_obj, nq, H, n_obj = ctx.meta
-        HQ, hqp = H * nq, ops.decoder_bwd_rows(nq, H)
+        HQ = H * nq
         with torch.no_grad():
-            Ap, Up, Ep = _pad_rows(A, hqp), _pad_rows(U, hqp), _pad_rows(E, 32)
             dxo_c = None if dxo is None else dxo.contiguous()
             dlg_c = None if dlogits is None else dlogits.contiguous()
-            if ctx.tc:            # tensor-core mode: the six GEMMs as 1x1 tcgen05 convolutions
-                dx, a, ds, dy, g, cols = ops.s2c_mask_bwd_tc(x, pos, Ap, _pad_rows(c, hqp), Up, bo, ln_w, ln_b, eps, Ep,
-                                                             q_obj, nq, H, n_obj, hqp, dxo_c, dlg_c, x_out)
-            else:
-                dx, a, ds, dy, g, cols = ops.s2c_mask_bwd(
-                    x, pos, Ap, Ap.t().contiguous(), _pad_rows(c, hqp), Up, Up.t().contiguous(), bo, ln_w, ln_b, eps, Ep,
-                    Ep.t().contiguous(), q_obj, nq, H, n_obj, hqp, dxo_c, dlg_c)
-            dA = _xt_dy([ds], x + pos, ctx.tc)               # dS^T x + dS^T pos
-            dU = _xt_dy([a], dy, ctx.tc)
-            dE = _xt_dy([g], x_out, ctx.tc)
+            if ctx.tc:            # tensor-core mode: GEMMs as 1x1 tcgen05 convolutions, any number of queries
+                dx, dA, dc, dU, dbo, dlw, dlb, dE = ops.s2c_mask_bwd_tc_any(
+                    x, pos, A, c, U, bo, ln_w, ln_b, eps, E, q_obj, nq, H, n_obj, dxo_c, dlg_c, x_out,
+                    lambda xs, dy: _xt_dy(xs, dy, True))
+                return dx, None, dA, dc, dU, dbo, dlw, dlb, dE, None, None, None, None, None
+            hqp = ops.decoder_bwd_rows(nq, H)
+            Ap, Up, Ep = _pad_rows(A, hqp), _pad_rows(U, hqp), _pad_rows(E, 32)
+            dx, a, ds, dy, g, cols = ops.s2c_mask_bwd(
+                x, pos, Ap, Ap.t().contiguous(), _pad_rows(c, hqp), Up, Up.t().contiguous(), bo, ln_w, ln_b, eps, Ep,
+                Ep.t().contiguous(), q_obj, nq, H, n_obj, hqp, dxo_c, dlg_c)
+            dA = _xt_dy([ds], x + pos, False)               # dS^T x + dS^T pos
+            dU = _xt_dy([a], dy, False)
+            dE = _xt_dy([g], x_out, False)
         return (dx, None, dA[0, :HQ], cols[384:384 + HQ], dU[0, :HQ], cols[:128], cols[128:256], cols[256:384],
                 dE[0, :nq], None, None, None, None, None)
 

@@ -139,6 +139,56 @@ def downsample(coords, new_stride):
     return out[:m], table, cap, parent
 
 
+MAX_SCENES = 256       # scenes per batched coordinate list (scene_offsets)
+
+
+def build_levels(coords, n_levels=4, want_offsets=False):
+    """Level-0 hash table + `n_levels` chained stride-2 levels (+ the scene row ranges) with ONE host read-back: the row
+    count of level l stays on the device and feeds the kernels of level l+1 (ag3d_downsample_dev).
+    -> (coords[1+n], tables[1+n], caps[1+n], parents[n], (dup, out_of_range), offsets list | None)"""
+    _need_cuda(coords)
+    n0, dev = coords.shape[0], coords.device
+    cap = lib().ag3d_hash_capacity(n0)
+    i32 = dict(dtype=torch.int32, device=dev)
+    meta = torch.zeros(2 + n_levels + MAX_SCENES + 2, **i32)        # status[2] | counts[n_levels] | offsets[MAX_SCENES + 2]
+    tables = [torch.empty(cap * SLOT_BYTES, dtype=torch.uint8, device=dev) for _ in range(1 + n_levels)]
+    with _Timed("maps", 16 * n0 + 16 * cap):
+        check(lib().ag3d_hash_build(_p(coords), n0, _p(tables[0]), cap, _p(meta), _stream()), "ag3d_hash_build")
+    if want_offsets:
+        check(lib().ag3d_scene_offsets(_p(coords), n0, MAX_SCENES, _p(meta[2 + n_levels:]), _stream()), "ag3d_scene_offsets")
+    wsb = lib().ag3d_downsample_workspace_bytes(n0)
+    ws = _workspace("downsample", dev, wsb)
+    bufs, parents = [coords], []
+    for lvl in range(n_levels):
+        out = torch.empty((n0, 4), **i32)
+        parent = torch.empty(n0, **i32)
+        cnt = meta[2 + lvl:3 + lvl]
+        with _Timed("maps", 16 * n0 + 16 * cap + 4 * n0):
+            if lvl == 0:
+                check(lib().ag3d_downsample(_p(bufs[lvl]), n0, 2 << lvl, _p(tables[lvl + 1]), cap, _p(parent), _p(out), _p(cnt),
+                                            _p(ws), ws.numel(), _stream()), "ag3d_downsample")
+            else:
+                check(lib().ag3d_downsample_dev(_p(bufs[lvl]), n0, _p(meta[1 + lvl:2 + lvl]), 2 << lvl, _p(tables[lvl + 1]), cap,
+                                                _p(parent), _p(out), _p(cnt), _p(ws), ws.numel(), _stream()),
+                      "ag3d_downsample_dev")
+        bufs.append(out)
+        parents.append(parent)
+    host = meta.cpu().tolist()                                       # the one synchronisation of the map build
+    sizes = [n0] + host[2:2 + n_levels]
+    levels = [bufs[l][:sizes[l]] for l in range(1 + n_levels)]
+    parents = [parents[l][:sizes[l]] for l in range(n_levels)]
+    offsets = None
+    if want_offsets:
+        offs = host[2 + n_levels:]
+        if offs[MAX_SCENES + 1]:
+            raise ValueError("rows of a scene must be contiguous and scenes in batch order (batched_coordinates)")
+        if offs[MAX_SCENES] != n0:
+            raise ValueError(f"more than {MAX_SCENES} scenes in one batched coordinate list")
+        n_scenes = max(b for b in range(MAX_SCENES) if offs[b] < n0) + 1
+        offsets = offs[:n_scenes] + [n0]
+    return levels, tables, [cap] * (1 + n_levels), parents, (host[0], host[1]), offsets
+
+
 def kernel_map(out_coords, in_table, cap, ksize, in_tensor_stride, dilation=1, count_pairs=False):
     """-> nbr int32 [K, N_out] (and pair counts int32 [K] if asked)."""
     _need_cuda(out_coords, in_table)
@@ -530,26 +580,46 @@ def c2s_attn_bwd(x, pos, qf, qft, dctx, dctxt, lse, dr, rowobj, hqp, label):
     return dx, ds
 
 
+def _pad32(n):
+    return (n + 31) // 32 * 32
+
+
+def _pad_rows(t, rows):
+    if t.shape[0] == rows:
+        return t.contiguous()
+    out = torch.zeros((rows,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    out[:t.shape[0]] = t
+    return out
+
+
 def c2s_attn_bwd_tc(x, pos, qf, dctx, lse, dr, rowobj, hqp, label):
-    """Same contract as c2s_attn_bwd (-> dx [Nv,128], dS [Nv,hqp]) with the four GEMMs of the backward as 1x1
-    tensor-core convolutions (bf16x3) and one point-wise kernel in between:
+    """Backward of the click -> scene attention with its four GEMMs as 1x1 tensor-core convolutions (bf16x3) and one
+    point-wise kernel in between, in chunks of at most 256 (head, query) rows (any number of click queries):
         S = (x+pos) qf^T,  dP = x dctx^T,  P = masked exp(S - lse),  dS = P (dP - dr),  dx = P dctx + dS qf.
-    qf, dctx: [hqp, 128] (rows padded to hqp, a multiple of 32)."""
+    qf, dctx: [hqp, 128]; lse, dr, rowobj: [hqp] (rows padded to hqp, a multiple of 32).
+    -> (dx [Nv,128], [dS chunk [Nv, w_j]] in row order)."""
     _need_cuda(x, pos, qf, dctx)
     nv, d = x.shape
     f32 = dict(dtype=torch.float32, device=x.device)
     xp = x + pos
-    qft, dct = qf.t().contiguous(), dctx.t().contiguous()
-    s_p, dp_ds = torch.empty((nv, hqp), **f32), torch.empty((nv, hqp), **f32)
-    spconv_fwd(xp, None, qft, s_p, algo=ALGO_TC, weight_tc=prepare_tc_weight(qft))
-    spconv_fwd(x, None, dct, dp_ds, algo=ALGO_TC, weight_tc=prepare_tc_weight(dct))
-    with _Timed("c2s_bwd", 4 * nv * hqp * 4):
-        check(lib().ag3d_c2s_bwd_pointwise(_p(s_p), _p(dp_ds), _p(lse), _p(dr), _p(rowobj), _p(label), nv, hqp, _stream()),
-              "ag3d_c2s_bwd_pointwise")
-    dx0, dx = torch.empty((nv, d), **f32), torch.empty((nv, d), **f32)
-    spconv_fwd(s_p, None, dctx, dx0, algo=ALGO_TC, weight_tc=prepare_tc_weight(dctx))
-    spconv_fwd(dp_ds, None, qf, dx, residual=dx0, algo=ALGO_TC, weight_tc=prepare_tc_weight(qf))
-    return dx, dp_ds
+    dx, ds_chunks = None, []
+    for a in range(0, hqp, 256):
+        b = min(a + 256, hqp)
+        w = b - a
+        qf_j, dc_j = qf[a:b].contiguous(), dctx[a:b].contiguous()
+        qft, dct = qf_j.t().contiguous(), dc_j.t().contiguous()
+        s_p, dp_ds = torch.empty((nv, w), **f32), torch.empty((nv, w), **f32)
+        spconv_fwd(xp, None, qft, s_p, algo=ALGO_TC, weight_tc=prepare_tc_weight(qft))
+        spconv_fwd(x, None, dct, dp_ds, algo=ALGO_TC, weight_tc=prepare_tc_weight(dct))
+        with _Timed("c2s_bwd", 4 * nv * w * 4):
+            check(lib().ag3d_c2s_bwd_pointwise(_p(s_p), _p(dp_ds), _p(lse[a:b]), _p(dr[a:b]), _p(rowobj[a:b]), _p(label), nv, w,
+                                               _stream()), "ag3d_c2s_bwd_pointwise")
+        dx0 = torch.empty((nv, d), **f32)
+        spconv_fwd(s_p, None, dc_j, dx0, residual=dx, algo=ALGO_TC, weight_tc=prepare_tc_weight(dc_j))
+        dx = torch.empty((nv, d), **f32)
+        spconv_fwd(dp_ds, None, qf_j, dx, residual=dx0, algo=ALGO_TC, weight_tc=prepare_tc_weight(qf_j))
+        ds_chunks.append(dp_ds)
+    return dx, ds_chunks
 
 
 def s2c_mask_bwd(x, pos, A, At, c, U, Ut, bo, ln_w, ln_b, ln_eps, E, Et, q_obj, nq, heads, n_obj, hqp, dxo, dlogits):
@@ -573,50 +643,75 @@ def s2c_mask_bwd(x, pos, A, At, c, U, Ut, bo, ln_w, ln_b, ln_eps, E, Et, q_obj, 
     return dx, a, ds, dy, g, cols
 
 
-def s2c_mask_bwd_tc(x, pos, A, c, U, bo, ln_w, ln_b, ln_eps, E, q_obj, nq, heads, n_obj, hqp, dxo, dlogits, x_out):
-    """Same contract as s2c_mask_bwd (-> dx, a [Nv,hqp], dS [Nv,hqp], dy [Nv,128], g [Nv,32], colsums) with the six
-    GEMMs of the backward as 1x1 tensor-core convolutions (bf16x3) and row-wise kernels in between:
+def s2c_mask_bwd_tc_any(x, pos, A, c, U, bo, ln_w, ln_b, ln_eps, E, q_obj, nq, heads, n_obj, dxo, dlogits, x_out, xt_dy):
+    """Backward of ag3d_s2c_mask_fwd for ANY number of click queries (<= 256), composed of 1x1 tensor-core convolutions
+    and row-wise kernels; the (head, query) columns are processed in chunks of whole heads of at most 256 columns:
         S = (x+pos) A^T + c -> a = per-head softmax        y = x + a U + bo -> n, rstd (LayerNorm statistics)
         G = x' E^T -> g = first-maximum routing of dlogits  t = g E + dxo -> dy = LayerNorm backward (+ column sums)
         da = dy U^T -> dS = a (da - <a, da>)                dx = dy + dS A
-    A, U: [hqp, 128] and c: [hqp] (rows padded to hqp), E: [32, 128]; x_out = x' saved by the forward."""
+    A, U: [heads*nq, 128] (rows h-major), c: [heads*nq], E: [nq, 128]; x_out = x' saved by the forward;
+    xt_dy(list of [Nv,cin], [Nv,cout]) -> [1,cin,cout] is the caller's X^T dY contraction.
+    -> (dx, dA, dc, dU, dbo, dln_w, dln_b, dE)."""
     _need_cuda(x, pos, A, U, E)
     nv, d = x.shape
-    f32 = dict(dtype=torch.float32, device=x.device)
+    dev = x.device
+    f32 = dict(dtype=torch.float32, device=dev)
     st = _stream()
     conv = lambda inp, w, out, **kw: spconv_fwd(inp, None, w, out, algo=ALGO_TC, weight_tc=prepare_tc_weight(w), **kw)
-    At, Ut, Et = A.t().contiguous(), U.t().contiguous(), E.t().contiguous()
-    a = torch.empty((nv, hqp), **f32)
-    conv(x + pos, At, a, shift=c.contiguous())
-    with _Timed("s2c_bwd", 8 * nv * hqp):
-        check(lib().ag3d_s2c_softmax_heads(_p(a), nv, heads, nq, hqp, st), "ag3d_s2c_softmax_heads")
-    y = torch.empty((nv, d), **f32)
-    conv(a, U, y, shift=bo, residual=x)
+    xp = x + pos
+    hc = max(1, 256 // nq)                                            # whole heads per chunk
+    chunks = [(h0, min(h0 + hc, heads)) for h0 in range(0, heads, hc)]
+    parts, y = [], torch.empty((nv, d), **f32)
+    for j, (h0, h1) in enumerate(chunks):
+        rows = slice(h0 * nq, h1 * nq)
+        w = (h1 - h0) * nq
+        wp = _pad32(w)
+        A_j, U_j, c_j = _pad_rows(A[rows], wp), _pad_rows(U[rows], wp), _pad_rows(c[rows], wp)
+        a = torch.empty((nv, wp), **f32)
+        conv(xp, A_j.t().contiguous(), a, shift=c_j)
+        with _Timed("s2c_bwd", 8 * nv * wp):
+            check(lib().ag3d_s2c_softmax_heads(_p(a), nv, h1 - h0, nq, wp, st), "ag3d_s2c_softmax_heads")
+        if j == 0:
+            conv(a, U_j, y, shift=bo, residual=x)
+        else:
+            conv(a, U_j, y, residual=y)
+        parts.append((rows, w, wp, A_j, U_j, a))
     n, rstd = torch.empty((nv, d), **f32), torch.empty(nv, **f32)
     with _Timed("s2c_bwd", 8 * nv * d):
         check(lib().ag3d_ln_fwd_stats(_p(y), nv, float(ln_eps), _p(n), _p(rstd), st), "ag3d_ln_fwd_stats")
-    G, g = torch.empty((nv, 32), **f32), torch.empty((nv, 32), **f32)
-    conv(x_out, Et, G)
-    check(lib().ag3d_s2c_route(_p(G), _p(dlogits), _p(q_obj), nq, n_obj, nv, _p(g), st), "ag3d_s2c_route")
-    t = y                                                         # reuse: y is no longer needed
+    nqp = _pad32(nq)
+    E_p = _pad_rows(E, nqp)
+    G, g = torch.empty((nv, nqp), **f32), torch.empty((nv, nqp), **f32)
+    conv(x_out, E_p.t().contiguous(), G)
+    arg = torch.empty((nv, n_obj), dtype=torch.int32, device=dev)
+    check(lib().ag3d_s2c_route_ld(_p(G), nqp, _p(dlogits), _p(q_obj), nq, n_obj, nv, _p(arg), _p(g), st), "ag3d_s2c_route_ld")
+    t = y                                                             # reuse: y is no longer needed
     if dxo is not None:
-        conv(g, E, t, residual=dxo)
+        conv(g, E_p, t, residual=dxo)
     else:
-        conv(g, E, t)
+        conv(g, E_p, t)
     dy = torch.empty((nv, d), **f32)
-    cols = torch.empty(3 * d + hqp, **f32)
+    cols = torch.empty(3 * d + 256, **f32)
     wsb = lib().ag3d_ln_bwd_workspace_bytes()
-    ws = _ws_for("ln_bwd", x.device, wsb)
+    ws = _ws_for("ln_bwd", dev, wsb)
     with _Timed("s2c_bwd", 16 * nv * d):
         check(lib().ag3d_ln_bwd(_p(t), _p(n), _p(rstd), _p(ln_w), nv, _p(dy), _p(cols), _p(ws), ws.numel(), st), "ag3d_ln_bwd")
-    ds = torch.empty((nv, hqp), **f32)
-    conv(dy, Ut, ds)
-    with _Timed("s2c_bwd", 12 * nv * hqp):
-        check(lib().ag3d_s2c_ds(_p(a), _p(ds), nv, heads, nq, hqp, st), "ag3d_s2c_ds")
-    cols[3 * d:] = col_sum(ds)
-    dx = torch.empty((nv, d), **f32)
-    conv(ds, A, dx, residual=dy)
-    return dx, a, ds, dy, g, cols
+    hq = heads * nq
+    dA, dU, dc = torch.empty((hq, d), **f32), torch.empty((hq, d), **f32), torch.empty(hq, **f32)
+    dx = None
+    for rows, w, wp, A_j, U_j, a in parts:
+        ds = torch.empty((nv, wp), **f32)
+        conv(dy, U_j.t().contiguous(), ds)
+        with _Timed("s2c_bwd", 12 * nv * wp):
+            check(lib().ag3d_s2c_ds(_p(a), _p(ds), nv, w // nq, nq, wp, st), "ag3d_s2c_ds")
+        dc[rows] = col_sum(ds)[:w]
+        dx_new = torch.empty((nv, d), **f32)
+        conv(ds, A_j, dx_new, residual=dy if dx is None else dx)
+        dx = dx_new
+        dA[rows] = xt_dy([ds], xp)[0, :w]
+        dU[rows] = xt_dy([a], dy)[0, :w]
+    dE = xt_dy([g], x_out)[0, :nq]
+    return dx, dA, dc, dU, cols[:d], cols[d:2 * d], cols[2 * d:3 * d], dE
 
 
 def loss_fwd(logits, target, w, eps=1e-6):

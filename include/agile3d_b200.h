@@ -82,6 +82,16 @@ int ag3d_downsample(const int32_t* coords, int64_t n, int32_t new_stride, void* 
                     int32_t* parent, int32_t* out_coords, int32_t* out_n, void* ws, size_t ws_bytes,
                     ag3d_stream_t stream);
 
+/* ag3d_downsample with the input row count on the DEVICE (n_dev; n_max bounds it and sizes grids, table and
+ * workspace): lets the four coordinate levels of the U-Net be built back to back with ONE host read-back of all
+ * counts instead of a synchronisation per level.                                                            */
+int ag3d_downsample_dev(const int32_t* coords, int64_t n_max, const int32_t* n_dev, int32_t new_stride, void* coarse_table,
+                        int64_t cap, int32_t* parent, int32_t* out_coords, int32_t* out_n, void* ws, size_t ws_bytes,
+                        ag3d_stream_t stream);
+/* Row ranges of the scenes of a batched coordinate list (ME.utils.batched_coordinates order):
+ * offsets[b] = first row of scene b for b = 0 .. max_scenes (= n past the last scene); offsets[max_scenes + 1] =
+ * number of rows out of batch order (must be 0).  Device int32[max_scenes + 2].                               */
+int ag3d_scene_offsets(const int32_t* coords, int64_t n, int32_t max_scenes, int32_t* offsets, ag3d_stream_t stream);
 /* ---- kernel maps --------------------------------------------------------------------------------------
  * Replaces CoordinateMapGPU::kernel_map (first conv of each (level, kernel) pair; cached afterwards).
  * Generic region: for every output coordinate o and offset k (ksize^3 offsets scaled by
@@ -288,6 +298,10 @@ int ag3d_ln_bwd(const float* t, const float* n, const float* rstd, const float* 
                 float* colsums, void* ws, size_t ws_bytes, ag3d_stream_t stream);
 int ag3d_s2c_route(const float* G, const float* dlogits, const int32_t* q_obj, int32_t nq, int32_t n_obj, int64_t nv,
                    float* g_out, ag3d_stream_t stream);
+/* ag3d_s2c_route for up to 256 queries: G and g_out are [nv, ld] (ld >= nq, padding columns of g_out are zeroed),
+ * arg_ws is an int32 [nv, n_obj] scratch.                                                                    */
+int ag3d_s2c_route_ld(const float* G, int32_t ld, const float* dlogits, const int32_t* q_obj, int32_t nq, int32_t n_obj,
+                      int64_t nv, int32_t* arg_ws, float* g_out, ag3d_stream_t stream);
 size_t ag3d_s2c_bwd_workspace_bytes(int32_t hqp);
 int ag3d_s2c_mask_bwd(const float* x, const float* pos, int64_t nv, const float* A, const float* At, const float* c,
                       const float* U, const float* Ut, const float* bo, const float* ln_w, const float* ln_b,

@@ -37,6 +37,20 @@ def downsample(coords, new_stride):
     return out, out.clone(), 0, parent
 
 
+def build_levels(coords, n_levels=4, want_offsets=False):
+    levels, tables, parents = [coords], [coords.clone()], []
+    for lvl in range(n_levels):
+        c, t, _, par = downsample(levels[-1], 2 << lvl)
+        levels.append(c)
+        tables.append(t)
+        parents.append(par)
+    offsets = None
+    if want_offsets:
+        b = coords[:, 0].long()
+        offsets = [0] + torch.cumsum(torch.bincount(b), 0).tolist()
+    return levels, tables, [0] * (1 + n_levels), parents, (0, 0), offsets
+
+
 def kernel_map(out_coords, in_table, cap, ksize, in_tensor_stride, dilation=1, count_pairs=False):
     cm, key = _cm(in_table)
     offs = ME.kernel_offsets(ksize, in_tensor_stride, dilation)
@@ -295,14 +309,26 @@ def wgrad_tc_supported(K, cin, cout):
 
 
 def c2s_attn_bwd_tc(x, pos, qf, dctx, lse, dr, rowobj, hqp, label):
-    """same contract as c2s_attn_bwd (ops.c2s_attn_bwd_tc only differs in how the GPU evaluates it)"""
-    return c2s_attn_bwd(x, pos, qf, qf.t().contiguous(), dctx, dctx.t().contiguous(), lse, dr, rowobj, hqp, label)
+    """same contract as c2s_attn_bwd, dS returned in column chunks of at most 256 (ops.c2s_attn_bwd_tc)"""
+    dx, ds = c2s_attn_bwd(x, pos, qf, qf.t().contiguous(), dctx, dctx.t().contiguous(), lse, dr, rowobj, hqp, label)
+    return dx, [ds[:, a:a + 256].contiguous() for a in range(0, hqp, 256)]
 
 
-def s2c_mask_bwd_tc(x, pos, A, c, U, bo, ln_w, ln_b, ln_eps, E, q_obj, nq, heads, n_obj, hqp, dxo, dlogits, x_out):
-    """same contract as s2c_mask_bwd (x_out, the forward's output, is only a shortcut for the GPU variant)"""
-    return s2c_mask_bwd(x, pos, A, A.t().contiguous(), c, U, U.t().contiguous(), bo, ln_w, ln_b, ln_eps, E,
-                        E.t().contiguous(), q_obj, nq, heads, n_obj, hqp, dxo, dlogits)
+def s2c_mask_bwd_tc_any(x, pos, A, c, U, bo, ln_w, ln_b, ln_eps, E, q_obj, nq, heads, n_obj, dxo, dlogits, x_out, xt_dy=None):
+    """gradients of s2c_mask_fwd by torch.autograd on its emulation (any number of queries)
+    -> (dx, dA, dc, dU, dbo, dln_w, dln_b, dE)"""
+    leaves = [t.detach().clone().requires_grad_(True) for t in (x, A, c, U, bo, ln_w, ln_b, E)]
+    with torch.enable_grad():
+        xl, Al, cl, Ul, bol, lwl, lbl, El = leaves
+        y, logits, _, _ = s2c_mask_fwd(xl, pos, Al, cl, Ul, bol, lwl, lbl, ln_eps, El, q_obj, nq, heads, n_obj)
+        loss = 0
+        if dxo is not None:
+            loss = loss + (y * dxo).sum()
+        if dlogits is not None:
+            fin = torch.isfinite(logits)
+            loss = loss + (torch.where(fin, logits, torch.zeros_like(logits)) * dlogits).sum()
+        grads = torch.autograd.grad(loss, leaves, allow_unused=True)
+    return tuple(g if g is not None else torch.zeros_like(l) for g, l in zip(grads, leaves))
 
 
 # ------------------------------------------------------------------------------------------------ click-query side (K11)
@@ -388,10 +414,10 @@ def query_update_b(q1, qh, kh, vh, qpos, blob, B, nq, heads=8, ln_eps=1e-5):
     return q3, A, c, U, E
 
 
-ALL = ["wgrad_tc_supported", "c2s_attn_bwd_tc", "s2c_mask_bwd_tc",
+ALL = ["wgrad_tc_supported", "c2s_attn_bwd_tc", "s2c_mask_bwd_tc_any",
        "bn_stats", "bn_apply", "bn_bwd", "col_sum", "spconv_bwd_weight", "stem_bwd_weight", "decoder_bwd_rows",
        "c2s_attn_bwd", "s2c_mask_bwd", "loss_fwd", "loss_bwd", "click_loss_weights", "grad_norm", "adamw_step",
-       "prepare_tc_weight", "hash_build", "downsample", "kernel_map", "kernel_map_transposed", "spconv_fwd", "stem_conv_fwd",
+       "prepare_tc_weight", "hash_build", "downsample", "build_levels", "kernel_map", "kernel_map_transposed", "spconv_fwd", "stem_conv_fwd",
        "fourier_posenc", "c2s_attn_fwd", "s2c_mask_fwd", "query_blob_floats", "query_init", "query_fold_c2s",
        "query_update_a", "query_update_b"]
 

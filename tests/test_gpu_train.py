@@ -214,7 +214,7 @@ def test_c2s_bwd_vs_emulation(nv, nq, n_obj):
         # the same backward with its four GEMMs as 1x1 tcgen05 convolutions (bf16x3) + the point-wise kernel
         dx_t, ds_t = ops.c2s_attn_bwd_tc(t(x), t(pos), t(qp), t(dp), t(lse_p.float()), t(dr.float()), t(rowobj), hqp, t(lab))
         assert rel_err(dx_t.cpu(), dx_r) < 1e-3
-        assert rel_err(ds_t.cpu(), ds_r) < 1e-3
+        assert rel_err(torch.cat(ds_t, 1).cpu(), ds_r) < 1e-3
 
 
 @pytest.mark.parametrize("nv,nq,n_obj", [(1000, 11, 2), (5003, 15, 3), (20000, 20, 6), (4100, 25, 9), (129, 32, 12)])
@@ -250,18 +250,36 @@ def test_s2c_bwd_vs_emulation(nv, nq, n_obj):
             assert rel_err(a_.cpu()[same], b_[same]) < 3e-4, name
         if bool(same.all()):
             assert rel_err(got[5].cpu(), ref[5]) < 1e-3
-        # the same backward with its six GEMMs as 1x1 tcgen05 convolutions (bf16x3) + row-wise kernels
-        s64 = ((d(x) + d(pos)) @ d(A).T + d(c)).view(nv, H, nq)
-        y64 = d(x) + torch.softmax(s64, dim=2).view(nv, H * nq) @ d(U) + d(bo)
-        xo = torch.nn.functional.layer_norm(y64, (128,), d(lw), d(lb), 1e-5).float()
-        got_tc = ops.s2c_mask_bwd_tc(t(x), t(pos), t(Ap), t(cp), t(Up), t(bo), t(lw), t(lb), 1e-5, t(Ep), t(q_obj), nq, H,
-                                     n_obj, hqp, t(dxo) if use_dxo else None, t(dlg), t(xo))
-        same = (got_tc[4].cpu().double() != 0).eq(ref[4] != 0).all(1)
-        assert float(same.float().mean()) > 0.99
-        for name, a_, b_ in zip(("dx", "a", "ds", "dy", "g"), got_tc[:5], ref[:5]):
-            assert rel_err(a_.cpu()[same], b_[same]) < 1e-3, ("tensor-core", name)
-        if bool(same.all()):
-            assert rel_err(got_tc[5].cpu(), ref[5]) < 2e-3
+
+
+@pytest.mark.parametrize("nv,nq,n_obj", [(1000, 11, 2), (5003, 20, 6), (4100, 25, 9), (129, 32, 12), (3000, 45, 7), (2500, 100, 11),
+                                         (6000, 210, 11), (700, 256, 5)])
+def test_s2c_bwd_tensor_core_any_query_count(nv, nq, n_obj):
+    """ops.s2c_mask_bwd_tc_any (1x1 tcgen05 convolutions + row-wise kernels, heads processed in chunks of <= 256 columns)
+    against torch.autograd on the fp64 emulation of the forward, up to 256 click queries per scene."""
+    from agile3d_b200 import ops
+    H = 8
+    g, x, pos, _, _ = _decoder_inputs(nv, min(nq, 40), n_obj, seed=nv * 3 + nq)
+    q_obj = torch.randint(0, n_obj, (nq,), generator=g, dtype=torch.int32)
+    q_obj[:n_obj] = torch.arange(n_obj, dtype=torch.int32)
+    A = torch.randn((H * nq, 128), generator=g) * 0.05
+    c = torch.randn(H * nq, generator=g) * 0.1
+    U = torch.randn((H * nq, 128), generator=g) * 0.3
+    bo, lw, lb = torch.randn(128, generator=g) * 0.1, torch.rand(128, generator=g) + 0.5, torch.randn(128, generator=g) * 0.1
+    E = torch.randn((nq, 128), generator=g) * 0.2
+    dxo, dlg = torch.randn((nv, 128), generator=g), torch.randn((nv, n_obj), generator=g)
+    d = lambda v: v.double()
+    ref = emulate.s2c_mask_bwd_tc_any(d(x), d(pos), d(A), d(c), d(U), d(bo), d(lw), d(lb), 1e-5, d(E), q_obj, nq, H, n_obj,
+                                      d(dxo), d(dlg), None)
+    xo = emulate.s2c_mask_fwd(d(x), d(pos), d(A), d(c), d(U), d(bo), d(lw), d(lb), 1e-5, d(E), q_obj, nq, H, n_obj)[0].float()
+    xt_dy = lambda xs, dy: sum(ops.spconv_bwd_weight(v, None, dy, 1) for v in xs)
+    got = ops.s2c_mask_bwd_tc_any(t(x), t(pos), t(A), t(c), t(U), t(bo), t(lw), t(lb), 1e-5, t(E), t(q_obj), nq, H, n_obj,
+                                  t(dxo), t(dlg), t(xo), xt_dy)
+    # the routing of a logit gradient can flip where two queries of one object tie to rounding: a handful of voxels then
+    # contribute to another query's row of dE; everything else is compared at 2e-3 (bf16x3 GEMMs chained six deep)
+    for name, a_, b_, tol in zip(("dx", "dA", "dc", "dU", "dbo", "dln_w", "dln_b", "dE"), got, ref,
+                                 (2e-3, 2e-3, 2e-3, 2e-3, 2e-3, 2e-3, 2e-3, 2e-2)):
+        assert rel_err(a_.cpu(), b_) < tol, (name, rel_err(a_.cpu(), b_))
 
 
 # ------------------------------------------------------------------------------------------------ loss / optimizer
