@@ -47,6 +47,12 @@ SIGNATURES = {
     "ag3d_s2c_workspace_bytes": (_sz, [_i32]),
     "ag3d_s2c_mask_fwd": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _i32, _i32, _i32,
                                  _vp, _vp, _vp, _vp, _i32, _vp, _sz, _vp]),
+    "ag3d_click_pred": (_i32, [_vp, _i32, _i64, _vp, _vp, _i32, _vp, _vp]),
+    "ag3d_scene_iou": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp]),
+    "ag3d_click_simulate_workspace_bytes": (_sz, [_i64]),
+    "ag3d_click_simulate": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _i32, _vp, _vp, _sz, _vp]),
+    "ag3d_quantize_points": (_i32, [_vp, _i64, _f32, _i32, _vp, _vp, _vp]),
+    "ag3d_first_rows": (_i32, [_vp, _i64, _i64, _vp, _vp]),
     "ag3d_query_blob_floats": (_i64, []),
     "ag3d_query_init": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ag3d_query_fold_c2s": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp, _vp]),

@@ -432,8 +432,11 @@ class Res16UNet34C(nn.Module):
         return y, fmaps, maps, (tape, stem, up_c)
 
     @torch.no_grad()
-    def train_backward(self, maps, saved, dy):
-        """dy: gradient of the backbone output [N0,96] (consumed).  -> {parameter name: gradient}."""
+    def train_backward(self, maps, saved, dy, sink=None):
+        """dy: gradient of the backbone output [N0,96] (consumed).  -> {parameter name: gradient}.
+        sink (optional): called with the gradients of every finished stage, last stage of the forward first, as soon as
+        they exist (the data-parallel exchange of that stage then overlaps the rest of the backward, optim.GradBuckets);
+        gradients handed to the sink are not returned."""
         tape, stem, up_c = saved
         W = self._train_weights()
         self._split_cache = {}
@@ -446,17 +449,24 @@ class Res16UNet34C(nn.Module):
             assert k == kind, "tape walk out of step with the graph"
             return rec
 
+        def stage_done():
+            if sink is not None and grads:
+                sink(dict(grads))
+                grads.clear()
+
         for j in reversed(range(4)):                               # decoder stages, level 0 first
             lvl = 3 - j
             for _ in range(len(getattr(self, f"block{5 + j}"))):
                 dy = self._block_train_bwd(pop("block"), dy, W, grads)
             skip_grads[lvl] = dy[:, up_c[lvl]:]                    # gradient of the skip half of the concat
             dy = self._conv_bn_bwd(pop("conv"), dy[:, :up_c[lvl]], W, grads)       # transposed conv -> coarser level
+            stage_done()
         for e in reversed(range(4)):                               # encoder stages, deepest first
             for _ in range(len(getattr(self, f"block{e + 1}"))):
                 dy = self._block_train_bwd(pop("block"), dy, W, grads)
             # the stride-2 conv's input (level e) also feeds the level-e concat: add that gradient in the epilogue
             dy = self._conv_bn_bwd(pop("conv"), dy, W, grads, dx_residual=skip_grads[e])
+            stage_done()
         assert not tape, "tape walk out of step with the graph"
         dp1 = dy                                                   # total gradient of the stem output
         bn0 = self.bn0.bn
@@ -466,4 +476,5 @@ class Res16UNet34C(nn.Module):
         self._split_cache = None
         grads["conv0p1s1.kernel"] = ops.stem_bwd_weight(maps.coords[0], stem["feats"], maps.tables[0], maps.caps[0],
                                                         self.conv1_kernel_size, dp1).view_as(self.conv0p1s1.kernel)
+        stage_done()
         return grads

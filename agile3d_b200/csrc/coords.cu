@@ -328,7 +328,7 @@ static int downsample_impl(const int32_t* coords, int64_t n, const int32_t* n_de
                            int64_t cap, int32_t* parent, int32_t* out_coords, int32_t* out_n, void* ws, size_t ws_bytes,
                            ag3d_stream_t stream) {
   AG3D_CHECK_ARG(n > 0 && n < INT_MAX, "row count out of range");
-  AG3D_CHECK_ARG(new_stride >= 2, "new_stride must be >= 2");
+  AG3D_CHECK_ARG(new_stride >= 1, "new_stride must be >= 1 (1 = unique-ify in first-occurrence order)");
   if (int rc = check_table(coarse_table, cap, n)) return rc;
   AG3D_CHECK_ARG(coords && aligned16(coords) && out_coords && aligned16(out_coords), "coords must be 16-byte aligned");
   AG3D_CHECK_ARG(parent && out_n, "parent / out_n missing");

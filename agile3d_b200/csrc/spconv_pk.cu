@@ -48,7 +48,10 @@ constexpr int PK_ND = 4;                  // accumulator buffers (groups in flig
 constexpr int PK_MAX_NA = 8, PK_MAX_NB = 8;
 constexpr uint32_t PK_STAGE = 16384;      // [128 pair rows x 128 B] gathered slab, SWIZZLE_128B
 constexpr int PK_BAR_BYTES = 512;
-constexpr int PK_REGS_E = 176, PK_REGS_P = 40, PK_REGS_M = 48;    // 256*176 + 256*40 + 128*48 = 61440 = 640 threads x the 96 registers the CTA is launched with (setmaxnreg only redistributes that pool)
+// setmaxnreg budgets (owners, producers, issuer group): 256 E + 256 P + 128 M registers-per-thread must equal 61440
+template <int COUT> struct PkRegs { static constexpr int E = 160, P = 48, M = 64; };       // 40960 + 12288 + 8192
+template <> struct PkRegs<128> { static constexpr int E = 176, P = 40, M = 48; };           // 45056 + 10240 + 6144
+constexpr int PK_REGS_unused = 0;    // 256*176 + 256*40 + 128*48 = 61440 = 640 threads x the 96 registers the CTA is launched with (setmaxnreg only redistributes that pool)
 
 struct PkParams {
   const int* nbr; int K; long long n_out;
@@ -85,7 +88,8 @@ __device__ __forceinline__ void pk_wait(uint32_t bar, uint32_t parity) {
     if (++spins > SPIN_LIMIT) __trap();
 }
 // wait that adds the cycles it blocked to acc (profiling builds of the roles pass their counters; cheap otherwise)
-__device__ __forceinline__ void pk_wait_t(uint32_t bar, uint32_t parity, long long& acc) {
+__device__ __forceinline__ void pk_wait_t(uint32_t bar, uint32_t parity, long long& acc, bool prof) {
+  if (!prof) { pk_wait(bar, parity); return; }
   const long long t0 = clock64();          // try_wait itself may block up to a hardware time limit: time the whole wait
   pk_wait(bar, parity);
   acc += clock64() - t0;
@@ -179,6 +183,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) spconv_pk_kernel(const __grid_c
   const uint32_t b_stage_bytes = (uint32_t)COUT * 128u;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool prof_on = p.prof != nullptr;
   const int n_slab = p.cin >> 5;
   const int K = p.K, NA = p.NA, NB = p.NB;
 
@@ -202,18 +207,19 @@ __global__ void __launch_bounds__(PK_THREADS, 1) spconv_pk_kernel(const __grid_c
 
   if (warp < PK_E_WARPS) {
     // =========================================================================== owners / epilogue
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(PK_REGS_E));
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(PkRegs<COUT>::E));
     const int q = warp & 3, h = warp >> 2;
     const uint32_t lt = (1u << lane) - 1u;
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * HALF);
     float acc0[HALF], acc1[HALF];
-    uint32_t dn = 0;
+    int d_slot = 0;
+    uint32_t d_phase = 0;
     int it = 0;
     long long w_plan = 0, w_d = 0;
     const long long t_begin = clock64();
     for (int t = blockIdx.x; t < p.n_super; t += gridDim.x, ++it) {
       const int buf = it & 1;
-      pk_wait_t(plan_full(buf), (uint32_t)(it >> 1) & 1u, w_plan);
+      pk_wait_t(plan_full(buf), (uint32_t)(it >> 1) & 1u, w_plan, prof_on);
       const uint32_t mask0 = plan_mask(buf)[q * PK_SEG + lane], mask1 = plan_mask(buf)[q * PK_SEG + 32 + lane];
       const int* npass = plan_npass(buf);
 #pragma unroll
@@ -224,10 +230,10 @@ __global__ void __launch_bounds__(PK_THREADS, 1) spconv_pk_kernel(const __grid_c
         const uint32_t b0 = __ballot_sync(0xffffffffu, p0), b1 = __ballot_sync(0xffffffffu, p1);
         const int rank0 = __popc(b0 & lt), rank1 = __popc(b0) + __popc(b1 & lt);
         for (int pass = 0; pass < np; ++pass) {
-          const int db = (int)(dn % PK_ND);
+          const int db = d_slot;
           if (p.debug & 32) continue;
-          pk_wait_t(d_full(db), (dn / PK_ND) & 1u, w_d);
-          ++dn;
+          pk_wait_t(d_full(db), d_phase, w_d, prof_on);
+          if (++d_slot == PK_ND) { d_slot = 0; d_phase ^= 1u; }
           tc_fence_after();
           const int s0 = rank0 - 32 * pass, s1 = rank1 - 32 * pass;
           const bool ok0 = p0 && (unsigned)s0 < 32u, ok1 = p1 && (unsigned)s1 < 32u;
@@ -269,19 +275,21 @@ __global__ void __launch_bounds__(PK_THREADS, 1) spconv_pk_kernel(const __grid_c
     if (p.prof && blockIdx.x == 0 && tid == 0) { p.prof[0] = clock64() - t_begin; p.prof[1] = w_plan; p.prof[2] = w_d; }
   } else if (warp < PK_E_WARPS + PK_P_WARPS) {
     // =========================================================================== TMA gather producers
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PK_REGS_P));
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PkRegs<COUT>::P));
     const int pw = warp - PK_E_WARPS, pair = pw >> 1, part = pw & 1;
     const bool active = lane < 16;
     const int g = part * 16 + (lane & 15);            // row group of the stage: pair rows 4g .. 4g+3
     const int q = g >> 3, gi = g & 7;
     const uint32_t a_base = smem_u32(a_smem) + (uint32_t)g * 512u;
-    uint32_t n = 0;
+    uint32_t n = 0;              // stage counter (low two bits: which producer pair issues it)
+    int a_slot = 0;              // ring slot and phase of stage n, kept incrementally (no divisions in the stage loop)
+    uint32_t a_phase = 0;
     int it = 0;
     long long w_plan = 0, w_a = 0;
     const long long t_begin = clock64();
     for (int t = blockIdx.x; t < p.n_super; t += gridDim.x, ++it) {
       const int buf = it & 1;
-      pk_wait_t(plan_full(buf), (uint32_t)(it >> 1) & 1u, w_plan);
+      pk_wait_t(plan_full(buf), (uint32_t)(it >> 1) & 1u, w_plan, prof_on);
       const int* list = plan_list(buf);
       const int* cnt = plan_cnt(buf);
       const int* npass = plan_npass(buf);
@@ -291,14 +299,16 @@ __global__ void __launch_bounds__(PK_THREADS, 1) spconv_pk_kernel(const __grid_c
         const int4 c4 = *reinterpret_cast<const int4*>(cnt + k * 4);
         const int cq = q == 0 ? c4.x : (q == 1 ? c4.y : (q == 2 ? c4.z : c4.w));
         for (int c = 0; c < n_slab; ++c) {
-          for (int pass = 0; pass < np; ++pass, ++n) {
-            if ((int)(n & 3u) != pair) continue;
-            const int slot = (int)(n % (uint32_t)NA);
+          for (int pass = 0; pass < np; ++pass) {
+            const int slot = a_slot;
+            const uint32_t phase = a_phase;
+            if (++a_slot == NA) { a_slot = 0; a_phase ^= 1u; }
+            if ((int)(n++ & 3u) != pair) continue;
             const int pos = 32 * pass + 4 * gi;
             const bool issue = active && pos < cq;
             int4 rows = make_int4(-1, -1, -1, -1);
             if (issue) rows = *reinterpret_cast<const int4*>(list + (k * 4 + q) * PK_SEG + pos);
-            pk_wait_t(a_empty(slot), ((n / (uint32_t)NA) & 1u) ^ 1u, w_a);
+            pk_wait_t(a_empty(slot), phase ^ 1u, w_a, prof_on);
             if (p.debug & 1) {
               if (part == 0 && lane == 0) mbar_arrive(a_full(slot));
               continue;
@@ -321,7 +331,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) spconv_pk_kernel(const __grid_c
     }
     if (p.prof && blockIdx.x == 0 && pw == 0 && lane == 0) { p.prof[8] = clock64() - t_begin; p.prof[9] = w_plan; p.prof[10] = w_a; }
   } else {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PK_REGS_M));
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PkRegs<COUT>::M));
     if (warp == PK_WARP_MMA) {
       // =========================================================================== MMA issuer
       const uint32_t idesc = umma_idesc_bf16(COUT);
@@ -330,31 +340,35 @@ __global__ void __launch_bounds__(PK_THREADS, 1) spconv_pk_kernel(const __grid_c
       const uint32_t a_hi32 = umma_desc_hi32(1024) | (2u << 29);          // SWIZZLE_128B, SBO = 1024 (eight rows)
       const uint32_t a_lo32 = umma_desc_lo32(smem_u32(a_smem), 16);
       const uint32_t b_lo32 = umma_desc_lo32(smem_u32(b_smem), b_lbo);
-      const uint32_t b_lo_off = (4u * b_lbo) >> 4, b_ks_off = (2u * b_lbo) >> 4, b_slot = b_stage_bytes >> 4;
-      uint32_t n = 0, nb = 0, dn = 0;
+      const uint32_t b_lo_off = (4u * b_lbo) >> 4, b_ks_off = (2u * b_lbo) >> 4, b_stride16 = b_stage_bytes >> 4;
+      uint32_t n = 0;
+      int a_slot = 0, b_slot = 0, d_slot = 0;                 // ring positions kept incrementally (no divisions per stage)
+      uint32_t a_phase = 0, b_phase = 0, d_phase = 0;
       int it = 0;
       long long w_plan = 0, w_a = 0, w_b = 0, w_d = 0;
       const long long t_begin = clock64();
       for (int t = blockIdx.x; t < p.n_super; t += gridDim.x, ++it) {
         const int buf = it & 1;
-        pk_wait_t(plan_full(buf), (uint32_t)(it >> 1) & 1u, w_plan);
+        pk_wait_t(plan_full(buf), (uint32_t)(it >> 1) & 1u, w_plan, prof_on);
         const int* npass = plan_npass(buf);
         for (int k = 0; k < K; ++k) {
           const int np = npass[k];
           int db[2] = {0, 0};
-          for (int c = 0; c < n_slab; ++c, ++nb) {
-            const int sb = (int)(nb % (uint32_t)NB);
-            if (!(p.debug & 64)) pk_wait_t(b_full(sb), (nb / (uint32_t)NB) & 1u, w_b);
-            const uint32_t b_cur = b_lo32 + (uint32_t)sb * b_slot;
+          for (int c = 0; c < n_slab; ++c) {
+            const int sb = b_slot;
+            if (!(p.debug & 64)) pk_wait_t(b_full(sb), b_phase, w_b, prof_on);
+            if (++b_slot == NB) { b_slot = 0; b_phase ^= 1u; }
+            const uint32_t b_cur = b_lo32 + (uint32_t)sb * b_stride16;
             for (int pass = 0; pass < np; ++pass, ++n) {
               if (c == 0) {
-                db[pass] = (int)(dn % PK_ND);
-                if (!(p.debug & 32)) pk_wait_t(d_empty(db[pass]), ((dn / PK_ND) & 1u) ^ 1u, w_d);
-                ++dn;
+                db[pass] = d_slot;
+                if (!(p.debug & 32)) pk_wait_t(d_empty(d_slot), d_phase ^ 1u, w_d, prof_on);
+                if (++d_slot == PK_ND) { d_slot = 0; d_phase ^= 1u; }
+                tc_fence_after();                                   // the owners' tcgen05.ld of this buffer happened-before
               }
-              const int slot = (int)(n % (uint32_t)NA);
-              pk_wait_t(a_full(slot), (n / (uint32_t)NA) & 1u, w_a);
-              tc_fence_after();
+              const int slot = a_slot;
+              pk_wait_t(a_full(slot), a_phase, w_a, prof_on);     // TMA (async proxy) -> MMA (async proxy): no fence needed
+              if (++a_slot == NA) { a_slot = 0; a_phase ^= 1u; }
               const uint32_t a_cur = a_lo32 + (uint32_t)slot * (PK_STAGE >> 4);
               const uint32_t d = tmem_base + (uint32_t)(db[pass] * COUT);
               if (elect_one()) {
@@ -385,12 +399,14 @@ __global__ void __launch_bounds__(PK_THREADS, 1) spconv_pk_kernel(const __grid_c
       }
     } else if (warp == PK_WARP_W) {
       // =========================================================================== weight stages
-      uint32_t nb = 0;
+      int b_slot = 0;
+      uint32_t b_phase = 0;
       for (int t = blockIdx.x; t < p.n_super && !(p.debug & 64); t += gridDim.x) {
         for (int k = 0; k < K; ++k) {
-          for (int c = 0; c < n_slab; ++c, ++nb) {
-            const int sb = (int)(nb % (uint32_t)NB);
-            pk_wait(b_empty(sb), ((nb / (uint32_t)NB) & 1u) ^ 1u);
+          for (int c = 0; c < n_slab; ++c) {
+            const int sb = b_slot;
+            pk_wait(b_empty(sb), b_phase ^ 1u);
+            if (++b_slot == NB) { b_slot = 0; b_phase ^= 1u; }
             if (p.debug & 2) {
               if (elect_one()) mbar_arrive(b_full(sb));
               __syncwarp();
@@ -414,7 +430,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) spconv_pk_kernel(const __grid_c
       const long long t_begin = clock64();
       for (int t = blockIdx.x; t < p.n_super; t += gridDim.x, ++it) {
         const int buf = it & 1;
-        if (it >= 2) pk_wait_t(plan_empty(buf), (uint32_t)((it >> 1) - 1) & 1u, w_plan);
+        if (it >= 2) pk_wait_t(plan_empty(buf), (uint32_t)((it >> 1) - 1) & 1u, w_plan, prof_on);
         int* list = plan_list(buf);
         int* cnt = plan_cnt(buf);
 #pragma unroll 1

@@ -35,6 +35,21 @@ def sparse_quantize(coordinates, features=None, labels=None, ignore_label=-100, 
     first occurrence; ``unique_map`` = index of the first point of each voxel, ``inverse_map[i]`` =
     output row of point i.  Maps are torch int64; coordinates keep the input container type.
     """
+    if torch.is_tensor(coordinates) and coordinates.is_cuda:
+        # device path (SURVEY.md 8(f)2): floor-divide + first-occurrence hash unique + maps in csrc/click_ops.cu / coords.cu
+        from . import ops
+        vox, unique_map, inverse_map = ops.quantize_unique(coordinates, 1.0 if quantization_size is None else quantization_size)
+        if return_maps_only:
+            return (unique_map, inverse_map) if return_inverse else unique_map
+        res = [vox[:, 1:].contiguous()]
+        for extra in (features, labels):
+            if extra is not None:
+                res.append(extra[unique_map])
+        if return_index:
+            res.append(unique_map)
+        if return_inverse:
+            res.append(inverse_map)
+        return res[0] if len(res) == 1 else tuple(res)
     is_np = isinstance(coordinates, np.ndarray)
     pts = coordinates if is_np else coordinates.detach().cpu().numpy()
     disc = np.floor(pts / quantization_size) if quantization_size is not None else np.floor(pts)

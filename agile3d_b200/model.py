@@ -117,17 +117,25 @@ class _BackboneFn(torch.autograd.Function):
         model, feats = ctx.model, ctx.feats
         bb, head = model.backbone, model.lin_squeeze_head
         dpcd = dpcd.contiguous()
+        sink = getattr(model, "grad_sink", None)          # optim.GradBuckets: gradients go straight to the flat buffer
         with torch.no_grad():
             grads = {"lin_squeeze_head.kernel": bb._wgrad(feats, None, dpcd, 1).view_as(head.kernel),
                      "lin_squeeze_head.bias": ops.col_sum(dpcd).view_as(head.bias)}
+            if sink is not None:
+                # every gradient outside the backbone is final now: autograd accumulates leaf gradients as soon as they
+                # are ready (AccumulateGrad nodes run first), and this node is the last consumer of the decoder's inputs
+                sink.write(grads)
+                sink.tail_done()
+                grads = {}
             wt = head.kernel.detach().t().contiguous()
             dfeats = torch.empty_like(feats)
             ops.spconv_fwd(dpcd, None, wt, dfeats, algo=bb.algo,
                            weight_tc=ops.prepare_tc_weight(wt) if bb.algo != ops.ALGO_SIMT else None)
-            for k, v in bb.train_backward(ctx.maps, ctx.saved, dfeats).items():
+            cb = None if sink is None else (lambda g: sink.stage({"backbone." + k: v for k, v in g.items()}))
+            for k, v in bb.train_backward(ctx.maps, ctx.saved, dfeats, sink=cb).items():
                 grads["backbone." + k] = v
         ctx.saved = None
-        return (None, None, None, None) + tuple(grads[n] for n in ctx.names)
+        return (None, None, None, None) + tuple(grads.get(n) for n in ctx.names)
 
 
 # X^T dY contractions over the voxels of the decoder backward (query-side gradients): tcgen05 weight-gradient kernel on

@@ -374,6 +374,64 @@ def s2c_mask_fwd(x, pos, A, c, U, bo, ln_w, ln_b, ln_eps, E, q_obj, nq, heads, n
     return x_out, logits, label, obj_count
 
 
+# =============================================================================================== interactive loop + voxelisation
+def click_pred(logits, nv, n_obj, click_rows=None, click_objs=None):
+    """pred int32 [nv] = argmax of logits (None: zeros) with the clicked voxels overwritten (eval_multi_obj.py:124-139)."""
+    dev = click_rows.device if logits is None else logits.device
+    pred = torch.empty(nv, dtype=torch.int32, device=dev)
+    n_clicks = 0 if click_rows is None else int(click_rows.shape[0])
+    check(lib().ag3d_click_pred(_p(logits), n_obj, nv, _p(click_rows), _p(click_objs), n_clicks, _p(pred), _stream()),
+          "ag3d_click_pred")
+    return pred
+
+
+def scene_iou_counts(pred, inverse_map, labels_full, n_obj):
+    """-> uint64-as-int64 [n_obj, 3] = (intersection, |pred == o|, |label == o|) at full resolution."""
+    _need_cuda(pred, labels_full)
+    counts = torch.empty((n_obj, 3), dtype=torch.int64, device=pred.device)
+    check(lib().ag3d_scene_iou(_p(pred), _p(inverse_map), _p(labels_full), labels_full.shape[0], n_obj, _p(counts), _stream()),
+          "ag3d_scene_iou")
+    return counts
+
+
+def click_simulate(pred, gt, xyz, top_n=-1, perm=None, max_new=32):
+    """utils/seg.py:173-226 on the device -> int32 [1 + 4 max_new] (see include/agile3d_b200.h)."""
+    _need_cuda(pred, gt, xyz)
+    nv = pred.shape[0]
+    out = torch.zeros(1 + 4 * max_new, dtype=torch.int32, device=pred.device)
+    wsb = lib().ag3d_click_simulate_workspace_bytes(nv)
+    ws = _workspace("click", pred.device, wsb)
+    check(lib().ag3d_click_simulate(_p(pred), _p(gt), _p(xyz), nv, top_n, _p(perm), max_new, _p(out), _p(ws), ws.numel(),
+                                    _stream()), "ag3d_click_simulate")
+    return out
+
+
+def quantize_unique(points, quantization_size, batch_index=0):
+    """ME.utils.sparse_quantize on the device: points f32 [n,3] -> (coords int32 [m,4] unique voxels in first-occurrence
+    order, unique_map int64 [m], inverse_map int64 [n]).  One host read-back (m)."""
+    _need_cuda(points)
+    pts = points.contiguous().float()
+    n, dev = pts.shape[0], pts.device
+    coords = torch.empty((n, 4), dtype=torch.int32, device=dev)
+    status = torch.zeros(2, dtype=torch.int32, device=dev)
+    check(lib().ag3d_quantize_points(_p(pts), n, float(quantization_size), batch_index, _p(coords), _p(status), _stream()),
+          "ag3d_quantize_points")
+    cap = lib().ag3d_hash_capacity(n)
+    table = torch.empty(cap * SLOT_BYTES, dtype=torch.uint8, device=dev)
+    parent = torch.empty(n, dtype=torch.int32, device=dev)
+    out = torch.empty((n, 4), dtype=torch.int32, device=dev)
+    wsb = lib().ag3d_downsample_workspace_bytes(n)
+    ws = _workspace("downsample", dev, wsb)
+    check(lib().ag3d_downsample(_p(coords), n, 1, _p(table), cap, _p(parent), _p(out), _p(status[1:]), _p(ws), ws.numel(),
+                                _stream()), "ag3d_downsample")
+    bad, m = status.tolist()
+    if bad:
+        raise ValueError(f"{bad} points quantise outside +-32767 voxels")
+    unique_map = torch.empty(m, dtype=torch.int64, device=dev)
+    check(lib().ag3d_first_rows(_p(parent), n, m, _p(unique_map), _stream()), "ag3d_first_rows")
+    return out[:m], unique_map, parent.to(torch.int64)
+
+
 # =============================================================================================== click-query side (K11)
 def query_blob_floats():
     return int(lib().ag3d_query_blob_floats())

@@ -59,7 +59,16 @@ class FlatAdamW:
 
 
 class GradBuckets:
-    """Sum-then-average all-reduce of FlatAdamW's gradient buffer in `n_buckets` contiguous slices."""
+    """Data-parallel gradient exchange of the training step: sum-then-average all-reduce (NCCL over NVLink / NVSwitch) of
+    FlatAdamW's flat gradient buffer, bucket by bucket, OVERLAPPED with the backward.
+
+    attach(model) makes the backward of the backbone write its gradients straight into the flat buffer, stage by stage in
+    the order they are produced (decoder + head first, then block8/up7 ... block1/down1, the stem last), and hands every
+    finished stage to this object: a stage is a contiguous slice of the flat buffer (parameters are registered in forward
+    order), so its all-reduce is launched on a side stream - behind an event recorded on the compute stream - while the
+    compute stream goes on with the data and weight gradients of the earlier stages.  finish() (called by all_reduce())
+    makes the compute stream wait for the exchange before clip + AdamW.  Without attach() the whole buffer is exchanged
+    after the backward in `n_buckets` slices (no overlap).  BatchNorm statistics stay local (the reference has no SyncBN)."""
 
     def __init__(self, opt: FlatAdamW, n_buckets: int = 6, group=None):
         self.opt, self.group = opt, group
@@ -67,16 +76,87 @@ class GradBuckets:
         edges = [round(i * n / n_buckets) for i in range(n_buckets + 1)]
         self.slices = [(a, b) for a, b in zip(edges[:-1], edges[1:]) if b > a]
         self.stream = torch.cuda.Stream() if opt.flat_g.is_cuda else None
+        self.model = None
+        self._works, self._done_to = [], None
+        self.overlap = True
+        self.launched = []             # (start, end) of the slices exchanged during the last backward (diagnostics)
 
     def world(self):
         return dist.get_world_size(self.group) if (dist.is_available() and dist.is_initialized()) else 1
 
-    def all_reduce(self):
-        """Call after backward.  Buckets go out last-slice-first (the decoder/head gradients live at the end of the
-        parameter order and are complete first); returns when the default stream may read the averaged gradients."""
+    # ---- overlapped mode -------------------------------------------------------------------------------------
+    def attach(self, model):
+        """route the backbone's gradients through this object (model.grad_sink)"""
+        by_param = {id(p): (off, k) for p, (off, k) in zip(self.opt.params, self.opt.offsets)}
+        self.ranges = {}
+        for name, p in model.named_parameters():
+            if id(p) in by_param:
+                self.ranges[name] = by_param[id(p)]
+        offs = [self.ranges[n][0] for n in self.ranges if not n.startswith("backbone.")]
+        self.tail_start = min(offs) if offs else self.opt.flat_g.numel()
+        if any(self.ranges[n][0] >= self.tail_start for n in self.ranges if n.startswith("backbone.")):
+            raise RuntimeError("GradBuckets.attach: backbone parameters must precede the decoder in parameter order")
+        self.model = model
+        model.grad_sink = self
+        return self
+
+    def detach(self):
+        if self.model is not None:
+            self.model.grad_sink = None
+            self.model = None
+
+    def write(self, grads):
+        lo, hi = None, None
+        for name, g in grads.items():
+            off, k = self.ranges[name]
+            self.opt.flat_g[off:off + k].copy_(g.reshape(-1))
+            lo = off if lo is None else min(lo, off)
+            hi = off + k if hi is None else max(hi, off + k)
+        return lo, hi
+
+    def _launch(self, a, b):
+        self.launched.append((a, b))
+        if self.world() == 1 or not self.overlap or b <= a:
+            return
+        ev = torch.cuda.Event()
+        ev.record()                                            # the slice is complete on the compute stream here
+        self.stream.wait_event(ev)
+        with torch.cuda.stream(self.stream):
+            self._works.append(dist.all_reduce(self.opt.flat_g[a:b], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def tail_done(self):
+        """everything from the first non-backbone parameter to the end of the buffer is final"""
+        self.launched = []
+        self._done_to = self.tail_start
+        self._launch(self.tail_start, self.opt.flat_g.numel())
+
+    def stage(self, grads):
+        """gradients of one backbone stage (a contiguous slice ending where the previous one began)"""
+        lo, _ = self.write(grads)
+        if lo is not None and lo < self._done_to:
+            self._launch(lo, self._done_to)
+            self._done_to = lo
+
+    def finish(self):
         w = self.world()
         if w == 1:
+            self._works = []
             return
+        g = self.opt.flat_g
+        if not self.overlap or self.model is None or self._done_to is None:
+            return self._all_reduce_after()
+        if self._done_to > 0:                                  # whatever the stages did not cover (nothing, normally)
+            self._launch(0, self._done_to)
+        with torch.cuda.stream(self.stream):
+            for wk in self._works:
+                wk.wait()
+            g.mul_(1.0 / w)
+        torch.cuda.current_stream().wait_stream(self.stream)
+        self._works, self._done_to = [], None
+
+    # ---- after-the-backward mode -------------------------------------------------------------------------------
+    def _all_reduce_after(self):
+        w = self.world()
         g = self.opt.flat_g
         if self.stream is not None:
             self.stream.wait_stream(torch.cuda.current_stream())
@@ -91,3 +171,11 @@ class GradBuckets:
             for a, b in reversed(self.slices):
                 dist.all_reduce(g[a:b], op=dist.ReduceOp.SUM, group=self.group)
             g.mul_(1.0 / w)
+        self._works, self._done_to = [], None
+
+    def all_reduce(self):
+        """Call after backward: returns when the compute stream may read the averaged gradients."""
+        if self.world() == 1:
+            self._works, self._done_to = [], None
+            return
+        self.finish()

@@ -147,6 +147,34 @@ int ag3d_fourier_posenc(const float* xyz, const int32_t* scene_offsets_host, int
                         const float* gauss_B, int32_t d_pos, float* out, float* range_out, void* ws,
                         size_t ws_bytes, ag3d_stream_t stream);
 
+/* ---- interactive loop around forward_mask and the voxelisation front end -----------
+ * ag3d_click_pred:     pred[v] = argmax_o logits[v, o] (first maximum; logits == NULL: all zeros, the first round of
+ *                      eval_multi_obj.py:120-121), then pred[click_rows[i]] = click_objs[i] (eval_multi_obj.py:136-138).
+ * ag3d_scene_iou:      counts[o] = (|p == o & l == o|, |p == o|, |l == o|) for p = pred[inverse_map] (NULL: identity),
+ *                      l = labels_full: the ingredients of utils/seg.py:9-17,44-59 (mean_iou_scene).  uint64 [n_obj, 3].
+ * ag3d_click_simulate: utils/seg.py:173-226.  Error clusters are the (gt, pred) pairs with gt != pred; the size of a
+ *                      cluster is the largest distance of one of its voxels to the nearest voxel outside the cluster
+ *                      (xyz: [nv, 3] fp32), its click the first voxel attaining it.  Clusters are ranked by size,
+ *                      descending (ties in ascending 96 gt + 11 pred, the reference's cluster id); the first top_n
+ *                      (top_n < 0: all) are taken in the order perm[0], perm[1], ... of their ranks (perm == NULL:
+ *                      rank order; the reference shuffles the selected list with random.shuffle).
+ *                      out int32 [1 + 4 max_new]: n, then n x (voxel row, object id = gt of the voxel, 32 gt + pred),
+ *                      then (from 1 + 3 max_new) the n sizes as float bits.
+ * ag3d_quantize_points: coords[i] = (batch_index, floor(points[i] / quantization_size)) as int32 [n, 4]; *status +=
+ *                      points outside +-32767.  ME.utils.sparse_quantize = this + ag3d_downsample(stride 1) (unique voxels
+ *                      in first-occurrence order, parent = inverse_map) + ag3d_first_rows (unique_map).
+ * ag3d_first_rows:     unique_map[j] = min{ i : parent[i] == j }  (int64 [m]).                                        */
+int ag3d_click_pred(const float* logits, int32_t n_obj, int64_t nv, const int32_t* click_rows, const int32_t* click_objs,
+                    int32_t n_clicks, int32_t* pred, ag3d_stream_t stream);
+int ag3d_scene_iou(const int32_t* pred, const int64_t* inverse_map, const int32_t* labels_full, int64_t n_full, int32_t n_obj,
+                   uint64_t* counts, ag3d_stream_t stream);
+size_t ag3d_click_simulate_workspace_bytes(int64_t nv);
+int ag3d_click_simulate(const int32_t* pred, const int32_t* gt, const float* xyz, int64_t nv, int32_t top_n,
+                        const int32_t* perm, int32_t max_new, int32_t* out, void* ws, size_t ws_bytes, ag3d_stream_t stream);
+int ag3d_quantize_points(const float* points, int64_t n, float quantization_size, int32_t batch_index, int32_t* coords,
+                         int32_t* status, ag3d_stream_t stream);
+int ag3d_first_rows(const int32_t* parent, int64_t n, int64_t m, int64_t* unique_map, ag3d_stream_t stream);
+
 /* ---- click-query side of a decoder layer (K11) -------------------------------------------------------------
  * Replaces the O(Nq) torch calls between the two voxel-streaming kernels of a layer (models/agile3d.py:273-325):
  * the q/k/v/out projections of CrossAttentionLayer / SelfAttentionLayer (models/modules/attention_block.py:28-38,
