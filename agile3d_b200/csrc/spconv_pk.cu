@@ -82,10 +82,24 @@ __device__ __forceinline__ void pk_ld16(uint32_t taddr, uint32_t* r) {
 }
 // mbarrier wait without a function call: ptxas cannot allocate a kernel that changes its register count
 // (setmaxnreg) around an ABI call such as the shared mbar_wait_slow()
+// try_wait with a suspend-time hint: a waiting warp sleeps in hardware until the phase completes (or ~2 us pass) instead of
+// spinning.  20 warps share four schedulers here and most of them wait most of the time: hot spin loops took the issue
+// slots of the one warp per scheduler that had work (the MMA issuer ran ~3x slower than its instruction stream).
+__device__ __forceinline__ uint32_t pk_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(2000u)
+      : "memory");
+  return ok;
+}
 __device__ __forceinline__ void pk_wait(uint32_t bar, uint32_t parity) {
   unsigned spins = 0;
-  while (!mbar_try(bar, parity))
-    if (++spins > SPIN_LIMIT) __trap();
+  while (!pk_try(bar, parity))
+    if (++spins > (1u << 22)) __trap();     // a protocol bug must fail loudly, never hang the GPU (~8 s)
 }
 // wait that adds the cycles it blocked to acc (profiling builds of the roles pass their counters; cheap otherwise)
 __device__ __forceinline__ void pk_wait_t(uint32_t bar, uint32_t parity, long long& acc, bool prof) {

@@ -118,6 +118,9 @@ class GradBuckets:
         self.launched.append((a, b))
         if self.world() == 1 or not self.overlap or b <= a:
             return
+        if self.stream is None:                                # CPU process group (gloo tests): exchange in place, now
+            dist.all_reduce(self.opt.flat_g[a:b], op=dist.ReduceOp.SUM, group=self.group)
+            return
         ev = torch.cuda.Event()
         ev.record()                                            # the slice is complete on the compute stream here
         self.stream.wait_event(ev)
@@ -147,6 +150,10 @@ class GradBuckets:
             return self._all_reduce_after()
         if self._done_to > 0:                                  # whatever the stages did not cover (nothing, normally)
             self._launch(0, self._done_to)
+        if self.stream is None:
+            g.mul_(1.0 / w)
+            self._works, self._done_to = [], None
+            return
         with torch.cuda.stream(self.stream):
             for wk in self._works:
                 wk.wait()
