@@ -176,7 +176,7 @@ int spconv_pk_launch(const float* in, long long n_in, int in_ld, int cin, const 
                      const void* wprep, int cout, const float* scale, const float* shift, const float* residual,
                      int res_ld, float* out, int out_ld, int flags, cudaStream_t st);
 bool spconv_pk_supported(int cin, int cout, int K);
-bool spconv_pk_preferred(long long n_out);
+bool spconv_pk_preferred(long long n_out, int K, int cin, int cout);
 size_t spconv_tc_workspace_bytes(long long n_out, int K, int cout);
 
 }  // namespace ag3d
@@ -201,7 +201,7 @@ int ag3d_spconv_fwd_rows(const float* in, int64_t n_in, int32_t in_ld, int32_t c
   if (algo == AG3D_ALGO_AUTO) {
     algo = (weight_tc && K <= 32 && spconv_tc_supported(cin, cout)) ? AG3D_ALGO_TC : AG3D_ALGO_SIMT;
     if (algo == AG3D_ALGO_TC && nbr && n_in > 0 && (flags & AG3D_IN_SPLIT) && spconv_pk_supported(cin, cout, K) &&
-        spconv_pk_preferred(n_out))
+        spconv_pk_preferred(n_out, K, cin, cout))
       algo = AG3D_ALGO_TC_PACKED;
   }
   if (algo == AG3D_ALGO_TC_PACKED)

@@ -29,7 +29,7 @@ import torch  # noqa: E402
 
 TARGET_VOXELS = 150000
 VOXEL = 0.02
-N_OBJ, CLICKS_PER_OBJ = 5, 2
+N_OBJ, CLICKS_PER_OBJ, N_BG = 5, 2, 0
 METRIC = "scenes/sec forward (150k voxels, 10 click queries)"
 WORKLOAD = "150k-voxel synthetic ScanNet-shape scene @2cm, 5 objects x 2 clicks (20 queries), eval forward_backbone+forward_mask"
 
@@ -39,7 +39,7 @@ def make_inputs(n_scenes, seed0, target=TARGET_VOXELS):
     scenes = []
     for i in range(n_scenes):
         sc = make_scene(target, VOXEL, seed=seed0 + i)
-        clicks, times, _ = make_clicks(sc, N_OBJ, CLICKS_PER_OBJ, 0, seed=seed0 + i)
+        clicks, times, _ = make_clicks(sc, N_OBJ, CLICKS_PER_OBJ, N_BG, seed=seed0 + i)
         scenes.append((sc, clicks, times))
     return scenes
 
@@ -96,6 +96,24 @@ def measured_peaks():
             d = json.load(f)
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def measured_tflops():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f).get("bf16_tflops_sustained", 1400.0))
+    return 1400.0
+
+
+def ncu_summary():
+    """per-launch DRAM bytes / tensor-pipe activity of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/ncu_dominant.json, written by tools/ncu_summary.py from the .ncu-rep of the same command)"""
+    p = os.path.join(ROOT, "profiles", "ncu_dominant.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f)
+    return {}
 
 
 # ------------------------------------------------------------------------------------------------ CPU baseline
@@ -260,6 +278,26 @@ def run_ours(args, rank, world, local_rank):
         ops.set_profiler(None)
         fam = prof.summary()
 
+    parity = None
+    if rank == 0 and not args.no_parity:
+        # measured parity of the timed workload itself: first scene of the first timed batch against the fp64 CPU oracle
+        # (oracle/compare.py: layers after a discrete label decision are compared on the same decisions)
+        from oracle.agile3d_ref import build_ref_model
+        from oracle.compare import decision_forced_errors, rel_err
+        sc0, ck0, tm0 = scenes[0]
+        c0 = np.concatenate([np.zeros((sc0["coords"].shape[0], 1), np.int32), sc0["coords"]], 1)
+        x0 = agile3d_b200.SparseTensor(coordinates=torch.from_numpy(c0), features=torch.from_numpy(sc0["feats"]), device=dev)
+        h0 = model.forward_backbone(x0, raw_coordinates=torch.from_numpy(sc0["raw_coords"]).to(dev))
+        o0 = model.forward_mask(*h0, click_idx=[ck0], click_time_idx=[tm0])
+        layers = [a["pred_masks"] for a in o0["aux_outputs"]] + [o0["pred_masks"]]
+        ref = build_ref_model(default_args()).eval()
+        ref.load_state_dict(synth_state_dict({k: tuple(v.shape) for k, v in ref.state_dict().items()}, seed=5))
+        r = decision_forced_errors(ref.double(), c0, sc0["feats"], sc0["raw_coords"], [ck0], [tm0], layers)
+        parity = {"checker": "oracle/ fp64 CPU restatement, scene 0 of the timed batch",
+                  "backbone_features_rel_err": rel_err(h0[0].F.cpu().numpy(), r["pcd"].F.numpy()),
+                  "mask_logits_rel_err_per_layer": r["forced"], "vs_free_running_oracle": r["free"],
+                  "differing_label_decisions": r["flips"], "not_near_ties": r["bad_flips"], "tolerance": 1e-3}
+
     agd.barrier()
     if rank != 0:
         if dist_on:
@@ -276,13 +314,28 @@ def run_ours(args, rank, world, local_rank):
                           "algorithmic_GB_per_step": round(f["bytes"] / 2 / 1e9, 4), "GBps": round(gbs, 1),
                           "frac_of_hbm_peak": round(gbs / peak, 4),
                           "TFLOPs": round(f["flops"] / (f["ms"] / 1e3) / 1e12, 3) if f["ms"] > 0 else 0.0}
+    tf_peak = measured_tflops()
+    for name, f in fam.items():
+        # the other roof: tensor pipe.  The sparse conv computes every product three times (bf16x3 = fp32 parity on bf16
+        # tensor cores), the decoder GEMMs likewise; "binding" names the roof that is closer.
+        if f["flops"]:
+            t_tensor = 3.0 * f["flops"] / (tf_peak * 1e12) * 1e3
+            t_hbm = f["bytes"] / (peak * 1e9) * 1e3
+            fam_rows[name].update({"hbm_bound_ms_per_step": round(t_hbm / 2, 4), "tensor_bound_ms_per_step": round(t_tensor / 2, 4),
+                                   "binding": "tensor" if t_tensor > t_hbm else "hbm",
+                                   "frac_of_binding_bound": round(max(t_tensor, t_hbm) / f["ms"], 4)})
     dom = max(fam, key=lambda k: fam[k]["ms"])
     d = fam[dom]
     achieved = d["bytes"] / (d["ms"] / 1e3) / 1e9
+    ncu = ncu_summary()
     roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                "frac": round(achieved / peak, 4), "traffic": ncu.get("dram_bytes_per_launch"),
+                "tensor_pipe_pct": ncu.get("tensor_pipe_pct"), "ncu_source": ncu.get("source"), "peak_source": peak_src,
                 "per_launch_algorithmic_bytes": int(d["bytes"] / max(d["launches"], 1)),
-                "per_launch_ms": round(d["ms"] / max(d["launches"], 1), 5), "families": fam_rows}
+                "per_launch_ms": round(d["ms"] / max(d["launches"], 1), 5),
+                "note": "the dominant family is the sparse convolution; at fp32 parity (bf16x3) its binding roof is the tensor "
+                        "pipe, see families.spconv.binding / frac_of_binding_bound",
+                "tensor_peak_TFLOPs": tf_peak, "families": fam_rows}
     # CPU baseline on a bounded sample: one crop sized for ~10-20 s of host work
     full = scenes[0]
     t_cal, ref_model = cpu_reference_run(crop_scene(full, 10000))
@@ -305,6 +358,7 @@ def run_ours(args, rank, world, local_rank):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
+        "parity": parity,
         "cpu_baseline": {"value": cpu_value, "unit": "scenes/s", "cores": os.cpu_count() or 1, "kind": "port",
                          "sample": f"{n_s}-voxel crop of a {n_full}-voxel scene, 1 run, scaled by voxel count; "
                                    "oracle/ fp32 torch restatement (MinkowskiEngine itself is not installable here)"},
@@ -343,14 +397,19 @@ def run_train(args, rank, world, local_rank):
     criterion = agile3d_b200.build_criterion(margs)
     opt = FlatAdamW(model.parameters(), lr=1e-4, weight_decay=1e-4, max_norm=0.1)        # main.py:62-69,125
     buckets = GradBuckets(opt, n_buckets=6)
+    # the exchange of a stage's gradients starts inside the backbone backward as soon as the stage is done
+    # (AG3D_NO_OVERLAP=1: exchange after the backward, for the comparison in profiles/)
+    if os.environ.get("AG3D_NO_OVERLAP", "0") != "1":
+        buckets.attach(model)
+    target_voxels = args.voxels or TARGET_VOXELS
     B, n_pool = args.batch, 2
     host = []
     for pidx in range(n_pool):
         batch, targets = [], []
         for i in range(B):
             seed = 2000 + 100 * rank + pidx * B + i
-            sc = make_scene(TARGET_VOXELS, VOXEL, seed=seed)
-            clicks, times, lab = make_clicks(sc, N_OBJ, CLICKS_PER_OBJ, 0, seed=seed)
+            sc = make_scene(target_voxels, VOXEL, seed=seed)
+            clicks, times, lab = make_clicks(sc, N_OBJ, CLICKS_PER_OBJ if target_voxels < 400000 else 3, 0, seed=seed)
             batch.append((sc, clicks, times))
             targets.append(torch.from_numpy(lab.astype(np.int32)))
         c, f, r, ck, tm = collate(batch)
@@ -438,7 +497,11 @@ def run_train(args, rank, world, local_rank):
         "metric": TRAIN_METRIC, "value": total_scenes / (ms / 1e3), "unit": "scenes/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": TRAIN_WORKLOAD, "scenes_per_step_per_gpu": B,
+        "config": {"workload": TRAIN_WORKLOAD if target_voxels < 400000 else TRAIN_WORKLOAD.replace(
+                       "configs[2]: batch of 150k-voxel", "configs[3]: batch of 500k-voxel (S3DIS-shape)").replace(
+                       "5 objects x 2 clicks (20 queries)", "5 objects x 3 clicks (25 queries)"),
+                   "scenes_per_step_per_gpu": B, "gradient_exchange": "overlapped with the backward (GradBuckets.attach)"
+                   if buckets.model is not None else "after the backward",
                    "voxels_per_step_per_gpu": int(np.mean(n_vox)),
                    "l2_policy": f"rotating pool of {n_pool} distinct batches; activations exceed the 126 MB L2"},
         "e2e": {"value": total_scenes / (ms_e2e / 1e3), "unit": "scenes/s",
@@ -448,6 +511,127 @@ def run_train(args, rank, world, local_rank):
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src, "families": fam_rows},
         "cpu_baseline": None,
+    }
+    emit(line)
+    if dist_on:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------ click loop (configs[4])
+CLICK_METRIC = "scenes/sec iterative-click evaluation (80k voxels @5cm, 10 objects, 200 clicks; eval_multi_obj.py protocol)"
+CLICK_WORKLOAD = ("BASELINE configs[4]: KITTI-360-shape outdoor scan ~80k voxels @5cm, 10 objects; forward_backbone once, then the "
+                  "click loop of eval_multi_obj.py:118-167 (forward_mask, prediction update, full-resolution IoU, simulated next "
+                  "click) until 20 clicks per object: ~192 rounds, click queries 20 -> 210")
+
+
+def run_clickloop(args, rank, world, local_rank):
+    """One step = the whole interactive protocol on one scene per GPU (scenes shard across ranks, no collective)."""
+    import copy
+    import random
+
+    import agile3d_b200
+    from agile3d_b200 import dist as agd
+    from agile3d_b200 import interactive, ops
+    from agile3d_b200.scenes import make_clicks, make_scene
+    from agile3d_b200.weights import default_args, synth_state_dict
+    import torch.distributed as dist
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    dist_on = world > 1
+    agd.init_from_env(backend="nccl", device=dev)
+    model = agile3d_b200.build_model(default_args()).eval()
+    model.load_state_dict(synth_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, seed=5))
+    model = model.to(dev)
+    K, max_per_obj = 10, 20                                              # eval_multi_obj.py --max_num_clicks 20
+    scenes = []
+    for i in range(2):
+        sc = make_scene(80000, 0.05, seed=5000 + 100 * rank + i, outdoor=True)
+        _, _, lab = make_clicks(sc, K, 1, 0, seed=5000 + i)
+        scenes.append((sc, torch.from_numpy(np.minimum(lab, K).astype(np.int64))))
+    host = []
+    for sc, lab in scenes:
+        coords = agile3d_b200.utils.batched_coordinates([sc["coords"]])
+        lab_full = lab[sc["inverse_map"]]
+        host.append((coords.pin_memory(), torch.from_numpy(sc["feats"]).pin_memory(), torch.from_numpy(sc["raw_coords"]).pin_memory(),
+                     lab.pin_memory(), lab_full.pin_memory(), sc["inverse_map"].pin_memory()))
+    rounds_seen, nq_seen = [], []
+
+    def protocol(i, resident):
+        c, f, r, lab, lab_full, inv = resident[i % len(resident)]
+        if not c.is_cuda:
+            c, f, r, lab, lab_full, inv = (t.to(dev, non_blocking=True) for t in (c, f, r, lab, lab_full, inv))
+        random.seed(i)
+        x = agile3d_b200.SparseTensor(coordinates=c, features=f, device=dev)
+        h = model.forward_backbone(x, raw_coordinates=r)
+        click_idx = {str(o): [] for o in range(K + 1)}
+        click_time = copy.deepcopy(click_idx)
+        n_clicks, rounds, iou = 0, 0, None
+        nv = c.shape[0]
+        while n_clicks <= K * max_per_obj:
+            if n_clicks == 0:
+                pred = ops.click_pred(None, nv, K + 1, torch.zeros(0, dtype=torch.int32, device=dev), torch.zeros(0, dtype=torch.int32, device=dev))
+            else:
+                out = model.forward_mask(*h, click_idx=[click_idx], click_time_idx=[click_time])
+                rows = torch.tensor([v for o in range(K + 1) for v in click_idx[str(o)]], dtype=torch.int32).pin_memory().to(dev, non_blocking=True)
+                objs = torch.tensor([o for o in range(K + 1) for _ in click_idx[str(o)]], dtype=torch.int32).pin_memory().to(dev, non_blocking=True)
+                pred = ops.click_pred(out["pred_masks"][0], nv, K + 1, rows, objs)
+                nq_seen.append(10 + n_clicks)
+            iou, _ = interactive.mean_iou_scene(pred, lab_full, inv)
+            new, _, _, new_t = interactive.get_simulated_clicks(pred, lab, r, n_clicks, training=False)
+            if new is not None:
+                click_idx, click_time = interactive.extend_clicks(click_idx, click_time, new, new_t)
+            n_clicks += K if n_clicks == 0 else 1
+            rounds += 1
+        rounds_seen.append(rounds)
+        return iou
+
+    resident = [tuple(t.to(dev) for t in hs) for hs in host]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist_on:
+            agd.barrier()
+            torch.cuda.synchronize()
+
+    def timed(res, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            protocol(i, res)
+        e1.record()
+        barrier()
+        return agd.max_over_ranks(e0.elapsed_time(e1), device=dev)
+
+    steps = max(1, min(args.steps, 5))
+    for i in range(max(1, min(args.warmup, 2))):
+        protocol(i, resident)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    l0 = ops.kernel_launches()
+    ms = timed(resident, steps)
+    launches = ops.kernel_launches() - l0
+    ms_e2e = timed(host, steps)
+    clocks = sampler.stop() if sampler else None
+    agd.barrier()
+    if rank != 0:
+        if dist_on:
+            dist.destroy_process_group()
+        return
+    rounds = rounds_seen[-1]
+    n_v = int(host[0][0].shape[0])
+    line = {
+        "metric": CLICK_METRIC, "value": world * steps / (ms / 1e3), "unit": "scenes/s", "n_gpus": world, "steps": steps,
+        "warmup": max(1, min(args.warmup, 2)), "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": CLICK_WORKLOAD, "voxels": n_v, "rounds_per_scene": rounds, "ms_per_round": ms / steps / rounds,
+                   "click_queries": [min(nq_seen), max(nq_seen)], "host_syncs_per_round": 2,
+                   "l2_policy": "two scenes rotated; a round streams the 41 MB voxel features + 41 MB encodings 6 times"},
+        "e2e": {"value": world * steps / (ms_e2e / 1e3), "unit": "scenes/s", "ms_per_step": ms_e2e / steps,
+                "h2d_bytes_per_step": n_v * (16 + 12 + 12 + 8) + int(host[0][4].shape[0]) * 16, "d2h_bytes_per_step": rounds * (64 * 4 + 11 * 24)},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": None, "cpu_baseline": None,
     }
     emit(line)
     if dist_on:
@@ -478,8 +662,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=8, help="scenes per step per GPU (BASELINE configs[2] batches 8 scenes)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="forward", choices=["forward", "train"],
-                    help="forward = the headline metric (default); train = BASELINE configs[2]/[3] training step")
+    ap.add_argument("--workload", default="forward", choices=["forward", "train", "c2", "clickloop"],
+                    help="forward = the headline metric (default); train = BASELINE configs[2]/[3] training step; c2 = configs[1] "
+                         "(150k voxels, 5 clicks, single object, batch 1); clickloop = configs[4] (80k voxels @5cm, the iterative-click "
+                         "protocol of eval_multi_obj.py end to end)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the fp64 oracle comparison of the timed workload")
+    ap.add_argument("--voxels", type=int, default=0, help="train workload: voxels per scene (default 150k; 500000 = configs[3])")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -494,6 +682,16 @@ def main():
     if args.workload == "train":
         run_train(args, rank, world, local_rank)
         return
+    if args.workload == "clickloop":
+        run_clickloop(args, rank, world, local_rank)
+        return
+    if args.workload == "c2":
+        global N_OBJ, CLICKS_PER_OBJ, N_BG, WORKLOAD, METRIC
+        N_OBJ, CLICKS_PER_OBJ, N_BG = 1, 3, 2
+        METRIC = "scenes/sec forward (150k voxels, 5 clicks, single object)"
+        WORKLOAD = "BASELINE configs[1]: 150k-voxel synthetic ScanNet-shape scene @2cm, 1 object, 3 fg + 2 bg clicks (15 queries), eval forward_backbone+forward_mask"
+        if args.batch == 8:
+            args.batch = 1
     run_ours(args, rank, world, local_rank)
 
 
