@@ -28,6 +28,9 @@ SIGNATURES = {
     "ag3d_hash_build": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp]),
     "ag3d_downsample_workspace_bytes": (_sz, [_i64]),
     "ag3d_downsample": (_i32, [_vp, _i64, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ag3d_row_order_workspace_bytes": (_sz, [_i64]),
+    "ag3d_row_order": (_i32, [_vp, _i32, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ag3d_permute_map": (_i32, [_vp, _i32, _i64, _vp, _vp, _vp, _vp]),
     "ag3d_downsample_dev": (_i32, [_vp, _i64, _vp, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ag3d_scene_offsets": (_i32, [_vp, _i64, _i32, _vp, _vp]),
     "ag3d_kernel_map": (_i32, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp]),
@@ -54,7 +57,7 @@ SIGNATURES = {
     "ag3d_quantize_points": (_i32, [_vp, _i64, _f32, _i32, _vp, _vp, _vp]),
     "ag3d_first_rows": (_i32, [_vp, _i64, _i64, _vp, _vp]),
     "ag3d_query_blob_floats": (_i64, []),
-    "ag3d_query_init": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ag3d_query_init": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ag3d_query_fold_c2s": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp, _vp]),
     "ag3d_query_update_a": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp]),
     "ag3d_query_update_b": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp]),

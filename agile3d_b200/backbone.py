@@ -30,7 +30,9 @@ class CoordinateMaps:
     hash tables, and the kernel maps of every (level, kernel) pair the U-Net uses.  Built once per
     SparseTensor on the GPU and cached on it."""
 
-    def __init__(self, coords: torch.Tensor, count_pairs: bool = False, want_offsets: bool = False):
+    REORDER_LEVELS = (0, 1, 2)       # levels whose rows are re-ordered by neighbour pattern (the others are tiny)
+
+    def __init__(self, coords: torch.Tensor, count_pairs: bool = False, want_offsets: bool = False, reorder: bool = False):
         if coords.dtype != torch.int32 or coords.dim() != 2 or coords.shape[1] != 4 or not coords.is_contiguous():
             raise ValueError("coords must be a contiguous int32 [N,4] tensor")
         # 5 coordinate levels (tensor strides 1 .. 16), their hash tables and the scene row ranges: the level sizes stay
@@ -52,6 +54,27 @@ class CoordinateMaps:
             self.up.append(ops.kernel_map_transposed(self.coords[lvl], self.parents[lvl], 1 << lvl))
             if count_pairs:
                 self.pair_counts[("up", lvl)] = self.sizes[lvl]
+        self.perm, self.inv = [None] * 5, [None] * 5
+        if reorder:
+            self._reorder()
+
+    def _reorder(self):
+        """Internal row order (csrc/coords.cu: ag3d_row_order): rows of a level sorted, scene by scene, by the pattern of
+        their existing 3x3x3 neighbours, so that the rows of a 128-row tile agree on the absent offsets and the dense-tile
+        convolution skips those stages.  perm[l][new] = old row, inv[l][old] = new row; every neighbour table is rewritten
+        into the new numbering, coords[l] follows.  The hash tables keep the OLD row ids: the level-0 table is how the stem
+        finds the input features, which stay in the caller's order."""
+        for l in self.REORDER_LEVELS:
+            if self.sizes[l] >= 256:
+                self.perm[l], self.inv[l] = ops.row_order(self.k3[l], self.coords[l])
+        for l in range(5):
+            if self.perm[l] is not None:
+                self.k3[l] = ops.permute_map(self.k3[l], self.perm[l], self.inv[l])
+                self.coords[l] = self.coords[l][self.perm[l].long()].contiguous()
+        for l in range(4):
+            if self.perm[l] is not None or self.perm[l + 1] is not None:
+                self.down[l] = ops.permute_map(self.down[l], self.perm[l + 1], self.inv[l])      # out: level l+1, in: level l
+                self.up[l] = ops.permute_map(self.up[l], self.perm[l], self.inv[l + 1])          # out: level l, in: level l+1
 
     def _keep(self, key, r, count_pairs):
         if count_pairs:
@@ -145,6 +168,7 @@ class Res16UNet34C(nn.Module):
             setattr(self, f"block{5 + j}", _stage(P[4 + j] + skips[j], P[4 + j], L[4 + j], m))
             c = P[4 + j]
         self.algo = ops.ALGO_AUTO
+        self.reorder_rows = True    # internal row order by neighbour pattern (CoordinateMaps._reorder); callers never see it
         self.split_rows = True      # keep activations as bf16 hi/lo pair rows between tensor-core layers
         self._fold_cache = None
 
@@ -206,6 +230,15 @@ class Res16UNet34C(nn.Module):
             x = self._block(f"{name}.{i}", blk, x, nbr, fold, out=final_out if i == len(blocks) - 1 else None)
         return x
 
+    def prepare_maps(self, st):
+        """coordinate levels, kernel maps and (reorder_rows) the internal row order of a SparseTensor, built once"""
+        if st.maps is None:
+            st.maps = CoordinateMaps(st.C)
+        if self.reorder_rows and st.maps.perm[0] is None and not getattr(st.maps, "reorder_done", False):
+            st.maps._reorder()
+            st.maps.reorder_done = True
+        return st.maps
+
     @torch.no_grad()
     def forward(self, st):
         """st: agile3d_b200.SparseTensor -> (features [N0, 96], [5 feature maps], CoordinateMaps).  Eval mode only;
@@ -213,9 +246,7 @@ class Res16UNet34C(nn.Module):
         if self.training:
             raise RuntimeError("Res16UNet34C.forward is the eval-mode graph; Agile3d.forward_backbone dispatches "
                                "to train_forward in train mode")
-        if st.maps is None:
-            st.maps = CoordinateMaps(st.C)
-        maps, fold, dev = st.maps, self._folded(), st.F.device
+        maps, fold, dev = self.prepare_maps(st), self._folded(), st.F.device
         N, P = maps.sizes, PLANES
         f32 = dict(dtype=torch.float32, device=dev)
         # concat buffers: [upsampled | skip]  (me.cat(out, skip), models/res16unet.py:257,267,277,287)
@@ -389,9 +420,7 @@ class Res16UNet34C(nn.Module):
     @torch.no_grad()
     def train_forward(self, st):
         """-> (features [N0,96], [5 feature maps], maps, tape).  tape feeds train_backward."""
-        if st.maps is None:
-            st.maps = CoordinateMaps(st.C)
-        maps, W, dev = st.maps, self._train_weights(), st.F.device
+        maps, W, dev = self.prepare_maps(st), self._train_weights(), st.F.device
         N, P = maps.sizes, PLANES
         f32 = dict(dtype=torch.float32, device=dev)
         skip_c = (INIT_DIM, P[0], P[1], P[2])

@@ -2,6 +2,7 @@
 // All integer work, HBM/L2-latency bound: one 128-bit coordinate load per row, one 128-bit slot load per probe.
 #include <limits.h>
 
+#include <cub/device/device_radix_sort.cuh>
 #include <mutex>
 
 #include "common.cuh"
@@ -260,6 +261,40 @@ __global__ void scene_order_kernel(const int4* __restrict__ coords, long long n,
   if (c) atomicAdd(bad, c);
 }
 
+// ---- internal row order.  Rows of a level are sorted, scene by scene, by their 3x3x3 neighbour
+// pattern (the 27-bit mask of existing offsets): rows of a 128-row tile then agree on which offsets are absent and the
+// dense-tile convolution skips those (tile, offset) stages (18.8 instead of 26.9 of 27 at 150k voxels; Morton order: 26.8 -
+// tools/order_analysis.py).  The permutation is internal: callers see their own row order (agile3d_b200/model.py).
+__global__ void order_key_kernel(const int* __restrict__ nbr, int K, long long n, const int4* __restrict__ coords,
+                                 unsigned long long* __restrict__ keys, int* __restrict__ vals) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long step = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += step) {
+    unsigned m = 0;
+    for (int k = 0; k < K; ++k) m |= (__ldg(nbr + (long long)k * n + i) >= 0 ? 1u : 0u) << k;
+    keys[i] = ((unsigned long long)(unsigned)__ldg(&coords[i].x) << 32) | m;
+    vals[i] = (int)i;
+  }
+}
+__global__ void invert_perm_kernel(const int* __restrict__ perm, long long n, int* __restrict__ inv) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long step = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += step) inv[perm[i]] = (int)i;
+}
+// out[k][i] = remap(nbr[k][perm_out ? perm_out[i] : i]),  remap(v) = v < 0 ? -1 : (inv_in ? inv_in[v] : v)
+__global__ void permute_map_kernel(const int* __restrict__ nbr, long long n_out, const int* __restrict__ perm_out,
+                                   const int* __restrict__ inv_in, int* __restrict__ out) {
+  const int k = blockIdx.y;
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long step = (long long)gridDim.x * blockDim.x;
+  for (; i < n_out; i += step) {
+    const long long src = perm_out ? perm_out[i] : i;
+    int v = __ldg(nbr + (long long)k * n_out + src);
+    if (v >= 0 && inv_in) v = __ldg(inv_in + v);
+    out[(long long)k * n_out + i] = v;
+  }
+}
+
 static inline int grid_for(long long n, int threads) {
   long long b = (n + threads - 1) / threads;
   long long cap = (long long)sm_count() * 16;
@@ -381,6 +416,43 @@ int ag3d_scene_offsets(const int32_t* coords, int64_t n, int32_t max_scenes, int
   AG3D_LAUNCH_CHECK("scene_offsets");
   scene_order_kernel<<<grid_for(n, 256), 256, 0, st>>>(reinterpret_cast<const int4*>(coords), n, offsets + max_scenes + 1);
   AG3D_LAUNCH_CHECK("scene_order");
+  return AG3D_OK;
+}
+
+size_t ag3d_row_order_workspace_bytes(int64_t n) {
+  size_t temp = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, temp, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
+                                  (const int*)nullptr, (int*)nullptr, (int)n, 0, 48);
+  return (size_t)n * (8 + 8 + 4) + temp + 1024;
+}
+
+int ag3d_row_order(const int32_t* nbr, int32_t K, int64_t n, const int32_t* coords, int32_t* perm, int32_t* inv, void* ws,
+                   size_t ws_bytes, ag3d_stream_t stream) {
+  AG3D_CHECK_ARG(n > 0 && n < INT_MAX && K >= 1 && K <= 32, "row_order: shape");
+  AG3D_CHECK_ARG(nbr && coords && aligned16(coords) && perm && inv, "row_order: pointers");
+  AG3D_CHECK_ARG(ws && aligned16(ws) && ws_bytes >= ag3d_row_order_workspace_bytes(n), "row_order: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  unsigned char* w = static_cast<unsigned char*>(ws);
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(w);
+  unsigned long long* keys_out = keys + n;
+  int* vals = reinterpret_cast<int*>(keys_out + n);
+  void* temp = w + (((size_t)n * 20 + 255) & ~(size_t)255);
+  size_t temp_bytes = ws_bytes - (((size_t)n * 20 + 255) & ~(size_t)255);
+  order_key_kernel<<<grid_for(n, 256), 256, 0, st>>>(nbr, K, n, reinterpret_cast<const int4*>(coords), keys, vals);
+  AG3D_LAUNCH_CHECK("order_key");
+  // stable LSD radix sort over (scene, mask): equal patterns keep the caller's order
+  AG3D_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys, keys_out, vals, perm, (int)n, 0, 48, st));
+  g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+  invert_perm_kernel<<<grid_for(n, 256), 256, 0, st>>>(perm, n, inv);
+  AG3D_LAUNCH_CHECK("invert_perm");
+  return AG3D_OK;
+}
+
+int ag3d_permute_map(const int32_t* nbr, int32_t K, int64_t n_out, const int32_t* perm_out, const int32_t* inv_in,
+                     int32_t* out, ag3d_stream_t stream) {
+  AG3D_CHECK_ARG(nbr && out && nbr != out && n_out > 0 && n_out < INT_MAX && K >= 1, "permute_map: arguments");
+  permute_map_kernel<<<dim3(grid_for(n_out, 256), K), 256, 0, as_stream(stream)>>>(nbr, n_out, perm_out, inv_in, out);
+  AG3D_LAUNCH_CHECK("permute_map");
   return AG3D_OK;
 }
 

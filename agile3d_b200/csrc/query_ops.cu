@@ -103,11 +103,11 @@ __device__ __forceinline__ void layer_norm16(float* v, const float* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------- query assembly
-// row (scene b, query q): src >= 0 -> clicked voxel (global row src): feature row + fourier(xyz) + time encoding;
-// src < 0 -> learned background query -(src + 1).   grid = total query rows, 128 threads (thread = channel)
+// row (scene b, query q): src >= 0 -> clicked voxel: fourier(xyz[src]) + time encoding, feature row feats[feat_row]
+// (feat_row: the same voxel in the row order of `feats`; NULL = src); src < 0 -> learned background query -(src + 1).   grid = total query rows, 128 threads (thread = channel)
 __global__ void query_init_kernel(const float* __restrict__ feats, const float* __restrict__ xyz,
                                   const float* __restrict__ range, const int* __restrict__ src_row,
-                                  const int* __restrict__ time_idx, const int* __restrict__ scene_of_row,
+                                  const int* __restrict__ feat_row, const int* __restrict__ time_idx, const int* __restrict__ scene_of_row,
                                   const float* __restrict__ gauss_B, const float* __restrict__ time_table,
                                   const float* __restrict__ bg_feat, const float* __restrict__ bg_pos,
                                   float* __restrict__ queries, float* __restrict__ qpos) {
@@ -131,7 +131,7 @@ __global__ void query_init_kernel(const float* __restrict__ feats, const float* 
   }
   float s, co;
   sincosf(arg, &s, &co);
-  queries[(size_t)row * QD + c] = feats[(size_t)src * QD + c];
+  queries[(size_t)row * QD + c] = feats[(size_t)(feat_row ? feat_row[row] : src) * QD + c];
   qpos[(size_t)row * QD + c] = (c < 64 ? s : co) + time_table[(size_t)time_idx[row] * QD + c];
 }
 
@@ -417,13 +417,13 @@ extern "C" {
 int64_t ag3d_query_blob_floats(void) { return Q_BLOB_FLOATS; }
 
 int ag3d_query_init(const float* feats, const float* xyz, const float* range, const int32_t* src_row,
-                    const int32_t* time_idx, const int32_t* scene_of_row, int32_t n_rows, const float* gauss_B,
+                    const int32_t* feat_row, const int32_t* time_idx, const int32_t* scene_of_row, int32_t n_rows, const float* gauss_B,
                     const float* time_table, const float* bg_feat, const float* bg_pos, float* queries, float* qpos,
                     ag3d_stream_t stream) {
   AG3D_CHECK_ARG(n_rows > 0, "no query rows");
   AG3D_CHECK_ARG(feats && xyz && range && src_row && time_idx && scene_of_row && gauss_B && time_table && bg_feat &&
                      bg_pos && queries && qpos, "bad pointers");
-  query_init_kernel<<<n_rows, QD, 0, as_stream(stream)>>>(feats, xyz, range, src_row, time_idx, scene_of_row, gauss_B,
+  query_init_kernel<<<n_rows, QD, 0, as_stream(stream)>>>(feats, xyz, range, src_row, feat_row, time_idx, scene_of_row, gauss_B,
                                                           time_table, bg_feat, bg_pos, queries, qpos);
   AG3D_LAUNCH_CHECK("query_init");
   return AG3D_OK;

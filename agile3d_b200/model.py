@@ -78,10 +78,42 @@ def _time_table(d_model, length):       # models/position_embedding.py:210-226
 
 
 class BackboneFeatures:
-    """Opaque handle for ``pcd_features`` / ``coordinates``: features of all scenes + per-scene row ranges."""
+    """Opaque handle for ``pcd_features`` / ``coordinates``: features of all scenes + per-scene row ranges.
 
-    def __init__(self, F_, offsets, C=None):
-        self.F, self.offsets, self.C = F_, offsets, C
+    The backbone works in an INTERNAL row order (rows of a scene sorted by neighbour pattern, CoordinateMaps._reorder);
+    ``Fp`` holds the rows in that order, ``perm[new] = caller row`` and ``inv[caller row] = new``.  ``F`` is the caller's
+    view (gathered on first use); scenes keep their row ranges in both orders."""
+
+    def __init__(self, F_, offsets, C=None, perm=None, inv=None):
+        self.Fp, self.offsets, self.C, self.perm, self.inv = F_, offsets, C, perm, inv
+        self._F, self._inv_local, self._inv64 = None, None, None
+
+    @property
+    def F(self):
+        if self.inv is None:
+            return self.Fp
+        if self._F is None:
+            self._F = self.Fp.index_select(0, self.inv64)
+        return self._F
+
+    @property
+    def inv64(self):
+        if self._inv64 is None and self.inv is not None:
+            self._inv64 = self.inv.long()
+        return self._inv64
+
+    def rows_internal(self, rows):
+        """caller row indices (device int64 tensor) -> internal rows"""
+        return rows if self.inv is None else self.inv64[rows]
+
+    def to_caller(self, b, t):
+        """rows of scene b in internal order -> caller order (differentiable)"""
+        if self.inv is None:
+            return t
+        if self._inv_local is None:
+            self._inv_local = [self.inv64[self.offsets[i]:self.offsets[i + 1]] - self.offsets[i]
+                               for i in range(len(self.offsets) - 1)]
+        return t.index_select(0, self._inv_local[b])
 
     @property
     def decomposed_features(self):
@@ -89,8 +121,36 @@ class BackboneFeatures:
 
     @property
     def device(self):
-        return self.F.device
+        return self.Fp.device
 
+
+class _AuxMap:
+    """One of the 5 backbone feature maps returned as ``aux``: rows in the backbone's internal order; ``dense()`` decodes
+    the bf16 hi/lo pair rows of the tensor-core eval mode into fp32."""
+
+    def __init__(self, rows, split):
+        self.rows, self.split = rows, split
+        self.shape = rows.shape
+
+    def dense(self):
+        return ops.unpack_split(self.rows) if self.split else self.rows
+
+
+class _PosList:
+    """per-scene positional encodings: ``[b]`` gives the caller's row order (as the reference's list would), the model
+    itself reads ``internal[b]`` (the backbone's row order)."""
+
+    def __init__(self, internal, handle):
+        self.internal, self._h = internal, handle
+
+    def __len__(self):
+        return len(self.internal)
+
+    def __getitem__(self, b):
+        return self._h.to_caller(b, self.internal[b])
+
+    def __iter__(self):
+        return (self[b] for b in range(len(self.internal)))
 
 
 # ================================================================================================ autograd bridges
@@ -295,27 +355,33 @@ class Agile3d(nn.Module):
         raw = raw_coordinates.to(device=x.F.device, dtype=torch.float32).contiguous()
         if raw.shape != (x.F.shape[0], 3):
             raise ValueError("raw_coordinates must be [N,3]")
-        # scene row ranges (scenes are contiguous and ordered: SURVEY.md A.2)
+        # scene row ranges (scenes are contiguous and ordered: SURVEY.md A.2); coordinate maps + the internal row order
         offsets = x.scene_offsets()
         n_scenes = len(offsets) - 1
         with torch.no_grad():
-            pos, rng = ops.fourier_posenc(raw, offsets, self.pos_enc.gauss_B)
+            maps = self.backbone.prepare_maps(x)
+            perm, inv = maps.perm[0], maps.inv[0]
+            raw_i = raw if perm is None else raw.index_select(0, perm.long())          # xyz in the internal row order
+            pos, rng = ops.fourier_posenc(raw_i, offsets, self.pos_enc.gauss_B)
         if self.training:
             # batch-statistics BatchNorm + recorded activations; one autograd node for backbone + head (engine.py:53)
             named = [(n, p) for n, p in self.named_parameters()
                      if n.startswith("backbone.") or n.startswith("lin_squeeze_head.")]
             holder = {}
             pcd = _BackboneFn.apply(self, x, tuple(n for n, _ in named), holder, *[p for _, p in named])
-            pcd_features = BackboneFeatures(pcd, offsets, x.C)
-            coordinates = BackboneFeatures(raw, offsets, x.C)
-            coordinates.range = rng
-            pos_encodings_pcd = [None, None, None, None, [[pos[offsets[b]:offsets[b + 1]] for b in range(n_scenes)]]]
-            return pcd_features, holder["fmaps"], coordinates, pos_encodings_pcd
-        with torch.no_grad():
-            return self._forward_backbone_eval(x, raw, offsets, pos, rng)
+            fmaps = holder["fmaps"]
+        else:
+            with torch.no_grad():
+                pcd, fmaps = self._forward_backbone_eval(x)
+        pcd_features = BackboneFeatures(pcd, offsets, x.C, perm, inv)
+        coordinates = BackboneFeatures(raw, offsets, x.C)
+        coordinates.range = rng
+        # only the full-resolution level is ever read (hlevels=[4], agile3d.py:278); keep the reference's indexing
+        plist = _PosList([pos[offsets[b]:offsets[b + 1]] for b in range(n_scenes)], pcd_features)
+        pos_encodings_pcd = [None, None, None, None, [plist]]
+        return pcd_features, fmaps, coordinates, pos_encodings_pcd
 
-    def _forward_backbone_eval(self, x, raw, offsets, pos, rng):
-        n_scenes = len(offsets) - 1
+    def _forward_backbone_eval(self, x):
         feats, fmaps, maps = self.backbone(x)
         pcd = torch.empty((feats.shape[0], self.hidden_dim), dtype=torch.float32, device=feats.device)
         head = self.lin_squeeze_head
@@ -323,15 +389,12 @@ class Agile3d(nn.Module):
         if getattr(self, "_head_tc", (None, None))[0] != hkey:
             wtc = ops.prepare_tc_weight(head.kernel) if self.backbone.algo != ops.ALGO_SIMT else None
             self._head_tc = (hkey, wtc)
+        split = self.backbone.split_rows and self.backbone.algo != ops.ALGO_SIMT
         ops.spconv_fwd(feats, None, head.kernel, pcd, None, head.bias.detach().reshape(-1).contiguous(), relu=False,
-                       algo=self.backbone.algo, weight_tc=self._head_tc[1],
-                       in_split=self.backbone.split_rows and self.backbone.algo != ops.ALGO_SIMT)
-        pcd_features = BackboneFeatures(pcd, offsets, x.C)
-        coordinates = BackboneFeatures(raw, offsets, x.C)
-        coordinates.range = rng
-        # only the full-resolution level is ever read (hlevels=[4], agile3d.py:278); keep the reference's indexing
-        pos_encodings_pcd = [None, None, None, None, [[pos[offsets[b]:offsets[b + 1]] for b in range(n_scenes)]]]
-        return pcd_features, fmaps, coordinates, pos_encodings_pcd
+                       algo=self.backbone.algo, weight_tc=self._head_tc[1], in_split=split)
+        # the 5 feature maps (`aux`) are opaque to every caller of the reference; in split mode they hold bf16 hi/lo pair
+        # rows in the internal row order - hand out objects that say so instead of tensors that look like features
+        return pcd, [_AuxMap(f, split) for f in fmaps]
 
     # ------------------------------------------------------------------------------------------ decoder glue
     # The O(Nq) query-side algebra is batched over all scenes of a batch that have the same number of queries
@@ -397,7 +460,7 @@ class Agile3d(nn.Module):
         """Same kernels with or without autograd: in train mode (engine.py:119-121) the two voxel-streaming kernels run as
         autograd nodes (their backward is ag3d_c2s_attn_bwd / ag3d_s2c_mask_bwd) and the voxel features of every
         layer are kept; otherwise layers > 0 update the features in place."""
-        grad = torch.is_grad_enabled() and (self.training or pcd_features.F.requires_grad)
+        grad = torch.is_grad_enabled() and (self.training or pcd_features.Fp.requires_grad)
         if not grad:
             with torch.no_grad():
                 if self.fused_queries:
@@ -456,7 +519,7 @@ class Agile3d(nn.Module):
 
     def _forward_mask_fused(self, pcd_features, coordinates, pos_encodings_pcd, click_idx, click_time_idx):
         H = self.num_heads
-        dev = pcd_features.F.device
+        dev = pcd_features.Fp.device
         offsets = pcd_features.offsets
         n_scenes = len(offsets) - 1
         tt = self.time_encode.to(dev) if self.time_encode.device != dev else self.time_encode
@@ -478,7 +541,7 @@ class Agile3d(nn.Module):
             meta.append((K, src, tix, q_obj))
             groups.setdefault(n_fg + nbg + n_bgc, []).append(b)
         results = [None] * n_scenes
-        pos_list = pos_encodings_pcd[self.hlevels[0]][0]
+        pos_list = pos_encodings_pcd[self.hlevels[0]][0].internal
         for nq, members in groups.items():
             B = len(members)
             if nq > ops.S2C_MAX_QUERIES:
@@ -487,9 +550,13 @@ class Agile3d(nn.Module):
                                      + [b for b in members for _ in range(nq)] + [v for b in members for v in meta[b][3]], dev)
             src_row, time_idx, scene_of_row, q_obj = ints[:B * nq], ints[B * nq:2 * B * nq], ints[2 * B * nq:3 * B * nq], \
                 ints[3 * B * nq:].view(B, nq)
-            queries, qpos = ops.query_init(pcd_features.F, coordinates.F, coordinates.range, src_row, time_idx, scene_of_row,
-                                           self.pos_enc.gauss_B, tt, self.bg_query_feat.weight, self.bg_query_pos.weight)
-            srcs = [pcd_features.F[offsets[b]:offsets[b + 1]] for b in members]
+            # clicked voxels: xyz is read in the caller's order, the features in the backbone's internal order
+            feat_row = src_row if pcd_features.inv is None else \
+                torch.where(src_row >= 0, pcd_features.inv[src_row.clamp(min=0).long()], src_row)
+            queries, qpos = ops.query_init(pcd_features.Fp, coordinates.F, coordinates.range, src_row, time_idx, scene_of_row,
+                                           self.pos_enc.gauss_B, tt, self.bg_query_feat.weight, self.bg_query_pos.weight,
+                                           feat_row=feat_row if pcd_features.inv is not None else None)
+            srcs = [pcd_features.Fp[offsets[b]:offsets[b + 1]] for b in members]
             labels, counts = [None] * B, [None] * B
             outs = [[] for _ in members]
             ctx = torch.empty((B, H * nq, self.hidden_dim), dtype=torch.float32, device=dev)
@@ -509,7 +576,7 @@ class Agile3d(nn.Module):
                         x_out=None if layer == 0 else srcs[i])      # never overwrite the caller's backbone features
                     outs[i].append(logits)
             for i, b in enumerate(members):
-                results[b] = outs[i]
+                results[b] = [pcd_features.to_caller(b, lg) for lg in outs[i]]      # logits back in the caller's row order
         per_layer = [list(p) for p in zip(*results)]
         out = {"pred_masks": per_layer[-1], "backbone_features": pcd_features}
         if self.aux:
@@ -518,7 +585,7 @@ class Agile3d(nn.Module):
 
     def _forward_mask(self, pcd_features, coordinates, pos_encodings_pcd, click_idx, click_time_idx, grad):
         H, d = self.num_heads, self.hidden_dim
-        dev = pcd_features.F.device
+        dev = pcd_features.Fp.device
         offsets = pcd_features.offsets
         n_scenes = len(offsets) - 1
         _WGRAD_TC[0] = self.backbone.algo != ops.ALGO_SIMT
@@ -540,7 +607,7 @@ class Agile3d(nn.Module):
             meta.append((K, n_fg, n_bgc, rows, times, q_obj))
             groups.setdefault((n_fg, n_bgc), []).append(b)
         results = [None] * n_scenes
-        pos_list = pos_encodings_pcd[self.hlevels[0]][0]
+        pos_list = pos_encodings_pcd[self.hlevels[0]][0].internal
         for (n_fg, n_bgc), members in groups.items():
             B, nq = len(members), n_fg + self.num_bg_queries + n_bgc
             n_click = n_fg + n_bgc
@@ -548,13 +615,13 @@ class Agile3d(nn.Module):
             tix = torch.tensor([t for b in members for t in meta[b][4]], dtype=torch.long, device=dev)
             q_obj = torch.tensor([meta[b][5] for b in members], dtype=torch.int32, device=dev)          # [B, nq]
             rng = coordinates.range[torch.tensor(members, device=dev)].repeat_interleave(n_click, dim=0)  # [B*n_click, 6]
-            click_feat = pcd_features.F[grow].view(B, n_click, d)
+            click_feat = pcd_features.Fp[pcd_features.rows_internal(grow)].view(B, n_click, d)
             click_pos = (self._click_pos(coordinates.F[grow], rng[:, :3], rng[:, 3:]) + tt[tix]).view(B, n_click, d)
             bgq = self.bg_query_feat.weight.unsqueeze(0).expand(B, -1, -1)
             bgp = self.bg_query_pos.weight.unsqueeze(0).expand(B, -1, -1)
             queries = torch.cat([click_feat[:, :n_fg], bgq, click_feat[:, n_fg:]], 1)                  # [B, nq, d]
             qpos = torch.cat([click_pos[:, :n_fg], bgp, click_pos[:, n_fg:]], 1)
-            srcs = [pcd_features.F[offsets[b]:offsets[b + 1]] for b in members]
+            srcs = [pcd_features.Fp[offsets[b]:offsets[b + 1]] for b in members]
             labels, counts = [None] * B, [None] * B
             outs = [[] for _ in members]
             ctx = torch.empty((B, H * nq, d), dtype=torch.float32, device=dev)
@@ -589,7 +656,7 @@ class Agile3d(nn.Module):
                         x_out=None if layer == 0 else srcs[i])      # never overwrite the caller's backbone features
                     outs[i].append(logits)
             for i, b in enumerate(members):
-                results[b] = outs[i]
+                results[b] = [pcd_features.to_caller(b, lg) for lg in outs[i]]      # logits back in the caller's row order
         per_layer = [list(p) for p in zip(*results)]
         out = {"pred_masks": per_layer[-1], "backbone_features": pcd_features}
         if self.aux:

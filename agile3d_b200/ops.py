@@ -189,6 +189,30 @@ def build_levels(coords, n_levels=4, want_offsets=False):
     return levels, tables, [cap] * (1 + n_levels), parents, (host[0], host[1]), offsets
 
 
+def row_order(nbr, coords):
+    """Internal row order of a level: rows sorted scene by scene by their neighbour pattern -> (perm [new] = old row,
+    inv [old] = new row), int32 (csrc/coords.cu: ag3d_row_order)."""
+    _need_cuda(nbr, coords)
+    K, n = nbr.shape
+    perm = torch.empty(n, dtype=torch.int32, device=nbr.device)
+    inv = torch.empty(n, dtype=torch.int32, device=nbr.device)
+    wsb = lib().ag3d_row_order_workspace_bytes(n)
+    ws = _workspace("row_order", nbr.device, wsb)
+    with _Timed("maps", 4 * K * n + 16 * n + 8 * n):
+        check(lib().ag3d_row_order(_p(nbr), K, n, _p(coords), _p(perm), _p(inv), _p(ws), ws.numel(), _stream()), "ag3d_row_order")
+    return perm, inv
+
+
+def permute_map(nbr, perm_out=None, inv_in=None):
+    """out[k][i] = inv_in[nbr[k][perm_out[i]]] (-1 stays; None = identity)."""
+    _need_cuda(nbr)
+    K, n = nbr.shape
+    out = torch.empty_like(nbr)
+    with _Timed("maps", 8 * K * n):
+        check(lib().ag3d_permute_map(_p(nbr), K, n, _p(perm_out), _p(inv_in), _p(out), _stream()), "ag3d_permute_map")
+    return out
+
+
 def kernel_map(out_coords, in_table, cap, ksize, in_tensor_stride, dilation=1, count_pairs=False):
     """-> nbr int32 [K, N_out] (and pair counts int32 [K] if asked)."""
     _need_cuda(out_coords, in_table)
@@ -437,13 +461,14 @@ def query_blob_floats():
     return int(lib().ag3d_query_blob_floats())
 
 
-def query_init(feats, xyz, rng, src_row, time_idx, scene_of_row, gauss_B, time_table, bg_feat, bg_pos):
-    """-> (queries, qpos) f32 [rows, 128]; src_row int32 [rows] (>= 0: clicked voxel row, -(k+1): learned bg query k)."""
+def query_init(feats, xyz, rng, src_row, time_idx, scene_of_row, gauss_B, time_table, bg_feat, bg_pos, feat_row=None):
+    """-> (queries, qpos) f32 [rows, 128]; src_row int32 [rows] (>= 0: clicked voxel row of xyz, -(k+1): learned bg query k);
+    feat_row (optional): the clicked voxels' rows in `feats` when it is stored in another row order."""
     _need_cuda(feats, xyz, rng, src_row)
     n = src_row.shape[0]
     q = torch.empty((n, 128), dtype=torch.float32, device=feats.device)
     qp = torch.empty_like(q)
-    check(lib().ag3d_query_init(_p(feats), _p(xyz), _p(rng), _p(src_row), _p(time_idx), _p(scene_of_row), n, _p(gauss_B),
+    check(lib().ag3d_query_init(_p(feats), _p(xyz), _p(rng), _p(src_row), _p(feat_row), _p(time_idx), _p(scene_of_row), n, _p(gauss_B),
                                 _p(time_table), _p(bg_feat), _p(bg_pos), _p(q), _p(qp), _stream()), "ag3d_query_init")
     return q, qp
 

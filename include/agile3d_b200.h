@@ -82,6 +82,15 @@ int ag3d_downsample(const int32_t* coords, int64_t n, int32_t new_stride, void* 
                     int32_t* parent, int32_t* out_coords, int32_t* out_n, void* ws, size_t ws_bytes,
                     ag3d_stream_t stream);
 
+/* Internal row order of a coordinate level (no counterpart in the reference: MinkowskiEngine's row order is
+ * unspecified).  perm[new] = old row, inv[old] = new row; rows are sorted scene by scene (coords[:,0]) by
+ * the 27-bit pattern of their existing 3x3x3 neighbours (nbr [K, n]), stably.  ag3d_permute_map rewrites a neighbour table
+ * into such an order: out[k][i] = inv_in[nbr[k][perm_out[i]]] (-1 stays; NULL = identity).                      */
+size_t ag3d_row_order_workspace_bytes(int64_t n);
+int ag3d_row_order(const int32_t* nbr, int32_t K, int64_t n, const int32_t* coords, int32_t* perm, int32_t* inv, void* ws,
+                   size_t ws_bytes, ag3d_stream_t stream);
+int ag3d_permute_map(const int32_t* nbr, int32_t K, int64_t n_out, const int32_t* perm_out, const int32_t* inv_in,
+                     int32_t* out, ag3d_stream_t stream);
 /* ag3d_downsample with the input row count on the DEVICE (n_dev; n_max bounds it and sizes grids, table and
  * workspace): lets the four coordinate levels of the U-Net be built back to back with ONE host read-back of all
  * counts instead of a synchronisation per level.                                                            */
@@ -182,7 +191,8 @@ int ag3d_first_rows(const int32_t* parent, int64_t n, int64_t m, int64_t* unique
  * a click round (models/agile3d.py:202-264).  All matrices [n_scenes, nq, 128] fp32 row-major; `blob` is the
  * per-layer weight blob of ag3d_query_blob_floats() floats (layout: csrc/query_ops.cu, built by
  * agile3d_b200/model.py::_layer_blob from the state_dict); nq <= 256.
- *   ag3d_query_init:     row r of (queries, qpos): src_row[r] >= 0 -> feats[src_row[r]] and fourier(xyz[src_row[r]];
+ *   ag3d_query_init:     row r of (queries, qpos): src_row[r] >= 0 -> feats[feat_row[r]] (feat_row == NULL: src_row; the
+ *                        features may live in another row order than xyz) and fourier(xyz[src_row[r]];
  *                        range of scene scene_of_row[r]) + time_table[time_idx[r]];  src_row[r] = -(k+1) -> learned
  *                        background query k (bg_feat[k], bg_pos[k]).
  *   ag3d_query_fold_c2s: qfold[(h,q),:] = Wk_h^T ((Wq_h (Q+qpos) + bq_h) / 4)            [n_scenes, 8 nq, 128]
@@ -191,7 +201,7 @@ int ag3d_first_rows(const int32_t* parent, int64_t n, int64_t m, int64_t* unique
  *                        A, c, U = folds for ag3d_s2c_mask_fwd;  E = mask_embed_head(decoder_norm(q3))               */
 int64_t ag3d_query_blob_floats(void);
 int ag3d_query_init(const float* feats, const float* xyz, const float* range, const int32_t* src_row,
-                    const int32_t* time_idx, const int32_t* scene_of_row, int32_t n_rows, const float* gauss_B,
+                    const int32_t* feat_row, const int32_t* time_idx, const int32_t* scene_of_row, int32_t n_rows, const float* gauss_B,
                     const float* time_table, const float* bg_feat, const float* bg_pos, float* queries, float* qpos,
                     ag3d_stream_t stream);
 int ag3d_query_fold_c2s(const float* queries, const float* qpos, const float* blob, int32_t n_scenes, int32_t nq,

@@ -51,6 +51,23 @@ def build_levels(coords, n_levels=4, want_offsets=False):
     return levels, tables, [0] * (1 + n_levels), parents, (0, 0), offsets
 
 
+def row_order(nbr, coords):
+    K, n = nbr.shape
+    mask = ((nbr >= 0).long() << torch.arange(K).unsqueeze(1)).sum(0)
+    key = (coords[:, 0].long() << 32) | mask
+    perm = torch.sort(key, stable=True)[1]
+    inv = torch.empty_like(perm)
+    inv[perm] = torch.arange(n)
+    return perm.to(torch.int32), inv.to(torch.int32)
+
+
+def permute_map(nbr, perm_out=None, inv_in=None):
+    out = nbr if perm_out is None else nbr[:, perm_out.long()]
+    if inv_in is not None:
+        out = torch.where(out >= 0, inv_in[out.clamp(min=0).long()], out)
+    return out.contiguous()
+
+
 def kernel_map(out_coords, in_table, cap, ksize, in_tensor_stride, dilation=1, count_pairs=False):
     cm, key = _cm(in_table)
     offs = ME.kernel_offsets(ksize, in_tensor_stride, dilation)
@@ -364,7 +381,7 @@ def _ln(x, w, b, eps):
     return torch.nn.functional.layer_norm(x, (x.shape[-1],), w, b, eps)
 
 
-def query_init(feats, xyz, rng, src_row, time_idx, scene_of_row, gauss_B, time_table, bg_feat, bg_pos):
+def query_init(feats, xyz, rng, src_row, time_idx, scene_of_row, gauss_B, time_table, bg_feat, bg_pos, feat_row=None):
     n = src_row.shape[0]
     q = torch.empty((n, _QD), dtype=feats.dtype)
     qp = torch.empty_like(q)
@@ -375,7 +392,8 @@ def query_init(feats, xyz, rng, src_row, time_idx, scene_of_row, gauss_B, time_t
         else:
             lo, hi = rng[int(scene_of_row[r]), :3], rng[int(scene_of_row[r]), 3:]
             t = (((xyz[s] - lo) / (hi - lo)) * (2 * math.pi)) @ gauss_B
-            q[r], qp[r] = feats[s], torch.cat([t.sin(), t.cos()]) + time_table[int(time_idx[r])]
+            q[r] = feats[s if feat_row is None else int(feat_row[r])]
+            qp[r] = torch.cat([t.sin(), t.cos()]) + time_table[int(time_idx[r])]
     return q, qp
 
 
@@ -417,7 +435,7 @@ def query_update_b(q1, qh, kh, vh, qpos, blob, B, nq, heads=8, ln_eps=1e-5):
 ALL = ["wgrad_tc_supported", "c2s_attn_bwd_tc", "s2c_mask_bwd_tc_any",
        "bn_stats", "bn_apply", "bn_bwd", "col_sum", "spconv_bwd_weight", "stem_bwd_weight", "decoder_bwd_rows",
        "c2s_attn_bwd", "s2c_mask_bwd", "loss_fwd", "loss_bwd", "click_loss_weights", "grad_norm", "adamw_step",
-       "prepare_tc_weight", "hash_build", "downsample", "build_levels", "kernel_map", "kernel_map_transposed", "spconv_fwd", "stem_conv_fwd",
+       "prepare_tc_weight", "hash_build", "downsample", "build_levels", "row_order", "permute_map", "kernel_map", "kernel_map_transposed", "spconv_fwd", "stem_conv_fwd",
        "fourier_posenc", "c2s_attn_fwd", "s2c_mask_fwd", "query_blob_floats", "query_init", "query_fold_c2s",
        "query_update_a", "query_update_b"]
 

@@ -67,6 +67,52 @@ def test_maps_bit_exact(n, extent, batch, neg):
         assert torch.equal(maps.up[lvl].cpu(), ref_t), f"transposed map level {lvl}"
 
 
+@pytest.mark.parametrize("n,extent,batch", [(20000, 64, 2), (3000, 40, 3)])
+def test_internal_row_order_is_a_relabelling(n, extent, batch):
+    """CoordinateMaps(reorder=True): the permutation equals the stable (scene, neighbour pattern) sort of the contract
+    emulation, and every neighbour table is the canonical one rewritten into the new numbering - which is how kernel-map
+    parity is stated once rows are re-ordered internally (compare after un-permuting)."""
+    from agile3d_b200.backbone import CoordinateMaps
+    coords = torch.from_numpy(_random_cloud(n, extent, seed=n + 1, batch=batch)).to(DEV)
+    ref = CoordinateMaps(coords)
+    got = CoordinateMaps(coords, reorder=True)
+    for l in range(5):
+        if got.perm[l] is None:
+            assert l not in CoordinateMaps.REORDER_LEVELS or ref.sizes[l] < 256
+            assert torch.equal(got.coords[l], ref.coords[l])
+            continue
+        perm_ref, inv_ref = emulate.row_order(ref.k3[l].cpu(), ref.coords[l].cpu())
+        assert torch.equal(got.perm[l].cpu(), perm_ref) and torch.equal(got.inv[l].cpu(), inv_ref)
+        assert torch.equal(got.coords[l], ref.coords[l][got.perm[l].long()])
+        b = got.coords[l][:, 0]
+        assert bool((b[1:] >= b[:-1]).all())                                   # scenes stay contiguous and ordered
+    ident = lambda m: torch.arange(m, dtype=torch.int32, device=DEV)
+    P = [got.perm[l] if got.perm[l] is not None else ident(ref.sizes[l]) for l in range(5)]
+    I = [got.inv[l] if got.inv[l] is not None else ident(ref.sizes[l]) for l in range(5)]
+    relabel = lambda nbr, p_out, i_in: torch.where(nbr[:, p_out.long()] >= 0, i_in[nbr[:, p_out.long()].clamp(min=0).long()],
+                                                   nbr[:, p_out.long()])
+    for l in range(5):
+        assert torch.equal(got.k3[l], relabel(ref.k3[l], P[l], I[l])), f"k3 level {l}"
+    for l in range(4):
+        assert torch.equal(got.down[l], relabel(ref.down[l], P[l + 1], I[l])), f"down {l}"
+        assert torch.equal(got.up[l], relabel(ref.up[l], P[l], I[l + 1])), f"up {l}"
+
+
+def test_row_order_changes_nothing_for_the_caller():
+    """same scene with and without the internal row order: features, encodings and logits in the caller's order agree to
+    fp32 reduction-order noise (the order only changes which rows share a tile)"""
+    g = load_golden("g3000_k3")
+    m = _gpu_model(g["wseed"])
+    h1, l1 = _run_gpu(m, g["coords"], g["feats"], g["raw_coords"], [g["clicks"]], [g["times"]])
+    m.backbone.reorder_rows = False
+    h0, l0 = _run_gpu(m, g["coords"], g["feats"], g["raw_coords"], [g["clicks"]], [g["times"]])
+    assert h1[0].perm is not None and h0[0].perm is None
+    assert rel_err(h1[0].F.cpu().numpy(), h0[0].F.cpu().numpy()) < 2e-5
+    assert torch.equal(h1[3][4][0][0], h0[3][4][0][0])
+    for l in range(3):
+        assert rel_err(l1[l][0].cpu().numpy(), l0[l][0].cpu().numpy()) < 1e-4
+
+
 def test_kernel_map_5x5x5_and_dilation():
     from agile3d_b200 import ops
     coords = torch.from_numpy(_random_cloud(4000, 30, seed=11))
