@@ -517,24 +517,19 @@ bool spconv_pk_supported(int cin, int cout, int K) {
          K <= 32;
 }
 
-// Where AUTO takes the packed kernel.  Measured on B200 (profiles/r02_pk_vs_dense_150k.txt, 8 x 150k voxels): both
-// kernels are bound by shared-memory bandwidth, not by the tensor pipe - a [128 x 32ch] stage moves ~70 KB through shared
-// memory (TMA writes 28 KB, the six bf16x3 MMAs read 42 KB; N = 96 MMAs run at 56 cycles = 125 B/cycle of operand reads,
-// tools/probes/mma_probe.cu) - so packing pays where it removes the most stages per useful pair: the stride-2 /
-// transposed maps (one present offset in eight: 1.15-1.33x) and the 32-channel layers (1.3x); on the 96/128-channel
-// 3x3x3 layers the dense kernel's two co-resident CTAs still win (0.7-0.85x).  AG3D_PK_MIN_ROWS / AG3D_PK_ALL override
-// for experiments.
+// AUTO never takes the packed kernel in this version; AG3D_ALGO_TC_PACKED (or AG3D_PK_ALL=1, experiments) selects it.
+// Measured on B200 (profiles/r02_pk_vs_dense_150k.txt, 8 x 150k voxels; profiles/r02_pk_role_waits.txt): both kernels are
+// bound by shared-memory bandwidth, not by the tensor pipe - a [128 x 32ch] stage moves ~70 KB through shared memory (TMA
+// writes 28 KB, the six bf16x3 MMAs read 42 KB; N = 96 MMAs run at 56 cycles = 125 B/cycle of operand reads,
+// tools/probes/mma_probe.cu) and the single MMA-issuing warp of the one resident CTA is busy ~930 cycles per stage.
+// Packing removes 1.8x of the stages, yet on the 96/128-channel 3x3x3 layers the dense kernel's two co-resident CTAs
+// still win (packed 0.7-0.85x); it wins 1.15-1.33x on the stride-2 / transposed maps and the 32-channel layers at
+// >= 1 M rows and loses below ~300 k rows (per-CTA prologue, 4-7 super tiles per CTA).
 bool spconv_pk_preferred(long long n_out, int K, int cin, int cout) {
-  static long long min_rows = -1;
   static int all = -1;
-  if (min_rows < 0) {
-    const char* e = getenv("AG3D_PK_MIN_ROWS");
-    min_rows = e ? atoll(e) : (long long)PK_R * sm_count() * 2;
-    const char* a = getenv("AG3D_PK_ALL");
-    all = a ? atoi(a) : 0;
-  }
-  if (n_out < min_rows) return false;
-  return all || K == 8 || (cin == 32 && cout == 32);
+  if (all < 0) { const char* a = getenv("AG3D_PK_ALL"); all = a ? atoi(a) : 0; }
+  (void)K; (void)cin; (void)cout;
+  return all && n_out >= (long long)PK_R * sm_count() * 2;
 }
 
 int spconv_pk_launch(const float* in, long long n_in, int in_ld, int cin, const int* nbr, int K, long long n_out,

@@ -465,7 +465,8 @@ def run_train(args, rank, world, local_rank):
     l0 = ops.kernel_launches()
     ms = timed(step_resident, args.steps)
     launches = ops.kernel_launches() - l0
-    step_e2e(0)
+    for i in range(n_pool):                      # one untimed pass per pool entry (allocator warm-up of the staging copies)
+        step_e2e(i)
     ms_e2e = timed(step_e2e, args.steps)
     clocks = sampler.stop() if sampler else None
     # per-family pass: every rank runs the step (it contains the gradient all-reduce), rank 0 records it

@@ -75,10 +75,14 @@ def test_internal_row_order_is_a_relabelling(n, extent, batch):
     from agile3d_b200.backbone import CoordinateMaps
     coords = torch.from_numpy(_random_cloud(n, extent, seed=n + 1, batch=batch)).to(DEV)
     ref = CoordinateMaps(coords)
-    got = CoordinateMaps(coords, reorder=True)
+    CoordinateMaps.REORDER_LEVELS = (0, 1, 2)          # exercise the coarse levels too (the model re-orders level 0 only)
+    try:
+        got = CoordinateMaps(coords, reorder=True)
+    finally:
+        CoordinateMaps.REORDER_LEVELS = (0,)
     for l in range(5):
         if got.perm[l] is None:
-            assert l not in CoordinateMaps.REORDER_LEVELS or ref.sizes[l] < 256
+            assert l not in (0, 1, 2) or ref.sizes[l] < 256
             assert torch.equal(got.coords[l], ref.coords[l])
             continue
         perm_ref, inv_ref = emulate.row_order(ref.k3[l].cpu(), ref.coords[l].cpu())

@@ -502,6 +502,7 @@ def test_backbone_backward_block_by_block_fp32():
     Res16UNet34C._block_train_bwd = patched
     try:
         m = _gpu_train_model(7, 1)
+        m.backbone.reorder_rows = False          # this test reads per-block tensors of the backbone: keep the caller's row order
         xg = agile3d_b200.SparseTensor(coordinates=torch.as_tensor(coords), features=torch.as_tensor(feats), device=DEV)
         pcd, *_ = m.forward_backbone(xg, torch.as_tensor(raw).to(DEV))
         (pcd.F * R.float().to(DEV)).sum().backward()

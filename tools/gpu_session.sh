@@ -2,15 +2,20 @@
 # Current GPU session (overwritten per call; results land in gpurun_out/ and the kept ones are copied to profiles/).
 cd "$GRAFT_REPO_ROOT" || exit 1
 mkdir -p gpurun_out
-timeout 1800 python -m pytest tests -x -q -m gpu > gpurun_out/s13_pytest_gpu.log 2>&1
-timeout 900 python bench.py --steps 8 --no-parity > gpurun_out/s13_bench_forward_b8.json 2> gpurun_out/s13_b8.err
-timeout 600 python tools/layer_times.py > gpurun_out/s13_layer_times.txt 2>&1
-tail -n 8 gpurun_out/s13_pytest_gpu.log
-python - <<PY
+timeout 1800 python -m pytest tests -x -q -m gpu > gpurun_out/s14_pytest_gpu.log 2>&1
+tail -n 4 gpurun_out/s14_pytest_gpu.log
+timeout 900 python bench.py --steps 8 --no-parity > gpurun_out/s14_bench_n1.json 2> gpurun_out/s14_n1.err
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 8 --no-parity > gpurun_out/s14_bench_n2.json 2> gpurun_out/s14_n2.err
+timeout 900 python bench.py --steps 5 --workload train --batch 4 > gpurun_out/s14_train_n1.json 2> gpurun_out/s14_train_n1.err
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus 2 --steps 5 --workload train --batch 4 > gpurun_out/s14_train_n2_overlap.json 2> gpurun_out/s14_train_n2a.err
+AG3D_NO_OVERLAP=1 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29519 bench.py --gpus 2 --steps 5 --workload train --batch 4 > gpurun_out/s14_train_n2_after.json 2> gpurun_out/s14_train_n2b.err
+for f in bench_n1 bench_n2 train_n1 train_n2_overlap train_n2_after; do python - <<PY
 import json
-d = json.load(open("gpurun_out/s13_bench_forward_b8.json"))
-print({k: d[k] for k in ("value", "ms_per_step", "gpu_launches")}, d["e2e"]["value"])
-for k, v in d["roofline"]["families"].items():
-    print("   ", k, v.get("ms_per_step"), v.get("frac_of_hbm_peak"), v.get("binding"), v.get("frac_of_binding_bound"))
+try:
+    d = json.load(open("gpurun_out/s14_$f.json"))
+    print("$f", {k: d[k] for k in ("value", "ms_per_step", "n_gpus")}, "e2e", d["e2e"]["value"], d["config"].get("gradient_exchange"))
+except Exception as e:
+    print("$f no json:", e)
 PY
-tail -n 4 gpurun_out/s13_b8.err; grep -E "spconv|^\{" gpurun_out/s13_layer_times.txt | tail -70
+done
+tail -n 3 gpurun_out/s14_*.err | tail -n 30
