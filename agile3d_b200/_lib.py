@@ -43,6 +43,9 @@ SIGNATURES = {
     "ag3d_spconv_fwd_rows": (_i32, [_vp, _i64, _i32, _i32, _vp, _i32, _i64, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _i32,
                                     _i32, _i32, _vp, _sz, _vp]),
     "ag3d_stem_conv_fwd": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
+    "ag3d_gather_rows": (_i32, [_vp, _i32, _vp, _i64, _vp, _vp]),
+    "ag3d_brick_rows": (_i32, [_vp, _vp, _vp, _i64, _i64, _vp, _vp]),
+    "ag3d_stem_conv_fwd_bricks": (_i32, [_vp, _vp, _i64, _vp, _i64, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
     "ag3d_posenc_workspace_bytes": (_sz, [_i32]),
     "ag3d_fourier_posenc": (_i32, [_vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _sz, _vp]),
     "ag3d_c2s_workspace_bytes": (_sz, [_i32, _i32]),
@@ -78,6 +81,7 @@ SIGNATURES = {
     "ag3d_spconv_bwd_weight_tc": (_i32, [_vp, _i64, _i32, _i32, _vp, _i32, _i64, _vp, _i32, _i32, _vp, _i32, _vp, _sz, _vp]),
     "ag3d_stem_bwd_weight_workspace_bytes": (_sz, [_i32]),
     "ag3d_stem_bwd_weight": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, _vp, _i32, _vp, _i32, _vp, _sz, _vp]),
+    "ag3d_stem_bwd_weight_bricks": (_i32, [_vp, _vp, _i64, _vp, _i64, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _sz, _vp]),
     "ag3d_decoder_bwd_rows": (_i32, [_i32, _i32]),
     "ag3d_c2s_attn_bwd": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
     "ag3d_c2s_bwd_pointwise": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
@@ -118,7 +122,7 @@ def lib():
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(handle, name)          # AttributeError if the symbol is not exported
             fn.restype, fn.argtypes = res, args
-        if handle.ag3d_abi_version() != 6:
+        if handle.ag3d_abi_version() != 7:
             raise Ag3dError("libagile3d_b200.so ABI version mismatch; rebuild")
         _lib = handle
     return _lib

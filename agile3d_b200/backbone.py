@@ -56,6 +56,10 @@ class CoordinateMaps:
             self.up.append(ops.kernel_map_transposed(self.coords[lvl], self.parents[lvl], 1 << lvl))
             if count_pairs:
                 self.pair_counts[("up", lvl)] = self.sizes[lvl]
+        # bricks: full-resolution rows of the 4x4x4 cells under every tensor-stride-4 voxel (level 2); the stem finds its
+        # 5x5x5 neighbours through them (8 probes of the level-2 table instead of 125 of the level-0 table)
+        self.bricks = (self.tables[2], self.caps[2], ops.brick_rows(self.coords[0], self.parents[0], self.parents[1],
+                                                                    self.sizes[2]))
         self.perm, self.inv = [None] * 5, [None] * 5
         if reorder:
             self._reorder()
@@ -72,7 +76,7 @@ class CoordinateMaps:
         for l in range(5):
             if self.perm[l] is not None:
                 self.k3[l] = ops.permute_map(self.k3[l], self.perm[l], self.inv[l])
-                self.coords[l] = self.coords[l][self.perm[l].long()].contiguous()
+                self.coords[l] = ops.gather_rows(self.coords[l], self.perm[l])
         for l in range(4):
             if self.perm[l] is not None or self.perm[l + 1] is not None:
                 self.down[l] = ops.permute_map(self.down[l], self.perm[l + 1], self.inv[l])      # out: level l+1, in: level l
@@ -259,7 +263,7 @@ class Res16UNet34C(nn.Module):
         s0, b0 = fold["bn0"]
         ops.stem_conv_fwd(maps.coords[0], st.F, maps.tables[0], maps.caps[0], self.conv1_kernel_size,
                           self.conv0p1s1.kernel, cat[0][:, up_c[0]:], s0, b0, relu=True,
-                          out_split=self.split_rows and self.algo != ops.ALGO_SIMT)
+                          out_split=self.split_rows and self.algo != ops.ALGO_SIMT, bricks=maps.bricks)
         y = cat[0][:, up_c[0]:]
         for i, tag in enumerate(_ENC):                                  # encoder
             conv = getattr(self, f"conv{tag}s2")
@@ -434,7 +438,7 @@ class Res16UNet34C(nn.Module):
         bn0 = self.bn0.bn
         z0 = torch.empty((N[0], INIT_DIM), **f32)
         ops.stem_conv_fwd(maps.coords[0], st.F, maps.tables[0], maps.caps[0], self.conv1_kernel_size,
-                          self.conv0p1s1.kernel.detach(), z0, None, None, relu=False)
+                          self.conv0p1s1.kernel.detach(), z0, None, None, relu=False, bricks=maps.bricks)
         mean, invstd = ops.bn_stats(z0, bn0.eps, bn0.momentum, bn0.running_mean, bn0.running_var)
         bn0.num_batches_tracked += 1
         y = cat[0][:, up_c[0]:]
@@ -506,6 +510,7 @@ class Res16UNet34C(nn.Module):
         grads["bn0.bn.weight"], grads["bn0.bn.bias"] = dgamma, dbeta
         self._split_cache = None
         grads["conv0p1s1.kernel"] = ops.stem_bwd_weight(maps.coords[0], stem["feats"], maps.tables[0], maps.caps[0],
-                                                        self.conv1_kernel_size, dp1).view_as(self.conv0p1s1.kernel)
+                                                        self.conv1_kernel_size, dp1,
+                                                        bricks=maps.bricks).view_as(self.conv0p1s1.kernel)
         stage_done()
         return grads

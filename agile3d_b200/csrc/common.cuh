@@ -86,6 +86,36 @@ __device__ __forceinline__ int table_find(const Slot* __restrict__ table, unsign
   }
 }
 
+// ---------------------------------------------------------------------------------------------- bricks
+// A "brick" is the 4x4x4 block of full-resolution cells under one tensor-stride-4 voxel (a level-2 row): brick_rows
+// [n_level2][64] holds the full-resolution row of every cell (bit = x&3 | (y&3)<<2 | (z&3)<<4), -1 = empty.  A window
+// of +-2 cells touches exactly 2x2x2 bricks, so the 125 neighbours of the stem cost 8 probes of the (small, cache
+// resident) level-2 table plus 125 four-byte reads out of eight 256-byte lines instead of 125 random 16-byte probes.
+// Warp-cooperative: lanes 0..7 probe, every lane then resolves its own offsets k = j*32 + lane (j < 4).
+__device__ __forceinline__ void brick_window_find(const int4 c, int lane, int ksize, int K, const Slot* __restrict__ table2,
+                                                  unsigned long long mask2, const int* __restrict__ brick_rows,
+                                                  int (&src)[4]) {
+  const int half = ksize / 2;
+  const int bx0 = (c.y - half) >> 2, by0 = (c.z - half) >> 2, bz0 = (c.w - half) >> 2;   // arithmetic shift = floor
+  int brick = -1;
+  if (lane < 8)
+    brick = table_find(table2, mask2, pack_key(c.x, (bx0 + (lane & 1)) * 4, (by0 + ((lane >> 1) & 1)) * 4,
+                                               (bz0 + (lane >> 2)) * 4));
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int k = j * 32 + lane;
+    int r = k;
+    const int jx = r % ksize; r /= ksize;
+    const int jy = r % ksize; r /= ksize;
+    const int x = c.y + jx - half, y = c.z + jy - half, z = c.w + r - half;
+    const int bi = (((x >> 2) - bx0) & 1) | ((((y >> 2) - by0) & 1) << 1) | ((((z >> 2) - bz0) & 1) << 2);
+    const int bid = __shfl_sync(0xffffffffu, brick, bi);
+    src[j] = -1;
+    if (k < K && bid >= 0 && coord_in_range(c.x, x, y, z))
+      src[j] = __ldg(brick_rows + (long long)bid * 64 + ((x & 3) | ((y & 3) << 2) | ((z & 3) << 4)));
+  }
+}
+
 __device__ __forceinline__ int floor_div(int a, int b) {  // b > 0
   int q = a / b;
   return (a % b != 0 && a < 0) ? q - 1 : q;

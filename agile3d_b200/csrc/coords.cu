@@ -303,6 +303,32 @@ static inline int grid_for(long long n, int threads) {
   return (int)b;
 }
 
+// dst[i] = src[idx[i]] for rows of `row_bytes` bytes (multiple of 4): one thread per 4-byte (or 16-byte) piece, so the
+// writes are coalesced and a row's pieces are read by neighbouring threads
+template <typename T>
+__global__ void gather_rows_kernel(const T* __restrict__ src, int pieces, const int* __restrict__ idx, long long n,
+                                   T* __restrict__ dst) {
+  long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long step = (long long)gridDim.x * blockDim.x, total = n * pieces;
+  for (; t < total; t += step) {
+    const long long i = t / pieces;
+    const int c = (int)(t - i * pieces);
+    dst[t] = __ldg(src + (long long)__ldg(idx + i) * pieces + c);
+  }
+}
+
+// --- bricks (see brick_window_find in common.cuh): full-resolution row of every cell of every tensor-stride-4 voxel
+__global__ void brick_rows_kernel(const int4* __restrict__ coords, const int* __restrict__ parent01,
+                                  const int* __restrict__ parent12, long long n, int* __restrict__ brick_rows) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long step = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += step) {
+    const int4 c = __ldg(coords + i);
+    const int b = __ldg(parent12 + __ldg(parent01 + i));
+    brick_rows[(long long)b * 64 + ((c.y & 3) | ((c.z & 3) << 2) | ((c.w & 3) << 4))] = (int)i;
+  }
+}
+
 }  // namespace ag3d
 
 using namespace ag3d;
@@ -482,6 +508,30 @@ int ag3d_kernel_map_transposed(const int32_t* fine_coords, const int32_t* parent
   kernel_map_transposed_kernel<<<grid_for(n_fine, 256), 256, 0, as_stream(stream)>>>(
       reinterpret_cast<const int4*>(fine_coords), parent, n_fine, fine_stride, nbr);
   AG3D_LAUNCH_CHECK("kernel_map_transposed");
+  return AG3D_OK;
+}
+
+int ag3d_gather_rows(const void* src, int32_t row_bytes, const int32_t* idx, int64_t n, void* dst, ag3d_stream_t stream) {
+  AG3D_CHECK_ARG(src && idx && dst && src != dst && n > 0 && n < INT_MAX && row_bytes > 0 && row_bytes % 4 == 0,
+                 "gather_rows: arguments");
+  if (row_bytes % 16 == 0 && aligned16(src) && aligned16(dst))
+    gather_rows_kernel<int4><<<grid_for(n * (row_bytes / 16), 256), 256, 0, as_stream(stream)>>>(
+        static_cast<const int4*>(src), row_bytes / 16, idx, n, static_cast<int4*>(dst));
+  else
+    gather_rows_kernel<int><<<grid_for(n * (row_bytes / 4), 256), 256, 0, as_stream(stream)>>>(
+        static_cast<const int*>(src), row_bytes / 4, idx, n, static_cast<int*>(dst));
+  AG3D_LAUNCH_CHECK("gather_rows");
+  return AG3D_OK;
+}
+
+int ag3d_brick_rows(const int32_t* coords, const int32_t* parent01, const int32_t* parent12, int64_t n,
+                    int64_t n_bricks, int32_t* brick_rows, ag3d_stream_t stream) {
+  AG3D_CHECK_ARG(n > 0 && n < INT_MAX && n_bricks > 0 && n_bricks < INT_MAX / 64, "row count out of range");
+  AG3D_CHECK_ARG(coords && aligned16(coords) && parent01 && parent12 && brick_rows, "bad pointers");
+  AG3D_CUDA(cudaMemsetAsync(brick_rows, 0xFF, (size_t)n_bricks * 64 * sizeof(int32_t), as_stream(stream)));
+  brick_rows_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<const int4*>(coords), parent01,
+                                                                     parent12, n, brick_rows);
+  AG3D_LAUNCH_CHECK("brick_rows");
   return AG3D_OK;
 }
 

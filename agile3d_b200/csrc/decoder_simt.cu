@@ -202,28 +202,41 @@ c2s_partial_kernel(const float* __restrict__ x, const float* __restrict__ pos, l
 }
 
 // grid heads*nq blocks of 128 threads: log-sum-exp merge of the per-CTA partials
-__global__ void c2s_merge_kernel(const float* __restrict__ part_m, const float* __restrict__ part_l,
-                                 const float* __restrict__ part_acc, int n_cta, int HQP, int nq, int nqg,
-                                 float* __restrict__ ctx, float* __restrict__ lse_out) {
+__global__ void __launch_bounds__(D) c2s_merge_kernel(const float* __restrict__ part_m, const float* __restrict__ part_l,
+                                                      const float* __restrict__ part_acc, int n_cta, int HQP, int nq, int nqg,
+                                                      float* __restrict__ ctx, float* __restrict__ lse_out) {
+  // one CTA per (head, query) row, thread = channel.  The partial maxima / sums of the n_cta partial results are folded
+  // by the whole CTA first (weights in shared memory), so the channel loop is n_cta independent, unrolled loads.
+  __shared__ float w_s[1024];
+  __shared__ float red_s[8];
   const int row = blockIdx.x;             // h*nq + q
   const int h = row / nq, q = row % nq;
   const int g = q / nqg, ql = q % nqg;
   const int nq_here = min(nqg, nq - g * nqg);
   const int r = h * nq_here + ql;
-  const int c = threadIdx.x;
+  const int c = threadIdx.x, warp = c >> 5, lane = c & 31;
+  const long long p0 = (long long)g * n_cta * HQP + r;          // partial i lives at p0 + i * HQP
   float M = NEG_INF;
-  for (int i = 0; i < n_cta; ++i) M = fmaxf(M, part_m[((long long)g * n_cta + i) * HQP + r]);
-  float L = 0.f, a = 0.f;
-  if (M != NEG_INF) {
-    for (int i = 0; i < n_cta; ++i) {
-      const long long p = ((long long)g * n_cta + i) * HQP + r;
-      const float m = part_m[p];
-      if (m == NEG_INF) continue;
-      const float w = __expf(m - M);
-      L += part_l[p] * w;
-      a += part_acc[p * D + c] * w;
-    }
+  for (int i = c; i < n_cta; i += D) M = fmaxf(M, part_m[p0 + (long long)i * HQP]);
+  for (int o = 16; o > 0; o >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));
+  if (lane == 0) red_s[warp] = M;
+  __syncthreads();
+  M = fmaxf(fmaxf(red_s[0], red_s[1]), fmaxf(red_s[2], red_s[3]));
+  float L = 0.f;
+  for (int i = c; i < n_cta; i += D) {
+    const float m = part_m[p0 + (long long)i * HQP];
+    const float w = (m == NEG_INF || M == NEG_INF) ? 0.f : __expf(m - M);
+    w_s[i] = w;
+    L += part_l[p0 + (long long)i * HQP] * w;
   }
+  for (int o = 16; o > 0; o >>= 1) L += __shfl_xor_sync(0xffffffffu, L, o);
+  if (lane == 0) red_s[4 + warp] = L;
+  __syncthreads();
+  L = (red_s[4] + red_s[5]) + (red_s[6] + red_s[7]);
+  float a = 0.f;
+  const float* acc = part_acc + p0 * D + c;
+#pragma unroll 8
+  for (int i = 0; i < n_cta; ++i) a = fmaf(acc[(long long)i * HQP * D], w_s[i], a);
   ctx[(long long)row * D + c] = (L > 0.f) ? a / L : 0.f;
   if (lse_out && c == 0) lse_out[row] = (L > 0.f) ? M + logf(L) : INFINITY;   // +inf: exp(s - lse) = 0 in the backward
 }

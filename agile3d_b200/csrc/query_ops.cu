@@ -73,11 +73,16 @@ __device__ __forceinline__ void gemm_rows(const float* xs, int ldx, const float*
                                           float* acc) {
 #pragma unroll
   for (int r = 0; r < 8; ++r) acc[r] = 0.f;
-#pragma unroll 4
-  for (int i = 0; i < KDIM; ++i) {
-    const float w = __ldg(WT + (size_t)i * ldw + o);
+  // 16 weight loads in flight per thread: the loop is bound by the L2 latency of the (coalesced) weight reads
+#pragma unroll 1
+  for (int i0 = 0; i0 < KDIM; i0 += 16) {
+    float w[16];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) acc[r] = fmaf(xs[(rb + r) * ldx + i], w, acc[r]);
+    for (int u = 0; u < 16; ++u) w[u] = __ldg(WT + (size_t)(i0 + u) * ldw + o);
+#pragma unroll
+    for (int u = 0; u < 16; ++u)
+#pragma unroll
+      for (int r = 0; r < 8; ++r) acc[r] = fmaf(xs[(rb + r) * ldx + i0 + u], w[u], acc[r]);
   }
 }
 

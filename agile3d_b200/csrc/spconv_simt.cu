@@ -96,9 +96,10 @@ spconv_simt_kernel(const float* __restrict__ in, int in_ld, int cin, const int* 
 constexpr int STEM_CIN = 3;
 constexpr int STEM_COUT = 32;
 
+template <bool BRICKS>
 __global__ void __launch_bounds__(256)
 stem_conv_kernel(const int4* __restrict__ coords, const float* __restrict__ feats, long long n,
-                 const Slot* __restrict__ table, unsigned long long mask, int ksize,
+                 const Slot* __restrict__ table, unsigned long long mask, const int* __restrict__ brick_rows, int ksize,
                  const float* __restrict__ weight, const float* __restrict__ scale,
                  const float* __restrict__ shift, float* __restrict__ out, int out_ld, int flags) {
   extern __shared__ float w_s[];  // [K][3][32]
@@ -117,16 +118,20 @@ stem_conv_kernel(const int4* __restrict__ coords, const float* __restrict__ feat
     // ascending offset order through shuffles: no global load sits on the serial accumulation chain.
     int src[4];
     float f0[4], f1[4], f2[4];
+    if constexpr (BRICKS) {     // `table` is the tensor-stride-4 table: 8 probes + reads of the bricks' row lists
+      brick_window_find(c, lane, ksize, K, table, mask, brick_rows, src);
+    } else {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int k = j * 32 + lane;
-      src[j] = -1;
-      if (k < K) {
-        int r = k;
-        const int jx = r % ksize; r /= ksize;
-        const int jy = r % ksize; r /= ksize;
-        const int x = c.y + jx - half, y = c.z + jy - half, z = c.w + r - half;
-        if (coord_in_range(c.x, x, y, z)) src[j] = table_find(table, mask, pack_key(c.x, x, y, z));
+      for (int j = 0; j < 4; ++j) {
+        const int k = j * 32 + lane;
+        src[j] = -1;
+        if (k < K) {
+          int r = k;
+          const int jx = r % ksize; r /= ksize;
+          const int jy = r % ksize; r /= ksize;
+          const int x = c.y + jx - half, y = c.z + jy - half, z = c.w + r - half;
+          if (coord_in_range(c.x, x, y, z)) src[j] = table_find(table, mask, pack_key(c.x, x, y, z));
+        }
       }
     }
 #pragma unroll
@@ -251,9 +256,9 @@ size_t ag3d_spconv_workspace_bytes(int64_t n_out, int32_t K, int32_t cin, int32_
   return spconv_tc_workspace_bytes(n_out, K, cout);
 }
 
-int ag3d_stem_conv_fwd(const int32_t* coords, const float* feats, int64_t n, const void* table, int64_t cap,
-                       int32_t ksize, const float* weight, const float* scale, const float* shift, float* out,
-                       int32_t out_ld, int32_t flags, ag3d_stream_t stream) {
+static int stem_conv_launch(const int32_t* coords, const float* feats, int64_t n, const void* table, int64_t cap,
+                            const int32_t* brick_rows, int32_t ksize, const float* weight, const float* scale,
+                            const float* shift, float* out, int32_t out_ld, int32_t flags, ag3d_stream_t stream) {
   AG3D_CHECK_ARG(n > 0 && n < 2147483647LL, "row count out of range");
   AG3D_CHECK_ARG(ksize == 1 || ksize == 3 || ksize == 5, "stem kernel size must be 1, 3 or 5");
   AG3D_CHECK_ARG(coords && aligned16(coords) && feats && weight && out, "bad pointers");
@@ -263,17 +268,37 @@ int ag3d_stem_conv_fwd(const int32_t* coords, const float* feats, int64_t n, con
   const size_t smem = (size_t)K * STEM_CIN * STEM_COUT * sizeof(float);
   static bool attr_done = false;
   if (!attr_done) {
-    AG3D_CUDA(cudaFuncSetAttribute(stem_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    AG3D_CUDA(cudaFuncSetAttribute(stem_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    AG3D_CUDA(cudaFuncSetAttribute(stem_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     attr_done = true;
   }
   long long blocks = (n + 7) / 8;
   const long long cap_blocks = (long long)sm_count() * 8;
   if (blocks > cap_blocks) blocks = cap_blocks;
-  stem_conv_kernel<<<(unsigned)blocks, 256, smem, as_stream(stream)>>>(
-      reinterpret_cast<const int4*>(coords), feats, n, static_cast<const Slot*>(table),
-      (unsigned long long)(cap - 1), ksize, weight, scale, shift, out, out_ld, flags);
+  if (brick_rows)
+    stem_conv_kernel<true><<<(unsigned)blocks, 256, smem, as_stream(stream)>>>(
+        reinterpret_cast<const int4*>(coords), feats, n, static_cast<const Slot*>(table),
+        (unsigned long long)(cap - 1), brick_rows, ksize, weight, scale, shift, out, out_ld, flags);
+  else
+    stem_conv_kernel<false><<<(unsigned)blocks, 256, smem, as_stream(stream)>>>(
+        reinterpret_cast<const int4*>(coords), feats, n, static_cast<const Slot*>(table),
+        (unsigned long long)(cap - 1), nullptr, ksize, weight, scale, shift, out, out_ld, flags);
   AG3D_LAUNCH_CHECK("stem_conv");
   return AG3D_OK;
+}
+
+int ag3d_stem_conv_fwd(const int32_t* coords, const float* feats, int64_t n, const void* table, int64_t cap,
+                       int32_t ksize, const float* weight, const float* scale, const float* shift, float* out,
+                       int32_t out_ld, int32_t flags, ag3d_stream_t stream) {
+  return stem_conv_launch(coords, feats, n, table, cap, nullptr, ksize, weight, scale, shift, out, out_ld, flags, stream);
+}
+
+int ag3d_stem_conv_fwd_bricks(const int32_t* coords, const float* feats, int64_t n, const void* table2, int64_t cap2,
+                              const int32_t* brick_rows, int32_t ksize, const float* weight, const float* scale,
+                              const float* shift, float* out, int32_t out_ld, int32_t flags, ag3d_stream_t stream) {
+  AG3D_CHECK_ARG(brick_rows && (ksize == 3 || ksize == 5), "brick stem: brick_rows and kernel size 3 or 5");
+  return stem_conv_launch(coords, feats, n, table2, cap2, brick_rows, ksize, weight, scale, shift, out, out_ld, flags,
+                          stream);
 }
 
 }  // extern "C"

@@ -318,9 +318,10 @@ static int tn_gemm_splits(long long rows, int M, int N, int nz, int* tiles_m, in
 
 // ============================================================================================ stem weight gradient
 // dW[k][ci][co] += f[src_k(v)][ci] * dz[v][co]: warp per voxel, lane = output channel, probes as in the forward.
+template <bool BRICKS>
 __global__ void __launch_bounds__(256)
 stem_wgrad_kernel(const int4* __restrict__ coords, const float* __restrict__ feats, long long n,
-                  const Slot* __restrict__ table, unsigned long long mask, int ksize,
+                  const Slot* __restrict__ table, unsigned long long mask, const int* __restrict__ brick_rows, int ksize,
                   const float* __restrict__ dz, int dz_ld, float* __restrict__ part) {
   extern __shared__ float dw_s[];  // [K][3][32]
   const int K = ksize * ksize * ksize;
@@ -337,16 +338,20 @@ stem_wgrad_kernel(const int4* __restrict__ coords, const float* __restrict__ fea
     // stem_conv_kernel): no global load on the dependent chain
     int src[4];
     float f0[4], f1[4], f2[4];
+    if constexpr (BRICKS) {
+      brick_window_find(c, lane, ksize, K, table, mask, brick_rows, src);
+    } else {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int k = j * 32 + lane;
-      src[j] = -1;
-      if (k < K) {
-        int r = k;
-        const int jx = r % ksize; r /= ksize;
-        const int jy = r % ksize; r /= ksize;
-        const int x = c.y + jx - half, y = c.z + jy - half, zz = c.w + r - half;
-        if (coord_in_range(c.x, x, y, zz)) src[j] = table_find(table, mask, pack_key(c.x, x, y, zz));
+      for (int j = 0; j < 4; ++j) {
+        const int k = j * 32 + lane;
+        src[j] = -1;
+        if (k < K) {
+          int r = k;
+          const int jx = r % ksize; r /= ksize;
+          const int jy = r % ksize; r /= ksize;
+          const int x = c.y + jx - half, y = c.z + jy - half, zz = c.w + r - half;
+          if (coord_in_range(c.x, x, y, zz)) src[j] = table_find(table, mask, pack_key(c.x, x, y, zz));
+        }
       }
     }
 #pragma unroll
@@ -651,9 +656,9 @@ size_t ag3d_stem_bwd_weight_workspace_bytes(int32_t ksize) {
   return (size_t)sm_count() * 2 * (size_t)ksize * ksize * ksize * 96 * sizeof(float);
 }
 
-int ag3d_stem_bwd_weight(const int32_t* coords, const float* feats, int64_t n, const void* table, int64_t cap,
-                         int32_t ksize, const float* dz, int32_t dz_ld, float* dweight, int32_t accumulate, void* ws,
-                         size_t ws_bytes, ag3d_stream_t stream) {
+static int stem_wgrad_launch(const int32_t* coords, const float* feats, int64_t n, const void* table, int64_t cap,
+                             const int32_t* brick_rows, int32_t ksize, const float* dz, int32_t dz_ld, float* dweight,
+                             int32_t accumulate, void* ws, size_t ws_bytes, ag3d_stream_t stream) {
   AG3D_CHECK_ARG(n > 0 && n < 2147483647LL, "stem_bwd_weight: row count");
   AG3D_CHECK_ARG(ksize == 1 || ksize == 3 || ksize == 5, "stem kernel size must be 1, 3 or 5");
   AG3D_CHECK_ARG(coords && aligned16(coords) && feats && dz && dweight, "stem_bwd_weight: pointers");
@@ -663,7 +668,8 @@ int ag3d_stem_bwd_weight(const int32_t* coords, const float* feats, int64_t n, c
   const size_t smem = (size_t)K * 96 * sizeof(float);
   static bool attr_done = false;
   if (!attr_done) {
-    AG3D_CUDA(cudaFuncSetAttribute(stem_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    AG3D_CUDA(cudaFuncSetAttribute(stem_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    AG3D_CUDA(cudaFuncSetAttribute(stem_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     attr_done = true;
   }
   cudaStream_t st = as_stream(stream);
@@ -671,12 +677,34 @@ int ag3d_stem_bwd_weight(const int32_t* coords, const float* feats, int64_t n, c
   const long long capb = (long long)sm_count() * 2;
   if (blocks > capb) blocks = capb;
   float* part = static_cast<float*>(ws);
-  stem_wgrad_kernel<<<(unsigned)blocks, 256, smem, st>>>(reinterpret_cast<const int4*>(coords), feats, n,
-                                                         static_cast<const Slot*>(table),
-                                                         (unsigned long long)(cap - 1), ksize, dz, dz_ld, part);
+  if (brick_rows)
+    stem_wgrad_kernel<true><<<(unsigned)blocks, 256, smem, st>>>(reinterpret_cast<const int4*>(coords), feats, n,
+                                                                 static_cast<const Slot*>(table),
+                                                                 (unsigned long long)(cap - 1), brick_rows, ksize, dz,
+                                                                 dz_ld, part);
+  else
+    stem_wgrad_kernel<false><<<(unsigned)blocks, 256, smem, st>>>(reinterpret_cast<const int4*>(coords), feats, n,
+                                                                  static_cast<const Slot*>(table),
+                                                                  (unsigned long long)(cap - 1), nullptr, ksize, dz,
+                                                                  dz_ld, part);
   AG3D_LAUNCH_CHECK("stem_wgrad");
   const long long count = (long long)K * 96;
   return launch_split_reduce(part, (int)blocks, count, count, accumulate, dweight, st);
+}
+
+int ag3d_stem_bwd_weight(const int32_t* coords, const float* feats, int64_t n, const void* table, int64_t cap,
+                         int32_t ksize, const float* dz, int32_t dz_ld, float* dweight, int32_t accumulate, void* ws,
+                         size_t ws_bytes, ag3d_stream_t stream) {
+  return stem_wgrad_launch(coords, feats, n, table, cap, nullptr, ksize, dz, dz_ld, dweight, accumulate, ws, ws_bytes,
+                           stream);
+}
+
+int ag3d_stem_bwd_weight_bricks(const int32_t* coords, const float* feats, int64_t n, const void* table2, int64_t cap2,
+                                const int32_t* brick_rows, int32_t ksize, const float* dz, int32_t dz_ld, float* dweight,
+                                int32_t accumulate, void* ws, size_t ws_bytes, ag3d_stream_t stream) {
+  AG3D_CHECK_ARG(brick_rows && (ksize == 3 || ksize == 5), "brick stem: brick_rows and kernel size 3 or 5");
+  return stem_wgrad_launch(coords, feats, n, table2, cap2, brick_rows, ksize, dz, dz_ld, dweight, accumulate, ws, ws_bytes,
+                           stream);
 }
 
 size_t ag3d_loss_workspace_bytes(void) { return (size_t)sm_count() * 4 * 4 * sizeof(float); }

@@ -86,7 +86,7 @@ class BackboneFeatures:
 
     def __init__(self, F_, offsets, C=None, perm=None, inv=None):
         self.Fp, self.offsets, self.C, self.perm, self.inv = F_, offsets, C, perm, inv
-        self._F, self._inv_local, self._inv64 = None, None, None
+        self._F, self._inv_local, self._inv64, self._inv_local32 = None, None, None, None
 
     @property
     def F(self):
@@ -110,6 +110,11 @@ class BackboneFeatures:
         """rows of scene b in internal order -> caller order (differentiable)"""
         if self.inv is None:
             return t
+        if not t.requires_grad and t.dim() == 2 and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous():
+            if self._inv_local32 is None:
+                self._inv_local32 = [self.inv[self.offsets[i]:self.offsets[i + 1]] - self.offsets[i]
+                                     for i in range(len(self.offsets) - 1)]
+            return ops.gather_rows(t, self._inv_local32[b])
         if self._inv_local is None:
             self._inv_local = [self.inv64[self.offsets[i]:self.offsets[i + 1]] - self.offsets[i]
                                for i in range(len(self.offsets) - 1)]
@@ -361,7 +366,7 @@ class Agile3d(nn.Module):
         with torch.no_grad():
             maps = self.backbone.prepare_maps(x)
             perm, inv = maps.perm[0], maps.inv[0]
-            raw_i = raw if perm is None else raw.index_select(0, perm.long())          # xyz in the internal row order
+            raw_i = raw if perm is None else ops.gather_rows(raw, perm)                # xyz in the internal row order
             pos, rng = ops.fourier_posenc(raw_i, offsets, self.pos_enc.gauss_B)
         if self.training:
             # batch-statistics BatchNorm + recorded activations; one autograd node for backbone + head (engine.py:53)

@@ -309,7 +309,32 @@ def spconv_fwd(x, nbr, weight, out, scale=None, shift=None, residual=None, relu=
     return out
 
 
-def stem_conv_fwd(coords, feats, table, cap, ksize, weight, out, scale=None, shift=None, relu=True, out_split=False):
+def gather_rows(src, idx):
+    """src[idx] for a contiguous 2-D tensor with 4-byte elements and an int32 index vector (row permutations)"""
+    _need_cuda(src, idx)
+    if src.dim() != 2 or not src.is_contiguous() or src.element_size() != 4 or idx.dtype != torch.int32:
+        raise _lib.Ag3dError("gather_rows: contiguous 2-D tensor of 4-byte elements and an int32 index")
+    out = torch.empty((idx.shape[0], src.shape[1]), dtype=src.dtype, device=src.device)
+    if idx.shape[0]:
+        check(lib().ag3d_gather_rows(_p(src), 4 * src.shape[1], _p(idx), idx.shape[0], _p(out), _stream()), "ag3d_gather_rows")
+    return out
+
+
+def brick_rows(coords, parent01, parent12, n_bricks):
+    """full-resolution row of every cell of every tensor-stride-4 voxel: int32 [n_bricks, 64], -1 = empty (csrc/common.cuh)"""
+    _need_cuda(coords, parent01, parent12)
+    n = coords.shape[0]
+    rows = torch.empty((n_bricks, 64), dtype=torch.int32, device=coords.device)
+    with _Timed("maps", 16 * n + 8 * n + 256 * n_bricks):
+        check(lib().ag3d_brick_rows(_p(coords), _p(parent01), _p(parent12), n, n_bricks, _p(rows), _stream()),
+              "ag3d_brick_rows")
+    return rows
+
+
+def stem_conv_fwd(coords, feats, table, cap, ksize, weight, out, scale=None, shift=None, relu=True, out_split=False,
+                  bricks=None):
+    """bricks = (tensor-stride-4 table, its capacity, brick_rows): the neighbours come from 8 probes + the bricks' row
+    lists instead of ksize^3 probes of the full-resolution table (same result)."""
     _need_cuda(coords, feats, table, weight, out)
     if feats.shape[1] != 3 or weight.shape[-2:] != (3, 32) or out.shape[1] != 32:
         raise _lib.Ag3dError("stem conv is 3 -> 32 channels")
@@ -317,11 +342,17 @@ def stem_conv_fwd(coords, feats, table, cap, ksize, weight, out, scale=None, shi
         raise _lib.Ag3dError("stem inputs must be contiguous")
     op, o_ld = _rows2d(out)
     n, K = coords.shape[0], ksize ** 3
+    flags = (RELU if relu else 0) | (OUT_SPLIT if out_split else 0)
     with _Timed("stem", 16 * n + 12 * n + 4 * n * 32 + 16 * K * n + 4 * K * 96):
-        check(lib().ag3d_stem_conv_fwd(_p(coords), _p(feats), n, _p(table), cap, ksize, _p(weight),
-                                       _p(scale), _p(shift), op, o_ld,
-                                       (RELU if relu else 0) | (OUT_SPLIT if out_split else 0), _stream()),
-              "ag3d_stem_conv_fwd")
+        if bricks is not None and ksize in (3, 5):
+            t2, cap2, rows = bricks
+            check(lib().ag3d_stem_conv_fwd_bricks(_p(coords), _p(feats), n, _p(t2), cap2, _p(rows), ksize, _p(weight),
+                                                  _p(scale), _p(shift), op, o_ld, flags, _stream()),
+                  "ag3d_stem_conv_fwd_bricks")
+        else:
+            check(lib().ag3d_stem_conv_fwd(_p(coords), _p(feats), n, _p(table), cap, ksize, _p(weight),
+                                           _p(scale), _p(shift), op, o_ld, flags, _stream()),
+                  "ag3d_stem_conv_fwd")
     return out
 
 
@@ -631,7 +662,7 @@ def spconv_bwd_weight(x, nbr, dout, K, dweight=None, accumulate=False):
     return dweight
 
 
-def stem_bwd_weight(coords, feats, table, cap, ksize, dz):
+def stem_bwd_weight(coords, feats, table, cap, ksize, dz, bricks=None):
     _need_cuda(coords, feats, dz)
     dp, d_ld = _rows2d(dz)
     n = coords.shape[0]
@@ -639,8 +670,13 @@ def stem_bwd_weight(coords, feats, table, cap, ksize, dz):
     wsb = lib().ag3d_stem_bwd_weight_workspace_bytes(ksize)
     ws = _ws_for("stem_wgrad", dz.device, wsb)
     with _Timed("stem_wgrad", 16 * n + 12 * n + 4 * n * 32 + 16 * ksize ** 3 * n):
-        check(lib().ag3d_stem_bwd_weight(_p(coords), _p(feats), n, _p(table), cap, ksize, dp, d_ld, _p(dw), 0, _p(ws),
-                                         ws.numel(), _stream()), "ag3d_stem_bwd_weight")
+        if bricks is not None and ksize in (3, 5):
+            t2, cap2, rows = bricks
+            check(lib().ag3d_stem_bwd_weight_bricks(_p(coords), _p(feats), n, _p(t2), cap2, _p(rows), ksize, dp, d_ld,
+                                                    _p(dw), 0, _p(ws), ws.numel(), _stream()), "ag3d_stem_bwd_weight_bricks")
+        else:
+            check(lib().ag3d_stem_bwd_weight(_p(coords), _p(feats), n, _p(table), cap, ksize, dp, d_ld, _p(dw), 0, _p(ws),
+                                             ws.numel(), _stream()), "ag3d_stem_bwd_weight")
     return dw
 
 

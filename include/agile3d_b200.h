@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define AG3D_ABI_VERSION 6
+#define AG3D_ABI_VERSION 7
 
 #define AG3D_OK 0
 #define AG3D_E_INVALID (-1)   /* bad argument (shape, alignment, unsupported size) */
@@ -144,6 +144,20 @@ int ag3d_spconv_fwd_rows(const float* in, int64_t n_in, int32_t in_ld, int32_t c
 int ag3d_stem_conv_fwd(const int32_t* coords, const float* feats, int64_t n, const void* table, int64_t cap,
                        int32_t ksize, const float* weight, const float* scale, const float* shift, float* out,
                        int32_t out_ld, int32_t flags, ag3d_stream_t stream);
+
+/* dst[i] = src[idx[i]] for rows of row_bytes bytes (a multiple of 4): the internal row order of ag3d_row_order applied
+ * to coordinates / raw xyz, and its inverse applied to the mask logits handed back to the caller.             */
+int ag3d_gather_rows(const void* src, int32_t row_bytes, const int32_t* idx, int64_t n, void* dst, ag3d_stream_t stream);
+/* Bricks: the 4x4x4 block of full-resolution cells under one tensor-stride-4 voxel (a level-2 row of the U-Net's
+ * coordinate hierarchy, models/res16unet.py:222-256).  brick_rows[n_bricks][64] = full-resolution row of cell
+ * (x&3 | (y&3)<<2 | (z&3)<<4) of the brick, -1 = empty; parent01 / parent12 are the parent_idx outputs of the two
+ * ag3d_downsample steps.  The *_bricks stem variants take the tensor-stride-4 table and this array instead of the
+ * full-resolution table: a 5^3 window is 8 probes + 125 short reads instead of 125 probes; results are identical. */
+int ag3d_brick_rows(const int32_t* coords, const int32_t* parent01, const int32_t* parent12, int64_t n,
+                    int64_t n_bricks, int32_t* brick_rows, ag3d_stream_t stream);
+int ag3d_stem_conv_fwd_bricks(const int32_t* coords, const float* feats, int64_t n, const void* table2, int64_t cap2,
+                              const int32_t* brick_rows, int32_t ksize, const float* weight, const float* scale,
+                              const float* shift, float* out, int32_t out_ld, int32_t flags, ag3d_stream_t stream);
 
 /* ---- fourier positional encoding ----------------------------------------------------------------------
  * Replaces Agile3d.get_pos_encs -> PositionEmbeddingCoordsSine.get_fourier_embeddings
@@ -305,6 +319,9 @@ size_t ag3d_stem_bwd_weight_workspace_bytes(int32_t ksize);
 int ag3d_stem_bwd_weight(const int32_t* coords, const float* feats, int64_t n, const void* table, int64_t cap,
                          int32_t ksize, const float* dz, int32_t dz_ld, float* dweight, int32_t accumulate, void* ws,
                          size_t ws_bytes, ag3d_stream_t stream);
+int ag3d_stem_bwd_weight_bricks(const int32_t* coords, const float* feats, int64_t n, const void* table2, int64_t cap2,
+                                const int32_t* brick_rows, int32_t ksize, const float* dz, int32_t dz_ld, float* dweight,
+                                int32_t accumulate, void* ws, size_t ws_bytes, ag3d_stream_t stream);
 
 /* ---- decoder backward -------------------------------------------------------------------------------------
  * Query-side matrices are row-padded with zeros to hqp = ag3d_decoder_bwd_rows(nq, heads) (head, query) rows

@@ -51,6 +51,19 @@ def build_levels(coords, n_levels=4, want_offsets=False):
     return levels, tables, [0] * (1 + n_levels), parents, (0, 0), offsets
 
 
+def gather_rows(src, idx):
+    return src[idx.long()].contiguous()
+
+
+def brick_rows(coords, parent01, parent12, n_bricks):
+    c = coords.long()
+    b = parent12.long()[parent01.long()]
+    bit = (c[:, 1] & 3) | ((c[:, 2] & 3) << 2) | ((c[:, 3] & 3) << 4)
+    rows = torch.full((n_bricks, 64), -1, dtype=torch.int32)
+    rows[b, bit] = torch.arange(c.shape[0], dtype=torch.int32)
+    return rows
+
+
 def row_order(nbr, coords):
     K, n = nbr.shape
     mask = ((nbr >= 0).long() << torch.arange(K).unsqueeze(1)).sum(0)
@@ -119,7 +132,8 @@ def spconv_fwd(x, nbr, weight, out, scale=None, shift=None, residual=None, relu=
     return out
 
 
-def stem_conv_fwd(coords, feats, table, cap, ksize, weight, out, scale=None, shift=None, relu=True, out_split=False):
+def stem_conv_fwd(coords, feats, table, cap, ksize, weight, out, scale=None, shift=None, relu=True, out_split=False,
+                  bricks=None):
     nbr = kernel_map(coords, table, cap, ksize, 1)
     return spconv_fwd(feats, nbr, weight, out, scale, shift, None, relu)
 
@@ -223,7 +237,7 @@ def spconv_bwd_weight(x, nbr, dout, K, dweight=None, accumulate=False):
     return dweight
 
 
-def stem_bwd_weight(coords, feats, table, cap, ksize, dz):
+def stem_bwd_weight(coords, feats, table, cap, ksize, dz, bricks=None):
     nbr = kernel_map(coords, table, cap, ksize, 1)
     return spconv_bwd_weight(feats, nbr, dz, ksize ** 3)
 
@@ -435,7 +449,7 @@ def query_update_b(q1, qh, kh, vh, qpos, blob, B, nq, heads=8, ln_eps=1e-5):
 ALL = ["wgrad_tc_supported", "c2s_attn_bwd_tc", "s2c_mask_bwd_tc_any",
        "bn_stats", "bn_apply", "bn_bwd", "col_sum", "spconv_bwd_weight", "stem_bwd_weight", "decoder_bwd_rows",
        "c2s_attn_bwd", "s2c_mask_bwd", "loss_fwd", "loss_bwd", "click_loss_weights", "grad_norm", "adamw_step",
-       "prepare_tc_weight", "hash_build", "downsample", "build_levels", "row_order", "permute_map", "kernel_map", "kernel_map_transposed", "spconv_fwd", "stem_conv_fwd",
+       "prepare_tc_weight", "hash_build", "downsample", "build_levels", "gather_rows", "brick_rows", "row_order", "permute_map", "kernel_map", "kernel_map_transposed", "spconv_fwd", "stem_conv_fwd",
        "fourier_posenc", "c2s_attn_fwd", "s2c_mask_fwd", "query_blob_floats", "query_init", "query_fold_c2s",
        "query_update_a", "query_update_b"]
 

@@ -21,7 +21,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     for n in names:
         assert hasattr(handle, n), f"{n} declared in the header but not exported"
     handle.ag3d_abi_version.restype = ctypes.c_int32
-    assert handle.ag3d_abi_version() == 6
+    assert handle.ag3d_abi_version() == 7
 
 
 def test_ctypes_signature_table_covers_the_header():

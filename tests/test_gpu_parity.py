@@ -209,6 +209,39 @@ def test_stem_conv_vs_oracle():
     assert float(buf[:, :96].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("ksize", [3, 5])
+def test_stem_conv_bricks_identical_to_hash_probes(ksize):
+    """the brick lookup (8 probes of the tensor-stride-4 table + the bricks' row lists) finds exactly the neighbours the
+    ksize^3 probes of the full-resolution table find: bit-identical stem output, brick table bit-exact vs the emulation"""
+    from agile3d_b200 import ops
+    from agile3d_b200.backbone import CoordinateMaps
+    coords = torch.from_numpy(_random_cloud(6000, 40, seed=21, batch=3, negative=True))
+    maps = CoordinateMaps(coords.to(DEV))
+    t2, cap2, rows = maps.bricks
+    lv, par = [coords], []
+    for lvl in range(2):
+        c, _, _, p = emulate.downsample(lv[-1], 2 << lvl)
+        lv.append(c)
+        par.append(p)
+    assert torch.equal(rows.cpu(), emulate.brick_rows(coords, par[0], par[1], lv[2].shape[0]))
+    g = torch.Generator().manual_seed(2)
+    f = torch.rand((coords.shape[0], 3), generator=g).to(DEV)
+    w = (torch.randn((ksize ** 3, 3, 32), generator=g) * 0.1).to(DEV)
+    a = torch.empty((coords.shape[0], 32), device=DEV)
+    b = torch.empty_like(a)
+    ops.stem_conv_fwd(maps.coords[0], f, maps.tables[0], maps.caps[0], ksize, w, a, relu=False)
+    ops.stem_conv_fwd(maps.coords[0], f, maps.tables[0], maps.caps[0], ksize, w, b, relu=False, bricks=maps.bricks)
+    assert torch.equal(a, b)
+    ref = emulate.stem_conv_fwd(coords, f.cpu(), coords, 0, ksize, w.cpu(), torch.empty(coords.shape[0], 32), relu=False)
+    assert rel_err(b.cpu().numpy(), ref.numpy()) < 1e-5
+    # rows in the internal (re-ordered) order still read the features in the caller's order
+    maps._reorder()
+    if maps.perm[0] is not None:
+        c = torch.empty_like(a)
+        ops.stem_conv_fwd(maps.coords[0], f, maps.tables[0], maps.caps[0], ksize, w, c, relu=False, bricks=maps.bricks)
+        assert torch.equal(c, a[maps.perm[0].long()])
+
+
 # ------------------------------------------------------------------------------------------------ pos-enc
 def test_fourier_posenc_vs_oracle():
     from agile3d_b200 import ops

@@ -175,6 +175,10 @@ def test_stem_bwd_weight_vs_emulation():
     table, cap, _ = ops.hash_build(t(coords))
     got = ops.stem_bwd_weight(t(coords), t(f), table, cap, 5, t(dz))
     assert rel_err(got.cpu(), ref) < 1e-4
+    from agile3d_b200.backbone import CoordinateMaps
+    maps = CoordinateMaps(t(coords))          # same neighbours through the bricks of the tensor-stride-4 level
+    got_b = ops.stem_bwd_weight(maps.coords[0], t(f), maps.tables[0], maps.caps[0], 5, t(dz), bricks=maps.bricks)
+    assert rel_err(got_b.cpu(), ref) < 1e-4
 
 
 # ------------------------------------------------------------------------------------------------ decoder backward
