@@ -48,11 +48,15 @@ SIGNATURES = {
     "ag3d_stem_conv_fwd_bricks": (_i32, [_vp, _vp, _i64, _vp, _i64, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
     "ag3d_posenc_workspace_bytes": (_sz, [_i32]),
     "ag3d_fourier_posenc": (_i32, [_vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "ag3d_fourier_posenc_split": (_i32, [_vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ag3d_c2s_workspace_bytes": (_sz, [_i32, _i32]),
     "ag3d_c2s_attn_fwd": (_i32, [_vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _sz, _vp]),
+    "ag3d_c2s_attn_fwd_split": (_i32, [_vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ag3d_s2c_workspace_bytes": (_sz, [_i32]),
     "ag3d_s2c_mask_fwd": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _i32, _i32, _i32,
                                  _vp, _vp, _vp, _vp, _i32, _vp, _sz, _vp]),
+    "ag3d_s2c_mask_fwd_split": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _i32, _i32, _i32,
+                                       _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ag3d_click_pred": (_i32, [_vp, _i32, _i64, _vp, _vp, _i32, _vp, _vp]),
     "ag3d_scene_iou": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp]),
     "ag3d_click_simulate_workspace_bytes": (_sz, [_i64]),
@@ -60,7 +64,7 @@ SIGNATURES = {
     "ag3d_quantize_points": (_i32, [_vp, _i64, _f32, _i32, _vp, _vp, _vp]),
     "ag3d_first_rows": (_i32, [_vp, _i64, _i64, _vp, _vp]),
     "ag3d_query_blob_floats": (_i64, []),
-    "ag3d_query_init": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ag3d_query_init": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "ag3d_query_fold_c2s": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp, _vp]),
     "ag3d_query_update_a": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp]),
     "ag3d_query_update_b": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp]),

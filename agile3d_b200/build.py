@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(CSRC, "libagile3d_b200.so")
-SOURCES = ["coords.cu", "spconv_simt.cu", "spconv_tc.cu", "spconv_pk.cu", "posenc.cu", "decoder_simt.cu", "decoder_tc.cu", "decoder_mq.cu", "decoder_c2s_tc.cu", "query_ops.cu", "click_ops.cu", "train_ops.cu", "decoder_bwd.cu", "wgrad_tc.cu"]
+SOURCES = ["coords.cu", "spconv_simt.cu", "spconv_tc.cu", "spconv_pk.cu", "posenc.cu", "decoder_simt.cu", "decoder_tc.cu", "decoder_mq.cu", "decoder_c2s_tc.cu", "decoder_c2s_tc2.cu", "query_ops.cu", "click_ops.cu", "train_ops.cu", "decoder_bwd.cu", "wgrad_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

@@ -503,6 +503,13 @@ int s2c_tc_launch(const float* x, const float* pos, long long nv, const float* A
                   const int* q_obj, int nq, int heads, int n_obj, float* x_out, float* logits, unsigned char* label,
                   int* obj_count, void* ws, size_t ws_bytes, cudaStream_t st);
 
+int c2s_split_launch(const float* x_split, const float* pos_split, long long nv, const float* qfold, int nq, int heads,
+                     const unsigned char* label, const int* q_obj, const int* obj_count, void* ws, size_t ws_bytes,
+                     cudaStream_t st, float** part_m, float** part_l, float** part_acc, int* n_cta_out, int* nqg_out);
+int s2c_split_launch(const float* x, const float* pos, long long nv, const float* A, const float* c, const float* U,
+                     const float* bo, const float* ln_w, const float* ln_b, float ln_eps, const float* E,
+                     const int* q_obj, int nq, int heads, int n_obj, float* x_out, float* logits, unsigned char* label,
+                     int* obj_count, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t s2c_mq_workspace_bytes(int nq);
 int s2c_mq_launch(const float* x, const float* pos, long long nv, const float* A, const float* c, const float* U,
                   const float* bo, const float* ln_w, const float* ln_b, float ln_eps, const float* E,
@@ -583,6 +590,29 @@ int ag3d_c2s_attn_fwd(const float* x, const float* pos, int64_t nv, const float*
   return AG3D_OK;
 }
 
+int ag3d_c2s_attn_fwd_split(const float* x_split, const float* pos_split, int64_t nv, const float* qfold, int32_t nq,
+                            int32_t heads, const uint8_t* label, const int32_t* q_obj, const int32_t* obj_count,
+                            float* ctx, float* lse, void* ws, size_t ws_bytes, ag3d_stream_t stream) {
+  AG3D_CHECK_ARG(nv > 0 && nq > 0, "empty problem");
+  AG3D_CHECK_ARG(heads == 8, "heads must be 8 (hidden 128 = 8 x 16)");
+  AG3D_CHECK_ARG(x_split && pos_split && qfold && ctx && aligned16(x_split) && aligned16(pos_split) && aligned16(qfold) &&
+                     aligned16(ctx), "bad pointers");
+  AG3D_CHECK_ARG(!label || (q_obj && obj_count), "a label mask needs q_obj and obj_count");
+  if (!ws || ws_bytes < ag3d_c2s_workspace_bytes(nq, heads)) {
+    set_error("c2s workspace too small");
+    return AG3D_E_WORKSPACE;
+  }
+  cudaStream_t st = as_stream(stream);
+  float *pm, *pl, *pa;
+  int n_cta_tc, nqg_tc;
+  if (int rc = c2s_split_launch(x_split, pos_split, nv, qfold, nq, heads, label, q_obj, obj_count, ws, ws_bytes, st, &pm,
+                                &pl, &pa, &n_cta_tc, &nqg_tc))
+    return rc;
+  c2s_merge_kernel<<<heads * nq, D, 0, st>>>(pm, pl, pa, n_cta_tc, 128, nq, nqg_tc, ctx, lse);
+  AG3D_LAUNCH_CHECK("c2s_merge");
+  return AG3D_OK;
+}
+
 size_t ag3d_s2c_workspace_bytes(int32_t nq) {
   if (nq < 1 || nq > 256) return 0;
   return nq <= 32 ? s2c_tc_workspace_bytes(nq) : s2c_mq_workspace_bytes(nq);
@@ -634,6 +664,23 @@ int ag3d_s2c_mask_fwd(const float* x, const float* pos, int64_t nv, const float*
 #undef LAUNCH_S2C
   AG3D_LAUNCH_CHECK("s2c_mask");
   return AG3D_OK;
+}
+
+int ag3d_s2c_mask_fwd_split(const float* x_split, const float* pos_split, int64_t nv, const float* A, const float* c,
+                            const float* U, const float* bo, const float* ln_w, const float* ln_b, float ln_eps,
+                            const float* E, const int32_t* q_obj, int32_t nq, int32_t heads, int32_t n_obj,
+                            float* x_out_split, float* logits, uint8_t* label, int32_t* obj_count, void* ws,
+                            size_t ws_bytes, ag3d_stream_t stream) {
+  AG3D_CHECK_ARG(nv > 0 && nq > 0, "empty problem");
+  AG3D_CHECK_ARG(heads == 8, "heads must be 8 (hidden 128 = 8 x 16)");
+  AG3D_CHECK_ARG(nq <= 24, "the split-row kernel handles at most 24 click queries per scene");
+  AG3D_CHECK_ARG(n_obj >= 1 && n_obj <= 32, "n_obj must be 1..32");
+  AG3D_CHECK_ARG(x_split && pos_split && A && c && U && bo && ln_w && ln_b && E && q_obj && logits && label && obj_count,
+                 "bad pointers");
+  AG3D_CHECK_ARG(aligned16(x_split) && aligned16(pos_split) && aligned16(A) && aligned16(U) && aligned16(E) &&
+                     (!x_out_split || aligned16(x_out_split)), "pointers must be 16-byte aligned");
+  return s2c_split_launch(x_split, pos_split, nv, A, c, U, bo, ln_w, ln_b, ln_eps, E, q_obj, nq, heads, n_obj, x_out_split,
+                          logits, label, obj_count, ws, ws_bytes, as_stream(stream));
 }
 
 }  // extern "C"

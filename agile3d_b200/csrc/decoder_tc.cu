@@ -8,11 +8,13 @@
 // from HBM exactly once.  Column layout of S/P: head-major with every head padded to NQ16 (16, 24 or 32) columns so
 // that a 16-column TMEM load never straddles heads; padded columns carry a bias of -inf (probability 0).
 // Roles: 8 compute warps (tile load + split, softmax, LayerNorm, mask head), 1 MMA-issuer thread, 1 loader thread.
+#include <cuda.h>
 #include <float.h>
 #include <math.h>
 
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 
 #include "tc_common.cuh"
 
@@ -452,6 +454,432 @@ static int s2c_tc_launch_t(const float* x, const float* pos, long long nv, const
   s2c_tc_kernel<NQ16><<<grid, DT_THREADS, Cfg::SMEM, st>>>(p);
   AG3D_LAUNCH_CHECK("s2c_tc");
   return AG3D_OK;
+}
+
+// ============================================================================================== split-row variant
+// Same three chained GEMMs, but the voxel tile never passes through registers on its way in: x and pos are "split" rows
+// (32-channel slabs of 64 B bf16 hi | 64 B bf16 lo) and the TMA engine drops their [128 voxels x 128 B] slab tiles
+// into SWIZZLE_128B shared memory, which is directly the K-major A operand of
+//   S = x . A^T + pos . A^T      (one weight slab serves both terms; no (x + pos) tile is formed)
+// The probabilities P and the LayerNorm output Y are written in the same swizzled slab format (conflict-free 16-byte
+// stores, no padding), Y in place over the x tile, whose values are the residual input of the LayerNorm.  The updated
+// voxel features leave as split rows (x_out_split, nullable: the last decoder layer's features are never read).
+// Roles: 8 compute warps (softmax, LayerNorm, mask head), MMA issuer, operand-ring loader, voxel-tile TMA producer.
+constexpr int DS_COMPUTE_WARPS = 16;                  // four threads per voxel row (TMEM lane quarter q4 = warp & 3, part = warp >> 2)
+constexpr int DS_THREADS = DS_COMPUTE_WARPS * 32 + 96;
+constexpr uint32_t DS_SLAB = 16384;                    // [128 voxels x 128 B]
+constexpr uint32_t DS_MISC = 8192;
+
+template <int NQ16>
+struct S2sCfg {
+  static constexpr int HQP = 8 * NQ16;
+  static constexpr int SLABS_P = HQP / 32;
+  static constexpr int G1_CHUNKS = HQP * 128 > 16384 ? 2 : 1;
+  static constexpr int G1_BYTES = HQP * 128 / G1_CHUNKS;
+  static constexpr int NBR = (HQP <= 128) ? 5 : 3;
+  static constexpr uint32_t OFF_X = 0;
+  static constexpr uint32_t OFF_P = 4 * DS_SLAB;                                  // pos tile, then P
+  static constexpr uint32_t P_BYTES = (SLABS_P > 4 ? SLABS_P : 4) * DS_SLAB;
+  static constexpr uint32_t OFF_RING = OFF_P + P_BYTES;
+  static constexpr uint32_t OFF_MISC = OFF_RING + NBR * 16384;
+  static constexpr size_t SMEM = OFF_MISC + DS_MISC;
+};
+
+struct S2sParams {
+  long long nv;
+  const uint4* img; const float* cpad;
+  const float* bo; const float* ln_w; const float* ln_b; float ln_eps;
+  const int* q_obj; int nq; int n_obj;
+  float* x_out; float* logits; unsigned char* label; int* obj_count;
+  int debug;     // measurement aid (AG3D_S2C_DEBUG): 1/2/4 no MMAs in G1/G2/G3, 8 no voxel-tile loads, 16 no operand-ring copies,
+                 // 32 no softmax, 64 no LayerNorm phase work
+};
+
+__device__ __forceinline__ void ds_tma_tile(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int col, int row) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(tm), "r"(bar), "r"(col), "r"(row)
+      : "memory");
+}
+// byte offset of the 16-byte chunk `ch` (0..3 hi pieces, 4..7 lo pieces of 8 channels) of row r inside a swizzled slab tile
+__device__ __forceinline__ uint32_t ds_chunk_off(int r, int ch) { return (uint32_t)(r * 128 + ((ch ^ (r & 7)) << 4)); }
+
+template <int NQ16>
+__global__ void __launch_bounds__(DS_THREADS, 1)
+s2c_split_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_pos,
+                 const __grid_constant__ CUtensorMap tm_out, const S2sParams p) {
+  using Cfg = S2sCfg<NQ16>;
+  constexpr int HQP = Cfg::HQP, SLABS_P = Cfg::SLABS_P, NBR = Cfg::NBR;
+  constexpr uint32_t B_STAGE = 16384;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* Xs = smem + Cfg::OFF_X;                         // x tile (4 slabs); later Y in place
+  unsigned char* Pb = smem + Cfg::OFF_P;                         // pos tile (4 slabs); later P (SLABS_P slabs)
+  unsigned char* ring = smem + Cfg::OFF_RING;
+  unsigned char* misc = smem + Cfg::OFF_MISC;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(misc);            // [0..6] phase barriers, [8..15] ring full, [16..23] ring empty
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 192);
+  int* hist_s = reinterpret_cast<int*>(misc + 256);              // [32]
+  int* qobj_s = reinterpret_cast<int*>(misc + 384);              // [32]
+  float* vec_s = reinterpret_cast<float*>(misc + 512);           // bo[128] | ln_w[128] | ln_b[128]
+  float* cpad_s = reinterpret_cast<float*>(misc + 2048);         // [HQP <= 256]
+  float* lnred_s = reinterpret_cast<float*>(misc + 3072);        // [2][128][4]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t bar_base = smem_u32(bars);
+  const uint32_t in_full = bar_base, s_full = bar_base + 8, p_full = bar_base + 16, o_full = bar_base + 24,
+                 y_full = bar_base + 32, z_full = bar_base + 40;
+  auto b_full = [&](int s) { return bar_base + 8u * (8 + s); };
+  auto b_empty = [&](int s) { return bar_base + 8u * (16 + s); };
+
+  if (tid == 0) {
+    if (smem_u32(smem) & 1023u) __trap();
+    mbar_init(in_full, 1); mbar_init(p_full, DS_COMPUTE_WARPS); mbar_init(y_full, DS_COMPUTE_WARPS);
+    mbar_init(s_full, 1); mbar_init(o_full, 1); mbar_init(z_full, 1);
+    for (int s = 0; s < NBR; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid < 32) { hist_s[tid] = 0; qobj_s[tid] = (tid < p.nq) ? p.q_obj[tid] : -1; }
+  for (int i = tid; i < 128; i += DS_THREADS) {
+    vec_s[i] = p.bo[i]; vec_s[128 + i] = p.ln_w[i]; vec_s[256 + i] = p.ln_b[i];
+  }
+  for (int i = tid; i < HQP; i += DS_THREADS) cpad_s[i] = p.cpad[i];
+  if (warp == DS_COMPUTE_WARPS) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const long long n_tiles = (p.nv + TC_BM - 1) / TC_BM;
+
+  if (warp < DS_COMPUTE_WARPS) {
+    // ======================================================================================= compute warps
+    const int q4 = warp & 3, g = warp >> 2;             // g = part: heads 2g, 2g+1 of the softmax, 32-channel slab g of the LayerNorm
+    const int r = q4 * 32 + lane;                       // tile row owned in all phases
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q4 * 32) << 16);
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const uint32_t ph = (uint32_t)it & 1u;
+      const long long row0 = tile * TC_BM;
+      // ---- P1: per-head softmax over the queries; this thread: row r, heads 2g, 2g+1
+      mbar_wait(s_full, ph);
+      tc_fence_after();
+      if (!(p.debug & 32))
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int col0 = (2 * g + hh) * NQ16;
+        float sc[NQ16];
+        if constexpr (NQ16 % 16 == 0) {
+#pragma unroll
+          for (int ch = 0; ch < NQ16 / 16; ++ch) tmem_ld16(t_lane + TM_S + col0 + ch * 16, sc + ch * 16);
+        } else {
+#pragma unroll
+          for (int ch = 0; ch < NQ16 / 8; ++ch) tmem_ld8(t_lane + TM_S + col0 + ch * 8, sc + ch * 8);
+        }
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < NQ16; ++i) { sc[i] += cpad_s[col0 + i]; mx = fmaxf(mx, sc[i]); }
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < NQ16; ++i) { sc[i] = __expf(sc[i] - mx); sum += sc[i]; }
+        const float inv = 1.f / sum;
+#pragma unroll
+        for (int c8 = 0; c8 < NQ16 / 8; ++c8) {
+          uint32_t h[4], l[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) split2(sc[c8 * 8 + 2 * e] * inv, sc[c8 * 8 + 2 * e + 1] * inv, h[e], l[e]);
+          const int col = col0 + c8 * 8;
+          unsigned char* slab = Pb + (size_t)(col >> 5) * DS_SLAB;
+          const int k = (col >> 3) & 3;
+          *reinterpret_cast<uint4*>(slab + ds_chunk_off(r, k)) = make_uint4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<uint4*>(slab + ds_chunk_off(r, 4 + k)) = make_uint4(l[0], l[1], l[2], l[3]);
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+
+      // ---- P2: o + bo + x -> LayerNorm -> y; this thread: row r, channels 32g .. 32g+31 (slab g)
+      mbar_wait(o_full, ph);
+      mbar_wait(in_full, ph);                           // the x tile was written by the TMA engine: observe its barrier
+      tc_fence_after();
+      const long long row = row0 + r;
+      const bool valid = row < p.nv;
+      if (!(p.debug & 64)) {
+        float v[32];
+        tmem_ld16(t_lane + TM_O + 32 * g, v);
+        tmem_ld16(t_lane + TM_O + 32 * g + 16, v + 16);
+        unsigned char* slab = Xs + (size_t)g * DS_SLAB;
+        float sum = 0.f;
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) {                // 8 channels: hi chunk c8, lo chunk 4 + c8
+          const uint4 hh = *reinterpret_cast<const uint4*>(slab + ds_chunk_off(r, c8));
+          const uint4 ll = *reinterpret_cast<const uint4*>(slab + ds_chunk_off(r, 4 + c8));
+          const uint32_t hw[4] = {hh.x, hh.y, hh.z, hh.w}, lw[4] = {ll.x, ll.y, ll.z, ll.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float x0 = __uint_as_float(hw[e] << 16) + __uint_as_float(lw[e] << 16);
+            const float x1 = __uint_as_float(hw[e] & 0xFFFF0000u) + __uint_as_float(lw[e] & 0xFFFF0000u);
+            const int c = c8 * 8 + 2 * e;
+            v[c] = x0 + (v[c] + vec_s[32 * g + c]);
+            v[c + 1] = x1 + (v[c + 1] + vec_s[32 * g + c + 1]);
+            sum += v[c] + v[c + 1];
+          }
+        }
+        lnred_s[(0 * 128 + r) * 4 + g] = sum;
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        const float4 s4 = *reinterpret_cast<const float4*>(lnred_s + (0 * 128 + r) * 4);
+        const float mean = ((s4.x + s4.y) + (s4.z + s4.w)) * (1.f / DT_D);
+        float sq = 0.f;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) { const float d = v[c] - mean; sq = fmaf(d, d, sq); }
+        lnred_s[(1 * 128 + r) * 4 + g] = sq;
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        const float4 q4v = *reinterpret_cast<const float4*>(lnred_s + (1 * 128 + r) * 4);
+        const float var = ((q4v.x + q4v.y) + (q4v.z + q4v.w)) * (1.f / DT_D);
+        const float rstd = 1.f / sqrtf(var + p.ln_eps);
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) {
+          float y[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int c = 32 * g + c8 * 8 + e;
+            y[e] = (v[c8 * 8 + e] - mean) * rstd * vec_s[128 + c] + vec_s[256 + c];
+          }
+          uint32_t h[4], l[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) split2(y[2 * e], y[2 * e + 1], h[e], l[e]);
+          *reinterpret_cast<uint4*>(slab + ds_chunk_off(r, c8)) = make_uint4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<uint4*>(slab + ds_chunk_off(r, 4 + c8)) = make_uint4(l[0], l[1], l[2], l[3]);
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(y_full);
+
+      // ---- P3: mask head (column half 0 only: 32 query columns)
+      mbar_wait(z_full, ph);
+      tc_fence_after();
+      if (g == 0) {
+        float z[DT_NQP];
+        tmem_ld16(t_lane + TM_Z, z);
+        tmem_ld16(t_lane + TM_Z + 16, z + 16);
+        if (valid) {
+          float best = -INFINITY;
+          int arg = 0;
+          for (int ob = 0; ob < p.n_obj; ++ob) {
+            float m = -INFINITY;
+#pragma unroll
+            for (int q = 0; q < DT_NQP; ++q) m = (qobj_s[q] == ob) ? fmaxf(m, z[q]) : m;
+            p.logits[(size_t)row * p.n_obj + ob] = m;
+            if (m > best || ob == 0) { best = m; arg = ob; }
+          }
+          p.label[row] = (unsigned char)arg;
+          atomicAdd(&hist_s[arg], 1);
+        }
+      }
+      tc_fence_before();
+    }
+  } else if (warp == DS_COMPUTE_WARPS) {
+    // ======================================================================================= MMA issuer
+    const uint32_t id_s = umma_idesc_bf16(HQP), id_o = umma_idesc_bf16(128), id_z = umma_idesc_bf16(DT_NQP);
+    const uint32_t d_hi32 = umma_desc_hi32(128);                     // ring operands: no swizzle, SBO = 128
+    const uint32_t sw_hi32 = umma_desc_hi32(1024) | (2u << 29);      // voxel-side operands: SWIZZLE_128B slab tiles
+    const uint32_t x_lo32 = umma_desc_lo32(smem_u32(Xs), 16), p_lo32 = umma_desc_lo32(smem_u32(Pb), 16);
+    const uint32_t ring_u32 = smem_u32(ring);
+    int nb = 0, it = 0;
+    // one GEMM = `slabs` K-slabs x n_a A tiles x (2 k-steps x 3 products); chunks: ring slots per slab (2: hi and lo piece
+    // in separate slots; 1: whole slab image in one slot; 0: all slabs in ONE slot)
+    auto gemm = [&](int slabs, uint32_t d, uint32_t idesc, uint32_t b_lbo, int chunks, uint32_t b_slab, uint32_t a0,
+                    uint32_t a1, bool skip) {
+      uint32_t b_hi = 0, b_lo = 0;
+      for (int s = 0; s < slabs; ++s) {
+        if (chunks || s == 0) {
+          const int sb = nb % NBR;
+          mbar_wait(b_full(sb), (uint32_t)(nb / NBR) & 1u);
+          b_hi = umma_desc_lo32(ring_u32 + (uint32_t)sb * B_STAGE, b_lbo);
+          b_lo = b_hi + ((4u * b_lbo) >> 4);
+          if (chunks == 2) {
+            const int sb2 = (nb + 1) % NBR;
+            mbar_wait(b_full(sb2), (uint32_t)((nb + 1) / NBR) & 1u);
+            b_lo = umma_desc_lo32(ring_u32 + (uint32_t)sb2 * B_STAGE, b_lbo);
+          }
+          tc_fence_after();
+        }
+        const uint32_t off = chunks ? 0u : ((uint32_t)s * b_slab) >> 4;
+        const bool release = chunks || s == slabs - 1;
+        if (elect_one()) {
+          if (!skip)
+#pragma unroll
+          for (int o = 0; o < 2; ++o) {
+            const uint32_t abase = o ? a1 : a0;
+            if (o && !a1) break;
+            const uint32_t ah = abase + (uint32_t)s * (DS_SLAB >> 4);
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+              const uint64_t da_hi = umma_desc_join(sw_hi32, ah + ks * 2u);
+              const uint64_t da_lo = umma_desc_join(sw_hi32, ah + ks * 2u + 4u);
+              const uint64_t db_hi = umma_desc_join(d_hi32, b_hi + off + ks * ((2u * b_lbo) >> 4));
+              const uint64_t db_lo = umma_desc_join(d_hi32, b_lo + off + ks * ((2u * b_lbo) >> 4));
+              umma_bf16(d, da_hi, db_hi, idesc, (s | ks | o) ? 1u : 0u);
+              umma_bf16(d, da_hi, db_lo, idesc, 1u);
+              umma_bf16(d, da_lo, db_hi, idesc, 1u);
+            }
+          }
+          if (release) {
+            umma_commit(b_empty(nb % NBR));
+            if (chunks == 2) umma_commit(b_empty((nb + 1) % NBR));
+          }
+        }
+        __syncwarp();
+        if (release) nb += chunks == 2 ? 2 : 1;
+      }
+    };
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const uint32_t ph = (uint32_t)it & 1u;
+      mbar_wait(in_full, ph);
+      tc_fence_after();
+      gemm(4, tmem_base + TM_S, id_s, (uint32_t)HQP * 16u, Cfg::G1_CHUNKS, 0, x_lo32, p_lo32, p.debug & 1);
+      if (elect_one()) umma_commit(s_full);
+      __syncwarp();
+      mbar_wait(p_full, ph);
+      tc_fence_after();
+      gemm(SLABS_P, tmem_base + TM_O, id_o, 128u * 16u, 1, 0, p_lo32, 0u, p.debug & 2);
+      if (elect_one()) umma_commit(o_full);
+      __syncwarp();
+      mbar_wait(y_full, ph);
+      tc_fence_after();
+      gemm(4, tmem_base + TM_Z, id_z, (uint32_t)DT_NQP * 16u, 0, 4096u, x_lo32, 0u, p.debug & 4);
+      if (elect_one()) umma_commit(z_full);
+      __syncwarp();
+    }
+  } else if (warp == DS_COMPUTE_WARPS + 1) {
+    // ======================================================================================= operand loader
+    const unsigned char* img = reinterpret_cast<const unsigned char*>(p.img);
+    int nb = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      size_t off = 0;
+      for (int st = 0; st < 4 * Cfg::G1_CHUNKS + SLABS_P + 1; ++st) {
+        const uint32_t bytes = st < 4 * Cfg::G1_CHUNKS ? (uint32_t)Cfg::G1_BYTES : 16384u;
+        const int sb = nb % NBR;
+        mbar_wait(b_empty(sb), ((uint32_t)(nb / NBR) & 1u) ^ 1u);
+        if (elect_one()) {
+          if (p.debug & 16) {
+            mbar_arrive(b_full(sb));
+          } else {
+            mbar_arrive_expect_tx(b_full(sb), bytes);
+            bulk_g2s(smem_u32(ring + (size_t)sb * B_STAGE), img + off, bytes, b_full(sb));
+          }
+        }
+        __syncwarp();
+        off += bytes;
+        ++nb;
+      }
+    }
+  } else {
+    // ======================================================================================= voxel-tile producer
+    // the x tile is dead once the mask-head GEMM of the previous tile has read Y (z_full), the pos/P region earlier
+    // ... and the updated features leave the same way: Y sits in the x region in exactly the layout of the output's
+    // tensor map, so one thread stores the tile with four bulk tensor copies (rows past the end are clipped) instead of
+    // every thread writing 16-byte pieces of its own row (32 rows per warp instruction)
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      if (it > 0) mbar_wait(z_full, (uint32_t)(it - 1) & 1u);
+      if (elect_one()) {
+        if (it > 0 && p.x_out) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the store has read Y
+        const int row = (int)(tile * TC_BM);
+        if (p.debug & 8) mbar_arrive(in_full);
+        else mbar_arrive_expect_tx(in_full, 8u * DS_SLAB);
+        if (!(p.debug & 8))
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          ds_tma_tile(smem_u32(Pb) + (uint32_t)c * DS_SLAB, &tm_pos, in_full, c * 64, row);
+          ds_tma_tile(smem_u32(Xs) + (uint32_t)c * DS_SLAB, &tm_x, in_full, c * 64, row);
+        }
+      }
+      __syncwarp();
+      if (p.x_out) {
+        mbar_wait(y_full, (uint32_t)it & 1u);            // Y of this tile is written (and fenced for the async proxy)
+        if (elect_one()) {
+          const int row = (int)(tile * TC_BM);
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tm_out),
+                         "r"(smem_u32(Xs) + (uint32_t)c * DS_SLAB), "r"(c * 64), "r"(row)
+                         : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        __syncwarp();
+      }
+    }
+    if (p.x_out && elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before exit
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (tid < p.n_obj && hist_s[tid]) atomicAdd(p.obj_count + tid, hist_s[tid]);
+  if (warp == DS_COMPUTE_WARPS) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+bool split_rows_tile_map(CUtensorMap* tm, const float* base, long long rows, int box_rows);   // decoder_c2s_tc2.cu
+size_t s2c_tc_workspace_bytes(int nq);
+
+template <int NQ16>
+static int s2c_split_launch_t(const float* x, const float* pos, long long nv, const float* A, const float* c,
+                              const float* U, const float* bo, const float* ln_w, const float* ln_b, float ln_eps,
+                              const float* E, const int* q_obj, int nq, int heads, int n_obj, float* x_out,
+                              float* logits, unsigned char* label, int* obj_count, void* ws, cudaStream_t st) {
+  using Cfg = S2sCfg<NQ16>;
+  constexpr int HQP = Cfg::HQP;
+  uint4* img = static_cast<uint4*>(ws);
+  float* cpad = reinterpret_cast<float*>(static_cast<unsigned char*>(ws) + s2c_img_bytes<NQ16>());
+  constexpr int total = 4 * 4 * HQP + Cfg::SLABS_P * 4 * 128 + 4 * 4 * DT_NQP;
+  s2c_prep_kernel<NQ16><<<(total + 255) / 256, 256, 0, st>>>(A, c, U, E, nq, heads, img, cpad);
+  AG3D_LAUNCH_CHECK("s2c_prep");
+  static bool attr = false;
+  if (!attr) {
+    AG3D_CUDA(cudaFuncSetAttribute(s2c_split_kernel<NQ16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    attr = true;
+  }
+  alignas(64) CUtensorMap tm_x, tm_pos;
+  memset(&tm_x, 0, sizeof(tm_x));
+  memset(&tm_pos, 0, sizeof(tm_pos));
+  AG3D_CHECK_ARG(split_rows_tile_map(&tm_x, x, nv, TC_BM) && split_rows_tile_map(&tm_pos, pos, nv, TC_BM),
+                 "cuTensorMapEncodeTiled failed for the voxel rows");
+  alignas(64) CUtensorMap tm_out;
+  memset(&tm_out, 0, sizeof(tm_out));
+  AG3D_CHECK_ARG(split_rows_tile_map(&tm_out, x_out ? x_out : x, nv, TC_BM), "cuTensorMapEncodeTiled failed for the output rows");
+  S2sParams p;
+  p.nv = nv; p.img = img; p.cpad = cpad; p.bo = bo; p.ln_w = ln_w; p.ln_b = ln_b;
+  p.ln_eps = ln_eps; p.q_obj = q_obj; p.nq = nq; p.n_obj = n_obj; p.x_out = x_out; p.logits = logits;
+  p.label = label; p.obj_count = obj_count;
+  { const char* e = getenv("AG3D_S2C_DEBUG"); p.debug = e ? atoi(e) : 0; }
+  long long tiles = (nv + TC_BM - 1) / TC_BM;
+  const int grid = (int)std::min<long long>(tiles, sm_count());
+  s2c_split_kernel<NQ16><<<grid, DS_THREADS, Cfg::SMEM, st>>>(tm_x, tm_pos, tm_out, p);
+  AG3D_LAUNCH_CHECK("s2c_split");
+  return AG3D_OK;
+}
+
+int s2c_split_launch(const float* x, const float* pos, long long nv, const float* A, const float* c, const float* U,
+                     const float* bo, const float* ln_w, const float* ln_b, float ln_eps, const float* E,
+                     const int* q_obj, int nq, int heads, int n_obj, float* x_out, float* logits, unsigned char* label,
+                     int* obj_count, void* ws, size_t ws_bytes, cudaStream_t st) {
+  AG3D_CHECK_ARG(heads == 8 && nq <= 24, "split-row s2c handles 8 heads and at most 24 queries");
+  AG3D_CHECK_ARG(nv < 2147483647LL, "too many voxels");
+  AG3D_CHECK_ARG(ws && aligned16(ws) && ws_bytes >= s2c_tc_workspace_bytes(nq), "s2c workspace too small");
+  if (nq <= 16)
+    return s2c_split_launch_t<16>(x, pos, nv, A, c, U, bo, ln_w, ln_b, ln_eps, E, q_obj, nq, heads, n_obj, x_out, logits,
+                                  label, obj_count, ws, st);
+  return s2c_split_launch_t<24>(x, pos, nv, A, c, U, bo, ln_w, ln_b, ln_eps, E, q_obj, nq, heads, n_obj, x_out, logits,
+                                label, obj_count, ws, st);
 }
 
 // heads are padded to 16, 24 or 32 query columns (AG3D_S2C_PACK=0 disables the 24-column variant: measurement aid)

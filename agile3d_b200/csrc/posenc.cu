@@ -3,6 +3,8 @@
 // Precise sinf/cosf (no fast-math): the arguments reach tens of radians and the result feeds fp32 parity.
 #include <float.h>
 
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace ag3d {
@@ -58,7 +60,7 @@ __global__ void range_decode_kernel(const unsigned* enc, float* out, int n) {
 // one thread per (voxel, frequency j): out[v][j] = sin(t), out[v][half + j] = cos(t)
 __global__ void posenc_kernel(const float* __restrict__ xyz, const int* __restrict__ offsets, int n_scenes,
                               const unsigned* __restrict__ enc, const float* __restrict__ gauss_B, int half,
-                              float* __restrict__ out, long long n_total) {
+                              float* __restrict__ out, float* __restrict__ out_split, long long n_total) {
   const int b = blockIdx.y;
   const long long lo = offsets[b], hi = offsets[b + 1];
   float mn[3], inv_den[3];
@@ -84,6 +86,15 @@ __global__ void posenc_kernel(const float* __restrict__ xyz, const int* __restri
     sincosf(arg, &s, &c);
     out[v * (2 * half) + j] = s;
     out[v * (2 * half) + half + j] = c;
+    if (out_split) {      // the same row as "split" bf16 pairs: 32-channel slab = 32 hi | 32 lo (csrc/spconv_tc.cu)
+      __nv_bfloat16* row = reinterpret_cast<__nv_bfloat16*>(out_split + v * (2 * half));
+      const int cs = j, cc = half + j;
+      const __nv_bfloat16 sh = __float2bfloat16_rn(s), ch = __float2bfloat16_rn(c);
+      row[(cs >> 5) * 64 + (cs & 31)] = sh;
+      row[(cs >> 5) * 64 + 32 + (cs & 31)] = __float2bfloat16_rn(s - __bfloat162float(sh));
+      row[(cc >> 5) * 64 + (cc & 31)] = ch;
+      row[(cc >> 5) * 64 + 32 + (cc & 31)] = __float2bfloat16_rn(c - __bfloat162float(ch));
+    }
   }
 }
 
@@ -95,9 +106,9 @@ extern "C" {
 
 size_t ag3d_posenc_workspace_bytes(int32_t n_scenes) { return (size_t)(n_scenes * 6 + n_scenes + 1 + 8) * 4; }
 
-int ag3d_fourier_posenc(const float* xyz, const int32_t* scene_offsets_host, int32_t n_scenes,
-                        const float* gauss_B, int32_t d_pos, float* out, float* range_out, void* ws,
-                        size_t ws_bytes, ag3d_stream_t stream) {
+static int posenc_launch(const float* xyz, const int32_t* scene_offsets_host, int32_t n_scenes, const float* gauss_B,
+                         int32_t d_pos, float* out, float* out_split, float* range_out, void* ws, size_t ws_bytes,
+                         ag3d_stream_t stream) {
   AG3D_CHECK_ARG(n_scenes >= 1 && n_scenes < 65535, "n_scenes out of range");
   AG3D_CHECK_ARG(d_pos > 0 && d_pos % 2 == 0, "d_pos must be even");
   AG3D_CHECK_ARG(xyz && scene_offsets_host && gauss_B && out, "bad pointers");
@@ -133,9 +144,22 @@ int ag3d_fourier_posenc(const float* xyz, const int32_t* scene_offsets_host, int
   int px = (int)((work + 256 * 4 - 1) / (256 * 4));
   if (px > sm_count() * 8) px = sm_count() * 8;
   if (px < 1) px = 1;
-  posenc_kernel<<<dim3(px, n_scenes), 256, 0, st>>>(xyz, offsets, n_scenes, enc, gauss_B, half, out, n_total);
+  posenc_kernel<<<dim3(px, n_scenes), 256, 0, st>>>(xyz, offsets, n_scenes, enc, gauss_B, half, out, out_split, n_total);
   AG3D_LAUNCH_CHECK("posenc");
   return AG3D_OK;
+}
+
+int ag3d_fourier_posenc(const float* xyz, const int32_t* scene_offsets_host, int32_t n_scenes,
+                        const float* gauss_B, int32_t d_pos, float* out, float* range_out, void* ws,
+                        size_t ws_bytes, ag3d_stream_t stream) {
+  return posenc_launch(xyz, scene_offsets_host, n_scenes, gauss_B, d_pos, out, nullptr, range_out, ws, ws_bytes, stream);
+}
+
+int ag3d_fourier_posenc_split(const float* xyz, const int32_t* scene_offsets_host, int32_t n_scenes,
+                              const float* gauss_B, int32_t d_pos, float* out, float* out_split, float* range_out,
+                              void* ws, size_t ws_bytes, ag3d_stream_t stream) {
+  AG3D_CHECK_ARG(out_split && d_pos % 64 == 0, "split rows need d_pos % 64 == 0");
+  return posenc_launch(xyz, scene_offsets_host, n_scenes, gauss_B, d_pos, out, out_split, range_out, ws, ws_bytes, stream);
 }
 
 }  // extern "C"

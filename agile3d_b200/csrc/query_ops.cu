@@ -115,7 +115,7 @@ __global__ void query_init_kernel(const float* __restrict__ feats, const float* 
                                   const int* __restrict__ feat_row, const int* __restrict__ time_idx, const int* __restrict__ scene_of_row,
                                   const float* __restrict__ gauss_B, const float* __restrict__ time_table,
                                   const float* __restrict__ bg_feat, const float* __restrict__ bg_pos,
-                                  float* __restrict__ queries, float* __restrict__ qpos) {
+                                  float* __restrict__ queries, float* __restrict__ qpos, int feats_split) {
   const int row = blockIdx.x, c = threadIdx.x;
   const int src = src_row[row];
   if (src < 0) {
@@ -136,7 +136,15 @@ __global__ void query_init_kernel(const float* __restrict__ feats, const float* 
   }
   float s, co;
   sincosf(arg, &s, &co);
-  queries[(size_t)row * QD + c] = feats[(size_t)(feat_row ? feat_row[row] : src) * QD + c];
+  const float* frow = feats + (size_t)(feat_row ? feat_row[row] : src) * QD;
+  float f;
+  if (feats_split) {      // "split" rows: 32-channel slab = 32 bf16 hi | 32 bf16 lo
+    const unsigned short* hp = reinterpret_cast<const unsigned short*>(frow) + (c >> 5) * 64 + (c & 31);
+    f = __uint_as_float((unsigned)hp[0] << 16) + __uint_as_float((unsigned)hp[32] << 16);
+  } else {
+    f = frow[c];
+  }
+  queries[(size_t)row * QD + c] = f;
   qpos[(size_t)row * QD + c] = (c < 64 ? s : co) + time_table[(size_t)time_idx[row] * QD + c];
 }
 
@@ -424,12 +432,12 @@ int64_t ag3d_query_blob_floats(void) { return Q_BLOB_FLOATS; }
 int ag3d_query_init(const float* feats, const float* xyz, const float* range, const int32_t* src_row,
                     const int32_t* feat_row, const int32_t* time_idx, const int32_t* scene_of_row, int32_t n_rows, const float* gauss_B,
                     const float* time_table, const float* bg_feat, const float* bg_pos, float* queries, float* qpos,
-                    ag3d_stream_t stream) {
+                    int32_t feats_split, ag3d_stream_t stream) {
   AG3D_CHECK_ARG(n_rows > 0, "no query rows");
   AG3D_CHECK_ARG(feats && xyz && range && src_row && time_idx && scene_of_row && gauss_B && time_table && bg_feat &&
                      bg_pos && queries && qpos, "bad pointers");
   query_init_kernel<<<n_rows, QD, 0, as_stream(stream)>>>(feats, xyz, range, src_row, feat_row, time_idx, scene_of_row, gauss_B,
-                                                          time_table, bg_feat, bg_pos, queries, qpos);
+                                                          time_table, bg_feat, bg_pos, queries, qpos, feats_split);
   AG3D_LAUNCH_CHECK("query_init");
   return AG3D_OK;
 }

@@ -82,11 +82,21 @@ class BackboneFeatures:
 
     The backbone works in an INTERNAL row order (rows of a scene sorted by neighbour pattern, CoordinateMaps._reorder);
     ``Fp`` holds the rows in that order, ``perm[new] = caller row`` and ``inv[caller row] = new``.  ``F`` is the caller's
-    view (gathered on first use); scenes keep their row ranges in both orders."""
+    view (gathered on first use); scenes keep their row ranges in both orders.
 
-    def __init__(self, F_, offsets, C=None, perm=None, inv=None):
-        self.Fp, self.offsets, self.C, self.perm, self.inv = F_, offsets, C, perm, inv
+    In tensor-core eval mode the features exist as ``Fs``: "split" rows (32-channel slabs of bf16 hi | bf16 lo, the
+    backbone's activation format), which is what the TMA-fed decoder kernels stream; the fp32 rows ``Fp`` are then
+    decoded on first use (callers that read ``.F``, click rounds with more than 24 queries)."""
+
+    def __init__(self, F_, offsets, C=None, perm=None, inv=None, Fs=None):
+        self._Fp, self.Fs, self.offsets, self.C, self.perm, self.inv = F_, Fs, offsets, C, perm, inv
         self._F, self._inv_local, self._inv64, self._inv_local32 = None, None, None, None
+
+    @property
+    def Fp(self):
+        if self._Fp is None:
+            self._Fp = ops.unpack_split(self.Fs)
+        return self._Fp
 
     @property
     def F(self):
@@ -126,7 +136,7 @@ class BackboneFeatures:
 
     @property
     def device(self):
-        return self.Fp.device
+        return (self.Fs if self._Fp is None else self._Fp).device
 
 
 class _AuxMap:
@@ -145,8 +155,8 @@ class _PosList:
     """per-scene positional encodings: ``[b]`` gives the caller's row order (as the reference's list would), the model
     itself reads ``internal[b]`` (the backbone's row order)."""
 
-    def __init__(self, internal, handle):
-        self.internal, self._h = internal, handle
+    def __init__(self, internal, handle, split=None):
+        self.internal, self._h, self.split = internal, handle, split      # split: the same rows as bf16 hi/lo pairs
 
     def __len__(self):
         return len(self.internal)
@@ -346,6 +356,7 @@ class Agile3d(nn.Module):
         self.decoder_norm = nn.LayerNorm(d)
         self.time_encode = _time_table(d, 200)       # plain attribute, not in the state_dict (agile3d.py:138)
         self.fused_queries = True                    # eval: click-query side in fused kernels (csrc/query_ops.cu)
+        self.split_decoder = True                    # eval, tensor-core mode: voxel features / encodings as split rows (TMA-fed decoder)
         # derived weight images (folded BatchNorm, tensor-core images) are cached per parameter generation
         self.register_load_state_dict_post_hook(lambda module, incompatible: ops.bump_param_generation())
 
@@ -367,7 +378,13 @@ class Agile3d(nn.Module):
             maps = self.backbone.prepare_maps(x)
             perm, inv = maps.perm[0], maps.inv[0]
             raw_i = raw if perm is None else ops.gather_rows(raw, perm)                # xyz in the internal row order
-            pos, rng = ops.fourier_posenc(raw_i, offsets, self.pos_enc.gauss_B)
+            split_dec = (not self.training) and self.split_decoder and self.backbone.split_rows \
+                and self.backbone.algo != ops.ALGO_SIMT and self.hidden_dim == 128
+            pos_s = None
+            if split_dec:
+                pos, rng, pos_s = ops.fourier_posenc(raw_i, offsets, self.pos_enc.gauss_B, want_split=True)
+            else:
+                pos, rng = ops.fourier_posenc(raw_i, offsets, self.pos_enc.gauss_B)
         if self.training:
             # batch-statistics BatchNorm + recorded activations; one autograd node for backbone + head (engine.py:53)
             named = [(n, p) for n, p in self.named_parameters()
@@ -377,16 +394,18 @@ class Agile3d(nn.Module):
             fmaps = holder["fmaps"]
         else:
             with torch.no_grad():
-                pcd, fmaps = self._forward_backbone_eval(x)
-        pcd_features = BackboneFeatures(pcd, offsets, x.C, perm, inv)
+                pcd, fmaps = self._forward_backbone_eval(x, split_dec)
+        pcd_features = BackboneFeatures(None, offsets, x.C, perm, inv, Fs=pcd) if split_dec \
+            else BackboneFeatures(pcd, offsets, x.C, perm, inv)
         coordinates = BackboneFeatures(raw, offsets, x.C)
         coordinates.range = rng
         # only the full-resolution level is ever read (hlevels=[4], agile3d.py:278); keep the reference's indexing
-        plist = _PosList([pos[offsets[b]:offsets[b + 1]] for b in range(n_scenes)], pcd_features)
+        plist = _PosList([pos[offsets[b]:offsets[b + 1]] for b in range(n_scenes)], pcd_features,
+                         None if pos_s is None else [pos_s[offsets[b]:offsets[b + 1]] for b in range(n_scenes)])
         pos_encodings_pcd = [None, None, None, None, [plist]]
         return pcd_features, fmaps, coordinates, pos_encodings_pcd
 
-    def _forward_backbone_eval(self, x):
+    def _forward_backbone_eval(self, x, out_split=False):
         feats, fmaps, maps = self.backbone(x)
         pcd = torch.empty((feats.shape[0], self.hidden_dim), dtype=torch.float32, device=feats.device)
         head = self.lin_squeeze_head
@@ -396,7 +415,7 @@ class Agile3d(nn.Module):
             self._head_tc = (hkey, wtc)
         split = self.backbone.split_rows and self.backbone.algo != ops.ALGO_SIMT
         ops.spconv_fwd(feats, None, head.kernel, pcd, None, head.bias.detach().reshape(-1).contiguous(), relu=False,
-                       algo=self.backbone.algo, weight_tc=self._head_tc[1], in_split=split)
+                       algo=self.backbone.algo, weight_tc=self._head_tc[1], in_split=split, out_split=out_split)
         # the 5 feature maps (`aux`) are opaque to every caller of the reference; in split mode they hold bf16 hi/lo pair
         # rows in the internal row order - hand out objects that say so instead of tensors that look like features
         return pcd, [_AuxMap(f, split) for f in fmaps]
@@ -465,7 +484,7 @@ class Agile3d(nn.Module):
         """Same kernels with or without autograd: in train mode (engine.py:119-121) the two voxel-streaming kernels run as
         autograd nodes (their backward is ag3d_c2s_attn_bwd / ag3d_s2c_mask_bwd) and the voxel features of every
         layer are kept; otherwise layers > 0 update the features in place."""
-        grad = torch.is_grad_enabled() and (self.training or pcd_features.Fp.requires_grad)
+        grad = torch.is_grad_enabled() and (self.training or (pcd_features.Fs is None and pcd_features.Fp.requires_grad))
         if not grad:
             with torch.no_grad():
                 if self.fused_queries:
@@ -524,7 +543,7 @@ class Agile3d(nn.Module):
 
     def _forward_mask_fused(self, pcd_features, coordinates, pos_encodings_pcd, click_idx, click_time_idx):
         H = self.num_heads
-        dev = pcd_features.Fp.device
+        dev = pcd_features.device
         offsets = pcd_features.offsets
         n_scenes = len(offsets) - 1
         tt = self.time_encode.to(dev) if self.time_encode.device != dev else self.time_encode
@@ -547,6 +566,7 @@ class Agile3d(nn.Module):
             groups.setdefault(n_fg + nbg + n_bgc, []).append(b)
         results = [None] * n_scenes
         pos_list = pos_encodings_pcd[self.hlevels[0]][0].internal
+        pos_list_s = pos_encodings_pcd[self.hlevels[0]][0].split
         for nq, members in groups.items():
             B = len(members)
             if nq > ops.S2C_MAX_QUERIES:
@@ -558,10 +578,15 @@ class Agile3d(nn.Module):
             # clicked voxels: xyz is read in the caller's order, the features in the backbone's internal order
             feat_row = src_row if pcd_features.inv is None else \
                 torch.where(src_row >= 0, pcd_features.inv[src_row.clamp(min=0).long()], src_row)
-            queries, qpos = ops.query_init(pcd_features.Fp, coordinates.F, coordinates.range, src_row, time_idx, scene_of_row,
+            # up to 24 queries per scene the voxel side runs on split rows through the TMA-fed kernels; beyond that on fp32
+            # rows (query groups, csrc/decoder_mq.cu), decoded once per scene batch
+            split = pcd_features.Fs is not None and pos_list_s is not None and nq <= ops.S2C_SPLIT_MAX_QUERIES
+            feats = pcd_features.Fs if split else pcd_features.Fp
+            queries, qpos = ops.query_init(feats, coordinates.F, coordinates.range, src_row, time_idx, scene_of_row,
                                            self.pos_enc.gauss_B, tt, self.bg_query_feat.weight, self.bg_query_pos.weight,
-                                           feat_row=feat_row if pcd_features.inv is not None else None)
-            srcs = [pcd_features.Fp[offsets[b]:offsets[b + 1]] for b in members]
+                                           feat_row=feat_row if pcd_features.inv is not None else None, feats_split=split)
+            srcs = [feats[offsets[b]:offsets[b + 1]] for b in members]
+            poss = pos_list_s if split else pos_list
             labels, counts = [None] * B, [None] * B
             outs = [[] for _ in members]
             ctx = torch.empty((B, H * nq, self.hidden_dim), dtype=torch.float32, device=dev)
@@ -570,15 +595,17 @@ class Agile3d(nn.Module):
                 s2c = self.s2c_attention[li][0]
                 blob = self._layer_blob(li)
                 qfold = ops.query_fold_c2s(queries, qpos, blob, B, nq, H)
+                last = layer == self.num_decoders - 1
                 for i, b in enumerate(members):
-                    ops.c2s_attn_fwd(srcs[i], pos_list[b], qfold[i], nq, H, labels[i], q_obj[i], counts[i], out=ctx[i])
+                    ops.c2s_attn_fwd(srcs[i], poss[b], qfold[i], nq, H, labels[i], q_obj[i], counts[i], out=ctx[i], split=split)
                 q1, qh, kh, vh = ops.query_update_a(ctx, queries, qpos, blob, B, nq, s2c.norm.eps)
                 queries, A, c, U, E = ops.query_update_b(q1, qh, kh, vh, qpos, blob, B, nq, H, s2c.norm.eps)
                 for i, b in enumerate(members):
                     srcs[i], logits, labels[i], counts[i] = ops.s2c_mask_fwd(
-                        srcs[i], pos_list[b], A[i], c[i], U[i], s2c.multihead_attn.out_proj.bias, s2c.norm.weight,
+                        srcs[i], poss[b], A[i], c[i], U[i], s2c.multihead_attn.out_proj.bias, s2c.norm.weight,
                         s2c.norm.bias, s2c.norm.eps, E[i], q_obj[i], nq, H, meta[b][0] + 1,
-                        x_out=None if layer == 0 else srcs[i])      # never overwrite the caller's backbone features
+                        x_out=None if layer == 0 else srcs[i],      # never overwrite the caller's backbone features
+                        split=split, write_x=not (split and last))  # the last layer's features are never read again
                     outs[i].append(logits)
             for i, b in enumerate(members):
                 results[b] = [pcd_features.to_caller(b, lg) for lg in outs[i]]      # logits back in the caller's row order

@@ -356,8 +356,9 @@ def stem_conv_fwd(coords, feats, table, cap, ksize, weight, out, scale=None, shi
     return out
 
 
-def fourier_posenc(xyz, scene_offsets, gauss_B):
-    """xyz f32 [N,3] (scenes contiguous), scene_offsets python list of B+1 ints -> (pos f32 [N,d], range f32 [B,6])."""
+def fourier_posenc(xyz, scene_offsets, gauss_B, want_split=False):
+    """xyz f32 [N,3] (scenes contiguous), scene_offsets python list of B+1 ints -> (pos f32 [N,d], range f32 [B,6]);
+    want_split: -> (pos, range, pos as "split" rows) for the TMA-fed decoder kernels."""
     _need_cuda(xyz, gauss_B)
     nb = len(scene_offsets) - 1
     d = 2 * gauss_B.shape[1]
@@ -366,6 +367,13 @@ def fourier_posenc(xyz, scene_offsets, gauss_B):
     wsb = lib().ag3d_posenc_workspace_bytes(nb)
     ws = torch.empty(wsb, dtype=torch.uint8, device=xyz.device)
     offs = (C.c_int32 * (nb + 1))(*scene_offsets)
+    if want_split:
+        outs = torch.empty_like(out)
+        with _Timed("posenc", 2 * 12 * xyz.shape[0] + 4 * d * xyz.shape[0]):
+            check(lib().ag3d_fourier_posenc_split(_p(xyz.contiguous()), C.cast(offs, C.c_void_p), nb, _p(gauss_B.contiguous()),
+                                                  d, _p(out), _p(outs), _p(rng), _p(ws), wsb, _stream()),
+                  "ag3d_fourier_posenc_split")
+        return out, rng, outs
     with _Timed("posenc", 2 * 12 * xyz.shape[0] + 4 * d * xyz.shape[0]):
         check(lib().ag3d_fourier_posenc(_p(xyz.contiguous()), C.cast(offs, C.c_void_p), nb, _p(gauss_B.contiguous()),
                                         d, _p(out), _p(rng), _p(ws), wsb, _stream()), "ag3d_fourier_posenc")
@@ -375,8 +383,10 @@ def fourier_posenc(xyz, scene_offsets, gauss_B):
 _c2s_ws = {}
 
 
-def c2s_attn_fwd(x, pos, qfold, nq, heads, label=None, q_obj=None, obj_count=None, algo=ALGO_AUTO, out=None, lse=None):
-    """-> ctx f32 [heads*nq, 128].  lse (optional f32 [heads*nq]) receives the rows' log-sum-exp (for the backward)."""
+def c2s_attn_fwd(x, pos, qfold, nq, heads, label=None, q_obj=None, obj_count=None, algo=ALGO_AUTO, out=None, lse=None,
+                 split=False):
+    """-> ctx f32 [heads*nq, 128].  lse (optional f32 [heads*nq]) receives the rows' log-sum-exp (for the backward).
+    split=True: x and pos are "split" rows (pack_split_rows / the tensor-core backbone's format), streamed by the TMA engine."""
     _need_cuda(x, pos, qfold)
     for t in (x, pos, qfold):
         if not t.is_contiguous() or t.dtype != torch.float32:
@@ -392,6 +402,11 @@ def c2s_attn_fwd(x, pos, qfold, nq, heads, label=None, q_obj=None, obj_count=Non
     nv = x.shape[0]
     # x + pos reads, bool mask bytes (layers 2-3), the three [nq,128] query-side matrices
     nbytes = 4 * nv * 128 * 2 + (nq * nv if label is not None else 0) + 4 * nq * 128 * 3
+    if split:
+        with _Timed("c2s", nbytes, 2 * 2 * nv * 128 * heads * nq):
+            check(lib().ag3d_c2s_attn_fwd_split(_p(x), _p(pos), nv, _p(qfold), nq, heads, _p(label), _p(q_obj), _p(obj_count),
+                                                _p(ctx), _p(lse), _p(ws), ws.numel(), _stream()), "ag3d_c2s_attn_fwd_split")
+        return ctx
     with _Timed("c2s", nbytes, 2 * 2 * nv * 128 * heads * nq):
         check(lib().ag3d_c2s_attn_fwd(_p(x), _p(pos), nv, _p(qfold), nq, heads, _p(label), _p(q_obj),
                                       _p(obj_count), _p(ctx), _p(lse), algo, _p(ws), ws.numel(), _stream()),
@@ -402,8 +417,13 @@ def c2s_attn_fwd(x, pos, qfold, nq, heads, label=None, q_obj=None, obj_count=Non
 S2C_MAX_QUERIES = 256       # per scene: 10 learned background queries + clicks (eval_multi_obj.py:116-167 reaches 210)
 
 
-def s2c_mask_fwd(x, pos, A, c, U, bo, ln_w, ln_b, ln_eps, E, q_obj, nq, heads, n_obj, x_out=None, algo=ALGO_AUTO):
-    """-> (x_out f32 [Nv,128], logits f32 [Nv,n_obj], label u8 [Nv], obj_count i32 [n_obj])."""
+S2C_SPLIT_MAX_QUERIES = 24  # the split-row (TMA-fed) variant: heads padded to 16 or 24 query columns
+
+
+def s2c_mask_fwd(x, pos, A, c, U, bo, ln_w, ln_b, ln_eps, E, q_obj, nq, heads, n_obj, x_out=None, algo=ALGO_AUTO,
+                 split=False, write_x=True):
+    """-> (x_out f32 [Nv,128], logits f32 [Nv,n_obj], label u8 [Nv], obj_count i32 [n_obj]).
+    split=True: x, pos and x_out are "split" rows (nq <= 24); write_x=False skips the feature write (last layer)."""
     _need_cuda(x, pos, A, c, U, E, q_obj)
     for t in (x, pos, A, c, U, bo, ln_w, ln_b, E):
         if not t.is_contiguous() or t.dtype != torch.float32:
@@ -411,7 +431,7 @@ def s2c_mask_fwd(x, pos, A, c, U, bo, ln_w, ln_b, ln_eps, E, q_obj, nq, heads, n
     if nq > S2C_MAX_QUERIES:
         raise _lib.Ag3dError(f"at most {S2C_MAX_QUERIES} click queries per scene, got {nq}")
     nv = x.shape[0]
-    if x_out is None:
+    if x_out is None and (write_x or not split):
         x_out = torch.empty_like(x)
     logits = torch.empty((nv, n_obj), dtype=torch.float32, device=x.device)
     label = torch.empty(nv, dtype=torch.uint8, device=x.device)
@@ -422,6 +442,15 @@ def s2c_mask_fwd(x, pos, A, c, U, bo, ln_w, ln_b, ln_eps, E, q_obj, nq, heads, n
     if algo != ALGO_SIMT:
         wsb = lib().ag3d_s2c_workspace_bytes(nq)
         ws = _workspace("s2c", x.device, wsb) if wsb else None
+    if split:
+        if nq > S2C_SPLIT_MAX_QUERIES or algo == ALGO_SIMT:
+            raise _lib.Ag3dError(f"the split-row s2c kernel handles at most {S2C_SPLIT_MAX_QUERIES} queries on the tensor-core path")
+        xo = x_out if write_x else None
+        with _Timed("s2c_mask", nbytes, 2 * nv * 128 * (2 * heads * nq + nq)):
+            check(lib().ag3d_s2c_mask_fwd_split(_p(x), _p(pos), nv, _p(A), _p(c), _p(U), _p(bo), _p(ln_w), _p(ln_b),
+                                                float(ln_eps), _p(E), _p(q_obj), nq, heads, n_obj, _p(xo), _p(logits),
+                                                _p(label), _p(obj_count), _p(ws), wsb, _stream()), "ag3d_s2c_mask_fwd_split")
+        return xo, logits, label, obj_count
     with _Timed("s2c_mask", nbytes, 2 * nv * 128 * (2 * heads * nq + nq)):
         check(lib().ag3d_s2c_mask_fwd(_p(x), _p(pos), nv, _p(A), _p(c), _p(U), _p(bo), _p(ln_w), _p(ln_b),
                                       float(ln_eps), _p(E), _p(q_obj), nq, heads, n_obj, _p(x_out), _p(logits),
@@ -492,15 +521,18 @@ def query_blob_floats():
     return int(lib().ag3d_query_blob_floats())
 
 
-def query_init(feats, xyz, rng, src_row, time_idx, scene_of_row, gauss_B, time_table, bg_feat, bg_pos, feat_row=None):
+def query_init(feats, xyz, rng, src_row, time_idx, scene_of_row, gauss_B, time_table, bg_feat, bg_pos, feat_row=None,
+               feats_split=False):
     """-> (queries, qpos) f32 [rows, 128]; src_row int32 [rows] (>= 0: clicked voxel row of xyz, -(k+1): learned bg query k);
-    feat_row (optional): the clicked voxels' rows in `feats` when it is stored in another row order."""
+    feat_row (optional): the clicked voxels' rows in `feats` when it is stored in another row order; feats_split: `feats`
+    holds "split" rows."""
     _need_cuda(feats, xyz, rng, src_row)
     n = src_row.shape[0]
     q = torch.empty((n, 128), dtype=torch.float32, device=feats.device)
     qp = torch.empty_like(q)
     check(lib().ag3d_query_init(_p(feats), _p(xyz), _p(rng), _p(src_row), _p(feat_row), _p(time_idx), _p(scene_of_row), n, _p(gauss_B),
-                                _p(time_table), _p(bg_feat), _p(bg_pos), _p(q), _p(qp), _stream()), "ag3d_query_init")
+                                _p(time_table), _p(bg_feat), _p(bg_pos), _p(q), _p(qp), 1 if feats_split else 0, _stream()),
+          "ag3d_query_init")
     return q, qp
 
 

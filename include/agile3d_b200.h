@@ -169,6 +169,11 @@ size_t ag3d_posenc_workspace_bytes(int32_t n_scenes);
 int ag3d_fourier_posenc(const float* xyz, const int32_t* scene_offsets_host, int32_t n_scenes,
                         const float* gauss_B, int32_t d_pos, float* out, float* range_out, void* ws,
                         size_t ws_bytes, ag3d_stream_t stream);
+/* ... and, additionally, the same encodings as "split" rows (out_split: [N, d_pos] as 32-channel slabs of 64 B bf16 hi |
+ * 64 B bf16 lo) for the TMA-fed decoder kernels (ag3d_c2s_attn_fwd_split / ag3d_s2c_mask_fwd_split).            */
+int ag3d_fourier_posenc_split(const float* xyz, const int32_t* scene_offsets_host, int32_t n_scenes,
+                              const float* gauss_B, int32_t d_pos, float* out, float* out_split, float* range_out,
+                              void* ws, size_t ws_bytes, ag3d_stream_t stream);
 
 /* ---- interactive loop around forward_mask and the voxelisation front end -----------
  * ag3d_click_pred:     pred[v] = argmax_o logits[v, o] (first maximum; logits == NULL: all zeros, the first round of
@@ -217,7 +222,7 @@ int64_t ag3d_query_blob_floats(void);
 int ag3d_query_init(const float* feats, const float* xyz, const float* range, const int32_t* src_row,
                     const int32_t* feat_row, const int32_t* time_idx, const int32_t* scene_of_row, int32_t n_rows, const float* gauss_B,
                     const float* time_table, const float* bg_feat, const float* bg_pos, float* queries, float* qpos,
-                    ag3d_stream_t stream);
+                    int32_t feats_split /* feats are "split" bf16 hi/lo rows */, ag3d_stream_t stream);
 int ag3d_query_fold_c2s(const float* queries, const float* qpos, const float* blob, int32_t n_scenes, int32_t nq,
                         float* qfold, ag3d_stream_t stream);
 int ag3d_query_update_a(const float* ctx, const float* queries, const float* qpos, const float* blob, int32_t n_scenes,
@@ -241,6 +246,12 @@ size_t ag3d_c2s_workspace_bytes(int32_t nq, int32_t heads);
 int ag3d_c2s_attn_fwd(const float* x, const float* pos, int64_t nv, const float* qfold, int32_t nq,
                       int32_t heads, const uint8_t* label, const int32_t* q_obj, const int32_t* obj_count,
                       float* ctx, float* lse, int32_t algo, void* ws, size_t ws_bytes, ag3d_stream_t stream);
+/* Same operator on "split" rows (x_split / pos_split: [nv, 128] rows of 4 x (64 B bf16 hi | 64 B bf16 lo), what
+ * ag3d_pack_split and the tensor-core backbone write): the voxel tiles go from HBM to the tensor core through the TMA
+ * engine (2-D box loads into SWIZZLE_128B tiles) with no thread touching them; scores are Qf.x^T + Qf.pos^T.   */
+int ag3d_c2s_attn_fwd_split(const float* x_split, const float* pos_split, int64_t nv, const float* qfold, int32_t nq,
+                            int32_t heads, const uint8_t* label, const int32_t* q_obj, const int32_t* obj_count,
+                            float* ctx, float* lse, void* ws, size_t ws_bytes, ag3d_stream_t stream);
 
 /* ---- scene -> click cross-attention + LayerNorm + mask head (s2c) --------------------------------------
  * Replaces CrossAttentionLayer.forward_post as called at models/agile3d.py:305-312 plus
@@ -259,6 +270,14 @@ int ag3d_s2c_mask_fwd(const float* x, const float* pos, int64_t nv, const float*
                       const float* E, const int32_t* q_obj, int32_t nq, int32_t heads, int32_t n_obj,
                       float* x_out, float* logits, uint8_t* label, int32_t* obj_count, int32_t algo, void* ws,
                       size_t ws_bytes, ag3d_stream_t stream);
+/* Same operator on "split" rows (see ag3d_c2s_attn_fwd_split) for at most 24 click queries: x_split / pos_split tiles
+ * arrive through the TMA engine, scores are x.A^T + pos.A^T, the updated features leave as split rows.  x_out_split
+ * may alias x_split (in place) and may be NULL (last decoder layer: the features are not read again).        */
+int ag3d_s2c_mask_fwd_split(const float* x_split, const float* pos_split, int64_t nv, const float* A, const float* c,
+                            const float* U, const float* bo, const float* ln_w, const float* ln_b, float ln_eps,
+                            const float* E, const int32_t* q_obj, int32_t nq, int32_t heads, int32_t n_obj,
+                            float* x_out_split, float* logits, uint8_t* label, int32_t* obj_count, void* ws,
+                            size_t ws_bytes, ag3d_stream_t stream);
 
 /* ======================================================================================================
  * Training step (e): what autograd + MinkowskiEngine's backward kernels + ATen do in

@@ -138,7 +138,14 @@ def stem_conv_fwd(coords, feats, table, cap, ksize, weight, out, scale=None, shi
     return spconv_fwd(feats, nbr, weight, out, scale, shift, None, relu)
 
 
-def fourier_posenc(xyz, scene_offsets, gauss_B):
+def unpack_split(xs):
+    return xs          # the emulation keeps "split" rows as plain fp32 values (the bf16 hi/lo format is a storage detail)
+
+
+def fourier_posenc(xyz, scene_offsets, gauss_B, want_split=False):
+    if want_split:
+        pos, r = fourier_posenc(xyz, scene_offsets, gauss_B)
+        return pos, r, pos.clone()
     outs, rng = [], []
     for b in range(len(scene_offsets) - 1):
         p = xyz[scene_offsets[b]:scene_offsets[b + 1]]
@@ -149,7 +156,7 @@ def fourier_posenc(xyz, scene_offsets, gauss_B):
     return torch.cat(outs, 0), torch.stack(rng, 0)
 
 
-def c2s_attn_fwd(x, pos, qfold, nq, heads, label=None, q_obj=None, obj_count=None, algo=0, out=None, lse=None):
+def c2s_attn_fwd(x, pos, qfold, nq, heads, label=None, q_obj=None, obj_count=None, algo=0, out=None, lse=None, split=False):
     s = qfold @ (x + pos).T                                   # [H*nq, Nv]
     if label is not None:
         s = s.clone()
@@ -167,7 +174,8 @@ def c2s_attn_fwd(x, pos, qfold, nq, heads, label=None, q_obj=None, obj_count=Non
     return r
 
 
-def s2c_mask_fwd(x, pos, A, c, U, bo, ln_w, ln_b, ln_eps, E, q_obj, nq, heads, n_obj, x_out=None, algo=0):
+def s2c_mask_fwd(x, pos, A, c, U, bo, ln_w, ln_b, ln_eps, E, q_obj, nq, heads, n_obj, x_out=None, algo=0, split=False,
+                 write_x=True):
     s = (x + pos) @ A.T + c                                   # [Nv, H*nq]
     a = torch.softmax(s.view(-1, heads, nq), dim=2).reshape(-1, heads * nq)
     y = torch.nn.functional.layer_norm(x + (a @ U + bo), (x.shape[1],), ln_w, ln_b, ln_eps)
@@ -182,7 +190,7 @@ def s2c_mask_fwd(x, pos, A, c, U, bo, ln_w, ln_b, ln_eps, E, q_obj, nq, heads, n
     if x_out is not None:
         x_out.copy_(y)
         y = x_out
-    return y, logits, label, obj_count
+    return (y if write_x else None), logits, label, obj_count
 
 
 # ------------------------------------------------------------------------------------------------ training step
@@ -395,7 +403,8 @@ def _ln(x, w, b, eps):
     return torch.nn.functional.layer_norm(x, (x.shape[-1],), w, b, eps)
 
 
-def query_init(feats, xyz, rng, src_row, time_idx, scene_of_row, gauss_B, time_table, bg_feat, bg_pos, feat_row=None):
+def query_init(feats, xyz, rng, src_row, time_idx, scene_of_row, gauss_B, time_table, bg_feat, bg_pos, feat_row=None,
+               feats_split=False):
     n = src_row.shape[0]
     q = torch.empty((n, _QD), dtype=feats.dtype)
     qp = torch.empty_like(q)
@@ -449,7 +458,7 @@ def query_update_b(q1, qh, kh, vh, qpos, blob, B, nq, heads=8, ln_eps=1e-5):
 ALL = ["wgrad_tc_supported", "c2s_attn_bwd_tc", "s2c_mask_bwd_tc_any",
        "bn_stats", "bn_apply", "bn_bwd", "col_sum", "spconv_bwd_weight", "stem_bwd_weight", "decoder_bwd_rows",
        "c2s_attn_bwd", "s2c_mask_bwd", "loss_fwd", "loss_bwd", "click_loss_weights", "grad_norm", "adamw_step",
-       "prepare_tc_weight", "hash_build", "downsample", "build_levels", "gather_rows", "brick_rows", "row_order", "permute_map", "kernel_map", "kernel_map_transposed", "spconv_fwd", "stem_conv_fwd",
+       "prepare_tc_weight", "hash_build", "downsample", "build_levels", "unpack_split", "gather_rows", "brick_rows", "row_order", "permute_map", "kernel_map", "kernel_map_transposed", "spconv_fwd", "stem_conv_fwd",
        "fourier_posenc", "c2s_attn_fwd", "s2c_mask_fwd", "query_blob_floats", "query_init", "query_fold_c2s",
        "query_update_a", "query_update_b"]
 

@@ -285,6 +285,64 @@ def test_c2s_vs_oracle(nv, nq, n_obj, algo):
     assert rel_err(got.cpu().numpy(), ref.numpy()) < 1e-4
 
 
+@pytest.mark.parametrize("nv,nq,n_obj", [(1000, 11, 2), (5003, 15, 3), (20000, 20, 6), (4100, 27, 9), (3000, 45, 11),
+                                         (64, 16, 3), (65, 12, 2), (150001, 20, 6)])
+def test_c2s_split_rows_vs_oracle(nv, nq, n_obj):
+    """the TMA-fed kernel on split rows: compared with the fp64 oracle evaluated on the values the split rows hold
+    (hi + lo, 2^-17 relative from x) and with the fp32-row kernel"""
+    from agile3d_b200 import ops
+    g, x, pos, qf, q_obj = _decoder_inputs(nv, nq, n_obj, seed=nv + nq)
+    xs, ps = ops.pack_split_rows(x.to(DEV)), ops.pack_split_rows(pos.to(DEV))
+    xv, pv = ops.unpack_split(xs).cpu().double(), ops.unpack_split(ps).cpu().double()
+    ref = emulate.c2s_attn_fwd(xv, pv, qf.double(), nq, 8)
+    got = ops.c2s_attn_fwd(xs, ps, qf.to(DEV), nq, 8, split=True)
+    assert rel_err(got.cpu().numpy(), ref.numpy()) < 1e-4
+    old = ops.c2s_attn_fwd(x.to(DEV), pos.to(DEV), qf.to(DEV), nq, 8, algo=2)
+    assert rel_err(got.cpu().numpy(), old.cpu().numpy()) < 1e-4
+    label = torch.randint(0, max(n_obj - 1, 1), (nv,), generator=g).to(torch.uint8)
+    cnt = torch.bincount(label.long(), minlength=n_obj).to(torch.int32)
+    ref = emulate.c2s_attn_fwd(xv, pv, qf.double(), nq, 8, label, q_obj, cnt)
+    lse = torch.empty(8 * nq, device=DEV)
+    got = ops.c2s_attn_fwd(xs, ps, qf.to(DEV), nq, 8, label.to(DEV), q_obj.to(DEV), cnt.to(DEV), split=True, lse=lse)
+    assert rel_err(got.cpu().numpy(), ref.numpy()) < 1e-4
+    assert bool(torch.isfinite(lse[: 8 * nq]).any())
+
+
+@pytest.mark.parametrize("nv,nq,n_obj", [(1000, 11, 2), (5003, 15, 3), (20000, 20, 6), (4100, 24, 9), (777, 24, 12),
+                                         (128, 16, 4), (129, 20, 5), (150001, 20, 6)])
+def test_s2c_mask_split_rows_vs_oracle(nv, nq, n_obj):
+    """the TMA-fed kernel on split rows vs the fp64 oracle evaluated on the values the split rows hold"""
+    from agile3d_b200 import ops
+    g, x, pos, _, q_obj = _decoder_inputs(nv, nq, n_obj, seed=nv * 3 + nq)
+    A = torch.randn((8 * nq, 128), generator=g) * 0.05
+    c = torch.randn(8 * nq, generator=g) * 0.1
+    U = torch.randn((8 * nq, 128), generator=g) * 0.3
+    bo, lw, lb = torch.randn(128, generator=g) * 0.1, torch.rand(128, generator=g) + 0.5, torch.randn(128, generator=g) * 0.1
+    E = torch.randn((nq, 128), generator=g) * 0.2
+    d = lambda t: t.double()
+    t = lambda v: v.to(DEV)
+    xs, ps = ops.pack_split_rows(t(x)), ops.pack_split_rows(t(pos))
+    xv, pv = ops.unpack_split(xs).cpu(), ops.unpack_split(ps).cpu()
+    ry, rl, rlab, rcnt = emulate.s2c_mask_fwd(d(xv), d(pv), d(A), d(c), d(U), d(bo), d(lw), d(lb), 1e-5, d(E), q_obj,
+                                              nq, 8, n_obj)
+    y, lg, lab, cnt = ops.s2c_mask_fwd(xs, ps, t(A), t(c), t(U), t(bo), t(lw), t(lb), 1e-5, t(E), t(q_obj), nq, 8, n_obj,
+                                       split=True)
+    assert rel_err(ops.unpack_split(y).cpu().numpy(), ry.numpy()) < 1e-4
+    assert rel_err(lg.cpu().numpy(), rl.numpy()) < 1e-4
+    top2 = torch.topk(rl, min(2, n_obj), dim=1)[0]
+    safe = (top2[:, 0] - top2[:, -1]) > 1e-3 if n_obj > 1 else torch.ones(nv, dtype=torch.bool)
+    assert torch.equal(lab.cpu()[safe], rlab[safe])
+    assert int(cnt.sum()) == nv and torch.equal(cnt.cpu(), torch.bincount(lab.cpu().long(), minlength=n_obj).int())
+    # in place (x_out aliases x) and without the feature write: same logits
+    xd = xs.clone()
+    y2, lg2, _, _ = ops.s2c_mask_fwd(xd, ps, t(A), t(c), t(U), t(bo), t(lw), t(lb), 1e-5, t(E), t(q_obj), nq, 8, n_obj,
+                                     x_out=xd, split=True)
+    assert torch.equal(y2, y) and torch.equal(lg2, lg)
+    y3, lg3, _, _ = ops.s2c_mask_fwd(xs, ps, t(A), t(c), t(U), t(bo), t(lw), t(lb), 1e-5, t(E), t(q_obj), nq, 8, n_obj,
+                                     split=True, write_x=False)
+    assert y3 is None and torch.equal(lg3, lg)
+
+
 @pytest.mark.parametrize("algo", [1, 2], ids=["simt", "tc"])
 @pytest.mark.parametrize("nv,nq,n_obj", [(1000, 11, 2), (5003, 15, 3), (20000, 20, 6), (4100, 25, 9), (777, 32, 12),
                                          (128, 16, 4), (129, 17, 5)])

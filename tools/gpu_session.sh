@@ -1,16 +1,15 @@
 #!/bin/bash
-# Current GPU session (overwritten per call; results land in gpurun_out/ and the kept ones are copied to profiles/).
 cd "$GRAFT_REPO_ROOT" || exit 1
 mkdir -p gpurun_out
-S=s17
+S=s21
 timeout 1800 python -m pytest tests -x -q -m gpu > gpurun_out/${S}_pytest_gpu.log 2>&1
-tail -n 5 gpurun_out/${S}_pytest_gpu.log
-timeout 900 python bench.py --steps 8 --no-parity > gpurun_out/${S}_bench_n1.json 2> gpurun_out/${S}_n1.err
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/${S}_launches.csv python tools/profile_step.py --batch 8 > gpurun_out/${S}_launches.log 2>&1
+tail -n 12 gpurun_out/${S}_pytest_gpu.log
+timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${S}_smoke.log 2>&1; tail -n 2 gpurun_out/${S}_smoke.log
+timeout 900 python bench.py --steps 8 > gpurun_out/${S}_bench_n1.json 2> gpurun_out/${S}_n1.err
 python - <<PY
 import json
 d = json.load(open("gpurun_out/${S}_bench_n1.json"))
-print({k: d[k] for k in ("value", "ms_per_step")}, "e2e", d["e2e"]["value"])
+print({k: d[k] for k in ("value", "ms_per_step", "parity")}, "e2e", d["e2e"]["value"])
 print({k: v["ms_per_step"] for k, v in d["roofline"]["families"].items()})
 PY
 tail -n 3 gpurun_out/${S}_n1.err
