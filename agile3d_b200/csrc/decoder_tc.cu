@@ -457,15 +457,20 @@ static int s2c_tc_launch_t(const float* x, const float* pos, long long nv, const
 }
 
 // ============================================================================================== split-row variant
-// Same three chained GEMMs, but the voxel tile never passes through registers on its way in: x and pos are "split" rows
-// (32-channel slabs of 64 B bf16 hi | 64 B bf16 lo) and the TMA engine drops their [128 voxels x 128 B] slab tiles
-// into SWIZZLE_128B shared memory, which is directly the K-major A operand of
-//   S = x . A^T + pos . A^T      (one weight slab serves both terms; no (x + pos) tile is formed)
-// The probabilities P and the LayerNorm output Y are written in the same swizzled slab format (conflict-free 16-byte
-// stores, no padding), Y in place over the x tile, whose values are the residual input of the LayerNorm.  The updated
-// voxel features leave as split rows (x_out_split, nullable: the last decoder layer's features are never read).
-// Roles: 8 compute warps (softmax, LayerNorm, mask head), MMA issuer, operand-ring loader, voxel-tile TMA producer.
-constexpr int DS_COMPUTE_WARPS = 16;                  // four threads per voxel row (TMEM lane quarter q4 = warp & 3, part = warp >> 2)
+// Same three chained GEMMs, but the voxel tile never passes through registers on its way in or out: x and pos are
+// "split" rows (32-channel slabs of 64 B bf16 hi | 64 B bf16 lo) and the TMA engine drops their [128 voxels x 128 B]
+// slab tiles into SWIZZLE_128B shared memory, which is directly the K-major A operand of
+//   S = pos . A^T + x . A^T      (two passes over the weight slabs: the pos tile of the NEXT voxel tile is fetched as
+//                                 soon as the score GEMM of this one has read it, the x tile once the mask head has
+//                                 read Y, and the pos pass runs while the x tile is still landing)
+// The probabilities P never touch shared memory: they overwrite the scores in TENSOR MEMORY (bf16 hi | lo, two queries
+// per 32-bit column) and are the A operand of O = P . U from there (tcgen05.mma with A in TMEM).  The LayerNorm
+// output Y is written in the swizzled slab format in place over the x tile (whose values are the residual input), is
+// the A operand of the mask-head GEMM, and leaves as split rows through four bulk tensor stores per tile (x_out_split,
+// nullable: the last decoder layer's features are never read).
+// Roles: 16 compute warps (softmax, LayerNorm, mask head; four threads per voxel row), MMA issuer, operand-ring loader,
+// voxel-tile TMA producer.
+constexpr int DS_COMPUTE_WARPS = 16;                  // TMEM lane quarter q4 = warp & 3, part g = warp >> 2
 constexpr int DS_THREADS = DS_COMPUTE_WARPS * 32 + 96;
 constexpr uint32_t DS_SLAB = 16384;                    // [128 voxels x 128 B]
 constexpr uint32_t DS_MISC = 8192;
@@ -476,11 +481,10 @@ struct S2sCfg {
   static constexpr int SLABS_P = HQP / 32;
   static constexpr int G1_CHUNKS = HQP * 128 > 16384 ? 2 : 1;
   static constexpr int G1_BYTES = HQP * 128 / G1_CHUNKS;
-  static constexpr int NBR = (HQP <= 128) ? 5 : 3;
+  static constexpr int NBR = 5;
   static constexpr uint32_t OFF_X = 0;
-  static constexpr uint32_t OFF_P = 4 * DS_SLAB;                                  // pos tile, then P
-  static constexpr uint32_t P_BYTES = (SLABS_P > 4 ? SLABS_P : 4) * DS_SLAB;
-  static constexpr uint32_t OFF_RING = OFF_P + P_BYTES;
+  static constexpr uint32_t OFF_POS = 4 * DS_SLAB;
+  static constexpr uint32_t OFF_RING = OFF_POS + 4 * DS_SLAB;
   static constexpr uint32_t OFF_MISC = OFF_RING + NBR * 16384;
   static constexpr size_t SMEM = OFF_MISC + DS_MISC;
 };
@@ -503,6 +507,15 @@ __device__ __forceinline__ void ds_tma_tile(uint32_t dst, const CUtensorMap* tm,
 }
 // byte offset of the 16-byte chunk `ch` (0..3 hi pieces, 4..7 lo pieces of 8 channels) of row r inside a swizzled slab tile
 __device__ __forceinline__ uint32_t ds_chunk_off(int r, int ch) { return (uint32_t)(r * 128 + ((ch ^ (r & 7)) << 4)); }
+// D[tmem] (+)= A[tmem] . B[smem]: A (bf16, two K elements per 32-bit column, row = lane) read from tensor memory
+__device__ __forceinline__ void ds_umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 
 template <int NQ16>
 __global__ void __launch_bounds__(DS_THREADS, 1)
@@ -513,7 +526,7 @@ s2c_split_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   constexpr uint32_t B_STAGE = 16384;
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* Xs = smem + Cfg::OFF_X;                         // x tile (4 slabs); later Y in place
-  unsigned char* Pb = smem + Cfg::OFF_P;                         // pos tile (4 slabs); later P (SLABS_P slabs)
+  unsigned char* Ps = smem + Cfg::OFF_POS;                       // pos tile (4 slabs)
   unsigned char* ring = smem + Cfg::OFF_RING;
   unsigned char* misc = smem + Cfg::OFF_MISC;
   uint64_t* bars = reinterpret_cast<uint64_t*>(misc);            // [0..6] phase barriers, [8..15] ring full, [16..23] ring empty
@@ -526,14 +539,14 @@ s2c_split_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t bar_base = smem_u32(bars);
-  const uint32_t in_full = bar_base, s_full = bar_base + 8, p_full = bar_base + 16, o_full = bar_base + 24,
-                 y_full = bar_base + 32, z_full = bar_base + 40;
+  const uint32_t x_full = bar_base, s_full = bar_base + 8, p_full = bar_base + 16, o_full = bar_base + 24,
+                 y_full = bar_base + 32, z_full = bar_base + 40, pos_full = bar_base + 48;
   auto b_full = [&](int s) { return bar_base + 8u * (8 + s); };
   auto b_empty = [&](int s) { return bar_base + 8u * (16 + s); };
 
   if (tid == 0) {
     if (smem_u32(smem) & 1023u) __trap();
-    mbar_init(in_full, 1); mbar_init(p_full, DS_COMPUTE_WARPS); mbar_init(y_full, DS_COMPUTE_WARPS);
+    mbar_init(x_full, 1); mbar_init(pos_full, 1); mbar_init(p_full, DS_COMPUTE_WARPS); mbar_init(y_full, DS_COMPUTE_WARPS);
     mbar_init(s_full, 1); mbar_init(o_full, 1); mbar_init(z_full, 1);
     for (int s = 0; s < NBR; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -563,48 +576,56 @@ s2c_split_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const uint32_t ph = (uint32_t)it & 1u;
       const long long row0 = tile * TC_BM;
-      // ---- P1: per-head softmax over the queries; this thread: row r, heads 2g, 2g+1
+      // ---- P1: per-head softmax over the queries; this thread: row r, heads 2g, 2g+1.  The probabilities replace the
+      //      scores in tensor memory (hi pairs in columns [0, HQP/2), lo pairs in [HQP/2, HQP)), so the four threads of a
+      //      row first read all their scores (named barrier 2 + q4) and only then write.
       mbar_wait(s_full, ph);
       tc_fence_after();
-      if (!(p.debug & 32))
+      float sc[2 * NQ16];
+      if constexpr (NQ16 % 16 == 0) {
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        const int col0 = (2 * g + hh) * NQ16;
-        float sc[NQ16];
-        if constexpr (NQ16 % 16 == 0) {
+        for (int ch = 0; ch < 2 * NQ16 / 16; ++ch) tmem_ld16(t_lane + TM_S + 2 * g * NQ16 + ch * 16, sc + ch * 16);
+      } else {
 #pragma unroll
-          for (int ch = 0; ch < NQ16 / 16; ++ch) tmem_ld16(t_lane + TM_S + col0 + ch * 16, sc + ch * 16);
-        } else {
+        for (int ch = 0; ch < 2 * NQ16 / 8; ++ch) tmem_ld8(t_lane + TM_S + 2 * g * NQ16 + ch * 8, sc + ch * 8);
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(2 + q4) : "memory");
+      uint32_t ph_[NQ16], pl_[NQ16];                    // 2 * NQ16 probabilities as bf16 pairs
+      if (p.debug & 32) {
 #pragma unroll
-          for (int ch = 0; ch < NQ16 / 8; ++ch) tmem_ld8(t_lane + TM_S + col0 + ch * 8, sc + ch * 8);
-        }
-        float mx = -INFINITY;
+        for (int i = 0; i < NQ16; ++i) ph_[i] = pl_[i] = 0u;
+      } else {
 #pragma unroll
-        for (int i = 0; i < NQ16; ++i) { sc[i] += cpad_s[col0 + i]; mx = fmaxf(mx, sc[i]); }
-        float sum = 0.f;
+        for (int hh = 0; hh < 2; ++hh) {
+          float* s = sc + hh * NQ16;
+          const int col0 = (2 * g + hh) * NQ16;
+          float mx = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < NQ16; ++i) { sc[i] = __expf(sc[i] - mx); sum += sc[i]; }
-        const float inv = 1.f / sum;
+          for (int i = 0; i < NQ16; ++i) { s[i] += cpad_s[col0 + i]; mx = fmaxf(mx, s[i]); }
+          float sum = 0.f;
 #pragma unroll
-        for (int c8 = 0; c8 < NQ16 / 8; ++c8) {
-          uint32_t h[4], l[4];
+          for (int i = 0; i < NQ16; ++i) { s[i] = __expf(s[i] - mx); sum += s[i]; }
+          const float inv = 1.f / sum;
 #pragma unroll
-          for (int e = 0; e < 4; ++e) split2(sc[c8 * 8 + 2 * e] * inv, sc[c8 * 8 + 2 * e + 1] * inv, h[e], l[e]);
-          const int col = col0 + c8 * 8;
-          unsigned char* slab = Pb + (size_t)(col >> 5) * DS_SLAB;
-          const int k = (col >> 3) & 3;
-          *reinterpret_cast<uint4*>(slab + ds_chunk_off(r, k)) = make_uint4(h[0], h[1], h[2], h[3]);
-          *reinterpret_cast<uint4*>(slab + ds_chunk_off(r, 4 + k)) = make_uint4(l[0], l[1], l[2], l[3]);
+          for (int i = 0; i < NQ16 / 2; ++i) split2(s[2 * i] * inv, s[2 * i + 1] * inv, ph_[hh * (NQ16 / 2) + i], pl_[hh * (NQ16 / 2) + i]);
         }
       }
+      {
+        const uint32_t c_hi = t_lane + TM_S + (uint32_t)(g * NQ16), c_lo = c_hi + HQP / 2;
+#pragma unroll
+        for (int ch = 0; ch < NQ16 / 8; ++ch) {
+          tmem_st8(c_hi + ch * 8, ph_ + ch * 8);
+          tmem_st8(c_lo + ch * 8, pl_ + ch * 8);
+        }
+      }
+      tmem_st_wait();
       tc_fence_before();
-      fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
 
       // ---- P2: o + bo + x -> LayerNorm -> y; this thread: row r, channels 32g .. 32g+31 (slab g)
       mbar_wait(o_full, ph);
-      mbar_wait(in_full, ph);                           // the x tile was written by the TMA engine: observe its barrier
+      mbar_wait(x_full, ph);                            // the x tile was written by the TMA engine: observe its barrier
       tc_fence_after();
       const long long row = row0 + r;
       const bool valid = row < p.nv;
@@ -661,7 +682,7 @@ s2c_split_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       __syncwarp();
       if (lane == 0) mbar_arrive(y_full);
 
-      // ---- P3: mask head (column half 0 only: 32 query columns)
+      // ---- P3: mask head (part 0 only: 32 query columns)
       mbar_wait(z_full, ph);
       tc_fence_after();
       if (g == 0) {
@@ -689,13 +710,14 @@ s2c_split_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     const uint32_t id_s = umma_idesc_bf16(HQP), id_o = umma_idesc_bf16(128), id_z = umma_idesc_bf16(DT_NQP);
     const uint32_t d_hi32 = umma_desc_hi32(128);                     // ring operands: no swizzle, SBO = 128
     const uint32_t sw_hi32 = umma_desc_hi32(1024) | (2u << 29);      // voxel-side operands: SWIZZLE_128B slab tiles
-    const uint32_t x_lo32 = umma_desc_lo32(smem_u32(Xs), 16), p_lo32 = umma_desc_lo32(smem_u32(Pb), 16);
+    const uint32_t x_lo32 = umma_desc_lo32(smem_u32(Xs), 16), pos_lo32 = umma_desc_lo32(smem_u32(Ps), 16);
     const uint32_t ring_u32 = smem_u32(ring);
     int nb = 0, it = 0;
-    // one GEMM = `slabs` K-slabs x n_a A tiles x (2 k-steps x 3 products); chunks: ring slots per slab (2: hi and lo piece
-    // in separate slots; 1: whole slab image in one slot; 0: all slabs in ONE slot)
-    auto gemm = [&](int slabs, uint32_t d, uint32_t idesc, uint32_t b_lbo, int chunks, uint32_t b_slab, uint32_t a0,
-                    uint32_t a1, bool skip) {
+    // one GEMM pass = `slabs` K-slabs x (2 k-steps x 3 products).  chunks: ring slots per slab (2: hi and lo piece in
+    // separate slots; 1: whole slab image in one slot; 0: all slabs in ONE slot).  a_smem: descriptor base of the
+    // swizzled A slab tiles; 0 = A is P in tensor memory (a_tmem: hi pairs, + HQP/2 columns: lo pairs)
+    auto gemm = [&](int slabs, uint32_t d, uint32_t idesc, uint32_t b_lbo, int chunks, uint32_t b_slab, uint32_t a_smem,
+                    uint32_t a_tmem, bool first, bool skip) {
       uint32_t b_hi = 0, b_lo = 0;
       for (int s = 0; s < slabs; ++s) {
         if (chunks || s == 0) {
@@ -713,21 +735,24 @@ s2c_split_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         const uint32_t off = chunks ? 0u : ((uint32_t)s * b_slab) >> 4;
         const bool release = chunks || s == slabs - 1;
         if (elect_one()) {
-          if (!skip)
-#pragma unroll
-          for (int o = 0; o < 2; ++o) {
-            const uint32_t abase = o ? a1 : a0;
-            if (o && !a1) break;
-            const uint32_t ah = abase + (uint32_t)s * (DS_SLAB >> 4);
+          if (!skip) {
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
-              const uint64_t da_hi = umma_desc_join(sw_hi32, ah + ks * 2u);
-              const uint64_t da_lo = umma_desc_join(sw_hi32, ah + ks * 2u + 4u);
               const uint64_t db_hi = umma_desc_join(d_hi32, b_hi + off + ks * ((2u * b_lbo) >> 4));
               const uint64_t db_lo = umma_desc_join(d_hi32, b_lo + off + ks * ((2u * b_lbo) >> 4));
-              umma_bf16(d, da_hi, db_hi, idesc, (s | ks | o) ? 1u : 0u);
-              umma_bf16(d, da_hi, db_lo, idesc, 1u);
-              umma_bf16(d, da_lo, db_hi, idesc, 1u);
+              const uint32_t acc0 = (!first || s || ks) ? 1u : 0u;
+              if (a_smem) {
+                const uint32_t ah = a_smem + (uint32_t)s * (DS_SLAB >> 4) + ks * 2u;
+                const uint64_t da_hi = umma_desc_join(sw_hi32, ah), da_lo = umma_desc_join(sw_hi32, ah + 4u);
+                umma_bf16(d, da_hi, db_hi, idesc, acc0);
+                umma_bf16(d, da_hi, db_lo, idesc, 1u);
+                umma_bf16(d, da_lo, db_hi, idesc, 1u);
+              } else {
+                const uint32_t ta = a_tmem + (uint32_t)(s * 16 + ks * 8);     // 16 queries = 8 columns per k-step
+                ds_umma_ts(d, ta, db_hi, idesc, acc0);
+                ds_umma_ts(d, ta, db_lo, idesc, 1u);
+                ds_umma_ts(d, ta + HQP / 2, db_hi, idesc, 1u);
+              }
             }
           }
           if (release) {
@@ -741,30 +766,36 @@ s2c_split_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     };
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const uint32_t ph = (uint32_t)it & 1u;
-      mbar_wait(in_full, ph);
+      mbar_wait(pos_full, ph);
       tc_fence_after();
-      gemm(4, tmem_base + TM_S, id_s, (uint32_t)HQP * 16u, Cfg::G1_CHUNKS, 0, x_lo32, p_lo32, p.debug & 1);
+      gemm(4, tmem_base + TM_S, id_s, (uint32_t)HQP * 16u, Cfg::G1_CHUNKS, 0, pos_lo32, 0u, true, p.debug & 1);
+      mbar_wait(x_full, ph);
+      tc_fence_after();
+      gemm(4, tmem_base + TM_S, id_s, (uint32_t)HQP * 16u, Cfg::G1_CHUNKS, 0, x_lo32, 0u, false, p.debug & 1);
       if (elect_one()) umma_commit(s_full);
       __syncwarp();
       mbar_wait(p_full, ph);
       tc_fence_after();
-      gemm(SLABS_P, tmem_base + TM_O, id_o, 128u * 16u, 1, 0, p_lo32, 0u, p.debug & 2);
+      gemm(SLABS_P, tmem_base + TM_O, id_o, 128u * 16u, 1, 0, 0u, tmem_base + TM_S, true, p.debug & 2);
       if (elect_one()) umma_commit(o_full);
       __syncwarp();
       mbar_wait(y_full, ph);
       tc_fence_after();
-      gemm(4, tmem_base + TM_Z, id_z, (uint32_t)DT_NQP * 16u, 0, 4096u, x_lo32, 0u, p.debug & 4);
+      gemm(4, tmem_base + TM_Z, id_z, (uint32_t)DT_NQP * 16u, 0, 4096u, x_lo32, 0u, true, p.debug & 4);
       if (elect_one()) umma_commit(z_full);
       __syncwarp();
     }
   } else if (warp == DS_COMPUTE_WARPS + 1) {
     // ======================================================================================= operand loader
+    // per tile: the score operand twice (pos pass, x pass), the out-projection slabs, the mask embeddings
     const unsigned char* img = reinterpret_cast<const unsigned char*>(p.img);
+    constexpr int N1 = 4 * Cfg::G1_CHUNKS;
     int nb = 0;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      size_t off = 0;
-      for (int st = 0; st < 4 * Cfg::G1_CHUNKS + SLABS_P + 1; ++st) {
-        const uint32_t bytes = st < 4 * Cfg::G1_CHUNKS ? (uint32_t)Cfg::G1_BYTES : 16384u;
+      for (int st = 0; st < 2 * N1 + SLABS_P + 1; ++st) {
+        const int k = st < N1 ? st : st - N1;                         // position in the image (consumption order G1 | G2 | G3)
+        const uint32_t bytes = k < N1 ? (uint32_t)Cfg::G1_BYTES : 16384u;
+        const size_t off = k < N1 ? (size_t)k * Cfg::G1_BYTES : (size_t)N1 * Cfg::G1_BYTES + (size_t)(k - N1) * 16384u;
         const int sb = nb % NBR;
         mbar_wait(b_empty(sb), ((uint32_t)(nb / NBR) & 1u) ^ 1u);
         if (elect_one()) {
@@ -776,34 +807,40 @@ s2c_split_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           }
         }
         __syncwarp();
-        off += bytes;
         ++nb;
       }
     }
   } else {
     // ======================================================================================= voxel-tile producer
-    // the x tile is dead once the mask-head GEMM of the previous tile has read Y (z_full), the pos/P region earlier
-    // ... and the updated features leave the same way: Y sits in the x region in exactly the layout of the output's
-    // tensor map, so one thread stores the tile with four bulk tensor copies (rows past the end are clipped) instead of
-    // every thread writing 16-byte pieces of its own row (32 rows per warp instruction)
-    int it = 0;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-      if (it > 0) mbar_wait(z_full, (uint32_t)(it - 1) & 1u);
+    // pos tile of tile i+1: as soon as the score GEMM of tile i is complete (s_full); x tile of tile i+1: once the mask
+    // head of tile i has read Y (z_full) and the bulk stores of Y have read it too.  The updated features leave the
+    // same way: Y sits in the x region in exactly the layout of the output's tensor map, so one thread stores the tile
+    // with four bulk tensor copies (rows past the end are clipped) instead of every thread writing 16-byte pieces.
+    auto load_tile = [&](unsigned char* dst, const CUtensorMap* tm, uint32_t bar, long long tile) {
       if (elect_one()) {
-        if (it > 0 && p.x_out) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the store has read Y
         const int row = (int)(tile * TC_BM);
-        if (p.debug & 8) mbar_arrive(in_full);
-        else mbar_arrive_expect_tx(in_full, 8u * DS_SLAB);
-        if (!(p.debug & 8))
+        if (p.debug & 8) {
+          mbar_arrive(bar);
+        } else {
+          mbar_arrive_expect_tx(bar, 4u * DS_SLAB);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          ds_tma_tile(smem_u32(Pb) + (uint32_t)c * DS_SLAB, &tm_pos, in_full, c * 64, row);
-          ds_tma_tile(smem_u32(Xs) + (uint32_t)c * DS_SLAB, &tm_x, in_full, c * 64, row);
+          for (int c = 0; c < 4; ++c) ds_tma_tile(smem_u32(dst) + (uint32_t)c * DS_SLAB, tm, bar, c * 64, row);
         }
       }
       __syncwarp();
+    };
+    int it = 0;
+    if ((long long)blockIdx.x < n_tiles) {
+      load_tile(Ps, &tm_pos, pos_full, blockIdx.x);
+      load_tile(Xs, &tm_x, x_full, blockIdx.x);
+    }
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const uint32_t ph = (uint32_t)it & 1u;
+      const long long next = tile + gridDim.x;
+      mbar_wait(s_full, ph);
+      if (next < n_tiles) load_tile(Ps, &tm_pos, pos_full, next);
       if (p.x_out) {
-        mbar_wait(y_full, (uint32_t)it & 1u);            // Y of this tile is written (and fenced for the async proxy)
+        mbar_wait(y_full, ph);                           // Y of this tile is written (and fenced for the async proxy)
         if (elect_one()) {
           const int row = (int)(tile * TC_BM);
 #pragma unroll
@@ -815,6 +852,10 @@ s2c_split_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         }
         __syncwarp();
       }
+      mbar_wait(z_full, ph);
+      if (p.x_out && elect_one()) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the store has read Y
+      __syncwarp();
+      if (next < n_tiles) load_tile(Xs, &tm_x, x_full, next);
     }
     if (p.x_out && elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before exit
     __syncwarp();
