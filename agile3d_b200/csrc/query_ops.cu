@@ -4,7 +4,7 @@
 //
 // The O(Nq) algebra of a layer is ~15 [Nq x 128] x [128 x 128] products, a 128 -> 1024 -> 128 FFN and an Nq x Nq
 // attention: launch-latency bound as ~40 library calls, microseconds as three kernels (plus one that assembles the
-// queries of a click round).  Every kernel runs one CTA per (16 query rows, scene); the operands of a CTA live in
+// queries of a click round).  Every kernel runs one CTA per (QRB = 4 query rows, scene); the operands of a CTA live in
 // shared memory, weights are read from a per-layer blob of PRE-TRANSPOSED matrices (ag3d_query_blob_floats, layout
 // below) so that the weight reads of a warp are coalesced and L2 resident.  fp32 FFMA throughout: this side carries no
 // measurable bytes or flops, only latency.
@@ -21,7 +21,9 @@
 namespace ag3d {
 
 constexpr int QD = 128, QHEADS = 8, QDH = 16, QF = 1024;
-constexpr int QRB = 16;                  // query rows per CTA
+constexpr int QRB = 4;                   // query rows per CTA (the kernels are bound by the LDS + FFMA stream of a CTA, so
+                                         // few rows per CTA = more SMs at work; every CTA re-reads the L2-resident weights)
+constexpr int RPT = QRB / 2;             // rows per thread
 constexpr int QT = 256;                  // threads per CTA: thread = (output column o = tid & 127, row half tid >> 7)
 constexpr int DD = QD * QD;
 
@@ -66,32 +68,38 @@ constexpr int O_M2T = O_M1B + QD;
 constexpr int O_M2B = O_M2T + DD;
 constexpr int Q_BLOB_FLOATS = O_M2B + QD;
 
-// acc[r] = sum_i xs[(rb + r) * ldx + i] * WT[i * ldw + o]   (r < 8); xs in shared memory (warp-wide broadcast reads),
-// WT in global memory (coalesced across o)
+// acc[r] = sum_i xs[(rb + r) * ldx + i] * WT[i * ldw + o]   (r < RPT); xs in shared memory (warp-wide broadcast reads, four
+// inputs per LDS.128), WT in global memory (coalesced across o, 16 weight loads in flight per thread)
 template <int KDIM>
 __device__ __forceinline__ void gemm_rows(const float* xs, int ldx, const float* __restrict__ WT, int ldw, int o, int rb,
                                           float* acc) {
 #pragma unroll
-  for (int r = 0; r < 8; ++r) acc[r] = 0.f;
-  // 16 weight loads in flight per thread: the loop is bound by the L2 latency of the (coalesced) weight reads
+  for (int r = 0; r < RPT; ++r) acc[r] = 0.f;
 #pragma unroll 1
   for (int i0 = 0; i0 < KDIM; i0 += 16) {
     float w[16];
 #pragma unroll
     for (int u = 0; u < 16; ++u) w[u] = __ldg(WT + (size_t)(i0 + u) * ldw + o);
 #pragma unroll
-    for (int u = 0; u < 16; ++u)
+    for (int r = 0; r < RPT; ++r) {
+      const float4* xr = reinterpret_cast<const float4*>(xs + (rb + r) * ldx + i0);
 #pragma unroll
-      for (int r = 0; r < 8; ++r) acc[r] = fmaf(xs[(rb + r) * ldx + i0 + u], w[u], acc[r]);
+      for (int u4 = 0; u4 < 4; ++u4) {
+        const float4 x4 = xr[u4];
+        acc[r] = fmaf(x4.x, w[4 * u4], acc[r]);
+        acc[r] = fmaf(x4.y, w[4 * u4 + 1], acc[r]);
+        acc[r] = fmaf(x4.z, w[4 * u4 + 2], acc[r]);
+        acc[r] = fmaf(x4.w, w[4 * u4 + 3], acc[r]);
+      }
+    }
   }
 }
 
-// LayerNorm of the 16 rows of v [16][128] in place (eps 1e-5, biased variance, as nn.LayerNorm); 8 warps x 2 rows
+// LayerNorm of the QRB rows of v [QRB][128] in place (eps 1e-5, biased variance, as nn.LayerNorm); warp w < QRB: row w
 __device__ __forceinline__ void layer_norm16(float* v, const float* __restrict__ w, const float* __restrict__ b, float eps) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-#pragma unroll
-  for (int rr = 0; rr < 2; ++rr) {
-    float* row = v + (warp * 2 + rr) * QD;
+  if (warp < QRB) {
+    float* row = v + warp * QD;
     float x[4], s = 0.f;
 #pragma unroll
     for (int e = 0; e < 4; ++e) { x[e] = row[lane + 32 * e]; s += x[e]; }
@@ -151,8 +159,8 @@ __global__ void query_init_kernel(const float* __restrict__ feats, const float* 
 // ---------------------------------------------------------------------------------------------- fold for c2s
 __global__ void __launch_bounds__(QT) query_fold_c2s_kernel(const float* __restrict__ Q, const float* __restrict__ qpos,
                                                            const float* __restrict__ blob, int nq, float* __restrict__ qfold) {
-  __shared__ float xs[QRB * QD], qp[QRB * QD];
-  const int b = blockIdx.y, r0 = blockIdx.x * QRB, tid = threadIdx.x, o = tid & 127, rb = (tid >> 7) * 8;
+  __shared__ __align__(16) float xs[QRB * QD], qp[QRB * QD];
+  const int b = blockIdx.y, r0 = blockIdx.x * QRB, tid = threadIdx.x, o = tid & 127, rb = (tid >> 7) * RPT;
   const float* Qb = Q + (size_t)b * nq * QD;
   const float* Pb = qpos + (size_t)b * nq * QD;
   for (int i = tid; i < QRB * QD; i += QT) {
@@ -160,17 +168,17 @@ __global__ void __launch_bounds__(QT) query_fold_c2s_kernel(const float* __restr
     xs[i] = q < nq ? Qb[(size_t)q * QD + (i % QD)] + Pb[(size_t)q * QD + (i % QD)] : 0.f;
   }
   __syncthreads();
-  float acc[8];
+  float acc[RPT];
   gemm_rows<QD>(xs, QD, blob + O_C2S_WQT, QD, o, rb, acc);
   const float bq = __ldg(blob + O_C2S_BQ + o);
 #pragma unroll
-  for (int r = 0; r < 8; ++r) qp[(rb + r) * QD + o] = (acc[r] + bq) * 0.25f;       // 1 / sqrt(16)
+  for (int r = 0; r < RPT; ++r) qp[(rb + r) * QD + o] = (acc[r] + bq) * 0.25f;       // 1 / sqrt(16)
   __syncthreads();
   float* out = qfold + (size_t)b * QHEADS * nq * QD;
   for (int h = 0; h < QHEADS; ++h) {
     gemm_rows<QDH>(qp + h * QDH, QD, blob + O_C2S_WK + (size_t)h * QDH * QD, QD, o, rb, acc);
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
+    for (int r = 0; r < RPT; ++r) {
       const int q = r0 + rb + r;
       if (q < nq) out[((size_t)h * nq + q) * QD + o] = acc[r];
     }
@@ -187,27 +195,27 @@ __global__ void __launch_bounds__(QT) query_update_a_kernel(const float* __restr
   float* cs = sm;                         // [8 heads][16 rows][128]
   float* xs = cs + QHEADS * QRB * QD;     // [16][128]
   float* ys = xs + QRB * QD;              // [16][128]
-  const int b = blockIdx.y, r0 = blockIdx.x * QRB, tid = threadIdx.x, o = tid & 127, rb = (tid >> 7) * 8;
+  const int b = blockIdx.y, r0 = blockIdx.x * QRB, tid = threadIdx.x, o = tid & 127, rb = (tid >> 7) * RPT;
   const float* cb = ctx + (size_t)b * QHEADS * nq * QD;
   for (int i = tid; i < QHEADS * QRB * QD; i += QT) {
     const int c = i % QD, r = (i / QD) % QRB, h = i / (QD * QRB), q = r0 + r;
     cs[i] = q < nq ? cb[((size_t)h * nq + q) * QD + c] : 0.f;
   }
   __syncthreads();
-  float acc[8];
+  float acc[RPT];
   // per-head value projection: heads[q][(h,d)] = sum_c ctx[(h,q)][c] Wv[(h,d)][c] + bv
   gemm_rows<QD>(cs + (o >> 4) * QRB * QD, QD, blob + O_C2S_WVT, QD, o, rb, acc);
   {
     const float bv = __ldg(blob + O_C2S_BV + o);
 #pragma unroll
-    for (int r = 0; r < 8; ++r) xs[(rb + r) * QD + o] = acc[r] + bv;
+    for (int r = 0; r < RPT; ++r) xs[(rb + r) * QD + o] = acc[r] + bv;
   }
   __syncthreads();
   gemm_rows<QD>(xs, QD, blob + O_C2S_WOT, QD, o, rb, acc);
   {
     const float bo = __ldg(blob + O_C2S_BO + o);
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
+    for (int r = 0; r < RPT; ++r) {
       const int q = r0 + rb + r;
       const float res = q < nq ? Q[((size_t)b * nq + q) * QD + o] : 0.f;
       ys[(rb + r) * QD + o] = res + (acc[r] + bo);
@@ -217,7 +225,7 @@ __global__ void __launch_bounds__(QT) query_update_a_kernel(const float* __restr
   layer_norm16(ys, blob + O_C2S_LNW, blob + O_C2S_LNB, ln_eps);
   __syncthreads();
 #pragma unroll
-  for (int r = 0; r < 8; ++r) {
+  for (int r = 0; r < RPT; ++r) {
     const int q = r0 + rb + r;
     const float v = ys[(rb + r) * QD + o];
     const float pp = q < nq ? qpos[((size_t)b * nq + q) * QD + o] : 0.f;
@@ -233,7 +241,7 @@ __global__ void __launch_bounds__(QT) query_update_a_kernel(const float* __restr
     gemm_rows<QD>(m == 2 ? ys : xs, QD, wts[m], QD, o, rb, acc);
     const float bias = __ldg(bss[m] + o);
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
+    for (int r = 0; r < RPT; ++r) {
       const int q = r0 + rb + r;
       if (q < nq) outs[m][((size_t)b * nq + q) * QD + o] = acc[r] + bias;
     }
@@ -253,7 +261,7 @@ __global__ void __launch_bounds__(QT) query_update_b_kernel(const float* __restr
   float* b2 = b1 + QRB * QD;
   float* b3 = b2 + QRB * QD;
   float* hid = b3 + QRB * QD;              // [16][1024]
-  const int b = blockIdx.y, r0 = blockIdx.x * QRB, tid = threadIdx.x, o = tid & 127, rb = (tid >> 7) * 8;
+  const int b = blockIdx.y, r0 = blockIdx.x * QRB, tid = threadIdx.x, o = tid & 127, rb = (tid >> 7) * RPT;
   const int warp = tid >> 5, lane = tid & 31;
   const size_t base = (size_t)b * nq * QD;
   // ---- click <-> click attention: warp = head, rows one after the other, lanes over the keys (nq <= 256: 8 per lane)
@@ -319,13 +327,13 @@ __global__ void __launch_bounds__(QT) query_update_b_kernel(const float* __restr
     }
   }
   __syncthreads();
-  float acc[8];
+  float acc[RPT];
   // ---- out-proj + residual + LayerNorm -> q2 (b1)
   gemm_rows<QD>(b0, QD, blob + O_C2C_WOT, QD, o, rb, acc);
   {
     const float bo = __ldg(blob + O_C2C_BO + o);
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
+    for (int r = 0; r < RPT; ++r) {
       const int q = r0 + rb + r;
       b1[(rb + r) * QD + o] = (q < nq ? q1[base + (size_t)q * QD + o] : 0.f) + (acc[r] + bo);
     }
@@ -338,20 +346,20 @@ __global__ void __launch_bounds__(QT) query_update_b_kernel(const float* __restr
     gemm_rows<QD>(b1, QD, blob + O_FFN_W1T + cbk * QD, QF, o, rb, acc);
     const float bias = __ldg(blob + O_FFN_B1 + cbk * QD + o);
 #pragma unroll
-    for (int r = 0; r < 8; ++r) hid[(rb + r) * QF + cbk * QD + o] = fmaxf(acc[r] + bias, 0.f);
+    for (int r = 0; r < RPT; ++r) hid[(rb + r) * QF + cbk * QD + o] = fmaxf(acc[r] + bias, 0.f);
   }
   __syncthreads();
   gemm_rows<QF>(hid, QF, blob + O_FFN_W2T, QD, o, rb, acc);
   {
     const float bias = __ldg(blob + O_FFN_B2 + o);
 #pragma unroll
-    for (int r = 0; r < 8; ++r) b2[(rb + r) * QD + o] = b1[(rb + r) * QD + o] + (acc[r] + bias);
+    for (int r = 0; r < RPT; ++r) b2[(rb + r) * QD + o] = b1[(rb + r) * QD + o] + (acc[r] + bias);
   }
   __syncthreads();
   layer_norm16(b2, blob + O_FFN_LNW, blob + O_FFN_LNB, ln_eps);
   __syncthreads();
 #pragma unroll
-  for (int r = 0; r < 8; ++r) {
+  for (int r = 0; r < RPT; ++r) {
     const int q = r0 + rb + r;
     const float v = b2[(rb + r) * QD + o];
     if (q < nq) q3[base + (size_t)q * QD + o] = v;
@@ -363,13 +371,13 @@ __global__ void __launch_bounds__(QT) query_update_b_kernel(const float* __restr
   {
     const float bias = __ldg(blob + O_S2C_BK + o);
 #pragma unroll
-    for (int r = 0; r < 8; ++r) b1[(rb + r) * QD + o] = acc[r] + bias;
+    for (int r = 0; r < RPT; ++r) b1[(rb + r) * QD + o] = acc[r] + bias;
   }
   gemm_rows<QD>(b2, QD, blob + O_S2C_WVT, QD, o, rb, acc);
   {
     const float bias = __ldg(blob + O_S2C_BV + o);
 #pragma unroll
-    for (int r = 0; r < 8; ++r) b3[(rb + r) * QD + o] = acc[r] + bias;
+    for (int r = 0; r < RPT; ++r) b3[(rb + r) * QD + o] = acc[r] + bias;
   }
   __syncthreads();
   {
@@ -378,13 +386,13 @@ __global__ void __launch_bounds__(QT) query_update_b_kernel(const float* __restr
     for (int h = 0; h < QHEADS; ++h) {
       gemm_rows<QDH>(b1 + h * QDH, QD, blob + O_S2C_WQ + (size_t)h * QDH * QD, QD, o, rb, acc);
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
+      for (int r = 0; r < RPT; ++r) {
         const int q = r0 + rb + r;
         if (q < nq) Ab[((size_t)h * nq + q) * QD + o] = acc[r] * 0.25f;
       }
       gemm_rows<QDH>(b3 + h * QDH, QD, blob + O_S2C_WOT + (size_t)h * QDH * QD, QD, o, rb, acc);
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
+      for (int r = 0; r < RPT; ++r) {
         const int q = r0 + rb + r;
         if (q < nq) Ub[((size_t)h * nq + q) * QD + o] = acc[r];
       }
@@ -407,14 +415,14 @@ __global__ void __launch_bounds__(QT) query_update_b_kernel(const float* __restr
   {
     const float bias = __ldg(blob + O_M1B + o);
 #pragma unroll
-    for (int r = 0; r < 8; ++r) b0[(rb + r) * QD + o] = fmaxf(acc[r] + bias, 0.f);
+    for (int r = 0; r < RPT; ++r) b0[(rb + r) * QD + o] = fmaxf(acc[r] + bias, 0.f);
   }
   __syncthreads();
   gemm_rows<QD>(b0, QD, blob + O_M2T, QD, o, rb, acc);
   {
     const float bias = __ldg(blob + O_M2B + o);
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
+    for (int r = 0; r < RPT; ++r) {
       const int q = r0 + rb + r;
       if (q < nq) E[base + (size_t)q * QD + o] = acc[r] + bias;
     }

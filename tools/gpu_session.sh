@@ -1,23 +1,13 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT" || exit 1
 mkdir -p gpurun_out
-S=s23
+S=s24
 timeout 1800 python -m pytest tests -x -q -m gpu > gpurun_out/${S}_pytest_gpu.log 2>&1
 tail -n 3 gpurun_out/${S}_pytest_gpu.log
-timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${S}_smoke.log 2>&1; tail -n 2 gpurun_out/${S}_smoke.log
-timeout 900 python bench.py --steps 8 > gpurun_out/${S}_bench_n1.json 2> gpurun_out/${S}_n1.err
-timeout 900 python bench.py --steps 8 --batch 1 --no-parity > gpurun_out/${S}_bench_b1.json 2> gpurun_out/${S}_b1.err
-timeout 900 python bench.py --steps 8 --workload c2 --no-parity > gpurun_out/${S}_bench_c2.json 2> gpurun_out/${S}_c2.err
-timeout 900 python bench.py --steps 3 --warmup 1 --workload clickloop > gpurun_out/${S}_bench_clickloop.json 2> gpurun_out/${S}_clickloop.err
-for f in n1 b1 c2 clickloop; do python - <<PY
+timeout 900 python bench.py --steps 8 --no-parity > gpurun_out/${S}_bench_n1.json 2> gpurun_out/${S}_n1.err
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/${S}_launches.csv python tools/profile_step.py --batch 8 > gpurun_out/${S}_launches.log 2>&1
+python - <<PY
 import json
-try:
-    d = json.load(open("gpurun_out/${S}_bench_$f.json"))
-    print("$f", {k: d[k] for k in ("value", "ms_per_step")}, "e2e", d["e2e"]["value"], d.get("parity") and d["parity"].get("mask_logits_rel_err_per_layer"))
-    if d.get("roofline"): print("   ", {k: v["ms_per_step"] for k, v in d["roofline"]["families"].items()})
-    if "ms_per_round" in d["config"]: print("   ms/round", d["config"]["ms_per_round"])
-except Exception as e:
-    print("$f no json:", e)
+d = json.load(open("gpurun_out/${S}_bench_n1.json"))
+print({k: d[k] for k in ("value", "ms_per_step")}, "e2e", d["e2e"]["value"])
 PY
-done
-tail -n 2 gpurun_out/${S}_*.err | tail -n 20
