@@ -102,8 +102,9 @@ stem_conv_kernel(const int4* __restrict__ coords, const float* __restrict__ feat
                  const Slot* __restrict__ table, unsigned long long mask, const int* __restrict__ brick_rows, int ksize,
                  const float* __restrict__ weight, const float* __restrict__ scale,
                  const float* __restrict__ shift, float* __restrict__ out, int out_ld, int flags) {
-  extern __shared__ float w_s[];  // [K][3][32]
+  extern __shared__ __align__(16) float w_s[];  // [K][3][32] weights, then the warps' hit lists [8][128] float4
   const int K = ksize * ksize * ksize;
+  float4* hit_s = reinterpret_cast<float4*>(w_s + ((K * STEM_CIN * STEM_COUT + 3) & ~3));
   for (int i = threadIdx.x; i < K * STEM_CIN * STEM_COUT; i += blockDim.x) w_s[i] = __ldg(weight + i);
   __syncthreads();
   const int lane = threadIdx.x & 31;
@@ -115,7 +116,7 @@ stem_conv_kernel(const int4* __restrict__ coords, const float* __restrict__ feat
     float acc = 0.f;
     // All probes of the voxel are issued before any result is used (up to 4 independent hash chains per lane), then
     // every lane fetches the 3 features of its own hits (independent loads), and only then the hits are folded in
-    // ascending offset order through shuffles: no global load sits on the serial accumulation chain.
+    // ascending offset order: no global load sits on the serial accumulation chain.
     int src[4];
     float f0[4], f1[4], f2[4];
     if constexpr (BRICKS) {     // `table` is the tensor-stride-4 table: 8 probes + reads of the bricks' row lists
@@ -142,20 +143,28 @@ stem_conv_kernel(const int4* __restrict__ coords, const float* __restrict__ feat
         f0[j] = __ldg(f + 0); f1[j] = __ldg(f + 1); f2[j] = __ldg(f + 2);
       }
     }
+    // The hits are compacted, in ascending offset order, into the warp's list in shared memory (features + weight row
+    // offset); the fold is then one broadcast LDS.128 + three weight LDS + three FMAs per hit.
+    {
+      float4* list = hit_s + (threadIdx.x >> 5) * 128;
+      int base = 0;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      unsigned hits = __ballot_sync(0xffffffffu, src[j] >= 0);
-      while (hits) {
-        const int b = __ffs(hits) - 1;
-        hits &= hits - 1;
-        const float a0 = __shfl_sync(0xffffffffu, f0[j], b);
-        const float a1 = __shfl_sync(0xffffffffu, f1[j], b);
-        const float a2 = __shfl_sync(0xffffffffu, f2[j], b);
-        const float* w = w_s + (j * 32 + b) * STEM_CIN * STEM_COUT + lane;
-        acc = fmaf(a0, w[0], acc);
-        acc = fmaf(a1, w[STEM_COUT], acc);
-        acc = fmaf(a2, w[2 * STEM_COUT], acc);
+      for (int j = 0; j < 4; ++j) {
+        const unsigned hits = __ballot_sync(0xffffffffu, src[j] >= 0);
+        if (src[j] >= 0)
+          list[base + __popc(hits & ((1u << lane) - 1u))] =
+              make_float4(f0[j], f1[j], f2[j], __int_as_float((j * 32 + lane) * STEM_CIN * STEM_COUT));
+        base += __popc(hits);
       }
+      __syncwarp();
+      for (int i = 0; i < base; ++i) {
+        const float4 e = list[i];
+        const float* w = w_s + __float_as_int(e.w) + lane;
+        acc = fmaf(e.x, w[0], acc);
+        acc = fmaf(e.y, w[STEM_COUT], acc);
+        acc = fmaf(e.z, w[2 * STEM_COUT], acc);
+      }
+      __syncwarp();
     }
     float v = acc;
     if (scale) v *= __ldg(scale + lane);
@@ -265,11 +274,11 @@ static int stem_conv_launch(const int32_t* coords, const float* feats, int64_t n
   AG3D_CHECK_ARG(table && aligned16(table) && cap >= 2 && (cap & (cap - 1)) == 0, "bad hash table");
   AG3D_CHECK_ARG(out_ld >= STEM_COUT, "out_ld");
   const int K = ksize * ksize * ksize;
-  const size_t smem = (size_t)K * STEM_CIN * STEM_COUT * sizeof(float);
+  const size_t smem = (size_t)((K * STEM_CIN * STEM_COUT + 3) & ~3) * sizeof(float) + 8 * 128 * sizeof(float4);
   static bool attr_done = false;
   if (!attr_done) {
-    AG3D_CUDA(cudaFuncSetAttribute(stem_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    AG3D_CUDA(cudaFuncSetAttribute(stem_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    AG3D_CUDA(cudaFuncSetAttribute(stem_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    AG3D_CUDA(cudaFuncSetAttribute(stem_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
     attr_done = true;
   }
   long long blocks = (n + 7) / 8;
