@@ -12,7 +12,7 @@
 //                                              hi and 32 lo channels, so hi and lo products land in separate column
 //                                              halves (all four products, "bf16x4") and are folded once at the end
 // No thread touches a voxel byte: the 256 loader threads, their global-load latency and the two fp32 -> bf16 hi/lo
-// conversions per element of the fp32 variant are gone; a two-stage tile ring keeps the next tile in flight.  The
+// conversions per element of the fp32 variant are gone; separate rings for the x tiles (3 deep: alive until the context GEMM) and the pos tiles (2 deep: dead after the score GEMM) keep two tiles in flight.  The
 // probabilities never touch shared memory either (A operand of the context GEMM in tensor memory, see C2_TM_P0).
 // Roles: 16 softmax warps (four threads per (head, query) row), 1 MMA-issuer warp, 1 TMA-producer warp.
 #include <cuda.h>
@@ -33,14 +33,15 @@ constexpr int C2_SOFT_WARPS = 16;                        // four threads per (he
 constexpr int C2_THREADS = C2_SOFT_WARPS * 32 + 64;      // + MMA warp + TMA warp
 constexpr uint32_t C2_SLAB = C2_TV * 128;                // [64 voxels x 128 B] slab tile (32 channels hi | lo)
 constexpr uint32_t C2_TILE = 4 * C2_SLAB;                // x or pos tile: 4 slabs
-constexpr uint32_t C2_STAGE = 2 * C2_TILE;               // x | pos
-constexpr int C2_NSTAGE = 2;
+constexpr int C2_NX = 3;                                 // x ring: a tile lives until its context GEMM has run
+constexpr int C2_NP = 2;                                 // pos ring: a tile is dead as soon as its score GEMM has run
+constexpr uint32_t C2_OFF_POS = C2_NX * C2_TILE;
 constexpr uint32_t C2_QLBO = 128 * 16;                   // Q pieces: no-swizzle K-major, 128 rows x 16 B per 8-channel chunk
 constexpr uint32_t C2_QPIECE = 16 * C2_QLBO;             // [128 rows x 128 channels] bf16
-constexpr uint32_t C2_OFF_Q = C2_NSTAGE * C2_STAGE;
+constexpr uint32_t C2_OFF_Q = C2_OFF_POS + C2_NP * C2_TILE;
 constexpr uint32_t C2_OFF_MISC = C2_OFF_Q + 2 * C2_QPIECE;
-constexpr uint32_t C2_MISC = 8192;                       // barriers | TMEM slot | tile-maximum exchange | partial sums
-constexpr size_t C2_SMEM = C2_OFF_MISC + C2_MISC;
+constexpr uint32_t C2_MISC = 3072;                       // barriers | TMEM slot | tile-maximum exchange (aliased: partial sums)
+constexpr size_t C2_SMEM = C2_OFF_MISC + C2_MISC;        // 232448 B = all 227 KB a CTA may have
 // TMEM columns: two score buffers [128 x 64] fp32, the [128 x 256] context accumulator, and two probability buffers -
 // P is the A operand of the context GEMM and lives in TENSOR MEMORY ([128 rows x 64 voxels] bf16 = 32 columns hi + 32
 // columns lo, two voxels per 32-bit column), written by the softmax threads with tcgen05.st: no shared-memory stores,
@@ -80,16 +81,18 @@ c2s_split_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   unsigned char* misc = smem + C2_OFF_MISC;
   uint64_t* bars = reinterpret_cast<uint64_t*>(misc);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 128);
-  float* tmax_s = reinterpret_cast<float*>(misc + 256);          // [2 tiles][4 parts][128 rows]
-  float* lsum_s = reinterpret_cast<float*>(misc + 256 + 4096);   // [4 parts][128]
+  float* tmax_s = reinterpret_cast<float*>(misc + 256);          // [4 parts][128 rows]
+  float* lsum_s = tmax_s;                                        // [4 parts][128] (after the last tile)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t bar_base = smem_u32(bars);
-  auto full = [&](int s) { return bar_base + 8u * s; };
-  auto empty = [&](int s) { return bar_base + 8u * (2 + s); };
-  auto s_full = [&](int t) { return bar_base + 8u * (4 + (t & 1)); };
-  auto p_ready = [&](int t) { return bar_base + 8u * (6 + (t & 1)); };   // one per probability buffer
-  auto g2_done = [&](int t) { return bar_base + 8u * (8 + (t & 1)); };
+  auto full_x = [&](int s) { return bar_base + 8u * s; };
+  auto empty_x = [&](int s) { return bar_base + 8u * (3 + s); };
+  auto full_p = [&](int s) { return bar_base + 8u * (6 + s); };
+  auto empty_p = [&](int s) { return bar_base + 8u * (8 + s); };
+  auto s_full = [&](int t) { return bar_base + 8u * (10 + (t & 1)); };
+  auto p_ready = [&](int t) { return bar_base + 8u * (12 + (t & 1)); };  // one per probability buffer
+  auto g2_done = [&](int t) { return bar_base + 8u * (14 + (t & 1)); };
   const int g = blockIdx.y;
   const int q0 = g * p.nqg;
   const int nq_here = min(p.nqg, p.nq - q0);
@@ -97,7 +100,8 @@ c2s_split_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
 
   if (tid == 0) {
     if (smem_u32(smem) & 1023u) __trap();              // SWIZZLE_128B tiles need 1024-byte alignment
-    for (int s = 0; s < C2_NSTAGE; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+    for (int s = 0; s < C2_NX; ++s) { mbar_init(full_x(s), 1); mbar_init(empty_x(s), 1); }
+    for (int s = 0; s < C2_NP; ++s) { mbar_init(full_p(s), 1); mbar_init(empty_p(s), 1); }
     mbar_init(s_full(0), 1);
     mbar_init(s_full(1), 1);
     mbar_init(p_ready(0), C2_SOFT_WARPS);
@@ -189,10 +193,11 @@ c2s_split_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         s[v] = dead ? -INFINITY : s[v];
         tmax = fmaxf(tmax, s[v]);
       }
-      float* tm = tmax_s + (it & 1) * 512 + r;
+      float* tm = tmax_s + r;
       tm[part * 128] = tmax;
       asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
       tmax = fmaxf(fmaxf(tm[0], tm[128]), fmaxf(tm[256], tm[384]));
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");   // all four have read before the next tile overwrites
       float alpha = 1.f;
       const bool grow = tmax > m_ref;
       if (grow) {
@@ -283,18 +288,17 @@ c2s_split_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     // probabilities are written.  Waiting for them in a fixed order would chain the load latency of tile t + 2 in
     // front of the context GEMM of tile t + 1, i.e. one HBM round trip per tile.
     auto issue_scores = [&](int t) {
-      const int s = t % C2_NSTAGE;
       tc_fence_after();
       if (elect_one()) {
         const uint32_t d = tmem_base + ((t & 1) ? C2_TM_S1 : C2_TM_S0);
-        const uint32_t xb = stage0 + (uint32_t)s * C2_STAGE;
+        const uint32_t tb[2] = {stage0 + (uint32_t)(t % C2_NX) * C2_TILE, stage0 + C2_OFF_POS + (uint32_t)(t % C2_NP) * C2_TILE};
         if (!(p.debug & 1))
 #pragma unroll
         for (int j = 0; j < 8; ++j) {                            // K = 128 channels, 16 per step: slab j >> 1, half j & 1
           const uint64_t a_h = umma_desc(q_hi + j * 2 * C2_QLBO, C2_QLBO, 128), a_l = umma_desc(q_lo + j * 2 * C2_QLBO, C2_QLBO, 128);
 #pragma unroll
           for (int o = 0; o < 2; ++o) {                          // operand: x tile, pos tile
-            const uint32_t b32 = umma_desc_lo32(xb + (uint32_t)o * C2_TILE + (uint32_t)(j >> 1) * C2_SLAB, 16) + (uint32_t)(j & 1) * 2u;
+            const uint32_t b32 = umma_desc_lo32(tb[o] + (uint32_t)(j >> 1) * C2_SLAB, 16) + (uint32_t)(j & 1) * 2u;
             const uint64_t b_h = umma_desc_join(sw_hi32, b32), b_l = umma_desc_join(sw_hi32, b32 + 4u);
             umma_bf16(d, a_h, b_h, id1, (j | o) ? 1u : 0u);
             umma_bf16(d, a_h, b_l, id1, 1u);
@@ -302,14 +306,14 @@ c2s_split_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           }
         }
         umma_commit(s_full(t));
+        umma_commit(empty_p(t % C2_NP));                         // the pos tile is dead
       }
       __syncwarp();
     };
     auto issue_context = [&](int it) {
-      const int s = it % C2_NSTAGE;
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t xb = stage0 + (uint32_t)s * C2_STAGE;
+        const uint32_t xb = stage0 + (uint32_t)(it % C2_NX) * C2_TILE;
         if (!(p.debug & 2))
 #pragma unroll
         for (int j = 0; j < 4; ++j) {                            // K = 64 voxels, 16 per step = 8 TMEM columns of P, 2048 B of x
@@ -320,7 +324,7 @@ c2s_split_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           umma_bf16_ts(tmem_base + C2_TM_CTX, pa + 32u, b, id2, 1u);
         }
         umma_commit(g2_done(it));
-        umma_commit(empty(s));
+        umma_commit(empty_x(it % C2_NX));
       }
       __syncwarp();
     };
@@ -329,7 +333,8 @@ c2s_split_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     while (nc < n_my) {
       uint32_t ready = 0;                                        // lane 0 polls, the warp follows (warp-uniform control flow)
       if (lane == 0) {
-        if (ns < n_my && ns <= nc + 1 && mbar_try(full(ns % C2_NSTAGE), (uint32_t)(ns / C2_NSTAGE) & 1u)) ready = 1;
+        if (ns < n_my && ns <= nc + 1 && mbar_try(full_x(ns % C2_NX), (uint32_t)(ns / C2_NX) & 1u) &&
+            mbar_try(full_p(ns % C2_NP), (uint32_t)(ns / C2_NP) & 1u)) ready = 1;
         else if (mbar_try(p_ready(nc), ((uint32_t)nc >> 1) & 1u)) ready = 2;
       }
       ready = __shfl_sync(0xffffffffu, ready, 0);
@@ -341,18 +346,29 @@ c2s_split_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     // ======================================================================================= TMA producer
     const uint32_t stage0 = smem_u32(smem);
     for (int t = 0; t < n_my; ++t) {
-      const int s = t % C2_NSTAGE;
-      mbar_wait(empty(s), ((uint32_t)(t / C2_NSTAGE) & 1u) ^ 1u);
+      const int row = (int)(((long long)blockIdx.x + (long long)t * gridDim.x) * C2_TV);
+      const int sx = t % C2_NX, sp = t % C2_NP;
+      mbar_wait(empty_x(sx), ((uint32_t)(t / C2_NX) & 1u) ^ 1u);
       if (elect_one()) {
-        const int row = (int)(((long long)blockIdx.x + (long long)t * gridDim.x) * C2_TV);
-        const uint32_t dst = stage0 + (uint32_t)s * C2_STAGE;
-        if (p.debug & 4) mbar_arrive(full(s));
-        else mbar_arrive_expect_tx(full(s), C2_STAGE);
-        if (!(p.debug & 4))
+        const uint32_t dst = stage0 + (uint32_t)sx * C2_TILE;
+        if (p.debug & 4) {
+          mbar_arrive(full_x(sx));
+        } else {
+          mbar_arrive_expect_tx(full_x(sx), C2_TILE);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          c2_tma_tile(dst + (uint32_t)c * C2_SLAB, &tm_x, full(s), c * 64, row);
-          c2_tma_tile(dst + C2_TILE + (uint32_t)c * C2_SLAB, &tm_pos, full(s), c * 64, row);
+          for (int c = 0; c < 4; ++c) c2_tma_tile(dst + (uint32_t)c * C2_SLAB, &tm_x, full_x(sx), c * 64, row);
+        }
+      }
+      __syncwarp();
+      mbar_wait(empty_p(sp), ((uint32_t)(t / C2_NP) & 1u) ^ 1u);
+      if (elect_one()) {
+        const uint32_t dst = stage0 + C2_OFF_POS + (uint32_t)sp * C2_TILE;
+        if (p.debug & 4) {
+          mbar_arrive(full_p(sp));
+        } else {
+          mbar_arrive_expect_tx(full_p(sp), C2_TILE);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) c2_tma_tile(dst + (uint32_t)c * C2_SLAB, &tm_pos, full_p(sp), c * 64, row);
         }
       }
       __syncwarp();
