@@ -403,6 +403,10 @@ loss_fwd_kernel(const float* __restrict__ logits, int C, long long n, const int*
     float sum = 0.f;
     for (int c = 0; c < C; ++c) sum += expf(__ldg(l + c) - mx);
     const int t = __ldg(target + v);
+    if ((unsigned)t >= (unsigned)C) {     // the reference asserts 0 <= class id < C (models/criterion.py: multiclass_dice_loss);
+      s_ce = s_dice = __int_as_float(0x7fc00000);   // here an invalid label (e.g. the ignore id -1) poisons the loss with NaN
+      continue;
+    }
     const float lt = __ldg(l + t);
     const float lse = mx + logf(sum);
     const float pt = expf(lt - lse);
@@ -445,6 +449,7 @@ loss_bwd_kernel(const float* __restrict__ logits, int C, long long n, const int*
       if (c < C) { p[c] = expf(__ldg(l + c) - mx); sum += p[c]; }
     const float inv = 1.f / sum;
     const int t = __ldg(target + v);
+    const bool bad = (unsigned)t >= (unsigned)C;       // invalid label: NaN gradients (see loss_fwd_kernel)
     float pt = 0.f;
 #pragma unroll
     for (int c = 0; c < LOSS_MAXC; ++c)
@@ -456,7 +461,7 @@ loss_bwd_kernel(const float* __restrict__ logits, int C, long long n, const int*
     for (int c = 0; c < LOSS_MAXC; ++c)
       if (c < C) {
         const float ind = (c == t) ? 1.f : 0.f;
-        dlogits[v * C + c] = wv * (g_bce * (p[c] - ind) + kd * (ind - p[c]));
+        dlogits[v * C + c] = bad ? __int_as_float(0x7fc00000) : wv * (g_bce * (p[c] - ind) + kd * (ind - p[c]));
       }
   }
 }

@@ -15,6 +15,10 @@ from . import ops
 
 
 class FlatAdamW:
+    """AdamW over the flat buffers.  One difference from torch.optim.AdamW: a parameter that received no gradient in a step
+    (torch: ``p.grad is None`` -> skipped) has a zero gradient here and still gets its weight decay and moment decay;
+    in the reference's training step every parameter of the model receives a gradient (engine.py:119-150)."""
+
     def __init__(self, params, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4, max_norm=0.0):
         self.params = [p for p in params if p.requires_grad]
         if not self.params:

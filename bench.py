@@ -224,19 +224,49 @@ def run_ours(args, rank, world, local_rank):
         return model.forward_mask(*h, click_idx=ck, click_time_idx=tm)
 
     out_host = {}
+    # End to end through the public API with HOST buffers: every step copies its inputs from pinned host memory and its
+    # logits back.  The copies run on their own streams, double-buffered, as a serving loop would: the inputs of step
+    # i+1 travel while step i computes, the logits of step i while step i+1 computes; every copy is issued inside the
+    # timed region and the region ends only when the last logits have landed (finish_e2e).
+    h2d_stream, d2h_stream = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    staged = {}
+
+    def stage_inputs(i):
+        c, f, r, ck, tm = host[i % n_pool]
+        with torch.cuda.stream(h2d_stream):
+            t = (c.to(dev, non_blocking=True), f.to(dev, non_blocking=True), r.to(dev, non_blocking=True))
+            ev = torch.cuda.Event()
+            ev.record(h2d_stream)
+        staged[i] = (t, ev)
 
     def step_e2e(i):
-        c, f, r, ck, tm = host[i % n_pool]
-        cd, fd, rd = c.to(dev, non_blocking=True), f.to(dev, non_blocking=True), r.to(dev, non_blocking=True)
+        if i not in staged:
+            stage_inputs(i)
+        (cd, fd, rd), ev = staged.pop(i)
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ev)
+        for t in (cd, fd, rd):
+            t.record_stream(cur)
+        stage_inputs(i + 1)                                        # next step's inputs travel under this step's kernels
+        _, _, _, ck, tm = host[i % n_pool]
         x = agile3d_b200.SparseTensor(coordinates=cd, features=fd, device=dev)
         h = model.forward_backbone(x, raw_coordinates=rd)
         out = model.forward_mask(*h, click_idx=ck, click_time_idx=tm)
-        for b, p in enumerate(out["pred_masks"]):                  # the caller reads the logits (eval_multi_obj.py:124-125)
-            key = (i % n_pool, b)
-            if key not in out_host:
-                out_host[key] = torch.empty(p.shape, dtype=p.dtype, pin_memory=True)
-            out_host[key].copy_(p, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(cur)
+        d2h_stream.wait_event(done)
+        with torch.cuda.stream(d2h_stream):
+            for b, p in enumerate(out["pred_masks"]):              # the caller reads the logits (eval_multi_obj.py:124-125)
+                key = (i % n_pool, b)
+                if key not in out_host:
+                    out_host[key] = torch.empty(p.shape, dtype=p.dtype, pin_memory=True)
+                out_host[key].copy_(p, non_blocking=True)
+                p.record_stream(d2h_stream)
         return out
+
+    def finish_e2e():
+        torch.cuda.current_stream().wait_stream(d2h_stream)
+        torch.cuda.current_stream().wait_stream(h2d_stream)
 
     def barrier():
         torch.cuda.synchronize()
@@ -244,12 +274,14 @@ def run_ours(args, rank, world, local_rank):
             agd.barrier()
             torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, finish=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(steps):
             fn(i)
+        if finish:
+            finish()
         e1.record()
         barrier()
         return agd.max_over_ranks(e0.elapsed_time(e1), device=dev)     # slowest rank = the job's time
@@ -265,7 +297,11 @@ def run_ours(args, rank, world, local_rank):
     launches = ops.kernel_launches() - l0
     for i in range(2):
         step_e2e(i)
-    ms_e2e = timed(step_e2e, args.steps)
+    finish_e2e()
+    torch.cuda.synchronize()
+    staged.clear()                                                 # step 0 of the timed region copies its own inputs
+    ms_e2e = timed(step_e2e, args.steps, finish_e2e)
+    staged.clear()
     clocks = sampler.stop() if sampler else None
 
     # per-family CUDA-event pass for the roofline (same workload, separate from the headline timing)
@@ -354,7 +390,9 @@ def run_ours(args, rank, world, local_rank):
                    "l2_policy": f"rotating pool of {n_pool} distinct batches; per-step activations (~1.7 GB/scene) exceed the 126 MB L2",
                    "spconv_algo": {0: "auto", 1: "simt_fp32", 2: "tcgen05_3xtf32"}[model.backbone.algo]},
         "e2e": {"value": e2e_value, "unit": "scenes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": ms_e2e / args.steps},
+                "ms_per_step": ms_e2e / args.steps,
+                "copies": "pinned host buffers, every step; H2D of step i+1 and D2H of step i on side streams under the kernels "
+                          "of the neighbouring step, all inside the timed region"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,

@@ -392,6 +392,8 @@ int ag3d_loss_fwd(const float* logits, int32_t C, int64_t n, const int32_t* targ
                   float* sums, void* ws, size_t ws_bytes, ag3d_stream_t stream);
 int ag3d_loss_bwd(const float* logits, int32_t C, int64_t n, const int32_t* target, const float* w, float eps,
                   const float* g, float* dlogits, ag3d_stream_t stream);
+/* target[v] outside [0, C) (the reference asserts this range; e.g. the dataset ignore id -1) yields NaN sums / NaN
+ * gradient rows instead of an out-of-bounds read: the failure is loud without a host synchronisation.           */
 int ag3d_click_loss_weights(const float* xyz, int64_t n, const float* clicks, int32_t n_clicks, float alpha, float beta,
                             float tita, float* w, ag3d_stream_t stream);
 

@@ -303,6 +303,14 @@ def test_loss_kernels_vs_oracle(n, C):
     assert abs(float(sums[1]) / n - float(ld["loss_dice"])) < 1e-4
     dl = ops.loss_bwd(t(logits.detach().float()), t(target.int()), t(w.float()), t(coef.float()))
     assert rel_err(dl.cpu(), logits.grad) < 1e-4
+    # a label outside [0, C) (the reference asserts the range; -1 is the dataset's ignore id) must fail loudly: NaN
+    if n >= 6:
+        bad = target.int().clone()
+        bad[n // 2] = -1
+        bad[n // 3] = C
+        assert bool(torch.isnan(ops.loss_fwd(t(logits.detach().float()), t(bad), t(w.float()))).all())
+        dlb = ops.loss_bwd(t(logits.detach().float()), t(bad), t(w.float()), t(coef.float()))
+        assert bool(torch.isnan(dlb[n // 2]).all()) and bool(torch.isnan(dlb[n // 3]).all()) and not bool(torch.isnan(dlb[0]).any())
 
 
 def test_click_loss_weights_vs_oracle():
