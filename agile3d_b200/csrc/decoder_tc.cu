@@ -572,7 +572,34 @@ s2c_split_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     const int q4 = warp & 3, g = warp >> 2;             // g = part: heads 2g, 2g+1 of the softmax, 32-channel slab g of the LayerNorm
     const int r = q4 * 32 + lane;                       // tile row owned in all phases
     const uint32_t t_lane = tmem_base + ((uint32_t)(q4 * 32) << 16);
+    // ---- P3 (mask head, part 0 only: 32 query columns) of a tile runs AFTER the softmax of the next tile: the mask-head
+    //      GEMM and its hand-off then sit under the out-projection GEMM of the next tile instead of on the chain
+    auto mask_head = [&](long long row0_prev, uint32_t ph_prev) {
+      mbar_wait(z_full, ph_prev);
+      tc_fence_after();
+      if (g == 0) {
+        const long long row = row0_prev + r;
+        float z[DT_NQP];
+        tmem_ld16(t_lane + TM_Z, z);
+        tmem_ld16(t_lane + TM_Z + 16, z + 16);
+        if (row < p.nv) {
+          float best = -INFINITY;
+          int arg = 0;
+          for (int ob = 0; ob < p.n_obj; ++ob) {
+            float m = -INFINITY;
+#pragma unroll
+            for (int q = 0; q < DT_NQP; ++q) m = (qobj_s[q] == ob) ? fmaxf(m, z[q]) : m;
+            p.logits[(size_t)row * p.n_obj + ob] = m;
+            if (m > best || ob == 0) { best = m; arg = ob; }
+          }
+          p.label[row] = (unsigned char)arg;
+          atomicAdd(&hist_s[arg], 1);
+        }
+      }
+      tc_fence_before();
+    };
     int it = 0;
+    long long row0_prev = -1;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const uint32_t ph = (uint32_t)it & 1u;
       const long long row0 = tile * TC_BM;
@@ -622,6 +649,7 @@ s2c_split_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
+      if (row0_prev >= 0) mask_head(row0_prev, ph ^ 1u);      // mask head of the previous tile (Z is not rewritten before y_full)
 
       // ---- P2: o + bo + x -> LayerNorm -> y; this thread: row r, channels 32g .. 32g+31 (slab g)
       mbar_wait(o_full, ph);
@@ -682,29 +710,9 @@ s2c_split_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       __syncwarp();
       if (lane == 0) mbar_arrive(y_full);
 
-      // ---- P3: mask head (part 0 only: 32 query columns)
-      mbar_wait(z_full, ph);
-      tc_fence_after();
-      if (g == 0) {
-        float z[DT_NQP];
-        tmem_ld16(t_lane + TM_Z, z);
-        tmem_ld16(t_lane + TM_Z + 16, z + 16);
-        if (valid) {
-          float best = -INFINITY;
-          int arg = 0;
-          for (int ob = 0; ob < p.n_obj; ++ob) {
-            float m = -INFINITY;
-#pragma unroll
-            for (int q = 0; q < DT_NQP; ++q) m = (qobj_s[q] == ob) ? fmaxf(m, z[q]) : m;
-            p.logits[(size_t)row * p.n_obj + ob] = m;
-            if (m > best || ob == 0) { best = m; arg = ob; }
-          }
-          p.label[row] = (unsigned char)arg;
-          atomicAdd(&hist_s[arg], 1);
-        }
-      }
-      tc_fence_before();
+      row0_prev = row0;
     }
+    if (row0_prev >= 0) mask_head(row0_prev, (uint32_t)(it - 1) & 1u);
   } else if (warp == DS_COMPUTE_WARPS) {
     // ======================================================================================= MMA issuer
     const uint32_t id_s = umma_idesc_bf16(HQP), id_o = umma_idesc_bf16(128), id_z = umma_idesc_bf16(DT_NQP);

@@ -156,6 +156,9 @@ spconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const TcParams p) {
   if constexpr (TMA) a_smem += (1024u - (smem_u32(a_smem) & 1023u)) & 1023u;   // swizzle atoms are 1024-byte aligned
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // Programmatic dependent launch: let the next kernel of the stream start its prologue as soon as SMs free up
+  // (its own griddepcontrol.wait keeps it from touching anything this grid reads or writes).
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const long long tiles_total = (p.n_out + TC_BM - 1) / TC_BM;
   const long long tile0 = (long long)blockIdx.x * p.T;
   const int T_here = (int)min((long long)p.T, tiles_total - tile0);
@@ -245,6 +248,10 @@ spconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const TcParams p) {
   __syncthreads();
   const int n_stage = *n_stage_s;
   const uint32_t tmem_base = *tmem_slot;
+  // Everything above read only the neighbour table (built before the previous kernels of the stream were launched),
+  // shared and tensor memory.  From here on the grid reads the previous layer's output and writes global memory:
+  // wait for the preceding grid to complete and flush (no-op when this grid was launched without the PDL attribute).
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (warp < TC_PROD_WARPS) {
     // =========================================================================== A producers
@@ -617,6 +624,8 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int kspl
                                      int out_ld, int flags) {
   const int c16n = cout >> 4;
   const long long total = n_out * c16n;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
        t += (long long)gridDim.x * blockDim.x) {
     const long long row = t / c16n;
@@ -825,16 +834,32 @@ int spconv_tc_launch(const float* in, long long n_in, int in_ld, int cin, const 
     attr = true;
   }
   const dim3 grid((unsigned)((tiles + p.T - 1) / p.T), (unsigned)plan.ksplit);
-  if (tma) spconv_tc_kernel<2><<<grid, TC_THREADS, smem, st>>>(tm_in, p);
-  else if (split) spconv_tc_kernel<1><<<grid, TC_THREADS, smem, st>>>(tm_in, p);
-  else spconv_tc_kernel<0><<<grid, TC_THREADS, smem, st>>>(tm_in, p);
+  // programmatic dependent launch (opt-in, AG3D_PDL=1): the grid may start while its predecessor drains; it does its
+  // prologue (barriers, TMEM allocation, stage list from the neighbour table) and then waits for the predecessor.
+  // Measured on the headline step: 22.95 vs 23.01 ms at batch 8, 5.71 vs 5.62 ms at batch 1 (profiles/r02_pdl_ab.txt) -
+  // no gain, because the SMs have no room for a second grid's CTAs until the first one's leave, so it stays off.
+  static int pdl = -1;
+  if (pdl < 0) { const char* e = getenv("AG3D_PDL"); pdl = (e && e[0] == '1') ? 1 : 0; }
+  cudaLaunchAttribute lattr[1];
+  lattr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  lattr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cfg.attrs = lattr; cfg.numAttrs = pdl ? 1 : 0;
+  if (tma) AG3D_CUDA(cudaLaunchKernelEx(&cfg, spconv_tc_kernel<2>, tm_in, p));
+  else if (split) AG3D_CUDA(cudaLaunchKernelEx(&cfg, spconv_tc_kernel<1>, tm_in, p));
+  else AG3D_CUDA(cudaLaunchKernelEx(&cfg, spconv_tc_kernel<0>, tm_in, p));
   AG3D_LAUNCH_CHECK("spconv_tc");
   if (plan.ksplit > 1) {
     const long long total = n_out * (cout / 16);
     long long blocks = (total + 255) / 256;
     if (blocks > (long long)sm_count() * 8) blocks = (long long)sm_count() * 8;
-    splitk_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(p.partial, plan.ksplit, n_out, cout, scale, shift, residual,
-                                                          res_ld, out, out_ld, flags);
+    cudaLaunchConfig_t rc{};
+    rc.gridDim = dim3((unsigned)blocks); rc.blockDim = dim3(256); rc.dynamicSmemBytes = 0; rc.stream = st;
+    rc.attrs = lattr; rc.numAttrs = pdl ? 1 : 0;
+    const float* partial_c = p.partial;
+    AG3D_CUDA(cudaLaunchKernelEx(&rc, splitk_reduce_kernel, partial_c, plan.ksplit, n_out, cout, scale, shift, residual, res_ld,
+                                 out, out_ld, flags));
     AG3D_LAUNCH_CHECK("splitk_reduce");
   }
   return AG3D_OK;
