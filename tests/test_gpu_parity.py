@@ -242,6 +242,25 @@ def test_stem_conv_bricks_identical_to_hash_probes(ksize):
         assert torch.equal(c, a[maps.perm[0].long()])
 
 
+def test_gather_rows_and_split_posenc():
+    from agile3d_b200 import ops
+    g = torch.Generator().manual_seed(8)
+    idx = torch.randperm(5003, generator=g).to(torch.int32)
+    for cols in (3, 4, 7, 128):                    # 12-byte rows (xyz), 16-byte rows (coordinates), odd, feature rows
+        src = torch.randn((5003, cols), generator=g)
+        assert torch.equal(ops.gather_rows(src.to(DEV), idx.to(DEV)).cpu(), src[idx.long()])
+    ints = torch.randint(-50, 50, (5003, 4), generator=g, dtype=torch.int32)
+    assert torch.equal(ops.gather_rows(ints.to(DEV), idx.to(DEV)).cpu(), ints[idx.long()])
+    # the split-row output of the positional encoding holds the fp32 output to 2^-17
+    xyz = torch.rand((4001, 3), generator=g) * torch.tensor([8.0, 6.0, 3.0])
+    B = torch.randn((3, 64), generator=g)
+    pos, rng, pos_s = ops.fourier_posenc(xyz.to(DEV), [0, 1500, 4001], B.to(DEV), want_split=True)
+    pos0, rng0 = ops.fourier_posenc(xyz.to(DEV), [0, 1500, 4001], B.to(DEV))
+    assert torch.equal(pos, pos0) and torch.equal(rng, rng0)
+    assert float((ops.unpack_split(pos_s) - pos).abs().max()) < 2e-5
+    assert torch.equal(pos_s, ops.pack_split_rows(pos))
+
+
 # ------------------------------------------------------------------------------------------------ pos-enc
 def test_fourier_posenc_vs_oracle():
     from agile3d_b200 import ops
