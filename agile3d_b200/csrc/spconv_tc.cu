@@ -115,6 +115,7 @@ struct TcParams {
   float* partial;   // split-K: raw accumulators [gridDim.y][n_out][cout]; NULL = fused epilogue
   int NI;           // MMA-issuing warps (1 or 2): issuer w owns the stages of tiles j with (j & 1) == w
   int debug;        // profiling experiments only (AG3D_TC_DEBUG): 1 = skip MMAs, 2 = skip gather loads (MODE 0/1), 4 = one product
+  int tma_out;      // MODE 2, split output: the tile is staged in the (idle) operand ring and stored by the TMA engine
   int cpad;         // TMEM columns per tile (pow2 >= cout)
   int tmem_cols;    // allocation (pow2, 32..512)
 };
@@ -138,7 +139,7 @@ __device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* tm,
 //         ring slot issues a whole stage with a single instruction (lane l = rows 4l..4l+3)
 template <int MODE>
 __global__ void __launch_bounds__(TC_THREADS, MODE ? 2 : 1)
-spconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const TcParams p) {
+spconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out, const TcParams p) {
   constexpr bool SPLIT = MODE != 0;
   constexpr bool TMA = MODE == 2;
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -505,7 +506,18 @@ spconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const TcParams p) {
             for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.f);
           }
           float4* dst = reinterpret_cast<float4*>(p.out + row * p.out_ld + c0);
-          if (p.out_split) {
+          if (TMA && p.tma_out) {          // swizzled slab tile in the operand ring: [128 rows x (32 hi | 32 lo)] per slab
+            uint32_t h[8], l[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) split2(v[2 * e], v[2 * e + 1], h[e], l[e]);
+            const int rr = q * 32 + lane;
+            unsigned char* slab = a_smem + (size_t)(c0 >> 5) * TMA_STAGE + rr * 128;
+            const int k0 = (c0 >> 3) & 3;                                  // first of the two 8-channel chunks
+            *reinterpret_cast<uint4*>(slab + (((k0) ^ (rr & 7)) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(slab + (((k0 + 1) ^ (rr & 7)) << 4)) = make_uint4(h[4], h[5], h[6], h[7]);
+            *reinterpret_cast<uint4*>(slab + (((4 + k0) ^ (rr & 7)) << 4)) = make_uint4(l[0], l[1], l[2], l[3]);
+            *reinterpret_cast<uint4*>(slab + (((5 + k0) ^ (rr & 7)) << 4)) = make_uint4(l[4], l[5], l[6], l[7]);
+          } else if (p.out_split) {
             store_split16(p.out + row * p.out_ld, c0, v);
           } else {
 #pragma unroll
@@ -514,7 +526,24 @@ spconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const TcParams p) {
           }
         }
       }
+      if (TMA && p.tma_out) {
+        // the tile sits in the operand ring in the layout of the output's tensor map: one thread hands it to the TMA engine
+        // (full 128-byte row writes, rows past the end clipped) instead of every thread writing 16-byte pieces of its row
+        fence_proxy_async();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (tid == 0) {
+          const int row_t = (int)(row0 + (long long)j * TC_BM);
+          for (int sl = 0; sl < (p.cout >> 5); ++sl)
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tm_out),
+                         "r"(smem_u32(a_smem) + (uint32_t)sl * TMA_STAGE), "r"(sl * 64), "r"(row_t)
+                         : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
     }
+    if (TMA && p.tma_out && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   } else if (warp != TC_PROD_WARPS + 1) {
     // =========================================================================== MMA issuers
     // Issuing is the serial resource of this kernel (one instruction stream per issuer), so two warps share it:
@@ -771,6 +800,17 @@ bool make_row_map(CUtensorMap* tm, const float* in, int in_ld, int cin, long lon
   return rc == CUDA_SUCCESS;
 }
 
+static bool make_out_map(CUtensorMap* tm, float* out, int out_ld, int cout, long long n_out) {
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc || n_out <= 0) return false;
+  cuuint64_t strides[1] = {(cuuint64_t)out_ld * 4};
+  cuuint64_t dims[2] = {(cuuint64_t)cout * 2, (cuuint64_t)n_out};
+  cuuint32_t box[2] = {64, (cuuint32_t)TC_BM};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 int spconv_tc_launch(const float* in, long long n_in, int in_ld, int cin, const int* nbr, int K, long long n_out,
                      const void* wprep, int cout, const float* scale, const float* shift, const float* residual,
                      int res_ld, float* out, int out_ld, int flags, void* ws, size_t ws_bytes, cudaStream_t st) {
@@ -824,6 +864,13 @@ int spconv_tc_launch(const float* in, long long n_in, int in_ld, int cin, const 
   p.NA = na;
   p.na_log2 = na == 8 ? 3 : (na == 4 ? 2 : 1);
   p.nb_log2 = p.NB == 4 ? 2 : 1;
+  // split-row output through the TMA engine: the finished tile is staged in the operand ring (cout / 32 slabs of 16 KB)
+  static int want_tma_out = -1;
+  if (want_tma_out < 0) { const char* e = getenv("AG3D_TC_TMA_OUT"); want_tma_out = (e && e[0] == '0') ? 0 : 1; }
+  alignas(64) CUtensorMap tm_out;
+  memset(&tm_out, 0, sizeof(tm_out));
+  p.tma_out = (tma && want_tma_out && p.out_split && plan.ksplit == 1 && cout / 32 <= na && n_out < 2147483647LL &&
+               make_out_map(&tm_out, out, out_ld, cout, n_out)) ? 1 : 0;
   size_t smem = fixed + (size_t)na * a_stage;
   if (!two) smem = std::max(smem, (size_t)116 * 1024);   // one CTA per SM: it may allocate all 512 TMEM columns
   static bool attr = false;
@@ -846,9 +893,9 @@ int spconv_tc_launch(const float* in, long long n_in, int in_ld, int cin, const 
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid; cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cfg.attrs = lattr; cfg.numAttrs = pdl ? 1 : 0;
-  if (tma) AG3D_CUDA(cudaLaunchKernelEx(&cfg, spconv_tc_kernel<2>, tm_in, p));
-  else if (split) AG3D_CUDA(cudaLaunchKernelEx(&cfg, spconv_tc_kernel<1>, tm_in, p));
-  else AG3D_CUDA(cudaLaunchKernelEx(&cfg, spconv_tc_kernel<0>, tm_in, p));
+  if (tma) AG3D_CUDA(cudaLaunchKernelEx(&cfg, spconv_tc_kernel<2>, tm_in, tm_out, p));
+  else if (split) AG3D_CUDA(cudaLaunchKernelEx(&cfg, spconv_tc_kernel<1>, tm_in, tm_out, p));
+  else AG3D_CUDA(cudaLaunchKernelEx(&cfg, spconv_tc_kernel<0>, tm_in, tm_out, p));
   AG3D_LAUNCH_CHECK("spconv_tc");
   if (plan.ksplit > 1) {
     const long long total = n_out * (cout / 16);
