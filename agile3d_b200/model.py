@@ -16,6 +16,8 @@ from __future__ import annotations
 
 import math
 
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -357,6 +359,8 @@ class Agile3d(nn.Module):
         self.time_encode = _time_table(d, 200)       # plain attribute, not in the state_dict (agile3d.py:138)
         self.fused_queries = True                    # eval: click-query side in fused kernels (csrc/query_ops.cu)
         self.split_decoder = True                    # eval, tensor-core mode: voxel features / encodings as split rows (TMA-fed decoder)
+        self.decoder_streams = int(os.environ.get("AG3D_DEC_STREAMS", "4"))   # eval: the per-scene voxel kernels of a layer alternate between a few side
+        #                                              streams, so the prologue / tail / merge of one scene run under the next
         # derived weight images (folded BatchNorm, tensor-core images) are cached per parameter generation
         self.register_load_state_dict_post_hook(lambda module, incompatible: ops.bump_param_generation())
 
@@ -541,6 +545,37 @@ class Agile3d(nn.Module):
             return t.to(dev)
         return t.pin_memory().to(dev, non_blocking=True)
 
+    # ---- the scenes of a batch are independent inside a decoder layer: their voxel-streaming kernels alternate between a few
+    #      side streams (forked from / joined into the caller's stream around every phase), so that one scene's kernel
+    #      prologue, tail and partial-result merge run under the next scene's kernel instead of between them
+    def _side_streams(self, dev):
+        if not self.decoder_streams:
+            return None
+        cache = self.__dict__.setdefault("_streams", {})
+        if dev not in cache:
+            cache[dev] = [torch.cuda.Stream(device=dev) for _ in range(self.decoder_streams)]
+        return cache[dev]
+
+    @staticmethod
+    def _fork(side):
+        if side:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            for st in side:
+                st.wait_event(ev)
+
+    @staticmethod
+    def _join(side):
+        if side:
+            cur = torch.cuda.current_stream()
+            for st in side:
+                cur.wait_stream(st)
+
+    @staticmethod
+    def _on(side, i):
+        import contextlib
+        return torch.cuda.stream(side[i % len(side)]) if side else contextlib.nullcontext()
+
     def _forward_mask_fused(self, pcd_features, coordinates, pos_encodings_pcd, click_idx, click_time_idx):
         H = self.num_heads
         dev = pcd_features.device
@@ -590,23 +625,31 @@ class Agile3d(nn.Module):
             labels, counts = [None] * B, [None] * B
             outs = [[] for _ in members]
             ctx = torch.empty((B, H * nq, self.hidden_dim), dtype=torch.float32, device=dev)
+            side = self._side_streams(dev) if (B > 1 and dev.type == "cuda") else None
             for layer in range(self.num_decoders):
                 li = 0 if self.shared_decoder else layer
                 s2c = self.s2c_attention[li][0]
                 blob = self._layer_blob(li)
                 qfold = ops.query_fold_c2s(queries, qpos, blob, B, nq, H)
                 last = layer == self.num_decoders - 1
+                self._fork(side)
                 for i, b in enumerate(members):
-                    ops.c2s_attn_fwd(srcs[i], poss[b], qfold[i], nq, H, labels[i], q_obj[i], counts[i], out=ctx[i], split=split)
+                    with self._on(side, i):
+                        ops.c2s_attn_fwd(srcs[i], poss[b], qfold[i], nq, H, labels[i], q_obj[i], counts[i], out=ctx[i],
+                                         split=split)
+                self._join(side)
                 q1, qh, kh, vh = ops.query_update_a(ctx, queries, qpos, blob, B, nq, s2c.norm.eps)
                 queries, A, c, U, E = ops.query_update_b(q1, qh, kh, vh, qpos, blob, B, nq, H, s2c.norm.eps)
+                self._fork(side)
                 for i, b in enumerate(members):
-                    srcs[i], logits, labels[i], counts[i] = ops.s2c_mask_fwd(
-                        srcs[i], poss[b], A[i], c[i], U[i], s2c.multihead_attn.out_proj.bias, s2c.norm.weight,
-                        s2c.norm.bias, s2c.norm.eps, E[i], q_obj[i], nq, H, meta[b][0] + 1,
-                        x_out=None if layer == 0 else srcs[i],      # never overwrite the caller's backbone features
-                        split=split, write_x=not (split and last))  # the last layer's features are never read again
+                    with self._on(side, i):
+                        srcs[i], logits, labels[i], counts[i] = ops.s2c_mask_fwd(
+                            srcs[i], poss[b], A[i], c[i], U[i], s2c.multihead_attn.out_proj.bias, s2c.norm.weight,
+                            s2c.norm.bias, s2c.norm.eps, E[i], q_obj[i], nq, H, meta[b][0] + 1,
+                            x_out=None if layer == 0 else srcs[i],      # never overwrite the caller's backbone features
+                            split=split, write_x=not (split and last))  # the last layer's features are never read again
                     outs[i].append(logits)
+                self._join(side)
             for i, b in enumerate(members):
                 results[b] = [pcd_features.to_caller(b, lg) for lg in outs[i]]      # logits back in the caller's row order
         per_layer = [list(p) for p in zip(*results)]
