@@ -385,10 +385,14 @@ class Agile3d(nn.Module):
             split_dec = (not self.training) and self.split_decoder and self.backbone.split_rows \
                 and self.backbone.algo != ops.ALGO_SIMT and self.hidden_dim == 128
             pos_s = None
-            if split_dec:
-                pos, rng, pos_s = ops.fourier_posenc(raw_i, offsets, self.pos_enc.gauss_B, want_split=True)
-            else:
-                pos, rng = ops.fourier_posenc(raw_i, offsets, self.pos_enc.gauss_B)
+            # the encodings do not depend on the backbone: they are computed on a side stream under its kernels (eval)
+            aux = self._side_streams(raw_i.device, 1) if (not self.training and raw_i.is_cuda and self.decoder_streams) else None
+            self._fork(aux)
+            with self._on(aux, 0):
+                if split_dec:
+                    pos, rng, pos_s = ops.fourier_posenc(raw_i, offsets, self.pos_enc.gauss_B, want_split=True)
+                else:
+                    pos, rng = ops.fourier_posenc(raw_i, offsets, self.pos_enc.gauss_B)
         if self.training:
             # batch-statistics BatchNorm + recorded activations; one autograd node for backbone + head (engine.py:53)
             named = [(n, p) for n, p in self.named_parameters()
@@ -399,6 +403,7 @@ class Agile3d(nn.Module):
         else:
             with torch.no_grad():
                 pcd, fmaps = self._forward_backbone_eval(x, split_dec)
+        self._join(aux)
         pcd_features = BackboneFeatures(None, offsets, x.C, perm, inv, Fs=pcd) if split_dec \
             else BackboneFeatures(pcd, offsets, x.C, perm, inv)
         coordinates = BackboneFeatures(raw, offsets, x.C)
@@ -548,13 +553,17 @@ class Agile3d(nn.Module):
     # ---- the scenes of a batch are independent inside a decoder layer: their voxel-streaming kernels alternate between a few
     #      side streams (forked from / joined into the caller's stream around every phase), so that one scene's kernel
     #      prologue, tail and partial-result merge run under the next scene's kernel instead of between them
-    def _side_streams(self, dev):
-        if not self.decoder_streams:
+    def _side_streams(self, dev, n=None):
+        """side streams owned by the CALLER's stream: memory allocated on them is only ever consumed by work that the caller's
+        stream orders (fork / join), so two callers on different streams (two batches in flight) never share a pool"""
+        n = self.decoder_streams if n is None else n
+        if not n:
             return None
         cache = self.__dict__.setdefault("_streams", {})
-        if dev not in cache:
-            cache[dev] = [torch.cuda.Stream(device=dev) for _ in range(self.decoder_streams)]
-        return cache[dev]
+        key = (dev, torch.cuda.current_stream(dev).cuda_stream, n)
+        if key not in cache:
+            cache[key] = [torch.cuda.Stream(device=dev) for _ in range(n)]
+        return cache[key]
 
     @staticmethod
     def _fork(side):

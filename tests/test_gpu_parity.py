@@ -555,6 +555,42 @@ def test_many_click_queries_vs_fp64_oracle():
         assert e < 1e-3, f"layer {l}: rel err {e}"
 
 
+def test_two_batches_in_flight_match_sequential():
+    """The serving pattern of bench.py: consecutive batches on alternating caller streams, sharing one model (its side
+    streams, workspaces and weight caches).  Every step must reproduce, bit for bit, what the same batch gives alone."""
+    from agile3d_b200.scenes import make_clicks, make_scene
+    import agile3d_b200
+    m = _gpu_model(7)
+    batches = []
+    for k, (n, seed) in enumerate([(7000, 41), (9000, 42)]):
+        scs = [make_scene(n + 500 * j, 0.02, seed=seed + 10 * j, n_box=8) for j in range(3)]
+        ck, tm = zip(*[make_clicks(sc, 3, 2, 1, seed=seed + j)[:2] for j, sc in enumerate(scs)])
+        coords = np.concatenate([np.concatenate([np.full((sc["coords"].shape[0], 1), j, np.int32), sc["coords"]], 1)
+                                 for j, sc in enumerate(scs)], 0)
+        feats = np.concatenate([sc["feats"] for sc in scs], 0)
+        raw = np.concatenate([sc["raw_coords"] for sc in scs], 0)
+        batches.append((torch.from_numpy(coords).to(DEV), torch.from_numpy(feats).to(DEV), torch.from_numpy(raw).to(DEV),
+                        list(ck), list(tm)))
+
+    def step(b):
+        c, f, r, ck, tm = batches[b]
+        x = agile3d_b200.SparseTensor(coordinates=c, features=f, device=DEV)
+        out = m.forward_mask(*m.forward_backbone(x, raw_coordinates=r), click_idx=ck, click_time_idx=tm)
+        return [p.clone() for p in out["pred_masks"]] + [p.clone() for a in out["aux_outputs"] for p in a["pred_masks"]]
+
+    ref = [step(0), step(1)]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    outs = []
+    for i in range(8):
+        with torch.cuda.stream(streams[i % 2]):
+            outs.append((i % 2, step(i % 2)))
+    torch.cuda.synchronize()
+    for b, got in outs:
+        for a, e in zip(got, ref[b]):
+            assert torch.equal(a, e)
+
+
 def test_forward_mask_is_repeatable_and_handles_unmutated():
     g = load_golden("g3000_k3")
     m = _gpu_model(g["wseed"])
