@@ -8,7 +8,10 @@ Workload (BASELINE.json metric, SURVEY.md §8(d) "headline"): synthetic ScanNet-
 (2 cm), 5 objects x 2 clicks = 10 clicks -> 20 click queries, eval-mode ``forward_backbone`` + ``forward_mask``
 (kernel maps are rebuilt for every scene, as the reference does per scene).  One step = one batch of B scenes.
 One JSON line on stdout (rank 0).  Weak scaling: every rank runs its own B scenes per step, no collectives on
-the data path (inference shards by scene).
+the data path (inference shards by scene).  `--pipeline P` (default 2): P batches in flight on
+alternating streams, as a serving loop would run them; every step is issued and completed inside the timed region;
+`--pipeline 1` runs the steps back to back.  The `e2e` value repeats the measurement with pinned HOST buffers: the
+inputs of every step are copied to the device and its logits back, on side streams, inside the timed region.
 
 `--impl reference` times the CPU restatement of the reference path (oracle/, fp32, all host threads): the
 reference's real CPU path needs MinkowskiEngine, which cannot be installed here.
