@@ -12,6 +12,7 @@ concatenated buffer.
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -175,6 +176,9 @@ class Res16UNet34C(nn.Module):
             c = P[4 + j]
         self.algo = ops.ALGO_AUTO
         self.reorder_rows = True    # internal row order by neighbour pattern (CoordinateMaps._reorder); callers never see it
+        # train: weight gradients on a side stream under the data-gradient chain.  Opt-in (AG3D_WGRAD_STREAM=1): measured
+        # 82.13 vs 82.20 ms/step at 4 x 150k voxels - the training step is bound by the host's ~1600 launches, not by the GPU
+        self.wgrad_overlap = os.environ.get("AG3D_WGRAD_STREAM", "0") == "1"
         self.split_rows = True      # keep activations as bf16 hi/lo pair rows between tensor-core layers
         self._fold_cache = None
 
@@ -355,6 +359,21 @@ class Res16UNet34C(nn.Module):
                 cache[key] = xs
         return xs
 
+    def _wgrad_stream(self, dev):
+        """side stream of the weight-gradient kernels, owned by the caller's stream (AG3D_WGRAD_STREAM=0: none)"""
+        if not self.wgrad_overlap or dev.type != "cuda":
+            return None
+        cache = self.__dict__.setdefault("_wg_streams", {})
+        key = (dev, torch.cuda.current_stream(dev).cuda_stream)
+        if key not in cache:
+            cache[key] = torch.cuda.Stream(device=dev)
+        return cache[key]
+
+    def _wgrad_join(self, dev):
+        side = self._wgrad_stream(dev)
+        if side is not None:
+            torch.cuda.current_stream(dev).wait_stream(side)
+
     def _wgrad(self, x, nbr, dy, K, xs=None, dys=None):
         """dW = x[nbr]^T dy: tcgen05 kernel on split copies of both operands in tensor-core mode, else fp32 SIMT."""
         cin, cout = x.shape[1], dy.shape[1]
@@ -387,7 +406,22 @@ class Res16UNet34C(nn.Module):
         K = W[rec["name"]][0].shape[0]
         dys = ops.pack_split_rows(dy) if self._tc_rows(rec["x"].shape[1], dy.shape[1], K,
                                                        min(rec["x"].shape[0], dy.shape[0])) else None
-        dw = self._wgrad(rec["x"], rec["nbr"], dy, K, xs=rec.get("xs"), dys=dys)
+        # the weight gradient is a leaf of the backward: it runs on a side stream under the data-gradient chain
+        side = self._wgrad_stream(dy.device)
+        if side is not None:
+            xs = rec.get("xs")
+            if xs is None and dys is not None:
+                xs = self._split_of(rec["x"])              # split copy made on the main stream, before the fork
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            side.wait_event(ev)
+            with torch.cuda.stream(side):
+                dw = self._wgrad(rec["x"], rec["nbr"], dy, K, xs=xs, dys=dys)
+            for t in (rec["x"], xs, dy, dys, rec["nbr"]):
+                if t is not None:
+                    t.record_stream(side)                  # keep the allocator from recycling them under the side stream
+        else:
+            dw = self._wgrad(rec["x"], rec["nbr"], dy, K, xs=rec.get("xs"), dys=dys)
         kernel = self.get_submodule(rec["name"]).kernel
         grads[rec["name"] + ".kernel"] = dw.view_as(kernel)
         if not want_dx:
@@ -485,6 +519,7 @@ class Res16UNet34C(nn.Module):
             return rec
 
         def stage_done():
+            self._wgrad_join(dy.device)                            # the stage's weight gradients are complete
             if sink is not None and grads:
                 sink(dict(grads))
                 grads.clear()

@@ -1,16 +1,15 @@
 #!/bin/bash
-# Current GPU session (overwritten per call; results land in gpurun_out/ and the kept ones are copied to profiles/).
 cd "$GRAFT_REPO_ROOT" || exit 1
 mkdir -p gpurun_out
-S=s45
-timeout 900 python bench.py > gpurun_out/${S}_bench_n1.json 2> gpurun_out/${S}_n1.err
-timeout 900 python bench.py --steps 10 --batch 1 --no-parity > gpurun_out/${S}_bench_b1.json 2> gpurun_out/${S}_b1.err
-timeout 900 python bench.py --steps 10 --workload c2 --no-parity > gpurun_out/${S}_bench_c2.json 2> gpurun_out/${S}_c2.err
-for f in n1 b1 c2; do python - <<PY
+S=s46
+timeout 1800 python -m pytest tests/test_gpu_train.py -x -q -m gpu > gpurun_out/${S}_pytest_train.log 2>&1
+tail -n 3 gpurun_out/${S}_pytest_train.log
+timeout 900 python bench.py --steps 6 --workload train --batch 4 > gpurun_out/${S}_train_on.json 2> gpurun_out/${S}_train_on.err
+AG3D_WGRAD_STREAM=0 timeout 900 python bench.py --steps 6 --workload train --batch 4 > gpurun_out/${S}_train_off.json 2> gpurun_out/${S}_train_off.err
+for f in train_on train_off; do python - <<PY
 import json
-d = json.load(open("gpurun_out/${S}_bench_$f.json"))
+d = json.load(open("gpurun_out/${S}_$f.json"))
 print("$f", {k: d.get(k) for k in ("value", "ms_per_step")}, "e2e", d["e2e"]["value"])
-print("   ", {k: (v["ms_per_step"], v.get("frac_of_hbm_peak")) for k, v in d["roofline"]["families"].items()})
 PY
 done
-tail -n 2 gpurun_out/${S}_n1.err
+tail -n 2 gpurun_out/${S}_train_on.err
