@@ -305,7 +305,7 @@ def test_c2s_vs_oracle(nv, nq, n_obj, algo):
 
 
 @pytest.mark.parametrize("nv,nq,n_obj", [(1000, 11, 2), (5003, 15, 3), (20000, 20, 6), (4100, 27, 9), (3000, 45, 11),
-                                         (64, 16, 3), (65, 12, 2), (150001, 20, 6)])
+                                         (64, 16, 3), (65, 12, 2), (150001, 20, 6), (1, 11, 2), (63, 20, 4)])
 def test_c2s_split_rows_vs_oracle(nv, nq, n_obj):
     """the TMA-fed kernel on split rows: compared with the fp64 oracle evaluated on the values the split rows hold
     (hi + lo, 2^-17 relative from x) and with the fp32-row kernel"""
@@ -328,7 +328,7 @@ def test_c2s_split_rows_vs_oracle(nv, nq, n_obj):
 
 
 @pytest.mark.parametrize("nv,nq,n_obj", [(1000, 11, 2), (5003, 15, 3), (20000, 20, 6), (4100, 24, 9), (777, 24, 12),
-                                         (128, 16, 4), (129, 20, 5), (150001, 20, 6)])
+                                         (128, 16, 4), (129, 20, 5), (150001, 20, 6), (1, 11, 2), (127, 20, 4)])
 def test_s2c_mask_split_rows_vs_oracle(nv, nq, n_obj):
     """the TMA-fed kernel on split rows vs the fp64 oracle evaluated on the values the split rows hold"""
     from agile3d_b200 import ops
