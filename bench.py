@@ -652,8 +652,7 @@ def run_clickloop(args, rank, world, local_rank):
                 objs = torch.tensor([o for o in range(K + 1) for _ in click_idx[str(o)]], dtype=torch.int32).pin_memory().to(dev, non_blocking=True)
                 pred = ops.click_pred(out["pred_masks"][0], nv, K + 1, rows, objs)
                 nq_seen.append(10 + n_clicks)
-            iou, _ = interactive.mean_iou_scene(pred, lab_full, inv)
-            new, _, _, new_t = interactive.get_simulated_clicks(pred, lab, r, n_clicks, training=False)
+            (iou, _), (new, _, _, new_t) = interactive.iou_and_simulated_clicks(pred, lab_full, inv, lab, r, n_clicks, n_obj=K + 1)
             if new is not None:
                 click_idx, click_time = interactive.extend_clicks(click_idx, click_time, new, new_t)
             n_clicks += K if n_clicks == 0 else 1
@@ -703,7 +702,7 @@ def run_clickloop(args, rank, world, local_rank):
         "warmup": max(1, min(args.warmup, 2)), "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": CLICK_WORKLOAD, "voxels": n_v, "rounds_per_scene": rounds, "ms_per_round": ms / steps / rounds,
-                   "click_queries": [min(nq_seen), max(nq_seen)], "host_syncs_per_round": 2,
+                   "click_queries": [min(nq_seen), max(nq_seen)], "host_syncs_per_round": 1,
                    "l2_policy": "two scenes rotated; a round streams the 41 MB voxel features + 41 MB encodings 6 times"},
         "e2e": {"value": world * steps / (ms_e2e / 1e3), "unit": "scenes/s", "ms_per_step": ms_e2e / steps,
                 "h2d_bytes_per_step": n_v * (16 + 12 + 12 + 8) + int(host[0][4].shape[0]) * 16, "d2h_bytes_per_step": rounds * (64 * 4 + 11 * 24)},

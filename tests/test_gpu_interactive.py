@@ -61,6 +61,24 @@ def test_simulated_clicks_vs_oracle(n, k, mode):
         assert all(torch.equal(a.cpu(), b) for o in got[2] for a, b in zip(got[2][o], want[2][o]))
 
 
+@pytest.mark.parametrize("n_clicks", [0, 7])
+def test_fused_round_equals_separate_calls(n_clicks):
+    """iou_and_simulated_clicks (one read-back per round) == mean_iou_scene + get_simulated_clicks"""
+    from agile3d_b200 import interactive
+    sc, xyz, labels, pred = _scene(77, 20000, 6)
+    inv = sc["inverse_map"]
+    lab_full = labels[inv]
+    p, l, lf, iv, x = pred.to(DEV), labels.to(DEV), lab_full.to(DEV), inv.to(DEV), xyz.to(DEV)
+    random.seed(3)
+    iou_a, ious_a = interactive.mean_iou_scene(p, lf, iv)
+    a = interactive.get_simulated_clicks(p, l, x, n_clicks, training=False)
+    random.seed(3)
+    (iou_b, ious_b), b = interactive.iou_and_simulated_clicks(p, lf, iv, l, x, n_clicks)
+    assert float(iou_a) == float(iou_b) and ious_a == ious_b
+    assert a[0] == b[0] and a[1] == b[1] and a[3] == b[3]
+    assert all(torch.equal(u, v) for k in a[2] for u, v in zip(a[2][k], b[2][k]))
+
+
 def test_nothing_wrong_returns_nones():
     from agile3d_b200 import interactive
     _, xyz, labels, _ = _scene(1, 3000, 3)
