@@ -560,7 +560,7 @@ class Agile3d(nn.Module):
         if not n:
             return None
         cache = self.__dict__.setdefault("_streams", {})
-        key = (dev, torch.cuda.current_stream(dev).cuda_stream, n)
+        key = (dev, ops._raw_stream(), n)
         if key not in cache:
             cache[key] = [torch.cuda.Stream(device=dev) for _ in range(n)]
         return cache[key]

@@ -58,7 +58,26 @@ class _Timed:
         return False
 
 
+class _NoTimed:
+    __slots__ = ()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_TIMED = _NoTimed()
+_TimedOn = _Timed
+
+
+def _Timed(family, nbytes, flops=0):      # noqa: N802 - keeps the call sites; no object, no events unless a profiler is set
+    return _TimedOn(family, nbytes, flops) if _prof is not None else _NO_TIMED
+
+
 _ws_cache = {}
+_spconv_ws_bytes = {}
 
 # Generation counter of the model parameters: bumped by every writer that changes parameter VALUES without going
 # through torch's version counter (FlatAdamW.step's raw kernel, load_state_dict, .to()).  Caches of derived weight
@@ -74,9 +93,15 @@ def param_generation():
     return _param_generation[0]
 
 
+def _raw_stream():
+    """raw cudaStream_t of torch's current stream on the current device (two C calls; torch.cuda.current_stream() builds
+    a Stream object and costs several microseconds per library call)"""
+    return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
+
+
 def _workspace(tag, device, nbytes):
     """Grow-only scratch buffer per (purpose, device, stream); stream-ordered reuse is safe on one stream."""
-    key = (tag, device, torch.cuda.current_stream().cuda_stream)
+    key = (tag, device, _raw_stream())
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = _ws_cache[key] = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=device)
@@ -88,11 +113,11 @@ def kernel_launches():
 
 
 def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return C.c_void_p(_raw_stream())
 
 
 def _p(t):
-    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+    return t.data_ptr() if t is not None else None          # ctypes converts int / None to void* (argtypes are set)
 
 
 def _need_cuda(*ts):
@@ -296,7 +321,12 @@ def spconv_fwd(x, nbr, weight, out, scale=None, shift=None, residual=None, relu=
         | (RES_SPLIT if (res_split and residual is not None) else 0)
     ws, wsb = None, 0
     if weight_tc is not None and algo != ALGO_SIMT:
-        wsb = lib().ag3d_spconv_workspace_bytes(n_out, K, cin, cout)
+        wkey = (n_out, K, cin, cout)
+        wsb = _spconv_ws_bytes.get(wkey)
+        if wsb is None:
+            wsb = _spconv_ws_bytes[wkey] = lib().ag3d_spconv_workspace_bytes(n_out, K, cin, cout)
+            if len(_spconv_ws_bytes) > 4096:
+                _spconv_ws_bytes.clear()
         if wsb:
             ws = _workspace("spconv", x.device, wsb)
     with _Timed("spconv", nbytes, 2 * pairs * cin * cout):
@@ -395,7 +425,7 @@ def c2s_attn_fwd(x, pos, qfold, nq, heads, label=None, q_obj=None, obj_count=Non
     if tuple(ctx.shape) != (heads * nq, x.shape[1]) or not ctx.is_contiguous():
         raise _lib.Ag3dError("c2s output must be contiguous [heads*nq, 128]")
     wsb = lib().ag3d_c2s_workspace_bytes(nq, heads)
-    key = (x.device, torch.cuda.current_stream().cuda_stream)
+    key = (x.device, _raw_stream())
     ws = _c2s_ws.get(key)
     if ws is None or ws.numel() < wsb:
         ws = _c2s_ws[key] = torch.empty(wsb, dtype=torch.uint8, device=x.device)
