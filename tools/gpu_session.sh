@@ -2,15 +2,10 @@
 # Current GPU session (overwritten per call; results land in gpurun_out/ and the kept ones are copied to profiles/).
 cd "$GRAFT_REPO_ROOT" || exit 1
 mkdir -p gpurun_out
-S=s52
-timeout 600 python -c "import __graft_entry__ as g; g.build(); g.smoke()" > gpurun_out/${S}_smoke.log 2>&1; tail -n 1 gpurun_out/${S}_smoke.log
-timeout 900 python bench.py > gpurun_out/${S}_bench_n1.json 2> gpurun_out/${S}_n1.err
-timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${S}_bench_reference.json 2> gpurun_out/${S}_ref.err
-timeout 900 python bench.py --steps 10 --workload c2 --no-parity > gpurun_out/${S}_bench_c2.json 2> gpurun_out/${S}_c2.err
-for f in n1 reference c2; do python - <<PY
-import json
-d = json.load(open("gpurun_out/${S}_bench_$f.json"))
-print("$f", {k: d.get(k) for k in ("value", "ms_per_step")}, "e2e", d["e2e"]["value"], d.get("parity") and d["parity"]["mask_logits_rel_err_per_layer"])
-PY
-done
-tail -n 2 gpurun_out/${S}_n1.err
+S=s53
+export AG3D_DEC_STREAMS=0
+timeout 1500 ncu --set full --clock-control none --profile-from-start off -k regex:spconv_tc_kernel -c 70 -o /tmp/${S}_ncu_spconv python tools/profile_step.py --batch 8 > gpurun_out/${S}_ncu_spconv.log 2>&1
+ncu -i /tmp/${S}_ncu_spconv.ncu-rep --page raw --csv > gpurun_out/${S}_ncu_spconv_raw.csv 2>/dev/null
+timeout 900 ncu --set full --clock-control none --profile-from-start off -k regex:"s2c_split_kernel|c2s_split_kernel" -c 4 -o /tmp/${S}_ncu_decoder python tools/profile_step.py --batch 8 > gpurun_out/${S}_ncu_decoder.log 2>&1
+ncu -i /tmp/${S}_ncu_decoder.ncu-rep --page raw --csv > gpurun_out/${S}_ncu_decoder_raw.csv 2>/dev/null
+ls -la gpurun_out/${S}_*; tail -n 2 gpurun_out/${S}_ncu_spconv.log
