@@ -425,7 +425,7 @@ def run_ours(args, rank, world, local_rank):
                    "l2_policy": f"rotating pool of {n_pool} distinct batches; per-step activations (~1.7 GB/scene) exceed the 126 MB L2",
                    "batches_in_flight": max(args.pipeline, 1),
                    "decoder_streams": int(model.decoder_streams),
-                   "spconv_algo": {0: "auto", 1: "simt_fp32", 2: "tcgen05_3xtf32"}[model.backbone.algo]},
+                   "spconv_algo": {0: "auto", 1: "simt_fp32", 2: "tcgen05_bf16x3"}[model.backbone.algo]},
         "e2e": {"value": e2e_value, "unit": "scenes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps,
                 "copies": "pinned host buffers, every step; H2D of step i+1 and D2H of step i on side streams under the kernels "
